@@ -1,0 +1,120 @@
+/* pylbl_b200.h -- C ABI of the B200 line-by-line absorption library (libpylbl_b200.so).
+ *
+ * This is the drop-in boundary for pyLBL's lines backend.  The reference reaches its C
+ * library through ctypes (pyLBL/c_lib/gas_optics.py:11-12,68-91) and that library exports
+ * exactly one entry point, absorption() (pyLBL/c_lib/absorption.c:19-30).  This header
+ * declares
+ *   (1) that same symbol with that same signature, and
+ *   (2) a handle-based, layer-batched form of it, which is what the Python `Gas` class of
+ *       this repository (pylbl_b200/gas_optics.py) binds.
+ * Only plain C types cross the boundary.  Every function returns 0 on success and 1 on
+ * error (the reference's convention, absorption.c:11-15, spectral_database.c:11-16); the
+ * message is printed to stderr like the reference does and kept for lbl_last_error().
+ * No function throws.  There is no CPU fallback: without a CUDA device every compute
+ * entry point fails with 1.
+ */
+#ifndef PYLBL_B200_H_
+#define PYLBL_B200_H_
+
+#include <stddef.h>
+
+#if defined(__GNUC__)
+#define LBL_API __attribute__((visibility("default")))
+#else
+#define LBL_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LBL_PRECISION_FP64 0
+#define LBL_PRECISION_FP32 1
+
+/* One molecule of one spectral database, packed into device memory. */
+typedef struct lbl_gas lbl_gas;
+
+/* Statistics of the most recent lbl_gas_compute()/lbl_gas_wait() on a handle. */
+typedef struct lbl_stats
+{
+    long long evals;        /* sum over layers and processed lines of (e-s+1), spectra.c:48-62 */
+    long long h2d_bytes;    /* bytes copied host->device by the call (layer states, first-use packing) */
+    long long d2h_bytes;    /* bytes copied device->host by the call (spectra) */
+    int n_lines;            /* transition rows of the molecule */
+    int n_active;           /* rows before the reference's early break (absorption.c:80-83) */
+    int n_layers;
+    int n_points;           /* (vn - v0)*n_per_v */
+    int points_per_thread;
+    int sum_launches;       /* launches of the summation kernel */
+    int total_launches;     /* all kernel launches */
+    float scale_ms;         /* K1, CUDA events on the launching stream */
+    float sum_ms;           /* K2 (dominant kernel), summed over launches */
+    float pedestal_ms;      /* K3 + K4 */
+    float total_ms;         /* first enqueue -> last copy complete */
+} lbl_stats;
+
+/* ---- (1) the reference's own entry point ---------------------------------------------
+ * Replaces: pyLBL/c_lib/absorption.c:19-30 (same argument order and meaning).
+ * k is caller-allocated, (vn-v0)*n_per_v doubles, overwritten (absorption.c:41).
+ * Handles are cached per (database, formula) inside the library, so the sqlite read and
+ * the device upload happen on the first call only.  Uses CUDA device 0 unless the
+ * environment variable PYLBL_B200_DEVICE says otherwise.
+ */
+LBL_API int absorption(double pressure, double temperature, double volume_mixing_ratio,
+               int v0, int vn, int n_per_v, double* k, char* database, char* formula,
+               int cut_off, int remove_pedestal);
+
+/* ---- (2) handle-based, batched form --------------------------------------------------
+ * lbl_gas_open replaces the per-call open_database/molecule_id/tips_data/mass_data/
+ * line_parameters sequence (absorption.c:45-79, spectral_database.c:19-180): it runs the
+ * same four queries once and packs the rows into sorted structure-of-arrays buffers on
+ * CUDA device `device`.  A molecule without TIPS rows opens successfully and computes
+ * all-zero spectra (absorption.c:53-59).  Unknown molecule -> 1 (spectral_database.c:152).
+ */
+LBL_API int lbl_gas_open(const char* database, const char* formula, int device, lbl_gas** out);
+LBL_API int lbl_gas_close(lbl_gas* gas);
+
+/* Layer-batched absorption(): for layer L, k_host[L*n .. L*n+n) receives what the
+ * reference's absorption(pressure[L], temperature[L], vmr[L], v0, vn, n_per_v, ...) writes
+ * to k.  n = (vn-v0)*n_per_v.  k_host may be pageable or pinned (lbl_host_alloc) memory; it
+ * may be NULL, in which case the spectra stay on the device (lbl_gas_device_result).
+ * precision: LBL_PRECISION_FP64 (parity target 1e-9) or LBL_PRECISION_FP32 (opt-in, 1e-4).
+ * lbl_gas_compute = lbl_gas_submit + lbl_gas_wait.  After lbl_gas_submit returns, work is
+ * enqueued on the handle's CUDA streams; k_host must stay valid until lbl_gas_wait.
+ */
+LBL_API int lbl_gas_compute(lbl_gas* gas, int n_layers, const double* pressure,
+                    const double* temperature, const double* volume_mixing_ratio,
+                    int v0, int vn, int n_per_v, int cut_off, int remove_pedestal,
+                    int precision, double* k_host);
+LBL_API int lbl_gas_submit(lbl_gas* gas, int n_layers, const double* pressure,
+                   const double* temperature, const double* volume_mixing_ratio,
+                   int v0, int vn, int n_per_v, int cut_off, int remove_pedestal,
+                   int precision, double* k_host);
+LBL_API int lbl_gas_wait(lbl_gas* gas);
+
+/* Results of the last call. */
+LBL_API int lbl_gas_stats(lbl_gas* gas, lbl_stats* out);
+/* Device pointer to the spectra of the last chunk of layers ([layers][n] doubles). */
+LBL_API int lbl_gas_device_result(lbl_gas* gas, double** device_ptr, long long* count);
+/* Window indices (s, e) of spectra.c:48-62 for every processed line of `layer`, in
+ * database row order; -1,-1 for lines the reference skips (s >= n).  capacity >= n_active. */
+LBL_API int lbl_gas_windows(lbl_gas* gas, int layer, int* s, int* e, int capacity);
+/* Scaled line parameters of `layer` (spectra.c:17-45) in database row order:
+ * out[4*r + {0,1,2,3}] = nu', alpha, gamma, sw'.  capacity >= n_active. */
+LBL_API int lbl_gas_scaled(lbl_gas* gas, int layer, double* out, int capacity);
+
+/* Pinned host memory for k_host (lets the device->host copy run asynchronously). */
+LBL_API int lbl_host_alloc(size_t bytes, void** ptr);
+LBL_API int lbl_host_free(void* ptr);
+
+LBL_API int lbl_device_count(int* count);
+/* Layers per launch group: 0 = automatic. */
+LBL_API int lbl_set_chunk_layers(int layers);
+LBL_API const char* lbl_last_error(void);
+LBL_API int lbl_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* PYLBL_B200_H_ */

@@ -1,0 +1,873 @@
+// lbl_api.cu -- C ABI (include/pylbl_b200.h), device packing and launch orchestration.
+//
+// Reference behaviour replaced here: pyLBL/c_lib/absorption.c:19-99 (driver of one
+// (gas, layer) call) -- batched over layers, with the database read hoisted into
+// lbl_gas_open().  Citations are relative to /root/reference/pyLBL/c_lib/.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/pylbl_b200.h"
+#include "lbl_db.h"
+#include "lbl_kernels.cuh"
+
+namespace lbl
+{
+namespace
+{
+
+thread_local std::string g_last_error;
+int g_chunk_layers = 0;
+
+int fail(const std::string& msg)
+{
+    g_last_error = msg;
+    fprintf(stderr, "%s\n", msg.c_str());
+    return 1;
+}
+
+#define LBL_CUDA(call)                                                                     \
+    do                                                                                     \
+    {                                                                                      \
+        cudaError_t err__ = (call);                                                        \
+        if (err__ != cudaSuccess)                                                          \
+        {                                                                                  \
+            return fail(std::string("Error: CUDA: ") + cudaGetErrorString(err__) + " at " + \
+                        #call);                                                            \
+        }                                                                                  \
+    } while (0)
+
+// Grow-only device buffer.
+struct DevBuf
+{
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T> T* as() const { return static_cast<T*>(p); }
+};
+
+// A packed, nu-sorted line list on the device.
+struct DeviceLines
+{
+    int n = 0;
+    DevBuf nu, sw, gamma_air, gamma_self, n_air, elower, delta_air, mass, iso, db_to_sorted;
+    bool has_perm = false;
+    size_t bytes = 0;
+    void release()
+    {
+        for (DevBuf* b : {&nu, &sw, &gamma_air, &gamma_self, &n_air, &elower, &delta_air, &mass,
+                          &iso, &db_to_sorted})
+        {
+            b->release();
+        }
+    }
+    LinesView view(int n_active) const
+    {
+        LinesView v;
+        v.n = n_active;
+        v.nu = nu.as<double>();
+        v.sw = sw.as<double>();
+        v.gamma_air = gamma_air.as<double>();
+        v.gamma_self = gamma_self.as<double>();
+        v.n_air = n_air.as<double>();
+        v.elower = elower.as<double>();
+        v.delta_air = delta_air.as<double>();
+        v.mass = mass.as<double>();
+        v.iso = iso.as<int>();
+        v.db_to_sorted = has_perm ? db_to_sorted.as<int>() : nullptr;
+        return v;
+    }
+};
+
+struct Plan  // which lines a given (v0, vn, cut_off) sees, and where they are on the device
+{
+    int v0 = 0, vn = 0, cut_off = 0;
+    int n_active = 0;
+    bool valid = false;
+    DeviceLines own;               // used only when the database rows are not nu-sorted
+    std::vector<int> sorted_to_db; // host copy of the permutation (empty = identity)
+};
+
+constexpr int kMaxEvents = 64;
+
+}  // namespace
+}  // namespace lbl
+
+using namespace lbl;
+
+struct lbl_gas
+{
+    int device = 0;
+    std::string database, formula;
+    MoleculeData mol;
+    DeviceLines base;  // all rows, valid when mol.sorted
+    DevBuf tips_t, tips_q;
+    Plan plan;
+    size_t open_h2d = 0;
+    bool open_h2d_reported = false;
+
+    cudaStream_t s_compute = nullptr, s_side = nullptr, s_copy = nullptr;
+    DevBuf rec_ab, rec_cc, rec_chk, rec_gen, layers_dev, evals_dev, pedbin, pedcorr, pednodes;
+    DevBuf out[2];
+    LayerIn* layers_host = nullptr;  // pinned
+    size_t layers_host_cap = 0;
+    unsigned long long* evals_host = nullptr;  // pinned
+    size_t evals_host_cap = 0;
+
+    // per-call state
+    std::vector<cudaEvent_t> ev_pool;
+    int ev_used = 0;
+    struct ChunkEvents
+    {
+        cudaEvent_t k1_begin, k1_end, k2_begin, k2_end, ped_begin, ped_end;
+        bool pedestal;
+    };
+    std::vector<ChunkEvents> chunk_events;
+    cudaEvent_t ev_call_begin = nullptr, ev_call_end = nullptr;
+    cudaEvent_t ev_out_ready[2] = {nullptr, nullptr}, ev_out_free[2] = {nullptr, nullptr};
+    bool out_busy[2] = {false, false};
+    bool pending = false;
+    lbl_stats stats{};
+    // what is resident after the last call (for windows/scaled/device_result)
+    GridSpec last_grid{};
+    int last_chunk_first = 0, last_chunk_layers = 0, last_slot = 0;
+    std::vector<LayerIn> last_layers;
+};
+
+namespace lbl
+{
+namespace
+{
+
+int upload(DevBuf& b, const void* src, size_t bytes, cudaStream_t s, size_t& counter)
+{
+    LBL_CUDA(b.reserve(std::max<size_t>(bytes, 16)));
+    if (bytes)
+    {
+        LBL_CUDA(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, s));
+    }
+    counter += bytes;
+    return 0;
+}
+
+// Uploads rows order[0..n) of the molecule (order empty = identity).
+int pack_lines(lbl_gas* g, DeviceLines& d, const std::vector<int>& order, int n)
+{
+    const MoleculeData& m = g->mol;
+    auto gather_d = [&](const std::vector<double>& src, std::vector<double>& tmp) {
+        if (order.empty()) return src.data();
+        tmp.resize(n);
+        for (int i = 0; i < n; ++i) tmp[i] = src[order[i]];
+        return (const double*)tmp.data();
+    };
+    std::vector<double> tmp;
+    size_t bytes = 0;
+    const std::vector<double>* cols[8] = {&m.nu, &m.sw, &m.gamma_air, &m.gamma_self,
+                                          &m.n_air, &m.elower, &m.delta_air, &m.mass};
+    DevBuf* bufs[8] = {&d.nu, &d.sw, &d.gamma_air, &d.gamma_self,
+                       &d.n_air, &d.elower, &d.delta_air, &d.mass};
+    for (int c = 0; c < 8; ++c)
+    {
+        const double* src = gather_d(*cols[c], tmp);
+        if (upload(*bufs[c], src, sizeof(double) * n, g->s_compute, bytes)) return 1;
+        LBL_CUDA(cudaStreamSynchronize(g->s_compute));  // tmp is reused
+    }
+    std::vector<int> iso0(n);
+    for (int i = 0; i < n; ++i) iso0[i] = m.iso[order.empty() ? i : order[i]] - 1;
+    if (upload(d.iso, iso0.data(), sizeof(int) * n, g->s_compute, bytes)) return 1;
+    d.has_perm = !order.empty();
+    if (d.has_perm)
+    {
+        std::vector<int> inv(n);
+        for (int i = 0; i < n; ++i) inv[order[i]] = i;
+        if (upload(d.db_to_sorted, inv.data(), sizeof(int) * n, g->s_compute, bytes)) return 1;
+    }
+    LBL_CUDA(cudaStreamSynchronize(g->s_compute));
+    d.n = n;
+    d.bytes = bytes;
+    g->open_h2d += bytes;
+    return 0;
+}
+
+// The reference walks rows in database order and STOPS at the first row outside
+// [v0-(cut+1), vn+cut+1] (absorption.c:80-83); rows after it are never seen.
+int active_prefix(const MoleculeData& m, int v0, int vn, int cut_off)
+{
+    const int n = (int)m.nu.size();
+    const double hi = (double)(vn + cut_off + 1);
+    const double lo = (double)(v0 - (cut_off + 1));
+    if (m.sorted)
+    {
+        if (n == 0 || m.nu[0] < lo) return 0;
+        return (int)(std::upper_bound(m.nu.begin(), m.nu.end(), hi) - m.nu.begin());
+    }
+    int r = 0;
+    for (; r < n; ++r)
+    {
+        if (m.nu[r] > hi || m.nu[r] < lo) break;
+    }
+    return r;
+}
+
+int make_plan(lbl_gas* g, int v0, int vn, int cut_off)
+{
+    Plan& p = g->plan;
+    if (p.valid && p.v0 == v0 && p.vn == vn && p.cut_off == cut_off) return 0;
+    p.valid = false;
+    p.v0 = v0;
+    p.vn = vn;
+    p.cut_off = cut_off;
+    p.n_active = active_prefix(g->mol, v0, vn, cut_off);
+    p.sorted_to_db.clear();
+    if (!g->mol.sorted && p.n_active > 0)
+    {
+        p.sorted_to_db.resize(p.n_active);
+        std::iota(p.sorted_to_db.begin(), p.sorted_to_db.end(), 0);
+        const std::vector<double>& nu = g->mol.nu;
+        std::stable_sort(p.sorted_to_db.begin(), p.sorted_to_db.end(),
+                         [&](int a, int b) { return nu[a] < nu[b]; });
+        if (pack_lines(g, p.own, p.sorted_to_db, p.n_active)) return 1;
+    }
+    p.valid = true;
+    return 0;
+}
+
+cudaEvent_t next_event(lbl_gas* g)
+{
+    if (g->ev_used == (int)g->ev_pool.size())
+    {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        g->ev_pool.push_back(e);
+    }
+    return g->ev_pool[g->ev_used++];
+}
+
+int pick_points_per_thread(int n_per_v)
+{
+    const int candidates[] = {10, 8, 5, 4, 2, 1};
+    for (int p : candidates)
+    {
+        if (n_per_v % p == 0) return p;
+    }
+    return 1;
+}
+
+template <int P>
+void launch_sum(const SumArgs& a, int n_layers, cudaStream_t s)
+{
+    const int threads = (a.grid.n + P - 1) / P;
+    dim3 grid((threads + kSumBlock - 1) / kSumBlock, n_layers);
+    sum_kernel<P><<<grid, kSumBlock, 0, s>>>(a);
+}
+
+void launch_sum_dispatch(int P, const SumArgs& a, int n_layers, cudaStream_t s)
+{
+    switch (P)
+    {
+        case 10: launch_sum<10>(a, n_layers, s); break;
+        case 8: launch_sum<8>(a, n_layers, s); break;
+        case 5: launch_sum<5>(a, n_layers, s); break;
+        case 4: launch_sum<4>(a, n_layers, s); break;
+        case 2: launch_sum<2>(a, n_layers, s); break;
+        default: launch_sum<1>(a, n_layers, s); break;
+    }
+}
+
+int set_device(lbl_gas* g)
+{
+    LBL_CUDA(cudaSetDevice(g->device));
+    return 0;
+}
+
+}  // namespace
+}  // namespace lbl
+
+// =========================================================================================
+extern "C" {
+
+const char* lbl_last_error(void)
+{
+    return g_last_error.c_str();
+}
+
+int lbl_version(void)
+{
+    return 100;
+}
+
+int lbl_set_chunk_layers(int layers)
+{
+    g_chunk_layers = layers < 0 ? 0 : layers;
+    return 0;
+}
+
+int lbl_device_count(int* count)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess)
+    {
+        *count = 0;
+        return fail(std::string("Error: CUDA: ") + cudaGetErrorString(e));
+    }
+    *count = n;
+    return 0;
+}
+
+int lbl_host_alloc(size_t bytes, void** ptr)
+{
+    *ptr = nullptr;
+    LBL_CUDA(cudaHostAlloc(ptr, bytes, cudaHostAllocPortable));
+    return 0;
+}
+
+int lbl_host_free(void* ptr)
+{
+    if (ptr) LBL_CUDA(cudaFreeHost(ptr));
+    return 0;
+}
+
+int lbl_gas_open(const char* database, const char* formula, int device, lbl_gas** out)
+{
+    *out = nullptr;
+    int ndev = 0;
+    if (lbl_device_count(&ndev)) return 1;
+    if (ndev == 0) return fail("Error: no CUDA device (this library has no CPU path).");
+    if (device < 0 || device >= ndev) return fail("Error: CUDA device index out of range.");
+    std::unique_ptr<lbl_gas> g(new lbl_gas);
+    g->device = device;
+    g->database = database;
+    g->formula = formula;
+    std::string err;
+    if (read_molecule(database, formula, g->mol, err)) return fail(err);
+    if (set_device(g.get())) return 1;
+    LBL_CUDA(cudaStreamCreateWithFlags(&g->s_compute, cudaStreamNonBlocking));
+    LBL_CUDA(cudaStreamCreateWithFlags(&g->s_side, cudaStreamNonBlocking));
+    LBL_CUDA(cudaStreamCreateWithFlags(&g->s_copy, cudaStreamNonBlocking));
+    LBL_CUDA(cudaEventCreate(&g->ev_call_begin));
+    LBL_CUDA(cudaEventCreate(&g->ev_call_end));
+    for (int i = 0; i < 2; ++i)
+    {
+        LBL_CUDA(cudaEventCreateWithFlags(&g->ev_out_ready[i], cudaEventDisableTiming));
+        LBL_CUDA(cudaEventCreateWithFlags(&g->ev_out_free[i], cudaEventDisableTiming));
+    }
+    if (g->mol.has_tips)
+    {
+        size_t bytes = 0;
+        if (upload(g->tips_t, g->mol.tips_t.data(), sizeof(double) * g->mol.tips_t.size(),
+                   g->s_compute, bytes)) return 1;
+        if (upload(g->tips_q, g->mol.tips_q.data(), sizeof(double) * g->mol.tips_q.size(),
+                   g->s_compute, bytes)) return 1;
+        g->open_h2d += bytes;
+        if (g->mol.sorted)
+        {
+            if (pack_lines(g.get(), g->base, std::vector<int>(), (int)g->mol.nu.size())) return 1;
+        }
+        LBL_CUDA(cudaStreamSynchronize(g->s_compute));
+    }
+    g->stats.n_lines = (int)g->mol.nu.size();
+    *out = g.release();
+    return 0;
+}
+
+int lbl_gas_close(lbl_gas* g)
+{
+    if (!g) return 0;
+    cudaSetDevice(g->device);
+    if (g->pending) lbl_gas_wait(g);
+    g->base.release();
+    g->plan.own.release();
+    for (DevBuf* b : {&g->tips_t, &g->tips_q, &g->rec_ab, &g->rec_cc, &g->rec_chk, &g->rec_gen,
+                      &g->layers_dev, &g->evals_dev, &g->pedbin, &g->pedcorr, &g->pednodes,
+                      &g->out[0], &g->out[1]})
+    {
+        b->release();
+    }
+    if (g->layers_host) cudaFreeHost(g->layers_host);
+    if (g->evals_host) cudaFreeHost(g->evals_host);
+    for (cudaEvent_t e : g->ev_pool) cudaEventDestroy(e);
+    if (g->ev_call_begin) cudaEventDestroy(g->ev_call_begin);
+    if (g->ev_call_end) cudaEventDestroy(g->ev_call_end);
+    for (int i = 0; i < 2; ++i)
+    {
+        if (g->ev_out_ready[i]) cudaEventDestroy(g->ev_out_ready[i]);
+        if (g->ev_out_free[i]) cudaEventDestroy(g->ev_out_free[i]);
+    }
+    if (g->s_compute) cudaStreamDestroy(g->s_compute);
+    if (g->s_side) cudaStreamDestroy(g->s_side);
+    if (g->s_copy) cudaStreamDestroy(g->s_copy);
+    delete g;
+    return 0;
+}
+
+int lbl_gas_submit(lbl_gas* g, int n_layers, const double* pressure, const double* temperature,
+                   const double* vmr, int v0, int vn, int n_per_v, int cut_off,
+                   int remove_pedestal, int precision, double* k_host)
+{
+    if (!g) return fail("Error: null handle.");
+    if (g->pending && lbl_gas_wait(g)) return 1;
+    if (precision != LBL_PRECISION_FP64)
+    {
+        return fail("Error: unsupported precision mode.");
+    }
+    if (n_layers < 0 || n_per_v < 1 || vn <= v0 || cut_off < 0)
+    {
+        return fail("Error: invalid grid or layer count.");
+    }
+    const long long n_ll = (long long)(vn - v0) * n_per_v;
+    if (n_ll > (1ll << 30) || (long long)(vn - v0 + 2 * cut_off + 4) * n_per_v > (1ll << 30))
+    {
+        return fail("Error: spectral grid too large for 32-bit indices.");
+    }
+    if (set_device(g)) return 1;
+
+    GridSpec grid;
+    grid.v0 = v0;
+    grid.vn = vn;
+    grid.n_per_v = n_per_v;
+    grid.cut_off = cut_off;
+    grid.n = (int)n_ll;
+    grid.ncell = vn - v0;
+    grid.dv = 1. / n_per_v;  // absorption.c:33
+
+    lbl_stats& st = g->stats;
+    st = lbl_stats{};
+    st.n_lines = (int)g->mol.nu.size();
+    st.n_layers = n_layers;
+    st.n_points = grid.n;
+    g->chunk_events.clear();
+    g->ev_used = 0;
+    g->last_chunk_layers = 0;
+    g->last_grid = grid;
+    if (!g->open_h2d_reported)
+    {
+        st.h2d_bytes += (long long)g->open_h2d;
+        g->open_h2d_reported = true;
+    }
+    if (n_layers == 0) return 0;
+
+    // No TIPS rows: "lines can't be calculated", absorption.c:53-59 -> zeros, success.
+    if (!g->mol.has_tips)
+    {
+        if (k_host) std::memset(k_host, 0, sizeof(double) * (size_t)n_layers * grid.n);
+        return 0;
+    }
+    const size_t h2d_before = g->open_h2d;
+    if (make_plan(g, v0, vn, cut_off)) return 1;
+    st.h2d_bytes += (long long)(g->open_h2d - h2d_before);
+    const Plan& plan = g->plan;
+    st.n_active = plan.n_active;
+    const int P = pick_points_per_thread(n_per_v);
+    st.points_per_thread = P;
+
+    // The reference indexes the TIPS table without a bounds check
+    // (spectral_database.c:102-103); outside the table that is undefined behaviour, so it
+    // is an error here.
+    const double t0 = g->mol.tips_t[0];
+    auto tips_ok = [&](double t) {
+        if (!(t == t)) return false;
+        const long long i = (long long)std::floor(t) - (long long)(int)t0;
+        return i >= 0 && i + 1 < g->mol.num_t;
+    };
+    if (!tips_ok(296.)) return fail("Error: TIPS table does not cover 296 K.");
+    for (int l = 0; l < n_layers; ++l)
+    {
+        if (!tips_ok(temperature[l]))
+        {
+            return fail("Error: layer temperature outside the TIPS table.");
+        }
+    }
+
+    if (plan.n_active == 0)
+    {
+        // Every row is past the early break: the reference returns the zeroed k.
+        if (k_host) std::memset(k_host, 0, sizeof(double) * (size_t)n_layers * grid.n);
+        return 0;
+    }
+    const DeviceLines& dl = g->mol.sorted ? g->base : plan.own;
+    const LinesView lines = dl.view(plan.n_active);
+    TipsView tips;
+    tips.num_iso = g->mol.num_iso;
+    tips.num_t = g->mol.num_t;
+    tips.t = g->tips_t.as<double>();
+    tips.q = g->tips_q.as<double>();
+
+    // ---- chunking over layers ------------------------------------------------------
+    const size_t rec_per_layer = (size_t)plan.n_active * (sizeof(FarAB) + sizeof(double) +
+                                                          sizeof(LineChk) + sizeof(LineGen));
+    const size_t out_per_layer = sizeof(double) * (size_t)grid.n;
+    const size_t budget = (size_t)6 << 30;
+    long long chunk = std::min<long long>(n_layers,
+                                          std::max<long long>(1, (long long)(budget / rec_per_layer)));
+    chunk = std::min<long long>(chunk, std::max<long long>(1, (long long)(budget / out_per_layer)));
+    if (g_chunk_layers > 0)
+    {
+        chunk = std::min<long long>(chunk, g_chunk_layers);
+    }
+    else if (k_host && n_layers >= 8)
+    {
+        // Four or more groups so the device->host copy of one overlaps the next one's kernels.
+        chunk = std::min<long long>(chunk, (n_layers + 3) / 4);
+    }
+    const int n_chunks = (int)((n_layers + chunk - 1) / chunk);
+
+    // ---- buffers -------------------------------------------------------------------
+    LBL_CUDA(g->rec_ab.reserve(sizeof(FarAB) * (size_t)plan.n_active * chunk));
+    LBL_CUDA(g->rec_cc.reserve(sizeof(double) * (size_t)plan.n_active * chunk));
+    LBL_CUDA(g->rec_chk.reserve(sizeof(LineChk) * (size_t)plan.n_active * chunk));
+    LBL_CUDA(g->rec_gen.reserve(sizeof(LineGen) * (size_t)plan.n_active * chunk));
+    LBL_CUDA(g->layers_dev.reserve(sizeof(LayerIn) * (size_t)n_layers));
+    LBL_CUDA(g->evals_dev.reserve(sizeof(unsigned long long) * (size_t)n_layers));
+    LBL_CUDA(g->out[0].reserve(out_per_layer * chunk));
+    if (n_chunks > 1) LBL_CUDA(g->out[1].reserve(out_per_layer * chunk));
+    const int nb = grid.ncell + 2 * cut_off + 2;
+    size_t ped_smem = 0;
+    if (remove_pedestal)
+    {
+        LBL_CUDA(g->pedbin.reserve(sizeof(double) * (size_t)nb * chunk));
+        LBL_CUDA(g->pedcorr.reserve(sizeof(double) * 2 * (size_t)grid.ncell * chunk));
+        ped_smem = sizeof(double) * (size_t)(grid.ncell + 1);
+        if (ped_smem > 200 * 1024)
+        {
+            LBL_CUDA(g->pednodes.reserve(ped_smem * chunk));
+            ped_smem = 0;
+        }
+        else if (ped_smem > 48 * 1024)
+        {
+            LBL_CUDA(cudaFuncSetAttribute(pedestal_kernel,
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)ped_smem));
+        }
+    }
+    if (g->layers_host_cap < (size_t)n_layers)
+    {
+        if (g->layers_host) cudaFreeHost(g->layers_host);
+        g->layers_host = nullptr;
+        LBL_CUDA(cudaHostAlloc((void**)&g->layers_host, sizeof(LayerIn) * n_layers,
+                               cudaHostAllocDefault));
+        g->layers_host_cap = n_layers;
+    }
+    if (g->evals_host_cap < (size_t)n_layers)
+    {
+        if (g->evals_host) cudaFreeHost(g->evals_host);
+        g->evals_host = nullptr;
+        LBL_CUDA(cudaHostAlloc((void**)&g->evals_host, sizeof(unsigned long long) * n_layers,
+                               cudaHostAllocDefault));
+        g->evals_host_cap = n_layers;
+    }
+
+    // ---- per-layer inputs ------------------------------------------------------------
+    g->last_layers.resize(n_layers);
+    for (int l = 0; l < n_layers; ++l)
+    {
+        LayerIn& ly = g->layers_host[l];
+        ly.pressure = pressure[l];
+        ly.temperature = temperature[l];
+        ly.vmr = vmr[l];
+        const double p_atm = std::fabs(pressure[l] * kPaToAtm);
+        ly.slack = p_atm * g->mol.max_abs_delta * (1. + 1e-9) + 1e-9;
+        // Near-zone half width D = xlim0*alpha/sqrt(ln2) <= 123.4/0.8325 * alpha, and
+        // alpha = nu*sqrt(r2*T/mass)/vlight (spectra.c:29, voigt.c:13,34).
+        const double mm = g->mol.min_mass > 0. ? g->mol.min_mass : 1.;
+        ly.kappa = 148.3 * std::sqrt(kR2 * std::fabs(temperature[l]) / mm) / kVlight;
+        ly.pad = 0.;
+        g->last_layers[l] = ly;
+    }
+
+    cudaStream_t sc = g->s_compute;
+    LBL_CUDA(cudaEventRecord(g->ev_call_begin, sc));
+    LBL_CUDA(cudaMemcpyAsync(g->layers_dev.p, g->layers_host, sizeof(LayerIn) * n_layers,
+                             cudaMemcpyHostToDevice, sc));
+    LBL_CUDA(cudaMemsetAsync(g->evals_dev.p, 0, sizeof(unsigned long long) * n_layers, sc));
+    st.h2d_bytes += (long long)(sizeof(LayerIn) * n_layers);
+
+    Records rec;
+    rec.ab = g->rec_ab.as<FarAB>();
+    rec.cc = g->rec_cc.as<double>();
+    rec.chk = g->rec_chk.as<LineChk>();
+    rec.gen = g->rec_gen.as<LineGen>();
+
+    for (int c = 0; c < n_chunks; ++c)
+    {
+        const int first = (int)(c * chunk);
+        const int nl = (int)std::min<long long>(chunk, n_layers - first);
+        const int slot = c & 1;
+        const LayerIn* layers_c = g->layers_dev.as<LayerIn>() + first;
+        lbl_gas::ChunkEvents ev;
+        ev.pedestal = remove_pedestal != 0;
+        ev.k1_begin = next_event(g);
+        ev.k1_end = next_event(g);
+        ev.k2_begin = next_event(g);
+        ev.k2_end = next_event(g);
+        ev.ped_begin = next_event(g);
+        ev.ped_end = next_event(g);
+
+        if (g->out_busy[slot])
+        {
+            // The previous copy out of this buffer must have drained.
+            LBL_CUDA(cudaStreamWaitEvent(sc, g->ev_out_free[slot], 0));
+            g->out_busy[slot] = false;
+        }
+
+        // K1
+        LBL_CUDA(cudaEventRecord(ev.k1_begin, sc));
+        {
+            dim3 grid1((plan.n_active + kScaleBlock - 1) / kScaleBlock, nl);
+            scale_kernel<<<grid1, kScaleBlock, 0, sc>>>(lines, tips, layers_c, grid, rec,
+                                                        g->evals_dev.as<unsigned long long>() + first);
+            st.total_launches++;
+        }
+        LBL_CUDA(cudaEventRecord(ev.k1_end, sc));
+
+        // K3 + K4a on the side stream, concurrent with K2.
+        if (remove_pedestal)
+        {
+            LBL_CUDA(cudaStreamWaitEvent(g->s_side, ev.k1_end, 0));
+            LBL_CUDA(cudaEventRecord(ev.ped_begin, g->s_side));
+            PedArgs pa;
+            pa.lines = lines;
+            pa.rec = rec;
+            pa.grid = grid;
+            pa.pedbin = g->pedbin.as<double>();
+            pedestal_kernel<<<nl, 32, ped_smem, g->s_side>>>(
+                pa, ped_smem ? nullptr : g->pednodes.as<double>());
+            const int cells = nl * grid.ncell;
+            pedestal_cells_kernel<<<(cells + 127) / 128, 128, 0, g->s_side>>>(
+                g->pedbin.as<double>(), grid, nl, g->pedcorr.as<double>());
+            st.total_launches += 2;
+            LBL_CUDA(cudaEventRecord(ev.ped_end, g->s_side));
+        }
+
+        // K2
+        SumArgs sa;
+        sa.lines = lines;
+        sa.rec = rec;
+        sa.layers = layers_c;
+        sa.grid = grid;
+        sa.out = g->out[slot].as<double>();
+        LBL_CUDA(cudaEventRecord(ev.k2_begin, sc));
+        launch_sum_dispatch(P, sa, nl, sc);
+        LBL_CUDA(cudaEventRecord(ev.k2_end, sc));
+        st.sum_launches++;
+        st.total_launches++;
+
+        if (remove_pedestal)
+        {
+            LBL_CUDA(cudaStreamWaitEvent(sc, ev.ped_end, 0));
+            const size_t total = (size_t)nl * grid.n;
+            const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
+            pedestal_apply_kernel<<<blocks, 256, 0, sc>>>(g->out[slot].as<double>(),
+                                                          g->pedcorr.as<double>(), grid, nl);
+            st.total_launches++;
+        }
+        LBL_CUDA(cudaGetLastError());
+        g->chunk_events.push_back(ev);
+
+        if (k_host)
+        {
+            LBL_CUDA(cudaEventRecord(g->ev_out_ready[slot], sc));
+            LBL_CUDA(cudaStreamWaitEvent(g->s_copy, g->ev_out_ready[slot], 0));
+            LBL_CUDA(cudaMemcpyAsync(k_host + (size_t)first * grid.n, g->out[slot].p,
+                                     out_per_layer * nl, cudaMemcpyDeviceToHost, g->s_copy));
+            LBL_CUDA(cudaEventRecord(g->ev_out_free[slot], g->s_copy));
+            g->out_busy[slot] = true;
+            st.d2h_bytes += (long long)(out_per_layer * nl);
+        }
+        g->last_chunk_first = first;
+        g->last_chunk_layers = nl;
+        g->last_slot = slot;
+    }
+    LBL_CUDA(cudaMemcpyAsync(g->evals_host, g->evals_dev.p, sizeof(unsigned long long) * n_layers,
+                             cudaMemcpyDeviceToHost, sc));
+    if (k_host)
+    {
+        // The call ends when the last copy has landed.
+        LBL_CUDA(cudaStreamWaitEvent(sc, g->ev_out_free[g->last_slot], 0));
+    }
+    LBL_CUDA(cudaEventRecord(g->ev_call_end, sc));
+    g->pending = true;
+    return 0;
+}
+
+int lbl_gas_wait(lbl_gas* g)
+{
+    if (!g) return fail("Error: null handle.");
+    if (!g->pending) return 0;
+    if (set_device(g)) return 1;
+    g->pending = false;
+    LBL_CUDA(cudaStreamSynchronize(g->s_compute));
+    LBL_CUDA(cudaStreamSynchronize(g->s_copy));
+    LBL_CUDA(cudaStreamSynchronize(g->s_side));
+    g->out_busy[0] = g->out_busy[1] = false;
+    lbl_stats& st = g->stats;
+    for (int l = 0; l < st.n_layers; ++l) st.evals += (long long)g->evals_host[l];
+    float ms = 0.f;
+    for (const lbl_gas::ChunkEvents& ev : g->chunk_events)
+    {
+        LBL_CUDA(cudaEventElapsedTime(&ms, ev.k1_begin, ev.k1_end));
+        st.scale_ms += ms;
+        LBL_CUDA(cudaEventElapsedTime(&ms, ev.k2_begin, ev.k2_end));
+        st.sum_ms += ms;
+        if (ev.pedestal)
+        {
+            LBL_CUDA(cudaEventElapsedTime(&ms, ev.ped_begin, ev.ped_end));
+            st.pedestal_ms += ms;
+        }
+    }
+    LBL_CUDA(cudaEventElapsedTime(&ms, g->ev_call_begin, g->ev_call_end));
+    st.total_ms = ms;
+    return 0;
+}
+
+int lbl_gas_compute(lbl_gas* g, int n_layers, const double* pressure, const double* temperature,
+                    const double* vmr, int v0, int vn, int n_per_v, int cut_off,
+                    int remove_pedestal, int precision, double* k_host)
+{
+    if (lbl_gas_submit(g, n_layers, pressure, temperature, vmr, v0, vn, n_per_v, cut_off,
+                       remove_pedestal, precision, k_host))
+    {
+        return 1;
+    }
+    return lbl_gas_wait(g);
+}
+
+int lbl_gas_stats(lbl_gas* g, lbl_stats* out)
+{
+    if (!g || !out) return fail("Error: null argument.");
+    *out = g->stats;
+    return 0;
+}
+
+int lbl_gas_device_result(lbl_gas* g, double** device_ptr, long long* count)
+{
+    if (!g) return fail("Error: null handle.");
+    if (g->pending && lbl_gas_wait(g)) return 1;
+    if (g->last_chunk_layers == 0) return fail("Error: no spectra resident on the device.");
+    *device_ptr = g->out[g->last_slot].as<double>();
+    *count = (long long)g->last_chunk_layers * g->last_grid.n;
+    return 0;
+}
+
+static int resident_layer(lbl_gas* g, int layer, int capacity, int* local)
+{
+    if (!g) return fail("Error: null handle.");
+    if (g->pending && lbl_gas_wait(g)) return 1;
+    *local = 0;
+    if (g->stats.n_active == 0 && layer >= 0 && layer < g->stats.n_layers)
+    {
+        return 0;  // nothing was processed (early break on the first row, or no TIPS data)
+    }
+    if (layer < g->last_chunk_first || layer >= g->last_chunk_first + g->last_chunk_layers)
+    {
+        return fail("Error: that layer's line records are no longer resident.");
+    }
+    if (capacity < g->stats.n_active) return fail("Error: output capacity too small.");
+    *local = layer - g->last_chunk_first;
+    return set_device(g);
+}
+
+int lbl_gas_windows(lbl_gas* g, int layer, int* s_out, int* e_out, int capacity)
+{
+    int local = 0;
+    if (resident_layer(g, layer, capacity, &local)) return 1;
+    const int na = g->stats.n_active;
+    if (na == 0) return 0;
+    std::vector<LineChk> chk(na);
+    LBL_CUDA(cudaMemcpy(chk.data(), g->rec_chk.as<LineChk>() + (size_t)local * na,
+                        sizeof(LineChk) * na, cudaMemcpyDeviceToHost));
+    const GridSpec& gr = g->last_grid;
+    const std::vector<int>& order = g->plan.sorted_to_db;
+    for (int j = 0; j < na; ++j)
+    {
+        const int r = order.empty() ? j : order[j];
+        // spectra.c:48-62 from the bit-exact cell of the shifted centre.
+        long long s = (long long)(chk[j].cb - gr.cut_off) * gr.n_per_v;
+        if (s >= gr.n)
+        {
+            s_out[r] = -1;
+            e_out[r] = -1;
+            continue;
+        }
+        if (s < 0) s = 0;
+        long long e = (long long)(chk[j].cb + gr.cut_off + 1) * gr.n_per_v;
+        if (e >= gr.n) e = gr.n - 1;
+        s_out[r] = (int)s;
+        e_out[r] = (int)e;
+    }
+    return 0;
+}
+
+int lbl_gas_scaled(lbl_gas* g, int layer, double* out, int capacity)
+{
+    int local = 0;
+    if (resident_layer(g, layer, capacity, &local)) return 1;
+    const int na = g->stats.n_active;
+    if (na == 0) return 0;
+    std::vector<LineGen> gen(na);
+    LBL_CUDA(cudaMemcpy(gen.data(), g->rec_gen.as<LineGen>() + (size_t)local * na,
+                        sizeof(LineGen) * na, cudaMemcpyDeviceToHost));
+    const std::vector<int>& order = g->plan.sorted_to_db;
+    for (int j = 0; j < na; ++j)
+    {
+        const int r = order.empty() ? j : order[j];
+        out[4 * r + 0] = gen[j].nu;
+        out[4 * r + 1] = kSqrLn2 / gen[j].repwid;                 // alpha
+        out[4 * r + 2] = gen[j].y / gen[j].repwid;                // gamma
+        out[4 * r + 3] = gen[j].cof / (kRsqrPi * gen[j].repwid);  // sw'
+    }
+    return 0;
+}
+
+// ---- the reference's own entry point (absorption.c:19-30) ---------------------------------
+int absorption(double pressure, double temperature, double volume_mixing_ratio, int v0, int vn,
+               int n_per_v, double* k, char* database, char* formula, int cut_off,
+               int remove_pedestal)
+{
+    static std::mutex mu;
+    static std::map<std::string, lbl_gas*> cache;
+    std::lock_guard<std::mutex> lock(mu);
+    int device = 0;
+    if (const char* env = getenv("PYLBL_B200_DEVICE")) device = atoi(env);
+    const std::string key = std::string(database) + "\n" + formula + "\n" + std::to_string(device);
+    lbl_gas* g = nullptr;
+    auto it = cache.find(key);
+    if (it == cache.end())
+    {
+        if (lbl_gas_open(database, formula, device, &g)) return 1;
+        cache[key] = g;
+    }
+    else
+    {
+        g = it->second;
+    }
+    return lbl_gas_compute(g, 1, &pressure, &temperature, &volume_mixing_ratio, v0, vn, n_per_v,
+                           cut_off, remove_pedestal, LBL_PRECISION_FP64, k);
+}
+
+}  // extern "C"

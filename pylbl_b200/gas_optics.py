@@ -1,0 +1,244 @@
+"""The B200 lines backend: a ``Gas`` class with pyLBL's plugin signature.
+
+Host-side mirror of the reference adapter pyLBL/c_lib/gas_optics.py:29-92: same
+constructor ``Gas(lines_database, formula)``, same method
+``absorption_coefficient(temperature, pressure, volume_mixing_ratio, grid,
+remove_pedestal=False, cut_off=25)``, same return value (float64 array of
+``(vn - v0)*n_per_v`` cross-sections [m2 per molecule], pyLBL/c_lib/gas_optics.py:61-65,92)
+and the same error (``ValueError("Error inside c functions.")``, :15-26).
+
+What differs is behind the boundary: the sqlite database is read once per
+(database, formula) and packed into device memory; a call computes one layer -- or, through
+``absorption_coefficients`` / ``prefetch``, a whole column of layers -- on the GPU.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+from ctypes import c_int, c_longlong, c_void_p
+
+import numpy as np
+
+from . import _lib
+
+
+def grid_to_ints(grid):
+    """(v0, vn, n_per_v) exactly as pyLBL/c_lib/gas_optics.py:61-63 derives them."""
+    v0 = int(round(grid[0]))
+    vn = int(round(grid[-1]) + 1)
+    n_per_v = int(round(1. / (grid[1] - grid[0])))
+    return v0, vn, n_per_v
+
+
+def default_device() -> int:
+    """PYLBL_B200_DEVICE, else LOCAL_RANK (one process per GPU under torchrun), else 0."""
+    for name in ("PYLBL_B200_DEVICE", "LOCAL_RANK"):
+        if os.environ.get(name, "") != "":
+            return int(os.environ[name])
+    return 0
+
+
+class _Handle(object):
+    """Owns one lbl_gas* (one molecule packed on one device)."""
+
+    def __init__(self, database, formula, device):
+        self.ptr = c_void_p()
+        self.device = device
+        _lib.library().lbl_gas_open(bytes(database, encoding="utf-8"),
+                                    bytes(formula, encoding="utf-8"), int(device),
+                                    ctypes.byref(self.ptr))
+
+    def close(self):
+        ptr, self.ptr = self.ptr, None
+        if ptr is not None and ptr.value:
+            _lib.library().lbl_gas_close(ptr)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def stats(self):
+        s = _lib.Stats()
+        _lib.library().lbl_gas_stats(self.ptr, ctypes.byref(s))
+        return s.as_dict()
+
+
+class Gas(object):
+    """API for gas optics calculation on B200 GPUs.
+
+    Attributes:
+        database: String path to the spectral sqlite3 database.
+        formula: String chemical formula.
+        devices: CUDA device indices this object spreads layers over.
+        precision: "fp64" (default) or "fp32".
+    """
+
+    def __init__(self, lines_database, formula, devices=None, precision="fp64"):
+        """Initializes the object.
+
+        Args:
+            lines_database: Database object (only its ``path`` is read,
+                            pyLBL/c_lib/gas_optics.py:43) or a path string.
+            formula: String chemical formula.
+            devices: int, list of ints, or None (see default_device()).
+            precision: "fp64" or "fp32".
+        """
+        self.database = getattr(lines_database, "path", lines_database)
+        self.formula = formula
+        if devices is None:
+            devices = [default_device()]
+        elif isinstance(devices, int):
+            devices = [devices]
+        self.devices = list(devices)
+        self.precision = {"fp64": _lib.PRECISION_FP64, "fp32": _lib.PRECISION_FP32}[precision]
+        self._handles = {}
+        self._cache = {}
+        self.last_stats = []
+
+    # -- handles -----------------------------------------------------------------------
+    def _handle(self, device):
+        if device not in self._handles:
+            self._handles[device] = _Handle(self.database, self.formula, device)
+        return self._handles[device]
+
+    def close(self):
+        for h in self._handles.values():
+            h.close()
+        self._handles = {}
+        self._cache = {}
+
+    # -- the plugin method ---------------------------------------------------------------
+    def absorption_coefficient(self, temperature, pressure, volume_mixing_ratio, grid,
+                               remove_pedestal=False, cut_off=25):
+        """Calculates absorption coefficient.
+
+        Args:
+            temperature: Temperature [K].
+            pressure: Pressure [Pa].
+            volume_mixing_ratio: Volume mixing ratio [mol mol-1].
+            grid: Numpy array defining the spectral grid [cm-1].
+            remove_pedestal: Flag specifying if a pedestal should be subtracted.
+            cut_off: Wavenumber cut-off distance [cm-1] from line centers.
+
+        Returns:
+            Numpy array of absorption coefficients [m2].
+        """
+        v0, vn, n_per_v = grid_to_ints(grid)
+        key = (float(temperature), float(pressure), float(volume_mixing_ratio), v0, vn, n_per_v,
+               int(cut_off), bool(remove_pedestal))
+        row = self._cache.pop(key, None)
+        if row is not None:
+            return row
+        k = self.absorption_coefficients([temperature], [pressure], [volume_mixing_ratio], grid,
+                                         remove_pedestal=remove_pedestal, cut_off=cut_off)
+        return k[0]
+
+    # -- batched forms -------------------------------------------------------------------
+    def absorption_coefficients(self, temperature, pressure, volume_mixing_ratio, grid=None,
+                                remove_pedestal=False, cut_off=25, bounds=None, out=None,
+                                to_host=True):
+        """Layer-batched ``absorption_coefficient``: row L of the result is what the scalar
+        call returns for (temperature[L], pressure[L], volume_mixing_ratio[L]).
+
+        Args:
+            grid: spectral grid array, or None with ``bounds=(v0, vn, n_per_v)``.
+            out: optional C-contiguous float64 array (n_layers, n) to fill (e.g. pinned).
+            to_host: False leaves the spectra on the device (benchmarks) and returns None.
+
+        Layers are split into contiguous shards, one per device in ``self.devices``; shards
+        are independent, so there is no inter-device communication.
+        """
+        v0, vn, n_per_v = bounds if bounds is not None else grid_to_ints(grid)
+        t = np.ascontiguousarray(temperature, dtype=np.float64).ravel()
+        p = np.ascontiguousarray(pressure, dtype=np.float64).ravel()
+        x = np.ascontiguousarray(volume_mixing_ratio, dtype=np.float64).ravel()
+        n_layers = t.size
+        n = (vn - v0) * n_per_v
+        if to_host and out is None:
+            out = np.empty((n_layers, n))
+        if to_host and (out.shape != (n_layers, n) or out.dtype != np.float64
+                        or not out.flags["C_CONTIGUOUS"]):
+            raise ValueError("out must be a C-contiguous float64 array of shape (n_layers, n)")
+        lib = _lib.library()
+        ped = 1 if remove_pedestal else 0
+        ndev = max(1, min(len(self.devices), n_layers))
+        edges = np.linspace(0, n_layers, ndev + 1).astype(int)
+        submitted = []
+        errors = []
+
+        def submit(d):
+            lo, hi = int(edges[d]), int(edges[d + 1])
+            h = self._handle(self.devices[d])
+            dst = out[lo:hi].ctypes.data_as(c_void_p) if to_host else None
+            lib.lbl_gas_submit(h.ptr, hi - lo, p[lo:hi], t[lo:hi], x[lo:hi], v0, vn, n_per_v,
+                               int(cut_off), ped, self.precision, dst)
+            return h
+
+        if ndev == 1:
+            submitted.append(submit(0))
+        else:
+            # One host thread per device: pageable destinations make the copies synchronous.
+            def work(d):
+                try:
+                    h = submit(d)
+                    lib.lbl_gas_wait(h.ptr)
+                    submitted.append(h)
+                except Exception as exc:  # re-raised below
+                    errors.append(exc)
+            threads = [threading.Thread(target=work, args=(d,)) for d in range(ndev)]
+            for th in threads:
+                th.start()
+            for th in threads:
+                th.join()
+            if errors:
+                raise errors[0]
+        for h in submitted:
+            lib.lbl_gas_wait(h.ptr)
+        self.last_stats = [h.stats() for h in submitted]
+        return out if to_host else None
+
+    def prefetch(self, temperature, pressure, volume_mixing_ratio, grid, remove_pedestal=False,
+                 cut_off=25):
+        """Computes every layer of a column in one batch and keeps the rows, so that the
+        scalar calls pyLBL's driver loop makes next (pyLBL/spectroscopy.py:179-191) return
+        immediately.  Rows are handed out once and dropped."""
+        v0, vn, n_per_v = grid_to_ints(grid)
+        k = self.absorption_coefficients(temperature, pressure, volume_mixing_ratio, grid,
+                                         remove_pedestal=remove_pedestal, cut_off=cut_off)
+        t = np.asarray(temperature, dtype=np.float64).ravel()
+        p = np.asarray(pressure, dtype=np.float64).ravel()
+        x = np.asarray(volume_mixing_ratio, dtype=np.float64).ravel()
+        for i in range(t.size):
+            key = (float(t[i]), float(p[i]), float(x[i]), v0, vn, n_per_v, int(cut_off),
+                   bool(remove_pedestal))
+            self._cache[key] = k[i]
+        return k
+
+    # -- introspection used by the parity tests -------------------------------------------
+    def windows(self, layer=0, device_index=0):
+        """(s, e) of pyLBL/c_lib/spectra.c:48-62 per processed line of the last call."""
+        h = self._handle(self.devices[device_index])
+        n = h.stats()["n_active"]
+        s = np.full(max(n, 1), -1, dtype=np.int32)
+        e = np.full(max(n, 1), -1, dtype=np.int32)
+        _lib.library().lbl_gas_windows(h.ptr, int(layer), s, e, int(s.size))
+        return np.stack([s[:n], e[:n]], axis=1)
+
+    def scaled_lines(self, layer=0, device_index=0):
+        """(nu', alpha, gamma, sw') of pyLBL/c_lib/spectra.c:17-45 per processed line."""
+        h = self._handle(self.devices[device_index])
+        n = h.stats()["n_active"]
+        out = np.zeros((max(n, 1), 4))
+        _lib.library().lbl_gas_scaled(h.ptr, int(layer), out, int(out.shape[0]))
+        return out[:n]
+
+    def device_result(self, device_index=0):
+        """(device pointer, element count) of the spectra left on the device."""
+        h = self._handle(self.devices[device_index])
+        ptr = c_void_p()
+        count = c_longlong(0)
+        _lib.library().lbl_gas_device_result(h.ptr, ctypes.byref(ptr), ctypes.byref(count))
+        return ptr.value, int(count.value)

@@ -1,0 +1,161 @@
+// emu.cpp -- CPU emulation of the kernels' per-thread bodies (TEST INFRASTRUCTURE ONLY).
+//
+// Compiles pylbl_b200/csrc/lbl_threads.cuh as plain C++ and runs the exact per-thread code
+// of K1/K2/K3/K4 in sequential loops over (layer, thread).  It lets the CPU-only test suite
+// check the gather logic (window membership, segment search, near/far split, pedestal
+// recurrence) against the oracle without a GPU.  The product never loads this file; the
+// MUFU reciprocal seed is emulated (see rcp_seed in lbl_core.cuh).
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "../../pylbl_b200/csrc/lbl_threads.cuh"
+
+using namespace lbl;
+
+template <int P>
+static void run_sum(const SumArgs& a, int n_layers)
+{
+    const int threads = (a.grid.n + P - 1) / P;
+    const int padded = (threads + 127) / 128 * 128;
+    for (int layer = 0; layer < n_layers; ++layer)
+    {
+        for (int tid = 0; tid < padded; ++tid)
+        {
+            sum_thread<P>(a, layer, tid);
+        }
+    }
+}
+
+struct NoSync
+{
+    void operator()() const {}
+};
+
+extern "C" int emu_absorption(int n_layers, const double* pressure, const double* temperature,
+                              const double* vmr, int v0, int vn, int n_per_v, double* k,
+                              int n_lines, const double* nu, const double* sw,
+                              const double* gamma_air, const double* gamma_self,
+                              const double* n_air, const double* elower, const double* delta_air,
+                              const int* local_iso_id, const double* iso_mass, int num_iso,
+                              int num_t, const double* tips_t, const double* tips_q, int cut_off,
+                              int remove_pedestal, int points_per_thread, long long* n_evals)
+{
+    GridSpec g;
+    g.v0 = v0;
+    g.vn = vn;
+    g.n_per_v = n_per_v;
+    g.cut_off = cut_off;
+    g.n = (vn - v0) * n_per_v;
+    g.ncell = vn - v0;
+    g.dv = 1. / n_per_v;
+    std::memset(k, 0, sizeof(double) * (size_t)n_layers * g.n);
+    *n_evals = 0;
+
+    // Early-break prefix in database order (absorption.c:80-83).
+    int na = 0;
+    for (; na < n_lines; ++na)
+    {
+        if (nu[na] > vn + cut_off + 1 || nu[na] < v0 - (cut_off + 1)) break;
+    }
+    if (na == 0) return 0;
+    // stable sort by unshifted centre
+    std::vector<int> order(na), inv(na);
+    for (int i = 0; i < na; ++i) order[i] = i;
+    for (int i = 1; i < na; ++i)  // insertion sort keeps it stable; inputs are near-sorted
+    {
+        int x = order[i], j = i - 1;
+        while (j >= 0 && nu[order[j]] > nu[x]) { order[j + 1] = order[j]; --j; }
+        order[j + 1] = x;
+    }
+    std::vector<double> c_nu(na), c_sw(na), c_ga(na), c_gs(na), c_na(na), c_el(na), c_da(na), c_m(na);
+    std::vector<int> c_iso(na);
+    double max_delta = 0., min_mass = 0.;
+    for (int j = 0; j < na; ++j)
+    {
+        const int r = order[j];
+        inv[r] = j;
+        c_nu[j] = nu[r]; c_sw[j] = sw[r]; c_ga[j] = gamma_air[r]; c_gs[j] = gamma_self[r];
+        c_na[j] = n_air[r]; c_el[j] = elower[r]; c_da[j] = delta_air[r];
+        int iso = local_iso_id[r];
+        if (iso == 0) iso = 10;
+        c_iso[j] = iso - 1;
+        c_m[j] = iso_mass[iso - 1];
+        if (fabs(c_da[j]) > max_delta) max_delta = fabs(c_da[j]);
+        if (c_m[j] > 0. && (min_mass == 0. || c_m[j] < min_mass)) min_mass = c_m[j];
+    }
+    (void)num_iso;
+    LinesView ln;
+    ln.n = na;
+    ln.nu = c_nu.data(); ln.sw = c_sw.data(); ln.gamma_air = c_ga.data();
+    ln.gamma_self = c_gs.data(); ln.n_air = c_na.data(); ln.elower = c_el.data();
+    ln.delta_air = c_da.data(); ln.mass = c_m.data(); ln.iso = c_iso.data();
+    ln.db_to_sorted = inv.data();
+    TipsView tips{num_iso, num_t, tips_t, tips_q};
+
+    std::vector<LayerIn> layers(n_layers);
+    for (int l = 0; l < n_layers; ++l)
+    {
+        layers[l].pressure = pressure[l];
+        layers[l].temperature = temperature[l];
+        layers[l].vmr = vmr[l];
+        layers[l].slack = fabs(pressure[l] * kPaToAtm) * max_delta * (1. + 1e-9) + 1e-9;
+        layers[l].kappa = 148.3 * sqrt(kR2 * fabs(temperature[l]) / (min_mass > 0. ? min_mass : 1.)) / kVlight;
+        layers[l].pad = 0.;
+    }
+    std::vector<FarAB> ab((size_t)na * n_layers);
+    std::vector<double> cc((size_t)na * n_layers);
+    std::vector<LineChk> chk((size_t)na * n_layers);
+    std::vector<LineGen> gen((size_t)na * n_layers);
+    Records rec{ab.data(), cc.data(), chk.data(), gen.data()};
+    for (int l = 0; l < n_layers; ++l)
+    {
+        for (int j = 0; j < na; ++j)
+        {
+            *n_evals += scale_thread(ln, tips, layers.data(), g, rec, l, j);
+        }
+    }
+    SumArgs sa;
+    sa.lines = ln;
+    sa.rec = rec;
+    sa.layers = layers.data();
+    sa.grid = g;
+    sa.out = k;
+    switch (points_per_thread)
+    {
+        case 10: run_sum<10>(sa, n_layers); break;
+        case 8: run_sum<8>(sa, n_layers); break;
+        case 5: run_sum<5>(sa, n_layers); break;
+        case 4: run_sum<4>(sa, n_layers); break;
+        case 2: run_sum<2>(sa, n_layers); break;
+        case 1: run_sum<1>(sa, n_layers); break;
+        default: return 1;
+    }
+    if (remove_pedestal)
+    {
+        const int nb = g.ncell + 2 * cut_off + 2;
+        std::vector<double> pedbin((size_t)nb * n_layers), nodes(g.ncell + 1);
+        std::vector<double> corr((size_t)2 * g.ncell * n_layers);
+        PedArgs pa;
+        pa.lines = ln;
+        pa.rec = rec;
+        pa.grid = g;
+        pa.pedbin = pedbin.data();
+        for (int l = 0; l < n_layers; ++l)
+        {
+            pedestal_layer(pa, l, 0, 1, nodes.data(), NoSync());
+            for (int c = 0; c < g.ncell; ++c)
+            {
+                pedestal_cell(pedbin.data() + (size_t)l * nb, c, cut_off,
+                              corr.data() + 2 * ((size_t)l * g.ncell + c));
+            }
+            for (int i = 0; i < g.n; ++i)
+            {
+                const int c = i / n_per_v;
+                const int r = i - c * n_per_v;
+                k[(size_t)l * g.n + i] -= corr[2 * ((size_t)l * g.ncell + c) + (r == 0 ? 1 : 0)];
+            }
+        }
+    }
+    return 0;
+}

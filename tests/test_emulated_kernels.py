@@ -1,0 +1,139 @@
+"""Kernel logic on the CPU: the per-thread bodies of K1-K4 (pylbl_b200/csrc/lbl_threads.cuh)
+compiled as plain C++ (tests/emu/emu.cpp) and compared with the oracle.
+
+This covers the host-visible logic of the gather formulation -- window membership per
+point, the five-segment line ranges, the near/far split, the pedestal recurrence -- on
+machines without a GPU.  It is not the product path (the reciprocal seed is emulated).
+"""
+import ctypes
+import subprocess
+from ctypes import POINTER, c_int, c_longlong
+from pathlib import Path
+
+import numpy as np
+import pytest
+from numpy.ctypeslib import ndpointer
+
+from oracle import OracleGas
+from pylbl_b200 import synth
+
+from helpers import FP64_TOL, relative_error, scaled_error
+
+EMU_DIR = Path(__file__).resolve().parent / "emu"
+
+
+@pytest.fixture(scope="module")
+def emu():
+    so, src = EMU_DIR / "libemu.so", EMU_DIR / "emu.cpp"
+    core = EMU_DIR.parent.parent / "pylbl_b200" / "csrc"
+    newest = max(p.stat().st_mtime for p in (src, core / "lbl_core.cuh", core / "lbl_threads.cuh"))
+    if not so.exists() or so.stat().st_mtime < newest:
+        subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off",
+                        "-o", str(so), str(src)], check=True)
+    lib = ctypes.CDLL(str(so))
+    f64 = ndpointer(np.float64, flags="C_CONTIGUOUS")
+    i32 = ndpointer(np.int32, flags="C_CONTIGUOUS")
+    lib.emu_absorption.argtypes = [c_int, f64, f64, f64, c_int, c_int, c_int, f64, c_int] + \
+        [f64] * 7 + [i32, f64, c_int, c_int, f64, f64, c_int, c_int, c_int, POINTER(c_longlong)]
+    lib.emu_absorption.restype = c_int
+    return lib
+
+
+def run(emu, gas, t, p, x, bounds, ped, cut=25, points=None):
+    d = gas.data
+    v0, vn, npv = bounds
+    n = (vn - v0) * npv
+    t, p, x = (np.ascontiguousarray(a, dtype=np.float64) for a in (t, p, x))
+    k = np.zeros(t.size * n)
+    if points is None:
+        points = [q for q in (10, 8, 5, 4, 2, 1) if npv % q == 0][0]
+    evals = c_longlong(0)
+    rc = emu.emu_absorption(t.size, p, t, x, v0, vn, npv, k, d["nu"].size, d["nu"], d["sw"],
+                            d["gamma_air"], d["gamma_self"], d["n_air"], d["elower"],
+                            d["delta_air"], d["local_iso_id"], d["mass"], d["num_iso"],
+                            d["num_t"], d["tips_t"], d["tips_q"], cut, int(ped), points,
+                            ctypes.byref(evals))
+    assert rc == 0
+    return k.reshape(t.size, n), int(evals.value)
+
+
+@pytest.mark.parametrize("bounds", [(1, 601, 10), (1, 301, 100), (1, 900, 1), (1, 500, 4),
+                                    (1, 400, 7), (1, 201, 8), (100, 161, 1000)])
+@pytest.mark.parametrize("ped", [0, 1])
+def test_emulated_vs_oracle(emu, small_db, atmosphere, bounds, ped):
+    for formula in ("H2O", "O3"):
+        gas = OracleGas(small_db, formula)
+        k, evals = run(emu, gas, atmosphere.t, atmosphere.p, atmosphere.vmr[formula], bounds, ped)
+        total = 0
+        for layer in range(atmosphere.t.size):
+            k_ref = gas.absorption(atmosphere.t[layer], atmosphere.p[layer],
+                                   atmosphere.vmr[formula][layer], *bounds, ped)
+            total += gas.last_evals
+            if not np.any(k_ref):
+                assert not np.any(k[layer])
+                continue
+            assert scaled_error(k[layer], k_ref, bounds[2]) <= FP64_TOL
+            if not ped:
+                assert relative_error(k[layer], k_ref) <= FP64_TOL
+        assert evals == total
+
+
+@pytest.mark.parametrize("points", [1, 2, 5, 10])
+def test_points_per_thread_variants_agree(emu, small_db, atmosphere, points):
+    gas = OracleGas(small_db, "CO2")
+    bounds = (600, 761, 10)
+    # 600 - 26 > first row: early break -> zeros for every variant
+    k, _ = run(emu, gas, atmosphere.t, atmosphere.p, atmosphere.vmr["CO2"], bounds, 1, points=points)
+    assert not np.any(k)
+    bounds = (1, 761, 10)
+    k, _ = run(emu, gas, atmosphere.t, atmosphere.p, atmosphere.vmr["CO2"], bounds, 1, points=points)
+    k_ref = gas.absorption(atmosphere.t[2], atmosphere.p[2], atmosphere.vmr["CO2"][2], *bounds, 1)
+    assert scaled_error(k[2], k_ref, 10) <= FP64_TOL
+
+
+@pytest.mark.parametrize("cut", [0, 1, 5, 40])
+def test_cut_off_variants(emu, small_db, atmosphere, cut):
+    gas = OracleGas(small_db, "H2O")
+    bounds = (1, 300, 10)
+    for ped in (0, 1):
+        k, _ = run(emu, gas, atmosphere.t, atmosphere.p, atmosphere.vmr["H2O"], bounds, ped, cut=cut)
+        for layer in (0, 3):
+            k_ref = gas.absorption(atmosphere.t[layer], atmosphere.p[layer],
+                                   atmosphere.vmr["H2O"][layer], *bounds, ped, cut)
+            assert scaled_error(k[layer], k_ref, 10, max(cut, 1)) <= FP64_TOL
+
+
+def test_unsorted_rows(emu, tmp_path, atmosphere):
+    lines = synth.make_line_list("CO2", 400, 560.0, 760.0, seed=3)
+    perm = np.random.default_rng(5).permutation(400)
+    path = str(tmp_path / "unsorted.db")
+    synth.write_database(path, {"CO2": {k: v[perm] for k, v in lines.items()}})
+    gas = OracleGas(path, "CO2")
+    bounds = (540, 781, 20)
+    for ped in (0, 1):
+        k, _ = run(emu, gas, atmosphere.t, atmosphere.p, atmosphere.vmr["CO2"], bounds, ped)
+        for layer in range(4):
+            k_ref = gas.absorption(atmosphere.t[layer], atmosphere.p[layer],
+                                   atmosphere.vmr["CO2"][layer], *bounds, ped)
+            assert scaled_error(k[layer], k_ref, 20) <= FP64_TOL
+
+
+def test_large_pressure_shift_near_integer_boundaries(emu, tmp_path):
+    """Lines sitting on integer wavenumbers with large shifts: the window cell must come from
+    the SHIFTED centre, bit-exactly (spectra.c:22,48)."""
+    lines = synth.make_line_list("O2", 200, 30.0, 130.0, seed=9)
+    lines["nu"] = np.sort(np.round(lines["nu"]) + np.tile([0.0, 1e-6, -1e-6, 0.5], 50))
+    lines["delta_air"] = np.tile([-0.02, 0.02, 0.0199, -0.0003], 50)
+    path = str(tmp_path / "shift.db")
+    synth.write_database(path, {"O2": lines})
+    gas = OracleGas(path, "O2")
+    t = np.array([250.0, 296.0]); p = np.array([101325.0, 5.0e4]); x = np.array([0.209, 0.209])
+    bounds = (5, 161, 20)
+    for ped in (0, 1):
+        k, evals = run(emu, gas, t, p, x, bounds, ped)
+        total = 0
+        for layer in range(2):
+            k_ref = gas.absorption(t[layer], p[layer], x[layer], *bounds, ped)
+            total += gas.last_evals
+            assert scaled_error(k[layer], k_ref, 20) <= FP64_TOL
+        assert evals == total

@@ -1,0 +1,214 @@
+"""Parity of the CUDA path against the oracle, through the C ABI (ctypes).
+
+Mirrors the reference's tests/test_gas_optics.py: same fixture atmosphere, same default
+keyword arguments, `Gas(database, formula).absorption_coefficient(...)`.
+"""
+import numpy as np
+import pytest
+
+from oracle import OracleGas, oracle_scale_line, oracle_tips
+from pylbl_b200 import Gas, synth
+from pylbl_b200 import _lib
+
+from helpers import FP64_TOL, relative_error, scaled_error
+
+pytestmark = pytest.mark.gpu
+
+
+class Db(object):
+    """Stand-in for pyLBL's Database: the backend only reads ``.path``."""
+    def __init__(self, path):
+        self.path = path
+
+
+@pytest.mark.parametrize("n_per_v", [10, 100])
+@pytest.mark.parametrize("formula", ["H2O", "CO2", "O3"])
+@pytest.mark.parametrize("remove_pedestal", [False, True])
+def test_fixture_atmosphere(small_db, atmosphere, formula, n_per_v, remove_pedestal):
+    grid = synth.grid_from_bounds(1, 1201, n_per_v)
+    gas = Gas(Db(small_db), formula)
+    ref = OracleGas(Db(small_db), formula)
+    for layer in range(atmosphere.t.size):
+        args = (atmosphere.t[layer], atmosphere.p[layer], atmosphere.vmr[formula][layer], grid)
+        k = gas.absorption_coefficient(*args, remove_pedestal=remove_pedestal)
+        k_ref = ref.absorption_coefficient(*args, remove_pedestal=remove_pedestal)
+        assert k.shape == k_ref.shape and k.dtype == np.float64
+        assert scaled_error(k, k_ref, n_per_v) <= FP64_TOL
+        if not remove_pedestal:
+            assert relative_error(k, k_ref) <= FP64_TOL
+        assert gas.last_stats[0]["evals"] == ref.last_evals
+
+
+def test_windows_bit_exact(small_db, atmosphere):
+    for formula in ("H2O", "CO2", "O3"):
+        gas = Gas(small_db, formula)
+        ref = OracleGas(small_db, formula)
+        for n_per_v, v0, vn in ((10, 1, 5001), (100, 200, 900), (3, 1, 3000)):
+            gas.absorption_coefficients(atmosphere.t, atmosphere.p, atmosphere.vmr[formula],
+                                        bounds=(v0, vn, n_per_v))
+            for layer in range(atmosphere.t.size):
+                ref.absorption(atmosphere.t[layer], atmosphere.p[layer],
+                               atmosphere.vmr[formula][layer], v0, vn, n_per_v, windows=True)
+                win = gas.windows(layer)
+                assert win.shape[0] == ref.last_active
+                assert np.array_equal(win, ref.last_windows[:ref.last_active])
+
+
+def test_scaled_line_parameters(small_db, atmosphere):
+    formula = "CO2"
+    gas = Gas(small_db, formula)
+    ref = OracleGas(small_db, formula)
+    d = ref.data
+    gas.absorption_coefficients(atmosphere.t, atmosphere.p, atmosphere.vmr[formula],
+                                bounds=(1, 5001, 10))
+    for layer in range(atmosphere.t.size):
+        got = gas.scaled_lines(layer)
+        t, p, x = atmosphere.t[layer], atmosphere.p[layer], atmosphere.vmr[formula][layer]
+        want = np.zeros_like(got)
+        for r in range(got.shape[0]):
+            iso = int(d["local_iso_id"][r])
+            q_ref = oracle_tips(d["tips_t"], d["tips_q"], d["num_t"], 296., iso - 1)
+            q_t = oracle_tips(d["tips_t"], d["tips_q"], d["num_t"], t, iso - 1)
+            want[r] = oracle_scale_line(t, p, x, d["nu"][r], d["sw"][r], d["gamma_air"][r],
+                                        d["gamma_self"][r], d["n_air"][r], d["elower"][r],
+                                        d["delta_air"][r], d["mass"][iso - 1], q_ref, q_t)
+        assert np.array_equal(got[:, 0], want[:, 0])          # shifted centre: bit-exact
+        np.testing.assert_allclose(got[:, 1:], want[:, 1:], rtol=1e-12, atol=0)
+
+
+def test_reference_entry_point(small_db, atmosphere):
+    """The library exports the reference's own symbol with its own signature
+    (pyLBL/c_lib/absorption.c:19-30), callable exactly as gas_optics.py:79-91 does."""
+    lib = _lib.library()
+    v0, vn, n_per_v = 1, 801, 10
+    k = np.zeros((vn - v0) * n_per_v)
+    layer = 3
+    lib.absorption(float(atmosphere.p[layer]), float(atmosphere.t[layer]),
+                   float(atmosphere.vmr["H2O"][layer]), v0, vn, n_per_v, k,
+                   bytes(small_db, encoding="utf-8"), b"H2O", 25, 0)
+    k_ref = OracleGas(small_db, "H2O").absorption(atmosphere.t[layer], atmosphere.p[layer],
+                                                  atmosphere.vmr["H2O"][layer], v0, vn, n_per_v)
+    assert relative_error(k, k_ref) <= FP64_TOL
+
+
+def test_batched_equals_scalar_and_prefetch(small_db, atmosphere):
+    grid = synth.grid_from_bounds(1, 601, 100)
+    gas = Gas(small_db, "O3")
+    batch = gas.absorption_coefficients(atmosphere.t, atmosphere.p, atmosphere.vmr["O3"], grid,
+                                        remove_pedestal=True)
+    for layer in range(atmosphere.t.size):
+        one = gas.absorption_coefficient(atmosphere.t[layer], atmosphere.p[layer],
+                                         atmosphere.vmr["O3"][layer], grid, remove_pedestal=True)
+        assert np.array_equal(one, batch[layer])
+    gas.prefetch(atmosphere.t, atmosphere.p, atmosphere.vmr["O3"], grid, remove_pedestal=True)
+    assert len(gas._cache) == atmosphere.t.size
+    one = gas.absorption_coefficient(atmosphere.t[2], atmosphere.p[2], atmosphere.vmr["O3"][2],
+                                     grid, remove_pedestal=True)
+    assert np.array_equal(one, batch[2]) and len(gas._cache) == atmosphere.t.size - 1
+
+
+@pytest.mark.parametrize("bounds", [(1, 3000, 1), (1, 400, 3), (1, 300, 7), (1, 200, 8),
+                                    (1, 120, 1000), (640, 700, 2000), (1, 5001, 4)])
+@pytest.mark.parametrize("remove_pedestal", [False, True])
+def test_grid_shapes(small_db, atmosphere, bounds, remove_pedestal):
+    """Every points-per-thread specialisation (n_per_v = 1, 3, 7 -> 1; 8; 1000, 2000 -> 10;
+    4) and grids that start inside the line list (the early break then yields zeros,
+    absorption.c:80-83)."""
+    v0, vn, n_per_v = bounds
+    gas = Gas(small_db, "CO2")
+    ref = OracleGas(small_db, "CO2")
+    k = gas.absorption_coefficients(atmosphere.t, atmosphere.p, atmosphere.vmr["CO2"],
+                                    bounds=bounds, remove_pedestal=remove_pedestal)
+    for layer in range(atmosphere.t.size):
+        k_ref = ref.absorption(atmosphere.t[layer], atmosphere.p[layer],
+                               atmosphere.vmr["CO2"][layer], v0, vn, n_per_v, remove_pedestal)
+        if not np.any(k_ref):
+            assert not np.any(k[layer])
+            continue
+        assert scaled_error(k[layer], k_ref, n_per_v) <= FP64_TOL
+
+
+@pytest.mark.parametrize("cut_off", [0, 1, 5, 40])
+def test_cut_off(small_db, atmosphere, cut_off):
+    gas = Gas(small_db, "H2O")
+    ref = OracleGas(small_db, "H2O")
+    bounds = (1, 500, 10)
+    for ped in (False, True):
+        k = gas.absorption_coefficients(atmosphere.t, atmosphere.p, atmosphere.vmr["H2O"],
+                                        bounds=bounds, remove_pedestal=ped, cut_off=cut_off)
+        for layer in range(atmosphere.t.size):
+            k_ref = ref.absorption(atmosphere.t[layer], atmosphere.p[layer],
+                                   atmosphere.vmr["H2O"][layer], *bounds, ped, cut_off)
+            assert scaled_error(k[layer], k_ref, 10, max(cut_off, 1)) <= FP64_TOL
+
+
+def test_dense_band(dense_db, atmosphere):
+    """Band grid 500-850 cm-1 with every line inside [v0-26, vn+26] (BASELINE config 3 shape)."""
+    bounds = (500, 851, 200)
+    gas = Gas(dense_db, "CO2")
+    ref = OracleGas(dense_db, "CO2")
+    for ped in (False, True):
+        k = gas.absorption_coefficients(atmosphere.t, atmosphere.p, atmosphere.vmr["CO2"],
+                                        bounds=bounds, remove_pedestal=ped)
+        for layer in range(atmosphere.t.size):
+            k_ref = ref.absorption(atmosphere.t[layer], atmosphere.p[layer],
+                                   atmosphere.vmr["CO2"][layer], *bounds, ped)
+            assert np.any(k_ref)
+            assert scaled_error(k[layer], k_ref, bounds[2]) <= FP64_TOL
+
+
+def test_unsorted_database(tmp_path, atmosphere):
+    """Rows out of nu order: the reference still walks them in row order (pedestal order,
+    early break); the packer must sort a copy and keep the row order for the recurrence."""
+    lines = synth.make_line_list("CO2", 600, 560.0, 760.0, seed=3)
+    rng = np.random.default_rng(5)
+    perm = rng.permutation(600)
+    shuffled = {k: v[perm] for k, v in lines.items()}
+    path = str(tmp_path / "unsorted.db")
+    synth.write_database(path, {"CO2": shuffled})
+    bounds = (540, 781, 50)
+    gas = Gas(path, "CO2")
+    ref = OracleGas(path, "CO2")
+    for ped in (False, True):
+        k = gas.absorption_coefficients(atmosphere.t, atmosphere.p, atmosphere.vmr["CO2"],
+                                        bounds=bounds, remove_pedestal=ped)
+        for layer in range(atmosphere.t.size):
+            k_ref = ref.absorption(atmosphere.t[layer], atmosphere.p[layer],
+                                   atmosphere.vmr["CO2"][layer], *bounds, ped, windows=True)
+            assert scaled_error(k[layer], k_ref, bounds[2]) <= FP64_TOL
+            assert np.array_equal(gas.windows(layer), ref.last_windows[:ref.last_active])
+
+
+def test_no_tips_gives_zeros_and_unknown_molecule_raises(tmp_path, atmosphere):
+    path = str(tmp_path / "notips.db")
+    synth.write_database(path, {"CO": synth.make_line_list("CO", 50, 1.0, 300.0)}, tips=False)
+    grid = synth.grid_from_bounds(1, 301, 10)
+    k = Gas(path, "CO").absorption_coefficient(250.0, 5.0e4, 1e-7, grid)
+    assert k.shape == (3000,) and not np.any(k)      # absorption.c:53-59
+    with pytest.raises(ValueError, match="Error inside c functions."):
+        Gas(path, "N2O").absorption_coefficient(250.0, 5.0e4, 1e-7, grid)
+    assert "not found in database" in _lib.last_error()
+
+
+def test_many_layers_chunked(small_db):
+    """60-layer column pushed through several launch groups with pinned output."""
+    col = synth.standard_column(60)
+    bounds = (1, 301, 100)
+    gas = Gas(small_db, "H2O")
+    ref = OracleGas(small_db, "H2O")
+    _lib.library().lbl_set_chunk_layers(7)
+    try:
+        pinned = _lib.PinnedArray((60, 30000))
+        k = gas.absorption_coefficients(col.t, col.p, col.vmr["H2O"], bounds=bounds,
+                                        remove_pedestal=True, out=pinned.array)
+    finally:
+        _lib.library().lbl_set_chunk_layers(0)
+    assert gas.last_stats[0]["sum_launches"] == 9
+    total = 0
+    for layer in (0, 6, 7, 13, 30, 59):
+        k_ref = ref.absorption(col.t[layer], col.p[layer], col.vmr["H2O"][layer], *bounds, True)
+        assert scaled_error(k[layer], k_ref, 100) <= FP64_TOL
+    for layer in range(60):
+        ref.absorption(col.t[layer], col.p[layer], col.vmr["H2O"][layer], *bounds, True)
+        total += ref.last_evals
+    assert gas.last_stats[0]["evals"] == total
