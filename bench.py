@@ -1,0 +1,440 @@
+#!/usr/bin/env python
+"""Benchmark of the line-by-line hot path (BASELINE.json metric: Voigt line-grid evals/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one clear-sky column of BASELINE.json configs[1]: 60 layers x 7 gases
+(H2O, CO2, O3, N2O, CO, CH4, O2; ~350 000 synthetic HITRAN-shaped lines) on the grid
+1-5000 cm-1 at 0.01 cm-1 (v0=1, vn=5001, n_per_v=100; 500 000 points per spectrum), with
+``remove_pedestal=True`` (what ``Spectroscopy.compute_absorption`` passes by default,
+pyLBL/spectroscopy.py:163-164) and ``cut_off=25``.  With N ranks, rank r computes its own
+column r (seeded perturbation of the standard column): weak scaling, no collective on the
+data path.
+
+Prints ONE JSON line (rank 0).  Keys beyond the base contract:
+  value      line-grid evaluations / s with the packed line lists resident in HBM and the
+             spectra left in HBM; device-timed (CUDA events), max over ranks
+  e2e        the same metric through the public ``Gas`` API with HOST buffers: per step the
+             (p, T, vmr) arrays go host->device and every spectrum comes back to pinned host
+             memory inside the timed region
+  roofline   FP64-pipe roofline of the summation kernel: algorithmic flops (7.3 per
+             evaluation) / CUDA-event duration of its launches,
+             against the FP64 FMA peak measured live on this GPU
+  cpu_baseline  the reference C library (oracle/_ref, or the oracle port when absent) on
+             the host cores, on a bounded sample of the same workload
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+from pylbl_b200 import synth  # noqa: E402
+
+METRIC = "voigt_line_grid_evals_per_s"
+UNIT = "evals/s"
+CONFIG = 2
+FLOP_PER_EVAL = 7.3  # mix-weighted algorithmic flops per evaluation
+GASES = ["H2O", "CO2", "O3", "N2O", "CO", "CH4", "O2"]
+N_LAYERS = 60
+REMOVE_PEDESTAL = True
+CUT_OFF = 25
+
+
+def workload_config(n_gpus):
+    v0, vn, npv = synth.config_grid(CONFIG)
+    return {
+        "workload": "BASELINE configs[1]: 60-layer clear-sky column x 7 gases "
+                    "(H2O,CO2,O3,N2O,CO,CH4,O2), ~350k synthetic HITRAN-shaped lines, "
+                    "grid 1-5000 cm-1 @0.01 cm-1",
+        "v0": v0, "vn": vn, "n_per_v": npv, "n_points": (vn - v0) * npv,
+        "n_layers": N_LAYERS, "gases": GASES,
+        "n_lines": int(sum(synth.CONFIG2_SHARES.values())),
+        "remove_pedestal": REMOVE_PEDESTAL, "cut_off": CUT_OFF,
+        "columns_per_step": n_gpus, "sharding": f"one column per GPU x{n_gpus}, no collective",
+        "l2_policy": "inputs larger than L2: per step ~1.5 GB of scaled line records are "
+                     "rewritten and ~1.7 GB of spectra written (L2 = 126 MB)",
+    }
+
+
+def database_path(local_rank, barrier):
+    """One synthetic database per node, written by local rank 0."""
+    cache = Path(tempfile.gettempdir()) / "pylbl_b200_bench"
+    cache.mkdir(exist_ok=True)
+    path = cache / f"config{CONFIG}.db"
+    done = cache / f"config{CONFIG}.done"
+    if local_rank == 0 and not done.exists():
+        synth.write_database(str(path), synth.config_line_lists(CONFIG))
+        done.write_text("ok")
+    barrier()
+    while not done.exists():
+        time.sleep(0.2)
+    return str(path)
+
+
+# --------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------
+class ClockSampler(object):
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                smax.append(float(parts[1]))
+                power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, flag in zip(names, parts[3:7]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        # "under load" = samples drawing more than half of the highest power seen
+        loaded = [s for s, w in zip(sm, power) if power and w >= 0.5 * max(power)] or sm
+        return {"sm_mhz": statistics.median(loaded) if loaded else None,
+                "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------
+# CPU arm: the reference C library on the host cores
+# --------------------------------------------------------------------------------------
+def cpu_reference_run(db, column, layers, threads):
+    """Runs absorption() for every gas x the given layers on `threads` host threads (ctypes
+    releases the GIL; the library is stateless).  Returns
+    (evals, seconds, kind)."""
+    from oracle import OracleGas, ReferenceGas, have_reference
+    v0, vn, npv = synth.config_grid(CONFIG)
+    kind = "reference" if have_reference() else "port"
+    counters = {f: OracleGas(db, f) for f in GASES} if kind == "port" else None
+    jobs = [(f, l) for l in layers for f in GASES]
+
+    def one(job):
+        f, l = job
+        if kind == "reference":
+            ReferenceGas(db, f).absorption(column.t[l], column.p[l], column.vmr[f][l], v0, vn, npv,
+                                           REMOVE_PEDESTAL, CUT_OFF)
+        else:
+            counters[f].absorption(column.t[l], column.p[l], column.vmr[f][l], v0, vn, npv,
+                                   REMOVE_PEDESTAL, CUT_OFF)
+        return 0
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=threads) as pool:
+        list(pool.map(one, jobs))
+    seconds = time.perf_counter() - t0
+    return seconds, kind, len(jobs)
+
+
+def count_evals(db, column, layers):
+    """Evaluation count of gas x layers from the window arithmetic alone (no Voigt work):
+    sum over lines of (e - s + 1), spectra.c:48-62, via the oracle's window function."""
+    from oracle import read_molecule
+    v0, vn, npv = synth.config_grid(CONFIG)
+    n = (vn - v0) * npv
+    total = 0
+    for f in GASES:
+        d = read_molecule(db, f)
+        nu, delta = d["nu"], d["delta_air"]
+        stop = np.nonzero((nu > vn + CUT_OFF + 1) | (nu < v0 - (CUT_OFF + 1)))[0]
+        na = int(stop[0]) if stop.size else nu.size
+        for l in layers:
+            p_atm = column.p[l] * 9.86923e-6
+            cb = np.floor(nu[:na] + p_atm * delta[:na]) - v0
+            s = (cb - CUT_OFF) * npv
+            e = np.minimum((cb + CUT_OFF + 1) * npv, n - 1)
+            keep = s < n
+            s = np.maximum(s, 0)
+            total += int(np.sum((e - s + 1)[keep & (e >= s)]))
+    return total
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    db = database_path(0, lambda: None)
+    column = synth.standard_column(N_LAYERS, column=0)
+    threads = os.cpu_count() or 1
+    layers = [0, 20, 40, 59]
+    evals = count_evals(db, column, layers)
+    times = []
+    kind = "port"
+    for step in range(args.warmup + args.steps):
+        seconds, kind, jobs = cpu_reference_run(db, column, layers, threads)
+        if step >= args.warmup:
+            times.append(seconds)
+    mean = sum(times) / len(times)
+    value = evals / mean
+    sample = (f"{len(GASES)} gases x layers {layers} of the 60-layer column "
+              f"({len(GASES) * len(layers)} absorption() calls, {evals:.3e} evaluations per step)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": mean * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": workload_config(args.gpus),
+        "layer_spectra_per_s": len(layers) / mean,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
+                         "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------
+def run_ours(args, rank, local_rank, world, dist):
+    import torch
+    from pylbl_b200 import Gas, _lib
+
+    torch.cuda.set_device(local_rank)
+    lib = _lib.library()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    db = database_path(local_rank, barrier)
+    bounds = synth.config_grid(CONFIG)
+    v0, vn, npv = bounds
+    n = (vn - v0) * npv
+    column = synth.standard_column(N_LAYERS, column=rank)
+    gases = {f: Gas(db, f, devices=[local_rank]) for f in GASES}
+
+    peak = ctypes.c_double(0.)
+    lib.lbl_measure_fp64_peak(local_rank, ctypes.byref(peak))
+
+    def step_resident():
+        """All gases, spectra left on the device.  Gases run one after another so that the
+        per-launch CUDA-event durations of the summation kernel are not inflated by overlap."""
+        stats = []
+        for f in GASES:
+            gases[f].absorption_coefficients(column.t, column.p, column.vmr[f], bounds=bounds,
+                                             remove_pedestal=REMOVE_PEDESTAL, cut_off=CUT_OFF,
+                                             to_host=False)
+            stats.append(gases[f].last_stats[0])
+        return stats
+
+    pinned = {f: _lib.PinnedArray((N_LAYERS, n)) for f in GASES}
+
+    def step_e2e():
+        """Public API with host buffers: submit every gas (each on its own CUDA streams), then
+        wait; inputs go up and every spectrum comes back to pinned host memory."""
+        handles = []
+        stats = []
+        for f in GASES:
+            g = gases[f]
+            h = g._handle(local_rank)
+            t = np.ascontiguousarray(column.t)
+            p = np.ascontiguousarray(column.p)
+            x = np.ascontiguousarray(column.vmr[f])
+            lib.lbl_gas_submit(h.ptr, N_LAYERS, p, t, x, v0, vn, npv, CUT_OFF,
+                               1 if REMOVE_PEDESTAL else 0, 0,
+                               pinned[f].array.ctypes.data_as(ctypes.c_void_p))
+            handles.append(h)
+        for h in handles:
+            lib.lbl_gas_wait(h.ptr)
+            stats.append(h.stats())
+        return stats
+
+    # ---- device-resident throughput ("value") ------------------------------------------
+    for _ in range(args.warmup):
+        step_resident()
+    torch.cuda.synchronize()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    lib.lbl_timer_start(local_rank)
+    evals = 0
+    sum_ms = 0.0
+    sum_launches = 0
+    launches = 0
+    for _ in range(args.steps):
+        for s in step_resident():
+            evals += s["evals"]
+            sum_ms += s["sum_ms"]
+            sum_launches += s["sum_launches"]
+            launches += s["total_launches"]
+    ms = ctypes.c_float(0.)
+    lib.lbl_timer_stop(local_rank, ctypes.byref(ms))
+    torch.cuda.synchronize()
+    barrier()
+    clocks = sampler.stop()
+    seconds = max_over_ranks(ms.value * 1e-3)
+    total_evals = sum_over_ranks(float(evals))
+    value = total_evals / seconds
+
+    # ---- end to end through the public API with host buffers ---------------------------
+    for _ in range(max(1, args.warmup // 2)):
+        step_e2e()
+    torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_evals = 0
+    h2d = d2h = 0
+    for _ in range(args.steps):
+        for s in step_e2e():
+            e2e_evals += s["evals"]
+            h2d += s["h2d_bytes"]
+            d2h += s["d2h_bytes"]
+    torch.cuda.synchronize()
+    e2e_seconds = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    e2e_value = sum_over_ranks(float(e2e_evals)) / e2e_seconds
+    # parity spot check of what came back (one spectrum, against the oracle)
+    check = None
+    if rank == 0 and not args.no_check:
+        from oracle import OracleGas
+        ref = OracleGas(db, "CO")
+        layer = 37
+        k_ref = ref.absorption(column.t[layer], column.p[layer], column.vmr["CO"][layer], v0, vn,
+                               npv, REMOVE_PEDESTAL, CUT_OFF)
+        check = float(np.max(np.abs(pinned["CO"].array[layer] - k_ref)) / np.max(np.abs(k_ref)))
+
+    # ---- roofline of the summation kernel ----------------------------------------------
+    flops = FLOP_PER_EVAL * evals                       # this rank, timed region
+    achieved = flops / (sum_ms * 1e-3) / 1e12 if sum_ms > 0 else 0.0
+    roofline = {
+        "bound": "fp64", "kernel": "lbl::sum_kernel<10>", "achieved": achieved,
+        "peak": peak.value, "unit": "TFLOP/s",
+        "frac": achieved / peak.value if peak.value else None, "traffic": None,
+        "flop_per_eval": FLOP_PER_EVAL,
+        "evals_per_launch": evals / max(sum_launches, 1),
+        "avg_launch_ms": sum_ms / max(sum_launches, 1),
+        "kernel_share_of_step": sum_ms / (ms.value if ms.value else 1.0),
+        "peak_source": "FP64 FMA peak measured live on this GPU (independent DFMA chains, "
+                       "lbl_measure_fp64_peak); MEASURED_PEAKS.json carries no FP64 figure",
+        "hbm_peak_gbs": json.loads((ROOT / "MEASURED_PEAKS.json").read_text()).get("hbm_gbs")
+        if (ROOT / "MEASURED_PEAKS.json").exists() else None,
+    }
+
+    # ---- CPU baseline on rank 0 at N=1 ---------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        layers = [0, 20, 40, 59]
+        base_column = synth.standard_column(N_LAYERS, column=0)
+        cpu_evals = count_evals(db, base_column, layers)
+        cpu_seconds, kind, jobs = cpu_reference_run(db, base_column, layers, threads)
+        cpu = {"value": cpu_evals / cpu_seconds, "unit": UNIT, "cores": threads, "kind": kind,
+               "sample": f"{len(GASES)} gases x layers {layers} of the 60-layer column "
+                         f"({jobs} absorption() calls incl. their sqlite reads, "
+                         f"{cpu_evals:.3e} evaluations, {cpu_seconds:.1f} s)"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": seconds * 1e3 / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": workload_config(world),
+            "layer_spectra_per_s": world * N_LAYERS * args.steps / seconds,
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT,
+                    "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps,
+                    "ms_per_step": e2e_seconds * 1e3 / args.steps,
+                    "layer_spectra_per_s": world * N_LAYERS * args.steps / e2e_seconds,
+                    "parity_spot_check_max_rel_to_peak": check},
+            "gpu_launches": launches,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    for g in gases.values():
+        g.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-check", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_mod
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist_mod.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+        dist = dist_mod
+    try:
+        run_ours(args, rank, local_rank, world, dist)
+    finally:
+        if dist is not None:
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

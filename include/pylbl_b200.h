@@ -49,6 +49,7 @@ typedef struct lbl_stats
     int total_launches;     /* all kernel launches */
     float scale_ms;         /* K1, CUDA events on the launching stream */
     float sum_ms;           /* K2 (dominant kernel), summed over launches */
+    float fixup_ms;         /* K2b (near-zone and node terms) */
     float pedestal_ms;      /* K3 + K4 */
     float total_ms;         /* first enqueue -> last copy complete */
 } lbl_stats;
@@ -106,6 +107,17 @@ LBL_API int lbl_gas_scaled(lbl_gas* gas, int layer, double* out, int capacity);
 /* Pinned host memory for k_host (lets the device->host copy run asynchronously). */
 LBL_API int lbl_host_alloc(size_t bytes, void** ptr);
 LBL_API int lbl_host_free(void* ptr);
+
+/* Device-side stopwatch over several handles (one per CUDA device): lbl_timer_start marks
+ * "now" on the device, lbl_timer_join makes the stopwatch wait for the end of the last call
+ * submitted on `gas`, lbl_timer_stop returns the elapsed milliseconds between the two marks
+ * as measured by CUDA events (it blocks until the joined work has finished). */
+LBL_API int lbl_timer_start(int device);
+LBL_API int lbl_timer_join(lbl_gas* gas);
+LBL_API int lbl_timer_stop(int device, float* ms);
+/* Measures this device's FP64 FMA throughput with independent DFMA chains (the roofline
+ * denominator of the summation kernel); result in TFLOP/s (2 flop per FMA). */
+LBL_API int lbl_measure_fp64_peak(int device, double* tflops);
 
 LBL_API int lbl_device_count(int* count);
 /* Layers per launch group: 0 = automatic. */

@@ -29,7 +29,8 @@ class Stats(Structure):
         ("evals", c_longlong), ("h2d_bytes", c_longlong), ("d2h_bytes", c_longlong),
         ("n_lines", c_int), ("n_active", c_int), ("n_layers", c_int), ("n_points", c_int),
         ("points_per_thread", c_int), ("sum_launches", c_int), ("total_launches", c_int),
-        ("scale_ms", c_float), ("sum_ms", c_float), ("pedestal_ms", c_float),
+        ("scale_ms", c_float), ("sum_ms", c_float), ("fixup_ms", c_float),
+        ("pedestal_ms", c_float),
         ("total_ms", c_float),
     ]
 
@@ -41,7 +42,8 @@ EXPORTS = (
     "absorption", "lbl_gas_open", "lbl_gas_close", "lbl_gas_compute", "lbl_gas_submit",
     "lbl_gas_wait", "lbl_gas_stats", "lbl_gas_device_result", "lbl_gas_windows",
     "lbl_gas_scaled", "lbl_host_alloc", "lbl_host_free", "lbl_device_count",
-    "lbl_set_chunk_layers", "lbl_last_error", "lbl_version",
+    "lbl_set_chunk_layers", "lbl_last_error", "lbl_version", "lbl_timer_start",
+    "lbl_timer_join", "lbl_timer_stop", "lbl_measure_fp64_peak",
 )
 
 _library = None
@@ -85,6 +87,10 @@ def library():
     lib.lbl_host_free.argtypes = [c_void_p]
     lib.lbl_device_count.argtypes = [POINTER(c_int)]
     lib.lbl_set_chunk_layers.argtypes = [c_int]
+    lib.lbl_timer_start.argtypes = [c_int]
+    lib.lbl_timer_join.argtypes = [c_void_p]
+    lib.lbl_timer_stop.argtypes = [c_int, POINTER(c_float)]
+    lib.lbl_measure_fp64_peak.argtypes = [c_int, POINTER(c_double)]
     for name in EXPORTS:
         if name not in ("absorption", "lbl_last_error", "lbl_version"):
             getattr(lib, name).restype = check_return_code

@@ -132,7 +132,8 @@ struct lbl_gas
     bool open_h2d_reported = false;
 
     cudaStream_t s_compute = nullptr, s_side = nullptr, s_copy = nullptr;
-    DevBuf rec_ab, rec_cc, rec_chk, rec_gen, layers_dev, evals_dev, pedbin, pedcorr, pednodes;
+    DevBuf rec_ab, rec_cc, rec_chk, rec_gen, layers_dev, evals_dev, pedbin, pedcorr, pednodes,
+        pedterms;
     DevBuf out[2];
     LayerIn* layers_host = nullptr;  // pinned
     size_t layers_host_cap = 0;
@@ -144,7 +145,7 @@ struct lbl_gas
     int ev_used = 0;
     struct ChunkEvents
     {
-        cudaEvent_t k1_begin, k1_end, k2_begin, k2_end, ped_begin, ped_end;
+        cudaEvent_t k1_begin, k1_end, k2_begin, k2_end, k2b_end, ped_begin, ped_end;
         bool pedestal;
     };
     std::vector<ChunkEvents> chunk_events;
@@ -299,6 +300,44 @@ void launch_sum_dispatch(int P, const SumArgs& a, int n_layers, cudaStream_t s)
     }
 }
 
+// K2b tile width: about one near zone (~0.3 cm-1) of grid points, a power of two in [4, 32].
+int pick_fixup_tile(int n_per_v)
+{
+    if (n_per_v >= 64) return 32;
+    if (n_per_v >= 32) return 16;
+    if (n_per_v >= 16) return 8;
+    return 4;
+}
+
+void launch_fixup_dispatch(int T, const SumArgs& a, int n_layers, cudaStream_t s)
+{
+    const int tiles = (a.grid.n + T - 1) / T;
+    const int lp = 32 / T;
+    dim3 grid((tiles + 3) / 4, (n_layers + lp - 1) / lp);
+    switch (T)
+    {
+        case 32: fixup_kernel<32><<<grid, 128, 0, s>>>(a); break;
+        case 16: fixup_kernel<16><<<grid, 128, 0, s>>>(a); break;
+        case 8: fixup_kernel<8><<<grid, 128, 0, s>>>(a); break;
+        default: fixup_kernel<4><<<grid, 128, 0, s>>>(a); break;
+    }
+}
+
+template <int K>
+cudaError_t launch_chain(const PedArgs& pa, const double* terms, double* scratch, int n_layers,
+                         size_t smem, cudaStream_t s)
+{
+    cudaError_t e = cudaSuccess;
+    if (smem > 48 * 1024)
+    {
+        e = cudaFuncSetAttribute(pedestal_chain_kernel<K>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    pedestal_chain_kernel<K><<<n_layers, 32, smem, s>>>(pa, terms, scratch);
+    return cudaGetLastError();
+}
+
 int set_device(lbl_gas* g)
 {
     LBL_CUDA(cudaSetDevice(g->device));
@@ -337,6 +376,95 @@ int lbl_device_count(int* count)
         return fail(std::string("Error: CUDA: ") + cudaGetErrorString(e));
     }
     *count = n;
+    return 0;
+}
+
+namespace
+{
+struct DeviceTimer
+{
+    cudaStream_t stream = nullptr;
+    cudaEvent_t begin = nullptr, end = nullptr;
+};
+std::mutex g_timer_mu;
+std::map<int, DeviceTimer> g_timers;
+
+int get_timer(int device, DeviceTimer** out)
+{
+    std::lock_guard<std::mutex> lock(g_timer_mu);
+    DeviceTimer& t = g_timers[device];
+    if (!t.stream)
+    {
+        LBL_CUDA(cudaSetDevice(device));
+        LBL_CUDA(cudaStreamCreateWithFlags(&t.stream, cudaStreamNonBlocking));
+        LBL_CUDA(cudaEventCreate(&t.begin));
+        LBL_CUDA(cudaEventCreate(&t.end));
+    }
+    *out = &t;
+    return 0;
+}
+}  // namespace
+
+int lbl_timer_start(int device)
+{
+    DeviceTimer* t = nullptr;
+    if (get_timer(device, &t)) return 1;
+    LBL_CUDA(cudaSetDevice(device));
+    LBL_CUDA(cudaEventRecord(t->begin, t->stream));
+    return 0;
+}
+
+int lbl_timer_join(lbl_gas* g)
+{
+    if (!g) return fail("Error: null handle.");
+    DeviceTimer* t = nullptr;
+    if (get_timer(g->device, &t)) return 1;
+    LBL_CUDA(cudaSetDevice(g->device));
+    if (g->pending)
+    {
+        LBL_CUDA(cudaStreamWaitEvent(t->stream, g->ev_call_end, 0));
+    }
+    return 0;
+}
+
+int lbl_timer_stop(int device, float* ms)
+{
+    DeviceTimer* t = nullptr;
+    if (get_timer(device, &t)) return 1;
+    LBL_CUDA(cudaSetDevice(device));
+    LBL_CUDA(cudaEventRecord(t->end, t->stream));
+    LBL_CUDA(cudaEventSynchronize(t->end));
+    LBL_CUDA(cudaEventElapsedTime(ms, t->begin, t->end));
+    return 0;
+}
+
+int lbl_measure_fp64_peak(int device, double* tflops)
+{
+    *tflops = 0.;
+    LBL_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    LBL_CUDA(cudaGetDeviceProperties(&prop, device));
+    double* out = nullptr;
+    LBL_CUDA(cudaMalloc(&out, 64));
+    cudaEvent_t a, b;
+    LBL_CUDA(cudaEventCreate(&a));
+    LBL_CUDA(cudaEventCreate(&b));
+    const int blocks = prop.multiProcessorCount * 8, iters = 20000;
+    float best = 1e30f;
+    for (int r = 0; r < 8; ++r)
+    {
+        LBL_CUDA(cudaEventRecord(a, 0));
+        dfma_probe_kernel<<<blocks, 256>>>(out, iters, 1.0000001, 1e-9);
+        LBL_CUDA(cudaEventRecord(b, 0));
+        LBL_CUDA(cudaEventSynchronize(b));
+        float ms = 0.f;
+        LBL_CUDA(cudaEventElapsedTime(&ms, a, b));
+        if (r >= 2 && ms < best) best = ms;
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(out);
+    *tflops = 2.0 * (double)blocks * 256 * 8 * iters / (best * 1e-3) / 1e12;
     return 0;
 }
 
@@ -405,6 +533,7 @@ int lbl_gas_close(lbl_gas* g)
     g->plan.own.release();
     for (DevBuf* b : {&g->tips_t, &g->tips_q, &g->rec_ab, &g->rec_cc, &g->rec_chk, &g->rec_gen,
                       &g->layers_dev, &g->evals_dev, &g->pedbin, &g->pedcorr, &g->pednodes,
+                      &g->pedterms,
                       &g->out[0], &g->out[1]})
     {
         b->release();
@@ -519,8 +648,13 @@ int lbl_gas_submit(lbl_gas* g, int n_layers, const double* pressure, const doubl
     tips.q = g->tips_q.as<double>();
 
     // ---- chunking over layers ------------------------------------------------------
-    const size_t rec_per_layer = (size_t)plan.n_active * (sizeof(FarAB) + sizeof(double) +
-                                                          sizeof(LineChk) + sizeof(LineGen));
+    // Pedestal chain: K slots per lane cover the 2*cut+3 tracked points of a line window.
+    const int ped_k = (2 * cut_off + 3 + 31) / 32;
+    const bool ped_chain = remove_pedestal && ped_k <= 4;
+    const int ped_wpad = 32 * ped_k;
+    const size_t rec_per_layer = (size_t)plan.n_active *
+        (sizeof(FarAB) + sizeof(double) + sizeof(LineChk) + sizeof(LineGen) +
+         (ped_chain ? sizeof(double) * ped_wpad : 0));
     const size_t out_per_layer = sizeof(double) * (size_t)grid.n;
     const size_t budget = (size_t)6 << 30;
     long long chunk = std::min<long long>(n_layers,
@@ -548,15 +682,26 @@ int lbl_gas_submit(lbl_gas* g, int n_layers, const double* pressure, const doubl
     if (n_chunks > 1) LBL_CUDA(g->out[1].reserve(out_per_layer * chunk));
     const int nb = grid.ncell + 2 * cut_off + 2;
     size_t ped_smem = 0;
+    bool ped_nodes_in_smem = true;
     if (remove_pedestal)
     {
         LBL_CUDA(g->pedbin.reserve(sizeof(double) * (size_t)nb * chunk));
         LBL_CUDA(g->pedcorr.reserve(sizeof(double) * 2 * (size_t)grid.ncell * chunk));
-        ped_smem = sizeof(double) * (size_t)(grid.ncell + 1);
+        const size_t node_bytes = sizeof(double) * (size_t)(grid.ncell + 1);
+        const size_t ring_bytes = ped_chain
+            ? (size_t)kPedStages * kPedTile * (sizeof(double) * ped_wpad + sizeof(int4)) : 0;
+        ped_smem = ring_bytes + node_bytes;
+        ped_nodes_in_smem = true;
         if (ped_smem > 200 * 1024)
         {
-            LBL_CUDA(g->pednodes.reserve(ped_smem * chunk));
-            ped_smem = 0;
+            // Grid too wide for shared memory: the node array goes to global memory.
+            LBL_CUDA(g->pednodes.reserve(node_bytes * chunk));
+            ped_smem = ring_bytes;
+            ped_nodes_in_smem = false;
+        }
+        if (ped_chain)
+        {
+            LBL_CUDA(g->pedterms.reserve(sizeof(double) * ped_wpad * (size_t)plan.n_active * chunk));
         }
         else if (ped_smem > 48 * 1024)
         {
@@ -625,6 +770,7 @@ int lbl_gas_submit(lbl_gas* g, int n_layers, const double* pressure, const doubl
         ev.k1_end = next_event(g);
         ev.k2_begin = next_event(g);
         ev.k2_end = next_event(g);
+        ev.k2b_end = next_event(g);
         ev.ped_begin = next_event(g);
         ev.ped_end = next_event(g);
 
@@ -655,8 +801,28 @@ int lbl_gas_submit(lbl_gas* g, int n_layers, const double* pressure, const doubl
             pa.rec = rec;
             pa.grid = grid;
             pa.pedbin = g->pedbin.as<double>();
-            pedestal_kernel<<<nl, 32, ped_smem, g->s_side>>>(
-                pa, ped_smem ? nullptr : g->pednodes.as<double>());
+            double* scratch = ped_nodes_in_smem ? nullptr : g->pednodes.as<double>();
+            if (ped_chain)
+            {
+                const long long per_layer = (long long)plan.n_active * ped_wpad;
+                dim3 tg((unsigned)((per_layer + 255) / 256), nl);
+                pedestal_terms_kernel<<<tg, 256, 0, g->s_side>>>(pa, ped_wpad,
+                                                                 g->pedterms.as<double>());
+                cudaError_t ce = cudaSuccess;
+                switch (ped_k)
+                {
+                    case 1: ce = launch_chain<1>(pa, g->pedterms.as<double>(), scratch, nl, ped_smem, g->s_side); break;
+                    case 2: ce = launch_chain<2>(pa, g->pedterms.as<double>(), scratch, nl, ped_smem, g->s_side); break;
+                    case 3: ce = launch_chain<3>(pa, g->pedterms.as<double>(), scratch, nl, ped_smem, g->s_side); break;
+                    default: ce = launch_chain<4>(pa, g->pedterms.as<double>(), scratch, nl, ped_smem, g->s_side); break;
+                }
+                LBL_CUDA(ce);
+                st.total_launches++;
+            }
+            else
+            {
+                pedestal_kernel<<<nl, 32, ped_smem, g->s_side>>>(pa, scratch);
+            }
             const int cells = nl * grid.ncell;
             pedestal_cells_kernel<<<(cells + 127) / 128, 128, 0, g->s_side>>>(
                 g->pedbin.as<double>(), grid, nl, g->pedcorr.as<double>());
@@ -671,11 +837,14 @@ int lbl_gas_submit(lbl_gas* g, int n_layers, const double* pressure, const doubl
         sa.layers = layers_c;
         sa.grid = grid;
         sa.out = g->out[slot].as<double>();
+        sa.n_layers = nl;
         LBL_CUDA(cudaEventRecord(ev.k2_begin, sc));
         launch_sum_dispatch(P, sa, nl, sc);
         LBL_CUDA(cudaEventRecord(ev.k2_end, sc));
+        launch_fixup_dispatch(pick_fixup_tile(n_per_v), sa, nl, sc);
+        LBL_CUDA(cudaEventRecord(ev.k2b_end, sc));
         st.sum_launches++;
-        st.total_launches++;
+        st.total_launches += 2;
 
         if (remove_pedestal)
         {
@@ -734,6 +903,8 @@ int lbl_gas_wait(lbl_gas* g)
         st.scale_ms += ms;
         LBL_CUDA(cudaEventElapsedTime(&ms, ev.k2_begin, ev.k2_end));
         st.sum_ms += ms;
+        LBL_CUDA(cudaEventElapsedTime(&ms, ev.k2_end, ev.k2b_end));
+        st.fixup_ms += ms;
         if (ev.pedestal)
         {
             LBL_CUDA(cudaEventElapsedTime(&ms, ev.ped_begin, ev.ped_end));

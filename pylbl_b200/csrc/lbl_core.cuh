@@ -416,7 +416,8 @@ LBL_HD Segments find_segments(const double* nu_sorted, int n_lines, int v0, int 
     const int c_hi = last / n_per_v;
     const double base = (double)v0;
     // Superset of lines whose window can touch any point of the group.
-    s.j[0] = lower_bound(nu_sorted, n_lines, base + (double)(c_lo - cut_off - 1) - slack);
+    // (The extra cell cb == c-cut-1 that reaches only a cell's first point is K2b's.)
+    s.j[0] = lower_bound(nu_sorted, n_lines, base + (double)(c_lo - cut_off) - slack);
     s.j[5] = lower_bound(nu_sorted, n_lines, base + (double)(c_hi + cut_off + 1) + slack);
     // Lines certainly inside every point's window.
     int core_lo = lower_bound(nu_sorted, n_lines, base + (double)(c_hi - cut_off) + slack);

@@ -106,9 +106,16 @@ LBL_HD long long scale_thread(const LinesView& ln, const TipsView& tips, const L
 }
 
 // ---------------------------------------------------------------------------------------
-// K2: gather summation.  One thread owns P consecutive grid points that lie in one
-// integer-wavenumber cell (P divides n_per_v); the 32 threads of a warp own 32*P
-// consecutive points and walk the same line ranges.
+// K2: gather summation of the far-wing (Lorentz) terms.  One thread owns P consecutive grid
+// points that lie in one integer-wavenumber cell (P divides n_per_v); the 32 threads of a
+// warp own 32*P consecutive points and walk the same line ranges.
+//
+// Every active (line, point) pair belongs to exactly one of three classes:
+//   near  : point inside the line's near zone [nlo, nhi]          -> K2b (full Humlicek)
+//   far   : otherwise, line cell cb in [cell-cut, cell+cut]        -> here
+//   node  : otherwise, cb == cell-cut-1 and the point is the cell's first (r == 0),
+//           because that line's inclusive end index e lands on it  -> K2b
+// (window membership: SURVEY section 8(a) Q3, derived from spectra.c:48-62).
 // ---------------------------------------------------------------------------------------
 struct SumArgs
 {
@@ -117,6 +124,7 @@ struct SumArgs
     const LayerIn* layers;
     GridSpec grid;
     double* out;  // [layer][n]
+    int n_layers;
 };
 
 template <int P>
@@ -128,19 +136,14 @@ LBL_HD void plain_range(const FarAB* __restrict__ ab, const double* __restrict__
     {
         const double2 l = LBL_LDG(reinterpret_cast<const double2*>(ab + j));
         const double c = LBL_LDG(cc + j);
-#pragma unroll
-        for (int p = 0; p < P; ++p)
-        {
-            acc[p] = far_term(v[p], l.x, l.y, c, acc[p]);
-        }
+        far_terms<P>(v, l.x, l.y, c, acc);
     }
 }
 
 template <int P>
-LBL_HD void checked_range(const FarAB* __restrict__ ab, const double* __restrict__ cc,
-                          const LineChk* __restrict__ chk, const LineGen* __restrict__ gen,
-                          int jb, int je, int i_first, int cell, bool owns_node, int cut_off,
-                          const double (&v)[P], double (&acc)[P])
+LBL_HD void masked_range(const FarAB* __restrict__ ab, const double* __restrict__ cc,
+                         const LineChk* __restrict__ chk, int jb, int je, int i_first, int cell,
+                         int cut_off, const double (&v)[P], double (&acc)[P])
 {
     const int cmin = cell - cut_off;
     const int cmax = cell + cut_off;
@@ -148,49 +151,25 @@ LBL_HD void checked_range(const FarAB* __restrict__ ab, const double* __restrict
     for (int j = jb; j < je; ++j)
     {
         const int4 ck = LBL_LDG(reinterpret_cast<const int4*>(chk + j));  // cb, nlo, nhi
-        // Window membership (from spectra.c:48-62): all points of
-        // cell c see lines with c-cut <= cb <= c+cut; the cell's first point (r == 0) also
-        // sees cb == c-cut-1, because that line's inclusive end index e lands on it.
-        const bool core = (ck.x >= cmin) && (ck.x <= cmax);
-        const bool node = core || (owns_node && ck.x == cmin - 1);
-        if (!node)
+        if (ck.x < cmin || ck.x > cmax)
         {
             continue;
         }
         const double2 l = LBL_LDG(reinterpret_cast<const double2*>(ab + j));
         const double c = LBL_LDG(cc + j);
-        const bool near = (ck.y <= i_last) && (ck.z >= i_first);
-        if (!near)
+        if (ck.y > i_last || ck.z < i_first)
         {
-            acc[0] = far_term(v[0], l.x, l.y, c, acc[0]);
-            if (core)
-            {
-#pragma unroll
-                for (int p = 1; p < P; ++p)
-                {
-                    acc[p] = far_term(v[p], l.x, l.y, c, acc[p]);
-                }
-            }
+            far_terms<P>(v, l.x, l.y, c, acc);
         }
         else
         {
-            const double2 g0 = LBL_LDG(reinterpret_cast<const double2*>(gen + j));
-            const double2 g1 = LBL_LDG(reinterpret_cast<const double2*>(gen + j) + 1);
+            // Some of this thread's points are in the near zone: they are K2b's.
 #pragma unroll
             for (int p = 0; p < P; ++p)
             {
-                if (p == 0 || core)
-                {
-                    const int i = i_first + p;
-                    if (i >= ck.y && i <= ck.z)
-                    {
-                        acc[p] += voigt_general(v[p], g0.x, g0.y, g1.x, g1.y);
-                    }
-                    else
-                    {
-                        acc[p] = far_term(v[p], l.x, l.y, c, acc[p]);
-                    }
-                }
+                const int i = i_first + p;
+                const double cp = (i >= ck.y && i <= ck.z) ? kBig : c;
+                acc[p] = far_term(v[p], l.x, l.y, cp, acc[p]);
             }
         }
     }
@@ -220,7 +199,6 @@ LBL_HD void sum_thread(const SumArgs& a, int layer, int tid)
         i_first = g.n - P;  // idle lanes of the last warp shadow a real thread, store nothing
     }
     const int cell = i_first / g.n_per_v;
-    const bool owns_node = (i_first - cell * g.n_per_v) == 0;
 
     double v[P], acc[P];
 #pragma unroll
@@ -233,13 +211,12 @@ LBL_HD void sum_thread(const SumArgs& a, int layer, int tid)
     const FarAB* ab = a.rec.ab + off;
     const double* cc = a.rec.cc + off;
     const LineChk* chk = a.rec.chk + off;
-    const LineGen* gen = a.rec.gen + off;
 
-    checked_range<P>(ab, cc, chk, gen, seg.j[0], seg.j[1], i_first, cell, owns_node, g.cut_off, v, acc);
+    masked_range<P>(ab, cc, chk, seg.j[0], seg.j[1], i_first, cell, g.cut_off, v, acc);
     plain_range<P>(ab, cc, seg.j[1], seg.j[2], v, acc);
-    checked_range<P>(ab, cc, chk, gen, seg.j[2], seg.j[3], i_first, cell, owns_node, g.cut_off, v, acc);
+    masked_range<P>(ab, cc, chk, seg.j[2], seg.j[3], i_first, cell, g.cut_off, v, acc);
     plain_range<P>(ab, cc, seg.j[3], seg.j[4], v, acc);
-    checked_range<P>(ab, cc, chk, gen, seg.j[4], seg.j[5], i_first, cell, owns_node, g.cut_off, v, acc);
+    masked_range<P>(ab, cc, chk, seg.j[4], seg.j[5], i_first, cell, g.cut_off, v, acc);
 
     if (valid)
     {
@@ -253,14 +230,100 @@ LBL_HD void sum_thread(const SumArgs& a, int layer, int tid)
 }
 
 // ---------------------------------------------------------------------------------------
-// K3: pedestal recurrence (spectra.c:66-78), one warp per layer.
+// K2b: near-zone and node terms, one grid point per lane (dense in the near zone, where K2's
+// P-points-per-thread layout would leave most lanes idle).  A warp covers T consecutive
+// points of 32/T consecutive layers; T shrinks with the grid resolution so that a tile stays
+// about as wide as a near zone.  Adds into the spectrum K2 wrote (same stream, no atomics:
+// each point still has exactly one owner).
+// ---------------------------------------------------------------------------------------
+template <int T>
+LBL_HD void fixup_thread(const SumArgs& a, int tile, int layer_group, int lane)
+{
+    const GridSpec& g = a.grid;
+    constexpr int LP = 32 / T;
+    int layer = layer_group * LP + lane / T;
+    int i = tile * T + lane % T;
+    const bool valid = (layer < a.n_layers) && (i < g.n);
+    if (layer >= a.n_layers) layer = a.n_layers - 1;
+    if (i >= g.n) i = g.n - 1;
+    const int t_first = tile * T;
+    int t_last = t_first + T - 1;
+    if (t_last > g.n - 1) t_last = g.n - 1;
+
+    const LayerIn ly = a.layers[layer];
+    const size_t off = (size_t)layer * a.lines.n;
+    const LineChk* chk = a.rec.chk + off;
+    const LineGen* gen = a.rec.gen + off;
+    const double v = grid_point(g.v0, g.dv, i);
+    const int cell = i / g.n_per_v;
+    const bool is_node = (i - cell * g.n_per_v) == 0;
+    double acc = 0.;
+
+    // (1) near zone: every line whose [nlo, nhi] contains i (same reach as find_segments).
+    {
+        const double base = (double)g.v0;
+        const double v_first = base + (double)t_first * g.dv;
+        const double v_last = base + (double)t_last * g.dv;
+        const double reach = (ly.kappa < 0.5)
+            ? (ly.kappa * fabs(v_last) / (1.0 - ly.kappa)) * (1.0 + 0x1p-20) + ly.slack + 3.0 * g.dv
+            : 1.0e300;
+        const int jlo = lower_bound(a.lines.nu, a.lines.n, v_first - reach);
+        const int jhi = lower_bound(a.lines.nu, a.lines.n, v_last + reach);
+        for (int j = jlo; j < jhi; ++j)
+        {
+            const int4 ck = LBL_LDG(reinterpret_cast<const int4*>(chk + j));
+            if (i < ck.y || i > ck.z)
+            {
+                continue;
+            }
+            // inside the line's window? s <= i <= e, spectra.c:48-62 (unclamped form)
+            const long long s = (long long)(ck.x - g.cut_off) * g.n_per_v;
+            const long long e = (long long)(ck.x + g.cut_off + 1) * g.n_per_v;
+            if ((long long)i < s || (long long)i > e)
+            {
+                continue;
+            }
+            const double2 g0 = LBL_LDG(reinterpret_cast<const double2*>(gen + j));
+            const double2 g1 = LBL_LDG(reinterpret_cast<const double2*>(gen + j) + 1);
+            acc += voigt_general(v, g0.x, g0.y, g1.x, g1.y);
+        }
+    }
+    // (2) node terms: lines with cb == cell-cut-1 reach exactly the cell's first point.
+    if (is_node)
+    {
+        const double key = (double)g.v0 + (double)(cell - g.cut_off - 1);
+        const int jlo = lower_bound(a.lines.nu, a.lines.n, key - ly.slack);
+        const int jhi = lower_bound(a.lines.nu, a.lines.n, key + 1.0 + ly.slack);
+        const FarAB* ab = a.rec.ab + off;
+        const double* cc = a.rec.cc + off;
+        for (int j = jlo; j < jhi; ++j)
+        {
+            const int4 ck = LBL_LDG(reinterpret_cast<const int4*>(chk + j));
+            if (ck.x != cell - g.cut_off - 1 || (i >= ck.y && i <= ck.z))
+            {
+                continue;  // other cell, or already taken by the near loop above
+            }
+            const double2 l = LBL_LDG(reinterpret_cast<const double2*>(ab + j));
+            acc = far_term(v, l.x, l.y, LBL_LDG(cc + j), acc);
+        }
+    }
+    if (valid)
+    {
+        a.out[(size_t)layer * g.n + i] += acc;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// K3: pedestal recurrence (spectra.c:66-78).
 //
 // The reference subtracts, after each line, min(k[s], k[e]) of the ACCUMULATED spectrum
 // from k[s..e], so the pedestal of line l depends on all earlier lines.
 // s and e are multiples of n_per_v (or the clamps 0 and n-1), hence only the running
 // spectrum at integer-wavenumber nodes -- plus the last grid point n-1 -- is needed.
-// This walks the lines in DATABASE order, keeps those tracked points in `nodes`
-// (ncell + 1 doubles), and accumulates each line's pedestal into `pedbin[cb + cut + 1]`.
+// Lines are walked in DATABASE order.  A line with window cell cb touches "slots"
+//   t = 0 .. 2*cut+1  -> node cb-cut+t      (valid if inside [max(cb-cut,0), min(cb+cut+1, ncell-1)])
+//   t = 2*cut+2       -> grid point n-1     (valid if e is clamped to n-1 and n_per_v > 1)
+// and each line's pedestal is accumulated into pedbin[cb + cut + 1].
 // ---------------------------------------------------------------------------------------
 struct PedArgs
 {
@@ -270,12 +333,163 @@ struct PedArgs
     double* pedbin;  // [layer][ncell + 2*cut + 2]
 };
 
+struct PedWindow
+{
+    int base;     // node of slot 0 (= cb - cut, may be negative)
+    int s_node;   // first node inside the window
+    int e_node;   // last node inside the window
+    int s_slot;   // slot of k[s]
+    int e_slot;   // slot of k[e]
+    bool tail;    // k[e] is grid point n-1, which is not a node
+    bool skip;    // the reference does not process this line on this grid
+};
+
+LBL_HD PedWindow ped_window(int cb, const GridSpec& g)
+{
+    PedWindow w;
+    const int e_raw = cb + g.cut_off + 1;
+    // s >= n: spectra.c:49-53.  e < 0: undefined behaviour in the reference.
+    w.skip = (cb - g.cut_off >= g.ncell) || (e_raw < 0);
+    w.base = cb - g.cut_off;
+    w.s_node = w.base > 0 ? w.base : 0;
+    const bool clamped = e_raw >= g.ncell;
+    w.tail = clamped && g.n_per_v > 1;
+    w.e_node = clamped ? g.ncell - 1 : e_raw;
+    w.s_slot = w.s_node - w.base;
+    w.e_slot = w.tail ? 2 * g.cut_off + 2 : w.e_node - w.base;
+    return w;
+}
+
+// Storage index (in the ncell+1 node array) of slot t, or -1 if the slot is outside the window.
+LBL_HD int ped_slot_index(const PedWindow& w, const GridSpec& g, int t)
+{
+    if (t == 2 * g.cut_off + 2)
+    {
+        return w.tail ? g.ncell : -1;
+    }
+    if (t > 2 * g.cut_off + 2)
+    {
+        return -1;
+    }
+    const int node = w.base + t;
+    return (node >= w.s_node && node <= w.e_node) ? node : -1;
+}
+
+// K3a: contribution of database row r to slot t (0 outside the window).
+LBL_HD double pedestal_term(const PedArgs& a, int layer, int r, int t)
+{
+    const GridSpec& g = a.grid;
+    const int j = a.lines.db_to_sorted ? a.lines.db_to_sorted[r] : r;
+    const size_t o = (size_t)layer * a.lines.n + j;
+    const LineChk chk = a.rec.chk[o];
+    const PedWindow w = ped_window(chk.cb, g);
+    if (w.skip)
+    {
+        return 0.;
+    }
+    const int idx = ped_slot_index(w, g, t);
+    if (idx < 0)
+    {
+        return 0.;
+    }
+    const int i = (idx == g.ncell) ? g.n - 1 : idx * g.n_per_v;
+    return line_point(grid_point(g.v0, g.dv, i), i, a.rec.ab[o], a.rec.cc[o], chk, a.rec.gen[o]);
+}
+
+// K3b: per-lane state of the sequential chain.  While consecutive lines share the same cb
+// the window does not move, so each lane keeps its K slots -- and a private copy of the two
+// nodes k[s], k[e] that decide the pedestal -- in registers; the node array is only touched
+// when cb changes.
+template <int K>
+struct PedLane
+{
+    int cb;
+    bool have;
+    PedWindow w;
+    double own[K];
+    double ks, ke;
+    double binsum;
+};
+
+template <int K>
+LBL_HD void ped_lane_init(PedLane<K>& st)
+{
+    st.have = false;
+    st.cb = 0;
+    st.binsum = 0.;
+    st.ks = st.ke = 0.;
+#pragma unroll
+    for (int k = 0; k < K; ++k) st.own[k] = 0.;
+}
+
+// Phase 1 of a window move: write the lane's slots back (and the finished bin's pedestal).
+template <int K>
+LBL_HD void ped_lane_flush(PedLane<K>& st, const GridSpec& g, int lane, double* nodes, double* bins)
+{
+    if (!st.have)
+    {
+        return;
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+    {
+        const int idx = ped_slot_index(st.w, g, lane + 32 * k);
+        if (idx >= 0) nodes[idx] = st.own[k];
+    }
+    if (lane == 0)
+    {
+        bins[st.cb + g.cut_off + 1] += st.binsum;
+    }
+}
+
+// Phase 2 (after a barrier): load the slots of the new window.
+template <int K>
+LBL_HD void ped_lane_reload(PedLane<K>& st, const GridSpec& g, int lane, int cb, const PedWindow& w,
+                            const double* nodes)
+{
+    st.cb = cb;
+    st.have = true;
+    st.w = w;
+    st.binsum = 0.;
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+    {
+        const int idx = ped_slot_index(w, g, lane + 32 * k);
+        st.own[k] = (idx >= 0) ? nodes[idx] : 0.;
+    }
+    st.ks = nodes[ped_slot_index(w, g, w.s_slot)];
+    st.ke = nodes[ped_slot_index(w, g, w.e_slot)];
+}
+
+// Per line: k[s..e] += f ; pedestal = min(k[s], k[e]) ; k[s..e] -= pedestal (spectra.c:65-77).
+// `row` holds the line's K3a terms, one per slot.
+template <int K>
+LBL_HD void ped_lane_line(PedLane<K>& st, int lane, const double* row)
+{
+    double f[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) f[k] = row[lane + 32 * k];
+    const double fs = row[st.w.s_slot];
+    const double fe = row[st.w.e_slot];
+    st.ks += fs;
+    st.ke += fe;
+    const double pedestal = (st.ke < st.ks) ? st.ke : st.ks;  // spectra.c:68-72
+    st.ks -= pedestal;
+    st.ke -= pedestal;
+    st.binsum += pedestal;
+#pragma unroll
+    for (int k = 0; k < K; ++k) st.own[k] = (st.own[k] + f[k]) - pedestal;
+}
+
+// Generic (slow) form of the whole recurrence for one layer, used when the window is wider
+// than the register-resident kernel supports, and by the CPU emulation harness.
 template <class Sync>
 LBL_HD void pedestal_layer(const PedArgs& a, int layer, int lane, int nlanes, double* nodes,
                            Sync sync)
 {
     const GridSpec& g = a.grid;
     const int nb = g.ncell + 2 * g.cut_off + 2;
+    const int nslots = 2 * g.cut_off + 3;
     double* bins = a.pedbin + (size_t)layer * nb;
     for (int c = lane; c <= g.ncell; c += nlanes)
     {
@@ -286,51 +500,29 @@ LBL_HD void pedestal_layer(const PedArgs& a, int layer, int lane, int nlanes, do
         bins[b] = 0.;
     }
     sync();
-    const size_t off = (size_t)layer * a.lines.n;
-    const bool tail_point = g.n_per_v > 1;  // is grid point n-1 distinct from the last node?
     for (int r = 0; r < a.lines.n; ++r)
     {
         const int j = a.lines.db_to_sorted ? a.lines.db_to_sorted[r] : r;
-        const LineChk chk = a.rec.chk[off + j];
-        const int cb = chk.cb;
-        if (cb - g.cut_off >= g.ncell)
+        const int cb = a.rec.chk[(size_t)layer * a.lines.n + j].cb;
+        const PedWindow w = ped_window(cb, g);
+        if (w.skip)
         {
-            continue;  // s >= n, spectra.c:49-53
+            continue;
         }
-        const int e_raw = cb + g.cut_off + 1;
-        if (e_raw < 0)
+        for (int t = lane; t < nslots; t += nlanes)
         {
-            continue;  // e < 0: undefined behaviour in the reference; contributes nothing
-        }
-        const int s_c = (cb - g.cut_off > 0) ? cb - g.cut_off : 0;
-        const bool e_clamped = e_raw >= g.ncell;
-        const int e_node = e_clamped ? g.ncell - 1 : e_raw;
-        const bool use_tail = e_clamped && tail_point;
-        const FarAB ab = a.rec.ab[off + j];
-        const double cc = a.rec.cc[off + j];
-        const LineGen gen = a.rec.gen[off + j];
-        for (int c = s_c + lane; c <= e_node; c += nlanes)
-        {
-            const int i = c * g.n_per_v;
-            nodes[c] += line_point(grid_point(g.v0, g.dv, i), i, ab, cc, chk, gen);
-        }
-        if (use_tail && lane == nlanes - 1)
-        {
-            const int i = g.n - 1;
-            nodes[g.ncell] += line_point(grid_point(g.v0, g.dv, i), i, ab, cc, chk, gen);
+            const int idx = ped_slot_index(w, g, t);
+            if (idx >= 0) nodes[idx] += pedestal_term(a, layer, r, t);
         }
         sync();
-        const double ks = nodes[s_c];
-        const double ke = use_tail ? nodes[g.ncell] : nodes[e_node];
+        const double ks = nodes[ped_slot_index(w, g, w.s_slot)];
+        const double ke = nodes[ped_slot_index(w, g, w.e_slot)];
         const double pedestal = (ke < ks) ? ke : ks;  // spectra.c:68-72
         sync();
-        for (int c = s_c + lane; c <= e_node; c += nlanes)
+        for (int t = lane; t < nslots; t += nlanes)
         {
-            nodes[c] -= pedestal;
-        }
-        if (use_tail && lane == nlanes - 1)
-        {
-            nodes[g.ncell] -= pedestal;
+            const int idx = ped_slot_index(w, g, t);
+            if (idx >= 0) nodes[idx] -= pedestal;
         }
         if (lane == 0)
         {

@@ -32,6 +32,54 @@ struct NoSync
     void operator()() const {}
 };
 
+template <int T>
+static void run_fixup(const SumArgs& a, int n_layers)
+{
+    const int tiles = (a.grid.n + T - 1) / T;
+    const int lp = 32 / T;
+    const int groups = (n_layers + lp - 1) / lp;
+    for (int group = 0; group < groups; ++group)
+    {
+        for (int tile = 0; tile < tiles; ++tile)
+        {
+            for (int lane = 0; lane < 32; ++lane)
+            {
+                fixup_thread<T>(a, tile, group, lane);
+            }
+        }
+    }
+}
+
+// The register-resident chain of K3b with its 32 lanes run phase by phase.
+template <int K>
+static void run_chain(const PedArgs& pa, int layer, double* nodes)
+{
+    const GridSpec& g = pa.grid;
+    const int wpad = 32 * K;
+    const int nb = g.ncell + 2 * g.cut_off + 2;
+    double* bins = pa.pedbin + (size_t)layer * nb;
+    for (int c = 0; c <= g.ncell; ++c) nodes[c] = 0.;
+    for (int b = 0; b < nb; ++b) bins[b] = 0.;
+    std::vector<PedLane<K>> lanes(32);
+    for (auto& st : lanes) ped_lane_init(st);
+    std::vector<double> row(wpad);
+    for (int r = 0; r < pa.lines.n; ++r)
+    {
+        const int j = pa.lines.db_to_sorted ? pa.lines.db_to_sorted[r] : r;
+        const int cb = pa.rec.chk[(size_t)layer * pa.lines.n + j].cb;
+        if (!lanes[0].have || cb != lanes[0].cb)
+        {
+            const PedWindow w = ped_window(cb, g);
+            if (w.skip) continue;
+            for (int lane = 0; lane < 32; ++lane) ped_lane_flush(lanes[lane], g, lane, nodes, bins);
+            for (int lane = 0; lane < 32; ++lane) ped_lane_reload(lanes[lane], g, lane, cb, w, nodes);
+        }
+        for (int t = 0; t < wpad; ++t) row[t] = pedestal_term(pa, layer, r, t);
+        for (int lane = 0; lane < 32; ++lane) ped_lane_line(lanes[lane], lane, row.data());
+    }
+    for (int lane = 0; lane < 32; ++lane) ped_lane_flush(lanes[lane], g, lane, nodes, bins);
+}
+
 extern "C" int emu_absorption(int n_layers, const double* pressure, const double* temperature,
                               const double* vmr, int v0, int vn, int n_per_v, double* k,
                               int n_lines, const double* nu, const double* sw,
@@ -121,6 +169,7 @@ extern "C" int emu_absorption(int n_layers, const double* pressure, const double
     sa.layers = layers.data();
     sa.grid = g;
     sa.out = k;
+    sa.n_layers = n_layers;
     switch (points_per_thread)
     {
         case 10: run_sum<10>(sa, n_layers); break;
@@ -131,6 +180,11 @@ extern "C" int emu_absorption(int n_layers, const double* pressure, const double
         case 1: run_sum<1>(sa, n_layers); break;
         default: return 1;
     }
+    // K2b: same tile rule as pick_fixup_tile() in lbl_api.cu.
+    if (n_per_v >= 64) run_fixup<32>(sa, n_layers);
+    else if (n_per_v >= 32) run_fixup<16>(sa, n_layers);
+    else if (n_per_v >= 16) run_fixup<8>(sa, n_layers);
+    else run_fixup<4>(sa, n_layers);
     if (remove_pedestal)
     {
         const int nb = g.ncell + 2 * cut_off + 2;
@@ -143,7 +197,14 @@ extern "C" int emu_absorption(int n_layers, const double* pressure, const double
         pa.pedbin = pedbin.data();
         for (int l = 0; l < n_layers; ++l)
         {
-            pedestal_layer(pa, l, 0, 1, nodes.data(), NoSync());
+            switch ((2 * cut_off + 3 + 31) / 32)
+            {
+                case 1: run_chain<1>(pa, l, nodes.data()); break;
+                case 2: run_chain<2>(pa, l, nodes.data()); break;
+                case 3: run_chain<3>(pa, l, nodes.data()); break;
+                case 4: run_chain<4>(pa, l, nodes.data()); break;
+                default: pedestal_layer(pa, l, 0, 1, nodes.data(), NoSync()); break;
+            }
             for (int c = 0; c < g.ncell; ++c)
             {
                 pedestal_cell(pedbin.data() + (size_t)l * nb, c, cut_off,

@@ -91,7 +91,7 @@ def test_points_per_thread_variants_agree(emu, small_db, atmosphere, points):
     assert scaled_error(k[2], k_ref, 10) <= FP64_TOL
 
 
-@pytest.mark.parametrize("cut", [0, 1, 5, 40])
+@pytest.mark.parametrize("cut", [0, 1, 5, 40, 70])
 def test_cut_off_variants(emu, small_db, atmosphere, cut):
     gas = OracleGas(small_db, "H2O")
     bounds = (1, 300, 10)

@@ -128,7 +128,7 @@ def test_grid_shapes(small_db, atmosphere, bounds, remove_pedestal):
         assert scaled_error(k[layer], k_ref, n_per_v) <= FP64_TOL
 
 
-@pytest.mark.parametrize("cut_off", [0, 1, 5, 40])
+@pytest.mark.parametrize("cut_off", [0, 1, 5, 40, 70])
 def test_cut_off(small_db, atmosphere, cut_off):
     gas = Gas(small_db, "H2O")
     ref = OracleGas(small_db, "H2O")
