@@ -271,7 +271,13 @@ cudaEvent_t next_event(lbl_gas* g)
 
 int pick_points_per_thread(int n_per_v)
 {
-    const int candidates[] = {10, 8, 5, 4, 2, 1};
+    // PYLBL_B200_POINTS overrides the choice (tuning experiments); it must divide n_per_v.
+    if (const char* env = getenv("PYLBL_B200_POINTS"))
+    {
+        const int p = atoi(env);
+        if ((p == 10 || p == 8 || p == 5 || p == 4 || p == 2 || p == 1) && n_per_v % p == 0) return p;
+    }
+    const int candidates[] = {5, 4, 8, 10, 2, 1};
     for (int p : candidates)
     {
         if (n_per_v % p == 0) return p;
@@ -324,10 +330,15 @@ void launch_fixup_dispatch(int T, const SumArgs& a, int n_layers, cudaStream_t s
 }
 
 template <int K>
-cudaError_t launch_chain(const PedArgs& pa, const double* terms, double* scratch, int n_layers,
+cudaError_t launch_chain(const PedArgs& pa, double* terms, double* scratch, int n_layers,
                          size_t smem, cudaStream_t s)
 {
     cudaError_t e = cudaSuccess;
+    {
+        const int rows_per_block = (256 / 32) * kTermRowsPerWarp;
+        dim3 tg((pa.lines.n + rows_per_block - 1) / rows_per_block, n_layers);
+        pedestal_terms_kernel<K><<<tg, 256, 0, s>>>(pa, terms);
+    }
     if (smem > 48 * 1024)
     {
         e = cudaFuncSetAttribute(pedestal_chain_kernel<K>,
@@ -496,7 +507,13 @@ int lbl_gas_open(const char* database, const char* formula, int device, lbl_gas*
     if (read_molecule(database, formula, g->mol, err)) return fail(err);
     if (set_device(g.get())) return 1;
     LBL_CUDA(cudaStreamCreateWithFlags(&g->s_compute, cudaStreamNonBlocking));
-    LBL_CUDA(cudaStreamCreateWithFlags(&g->s_side, cudaStreamNonBlocking));
+    {
+        // The pedestal chain is a long, thin dependency chain: give its stream priority so
+        // that its blocks are placed ahead of the summation kernel's backlog.
+        int least = 0, greatest = 0;
+        LBL_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        LBL_CUDA(cudaStreamCreateWithPriority(&g->s_side, cudaStreamNonBlocking, greatest));
+    }
     LBL_CUDA(cudaStreamCreateWithFlags(&g->s_copy, cudaStreamNonBlocking));
     LBL_CUDA(cudaEventCreate(&g->ev_call_begin));
     LBL_CUDA(cudaEventCreate(&g->ev_call_end));
@@ -690,7 +707,9 @@ int lbl_gas_submit(lbl_gas* g, int n_layers, const double* pressure, const doubl
         const size_t node_bytes = sizeof(double) * (size_t)(grid.ncell + 1);
         const size_t ring_bytes = ped_chain
             ? (size_t)kPedStages * kPedTile * (sizeof(double) * ped_wpad + sizeof(int4)) : 0;
-        ped_smem = ring_bytes + node_bytes;
+        // The chain kernel also keeps the per-cell pedestal bins in shared memory.
+        const size_t bins_bytes = ped_chain ? sizeof(double) * (size_t)nb : 0;
+        ped_smem = ring_bytes + node_bytes + bins_bytes;
         ped_nodes_in_smem = true;
         if (ped_smem > 200 * 1024)
         {
@@ -804,10 +823,6 @@ int lbl_gas_submit(lbl_gas* g, int n_layers, const double* pressure, const doubl
             double* scratch = ped_nodes_in_smem ? nullptr : g->pednodes.as<double>();
             if (ped_chain)
             {
-                const long long per_layer = (long long)plan.n_active * ped_wpad;
-                dim3 tg((unsigned)((per_layer + 255) / 256), nl);
-                pedestal_terms_kernel<<<tg, 256, 0, g->s_side>>>(pa, ped_wpad,
-                                                                 g->pedterms.as<double>());
                 cudaError_t ce = cudaSuccess;
                 switch (ped_k)
                 {

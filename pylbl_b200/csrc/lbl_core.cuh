@@ -33,7 +33,7 @@ constexpr double kR2 = 0x1.683271f84129fp+13;     // 2*log(2)*8314.472       spe
 constexpr double kVlight = 2.99792458e8;          //                         spectra.c:12
 constexpr double kPaToAtm = 9.86923e-6;           //                         spectra.c:13
 constexpr double kC2 = 1.4387752;                 //                         spectra.c:15
-constexpr double kBig = 1.0e300;                  // "infinite" denominator: masks a term
+constexpr double kBig = 1.0e150;                  // "infinite" denominator: masks a term
 constexpr double kLorentzY = 70.55;               // voigt.c:17
 constexpr int kIdxClamp = 1 << 30;
 
@@ -50,12 +50,14 @@ struct alignas(16) LineChk  // integer bookkeeping of one (layer, line)
     int nhi;
     int pad;
 };
-struct alignas(16) LineGen  // operands of the full profile (voigt.c:13-15,188)
+struct alignas(16) LineGen  // operands of the full profile (voigt.c:13-15,34-43,188)
 {
     double nu;      // shifted centre
     double repwid;  // sqrt(ln2)/alpha
     double y;       // repwid*gamma
     double cof;     // sw*rsqrpi*repwid
+    double xlim0;   // sqrt(15100 + y*(40 - 3.6*y))                  voigt.c:34
+    double xlim1;   // y >= 8.425 ? 0 : sqrt(164 - y*(4.3 + 1.8*y))  voigt.c:36-43
 };
 
 struct LayerIn
@@ -113,6 +115,36 @@ LBL_HD double rcp_seed(double q)
 #endif
 }
 
+// Seed whose low word is borrowed from `dead` (any double that is no longer needed).  The
+// hardware instruction writes only the high word; rcp_seed() has to zero the low word with an
+// extra MOV per evaluation, whereas arbitrary low bits merely perturb the seed by < 2^-20,
+// which the Newton step squares away exactly like the seed's own error.
+LBL_HD double rcp_seed_lo(double q, double dead)
+{
+#if defined(__CUDA_ARCH__)
+    double r;
+    asm("{\n\t"
+        ".reg .b32 lo, hi, zlo, zhi;\n\t"
+        ".reg .f64 t;\n\t"
+        "rcp.approx.ftz.f64 t, %1;\n\t"
+        "mov.b64 {zlo, zhi}, t;\n\t"
+        "mov.b64 {lo, hi}, %2;\n\t"
+        "mov.b64 %0, {lo, zhi};\n\t"
+        "}"
+        : "=d"(r)
+        : "d"(q), "d"(dead));
+    return r;
+#else
+    union { double d; uint64_t u; } in, out, low;
+    in.d = q;
+    in.u &= 0xFFFFFFFF00000000ull;
+    out.d = 1.0 / in.d;
+    low.d = dead;
+    out.u = (out.u & 0xFFFFFFFF00000000ull) | (low.u & 0x00000000FFFFFFFFull);
+    return out.d;
+#endif
+}
+
 LBL_HD double fma_(double a, double b, double c)
 {
 #if defined(__CUDA_ARCH__)
@@ -141,21 +173,21 @@ LBL_HD double far_term(double v, double a, double b, double c, double acc)
 template <int P>
 LBL_HD void far_terms(const double (&v)[P], double a, double b, double c, double (&acc)[P])
 {
-    double q[P], r[P];
+    double d[P], q[P], r[P];
 #pragma unroll
     for (int p = 0; p < P; ++p)
     {
-        q[p] = fma_(v[p], a, b);
+        d[p] = fma_(v[p], a, b);
     }
 #pragma unroll
     for (int p = 0; p < P; ++p)
     {
-        q[p] = fma_(q[p], q[p], c);
+        q[p] = fma_(d[p], d[p], c);
     }
 #pragma unroll
     for (int p = 0; p < P; ++p)
     {
-        r[p] = rcp_seed(q[p]);
+        r[p] = rcp_seed_lo(q[p], d[p]);
     }
 #pragma unroll
     for (int p = 0; p < P; ++p)
@@ -169,41 +201,101 @@ LBL_HD void far_terms(const double (&v)[P], double a, double b, double c, double
     }
 }
 
+// Reciprocal to ~1e-16: hardware seed (2^-20) and two Newton steps.  Used by the full
+// profile below, where the reference divides (voigt.c:82,95,113,145,159-183).
+LBL_HD double rcp_newton2(double q)
+{
+    double r = rcp_seed(q);
+    r = r * fma_(-q, r, 2.0);
+    r = r * fma_(-q, r, 2.0);
+    return r;
+}
+
+// Two lines at once for P points: 1/q1 + 1/q2 = (q1 + q2)/(q1*q2) needs ONE reciprocal.
+// 9 FP64-pipe instructions and 1 MUFU per two evaluations (instead of 8 and 2): the MUFU
+// pipe, which a one-reciprocal-per-evaluation loop saturates together with the FP64 pipe,
+// is relieved at the price of half an FMA per evaluation.
+template <int P>
+LBL_HD void far_terms_pair(const double (&v)[P], double a1, double b1, double c1, double a2,
+                           double b2, double c2, double (&acc)[P])
+{
+    double d[P], s[P], m[P], r[P];
+#pragma unroll
+    for (int p = 0; p < P; ++p)
+    {
+        d[p] = fma_(v[p], a1, b1);
+        m[p] = fma_(v[p], a2, b2);
+    }
+#pragma unroll
+    for (int p = 0; p < P; ++p)
+    {
+        d[p] = fma_(d[p], d[p], c1);   // q1
+        m[p] = fma_(m[p], m[p], c2);   // q2
+    }
+#pragma unroll
+    for (int p = 0; p < P; ++p)
+    {
+        s[p] = d[p] + m[p];
+        m[p] = d[p] * m[p];
+    }
+#pragma unroll
+    for (int p = 0; p < P; ++p)
+    {
+        r[p] = rcp_seed_lo(m[p], d[p]);
+    }
+#pragma unroll
+    for (int p = 0; p < P; ++p)
+    {
+        m[p] = fma_(-m[p], r[p], 2.0);
+        s[p] = s[p] * r[p];
+    }
+#pragma unroll
+    for (int p = 0; p < P; ++p)
+    {
+        acc[p] = fma_(s[p], m[p], acc[p]);
+    }
+}
+
 // ---- full Humlicek W4 / CPF12 profile for one point (voigt.c:74-188) -------------------
-// Only reached for y < 70.55 (the y >= 70.55 branch is pure Lorentz and has an empty
-// near zone).  Returns cof*K(x,y).
-static LBL_HD_NOINLINE double voigt_general(double v, double nu, double repwid, double y, double cof)
+// Only reached for y < 70.55 (the y >= 70.55 branch is pure Lorentz and has an empty near
+// zone).  The region limits that need a square root are computed once per (layer, line) by
+// the scaling kernel.  The profile is split at xlim1 into
+//   outer : region 0 (Lorentz form) and Humlicek W4 region 1  -- ~98 % of the near zone, cheap
+//   core  : W4 regions 2, 3 and CPF12                          -- a few points per line, long
+// so that the near-zone kernel can run the long part with the lanes packed.
+
+// voigt.c:48-53: for y <= 1e-6 the W4 regions 1 and 2 are switched off.
+LBL_HD double voigt_outer_limit(double y, double xlim0, double xlim1)
+{
+    return (y <= 0.000001) ? xlim0 : xlim1;
+}
+
+// Regions 0 and 1 (voigt.c:79-97); requires abx >= voigt_outer_limit().  Returns K(x,y).
+LBL_HD double voigt_outer(double abx, double xq, double y, double xlim0)
 {
     const double yq = y * y;
-    const double xi = (v - nu) * repwid;
-    const double abx = fabs(xi);
-    const double xq = abx * abx;
-
-    const double xlim0 = sqrt(15100. + y * (40. - y * 3.6));
-    double xlim1 = (y >= 8.425) ? 0. : sqrt(164. - y * (4.3 + y * 1.8));
-    double xlim2 = 6.8 - y;
-    const double xlim3 = 2.4 * y;
-    const double xlim4 = 18.1 * y + 1.65;
-    if (y <= 0.000001)
-    {
-        xlim1 = xlim0;
-        xlim2 = xlim0;
-    }
-
-    double buf;
     if (abx >= xlim0)
     {
-        buf = (y * kRsqrPi) / (xq + yq);
+        return (y * kRsqrPi) * rcp_newton2(xq + yq);
     }
-    else if (abx >= xlim1)
-    {
-        const double a0 = yq + 0.5;
-        const double d0 = a0 * a0;
-        const double d2 = yq + yq - 1.;
-        const double d = kRsqrPi / (d0 + xq * (d2 + xq));
-        buf = d * y * (a0 + xq);
-    }
-    else if (abx >= xlim2)
+    const double a0 = yq + 0.5;
+    const double d0 = a0 * a0;
+    const double d2 = yq + yq - 1.;
+    const double d = kRsqrPi * rcp_newton2(d0 + xq * (d2 + xq));
+    return d * y * (a0 + xq);
+}
+
+// Regions 2, 3 and CPF12 (voigt.c:98-186); requires abx < voigt_outer_limit().  Returns K(x,y).
+static LBL_HD_NOINLINE double voigt_core(double xi, double y, double xlim0)
+{
+    const double yq = y * y;
+    const double abx = fabs(xi);
+    const double xq = abx * abx;
+    const double xlim2 = (y <= 0.000001) ? xlim0 : 6.8 - y;
+    const double xlim3 = 2.4 * y;
+    const double xlim4 = 18.1 * y + 1.65;
+    double buf;
+    if (abx >= xlim2)
     {
         const double h0 = 0.5625 + yq * (4.5 + yq * (10.5 + yq * (6.0 + yq)));
         const double h2 = -4.5 + yq * (9.0 + yq * (6.0 + yq * 4.0));
@@ -212,7 +304,7 @@ static LBL_HD_NOINLINE double voigt_general(double v, double nu, double repwid, 
         const double e0 = 1.875 + yq * (8.25 + yq * (5.5 + yq));
         const double e2 = 5.25 + yq * (1.0 + yq * 3.0);
         const double e4 = 0.75 * h6;
-        const double d = kRsqrPi / (h0 + xq * (h2 + xq * (h4 + xq * (h6 + xq))));
+        const double d = kRsqrPi * rcp_newton2(h0 + xq * (h2 + xq * (h4 + xq * (h6 + xq))));
         buf = d * y * (e0 + xq * (e2 + xq * (e4 + xq)));
     }
     else if (abx < xlim3)
@@ -239,7 +331,7 @@ static LBL_HD_NOINLINE double voigt_general(double v, double nu, double repwid, 
         const double p6 = -0.07272979 + y * (0.9377051 + y * (4.266322 + y * 1.273316));
         const double p8 = 0.0005480304 + y * 0.3183291;
         // The reference writes sqrt(pi) as the 8-digit literal here (voigt.c:145).
-        const double d = 1.7724538 / (z0 + xq * (z2 + xq * (z4 + xq * (z6 + xq * (z8 + xq)))));
+        const double d = 1.7724538 * rcp_newton2(z0 + xq * (z2 + xq * (z4 + xq * (z6 + xq * (z8 + xq)))));
         buf = d * (p0 + xq * (p2 + xq * (p4 + xq * (p6 + xq * p8))));
     }
     else
@@ -261,12 +353,12 @@ static LBL_HD_NOINLINE double voigt_general(double v, double nu, double repwid, 
         {
             const double dm = xi - tc[j];
             const double mq = dm * dm;
-            const double mf = 1. / (mq + ypy0q);
+            const double mf = rcp_newton2(mq + ypy0q);
             const double xm = mf * dm;
             const double ym = mf * ypy0;
             const double dp = xi + tc[j];
             const double pq = dp * dp;
-            const double pf = 1. / (pq + ypy0q);
+            const double pf = rcp_newton2(pq + ypy0q);
             const double xp = pf * dp;
             const double yp = pf * ypy0;
             if (inner)
@@ -275,8 +367,8 @@ static LBL_HD_NOINLINE double voigt_general(double v, double nu, double repwid, 
             }
             else
             {
-                buf += (cc[j] * (mq * mf - y0 * ym) + sc[j] * yf * xm) / (mq + y0q)
-                     + (cc[j] * (pq * pf - y0 * yp) - sc[j] * yf * xp) / (pq + y0q);
+                buf += (cc[j] * (mq * mf - y0 * ym) + sc[j] * yf * xm) * rcp_newton2(mq + y0q)
+                     + (cc[j] * (pq * pf - y0 * yp) - sc[j] * yf * xp) * rcp_newton2(pq + y0q);
             }
         }
         if (!inner)
@@ -284,7 +376,20 @@ static LBL_HD_NOINLINE double voigt_general(double v, double nu, double repwid, 
             buf = y * buf + exp(-xq);
         }
     }
-    return cof * buf;
+    return buf;
+}
+
+// The whole profile for one point: cof*K(x,y)  (voigt.c:76-188).
+LBL_HD double voigt_general(double v, double nu, double repwid, double y, double cof,
+                            double xlim0, double xlim1)
+{
+    const double xi = (v - nu) * repwid;
+    const double abx = fabs(xi);
+    if (abx >= voigt_outer_limit(y, xlim0, xlim1))
+    {
+        return cof * voigt_outer(abx, abx * abx, y, xlim0);
+    }
+    return cof * voigt_core(xi, y, xlim0);
 }
 
 // ---- per-(layer, line) scaling: spectra.c:17-45 plus the derived records -----------------
@@ -324,6 +429,8 @@ LBL_HD void scale_line(const LineIn& ln, const LayerIn& ly, double q_ref, double
     gen.repwid = repwid;
     gen.y = y;
     gen.cof = cof;
+    gen.xlim0 = (y < kLorentzY) ? sqrt(15100. + y * (40. - y * 3.6)) : 0.;
+    gen.xlim1 = (y >= 8.425) ? 0. : sqrt(164. - y * (4.3 + y * 1.8));
 
     // Window cell (spectra.c:48): floor(nu') relative to the first grid wavenumber.
     double cbd = floor(nu) - (double)v0;
@@ -333,15 +440,20 @@ LBL_HD void scale_line(const LineIn& ln, const LayerIn& ly, double q_ref, double
 
     // Lorentz amplitude in x-space: term = ax/(x^2+y^2), ax = cof*y*rsqrpi (voigt.c:82,:188;
     // the y >= 70.55 branch voigt.c:24 is the same quantity).
+    // The summation multiplies two denominators q = (v*a+b)^2 + c (far_terms_pair), so q
+    // must stay below ~1e150: lines so weak that a > 1e70 (amplitude below ~1e-130 m2, a
+    // hundred orders of magnitude under any HITRAN intensity) are dropped.
     const double ax = cof * (y * kRsqrPi);
-    if (ax >= 1.0e-150 && ax <= 1.0e100 && repwid <= 1.0e50 && y <= 1.0e50)
+    bool usable = ax >= 1.0e-200 && ax <= 1.0e100 && repwid <= 1.0e50 && y <= 1.0e50;
+    if (usable)
     {
         const double inv = 1. / ax;
         ab.a = repwid * sqrt(inv);
         ab.b = -nu * ab.a;
         cc = (y * y) * inv;
+        usable = ab.a <= 1.0e70 && cc <= 1.0e140 && fabs(ab.b) <= 1.0e74;
     }
-    else
+    if (!usable)
     {
         ab.a = 0.;
         ab.b = 0.;
@@ -357,8 +469,7 @@ LBL_HD void scale_line(const LineIn& ln, const LayerIn& ly, double q_ref, double
     }
     else
     {
-        const double xlim0 = sqrt(15100. + y * (40. - y * 3.6));
-        const double half = (xlim0 / repwid) * (1. + 0x1p-30);
+        const double half = (gen.xlim0 / repwid) * (1. + 0x1p-30);
         double lo = floor((nu - half - (double)v0) * (double)n_per_v) - 1.;
         double hi = ceil((nu + half - (double)v0) * (double)n_per_v) + 1.;
         lo = fmin(fmax(lo, -(double)kIdxClamp), (double)kIdxClamp);
@@ -375,7 +486,7 @@ LBL_HD double line_point(double v, int i, const FarAB& ab, double cc, const Line
 {
     if (i >= chk.nlo && i <= chk.nhi)
     {
-        return voigt_general(v, gen.nu, gen.repwid, gen.y, gen.cof);
+        return voigt_general(v, gen.nu, gen.repwid, gen.y, gen.cof, gen.xlim0, gen.xlim1);
     }
     return far_term(v, ab.a, ab.b, cc, 0.0);
 }

@@ -51,16 +51,170 @@ sum_kernel(const SumArgs a)
 }
 
 // K2b.  One warp per tile of T points x 32/T layers; grid = (ceil(tiles/4), ceil(layers/(32/T))).
+//
+// Warp-level form of fixup_thread() (lbl_threads.cuh), same terms, different schedule: the
+// candidate lines are walked warp-uniformly; lanes whose point falls in a line's outer near
+// zone (regions 0/1, the bulk) evaluate it on the spot; the few points per line that need
+// the long core branches (regions 2/3, CPF12) are queued as (line, lane) pairs in shared
+// memory and evaluated 32 at a time with the lanes packed, instead of once per line with
+// two or three lanes active.
+constexpr int kFixQueue = 64;
+
+template <int T>
+__device__ __forceinline__ double fixup_drain(const SumArgs& a, const int* queue, int cnt, int lane,
+                                              int layer, double v, double acc)
+{
+    const int entry = queue[lane < cnt ? lane : 0];
+    const int src = entry & 31;
+    const int jj = entry >> 5;
+    const double v_src = __shfl_sync(0xffffffffu, v, src);
+    const int layer_src = (T == 32) ? layer : __shfl_sync(0xffffffffu, layer, src);
+    double val = 0.;
+    if (lane < cnt)
+    {
+        const LineGen* gp = a.rec.gen + (size_t)layer_src * a.lines.n + jj;
+        const double2 g0 = __ldg(reinterpret_cast<const double2*>(gp));
+        const double2 g1 = __ldg(reinterpret_cast<const double2*>(gp) + 1);
+        const double2 g2 = __ldg(reinterpret_cast<const double2*>(gp) + 2);
+        val = g1.y * voigt_core((v_src - g0.x) * g0.y, g1.x, g2.x);
+    }
+    for (int e = 0; e < cnt; ++e)
+    {
+        const double val_e = __shfl_sync(0xffffffffu, val, e);
+        const int src_e = __shfl_sync(0xffffffffu, src, e);
+        if (lane == src_e) acc += val_e;
+    }
+    return acc;
+}
+
+template <int T>
+__device__ __forceinline__ void fixup_warp(const SumArgs& a, int tile, int layer_group, int lane,
+                                           int* queue)
+{
+    const GridSpec& g = a.grid;
+    constexpr int LP = 32 / T;
+    int layer = layer_group * LP + lane / T;
+    int i = tile * T + lane % T;
+    const bool valid = (layer < a.n_layers) && (i < g.n);
+    if (layer >= a.n_layers) layer = a.n_layers - 1;
+    if (i >= g.n) i = g.n - 1;
+    const int t_first = tile * T;
+    int t_last = t_first + T - 1;
+    if (t_last > g.n - 1) t_last = g.n - 1;
+
+    const LayerIn ly = a.layers[layer];
+    const size_t off = (size_t)layer * a.lines.n;
+    const LineChk* chk = a.rec.chk + off;
+    const LineGen* gen = a.rec.gen + off;
+    const double v = grid_point(g.v0, g.dv, i);
+    const int cell = i / g.n_per_v;
+    const bool is_node = (i - cell * g.n_per_v) == 0;
+    double acc = 0.;
+
+    int jlo, jhi;
+    near_candidates(a.lines, g, ly, t_first, t_last, jlo, jhi);
+    int wlo = jlo, whi = jhi;
+    if (T != 32)
+    {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+        {
+            wlo = min(wlo, __shfl_xor_sync(0xffffffffu, wlo, o));
+            whi = max(whi, __shfl_xor_sync(0xffffffffu, whi, o));
+        }
+    }
+    int qn = 0;
+    for (int j = wlo; j < whi; ++j)
+    {
+        bool core = false;
+        if (j >= jlo && j < jhi)
+        {
+            const int4 ck = __ldg(reinterpret_cast<const int4*>(chk + j));
+            if (i >= ck.y && i <= ck.z)
+            {
+                // inside the line's window? s <= i <= e, spectra.c:48-62 (unclamped form)
+                const long long s = (long long)(ck.x - g.cut_off) * g.n_per_v;
+                const long long e = (long long)(ck.x + g.cut_off + 1) * g.n_per_v;
+                if ((long long)i >= s && (long long)i <= e)
+                {
+                    const double2 g0 = __ldg(reinterpret_cast<const double2*>(gen + j));
+                    const double2 g1 = __ldg(reinterpret_cast<const double2*>(gen + j) + 1);
+                    const double2 g2 = __ldg(reinterpret_cast<const double2*>(gen + j) + 2);
+                    const double abx = fabs((v - g0.x) * g0.y);
+                    if (abx >= voigt_outer_limit(g1.x, g2.x, g2.y))
+                    {
+                        acc += g1.y * voigt_outer(abx, abx * abx, g1.x, g2.x);
+                    }
+                    else
+                    {
+                        core = true;
+                    }
+                }
+            }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, core);
+        if (m)
+        {
+            if (core)
+            {
+                queue[qn + __popc(m & ((1u << lane) - 1u))] = (j << 5) | lane;
+            }
+            qn += __popc(m);
+            __syncwarp();
+            if (qn >= 32)
+            {
+                acc = fixup_drain<T>(a, queue, 32, lane, layer, v, acc);
+                __syncwarp();
+                const int keep = qn - 32;
+                const int moved = (lane < keep) ? queue[32 + lane] : 0;
+                __syncwarp();
+                if (lane < keep) queue[lane] = moved;
+                qn = keep;
+                __syncwarp();
+            }
+        }
+    }
+    if (qn > 0)
+    {
+        acc = fixup_drain<T>(a, queue, qn, lane, layer, v, acc);
+    }
+
+    // node terms: lines with cb == cell-cut-1 reach exactly the cell's first point.
+    if (is_node)
+    {
+        const double key = (double)g.v0 + (double)(cell - g.cut_off - 1);
+        const int nlo = lower_bound(a.lines.nu, a.lines.n, key - ly.slack);
+        const int nhi = lower_bound(a.lines.nu, a.lines.n, key + 1.0 + ly.slack);
+        const FarAB* ab = a.rec.ab + off;
+        const double* cc = a.rec.cc + off;
+        for (int j = nlo; j < nhi; ++j)
+        {
+            const int4 ck = __ldg(reinterpret_cast<const int4*>(chk + j));
+            if (ck.x != cell - g.cut_off - 1 || (i >= ck.y && i <= ck.z))
+            {
+                continue;  // other cell, or already taken by the near loop above
+            }
+            const double2 l = __ldg(reinterpret_cast<const double2*>(ab + j));
+            acc = far_term(v, l.x, l.y, __ldg(cc + j), acc);
+        }
+    }
+    if (valid)
+    {
+        a.out[(size_t)layer * g.n + i] += acc;
+    }
+}
+
 template <int T>
 __global__ void __launch_bounds__(128)
 fixup_kernel(const SumArgs a)
 {
+    __shared__ int queues[4][kFixQueue];
     const int tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (tile * T >= a.grid.n)
     {
         return;
     }
-    fixup_thread<T>(a, tile, blockIdx.y, threadIdx.x & 31);
+    fixup_warp<T>(a, tile, blockIdx.y, threadIdx.x & 31, queues[threadIdx.x >> 5]);
 }
 
 struct WarpSync
@@ -78,19 +232,27 @@ pedestal_kernel(const PedArgs a, double* scratch)
     pedestal_layer(a, blockIdx.x, threadIdx.x, 32, nodes, WarpSync());
 }
 
-// K3a.  terms[layer][row r][slot t], wpad slots per row (zero beyond the window).
+// K3a.  terms[layer][row r][slot t], 32*K slots per row (zero beyond the window).
+// grid = (ceil(n / (8 warps * 4 rows)), layers), block = 256.
+constexpr int kTermRowsPerWarp = 4;
+template <int K>
 __global__ void __launch_bounds__(256)
-pedestal_terms_kernel(const PedArgs a, int wpad, double* __restrict__ terms)
+pedestal_terms_kernel(const PedArgs a, double* __restrict__ terms)
 {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int layer = blockIdx.y;
-    if (idx >= (long long)a.lines.n * wpad)
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const int first = warp * kTermRowsPerWarp;
+    double* base = terms + (size_t)layer * a.lines.n * (32 * K);
+#pragma unroll
+    for (int m = 0; m < kTermRowsPerWarp; ++m)
     {
-        return;
+        const int r = first + m;
+        if (r < a.lines.n)
+        {
+            pedestal_terms_row<K>(a, layer, r, lane, base + (size_t)r * (32 * K));
+        }
     }
-    const int r = (int)(idx / wpad);
-    const int t = (int)(idx - (long long)r * wpad);
-    terms[(size_t)layer * a.lines.n * wpad + idx] = pedestal_term(a, layer, r, t);
 }
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
@@ -111,10 +273,17 @@ __device__ __forceinline__ void cp_async_wait()
 constexpr int kPedTile = 32;    // lines per staged tile
 constexpr int kPedStages = 4;   // cp.async ring depth
 
-// K3b.  grid = layers, block = one warp.  The sequential chain of the recurrence: per line
-// three dependent FP64 operations on register-resident nodes; the per-line terms (K3a) and
-// window cells stream in through a 4-stage cp.async ring so that no global-memory latency
-// sits on the chain.  K = slots per lane (32*K >= 2*cut+3), wpad = 32*K.
+__device__ __forceinline__ double shfl_up_f64(double x, int delta)
+{
+    return __shfl_up_sync(0xffffffffu, x, delta);
+}
+
+// K3b.  grid = layers, block = one warp.  Walks the database-ordered lines of one layer in
+// runs of equal window cell (see PedLane).  The per-line terms (K3a) and window cells stream
+// in through a 4-stage cp.async ring so that no global-memory latency sits on the chain.
+// K = slots per lane (32*K >= 2*cut+3), wpad = 32*K.
+// Dynamic shared memory: ring | cells | nodes (ncell+1) | bins (nb)   -- the last two move to
+// global memory (`scratch`, a.pedbin) when the grid is too wide.
 template <int K>
 __global__ void __launch_bounds__(32)
 pedestal_chain_kernel(const PedArgs a, const double* __restrict__ terms, double* scratch)
@@ -125,12 +294,13 @@ pedestal_chain_kernel(const PedArgs a, const double* __restrict__ terms, double*
     const int layer = blockIdx.x;
     const int lane = threadIdx.x;
     const int n = a.lines.n;
+    const int nb = g.ncell + 2 * g.cut_off + 2;
     double* ring = reinterpret_cast<double*>(smem_raw);
     int4* hdr = reinterpret_cast<int4*>(ring + kPedStages * kPedTile * wpad);
-    double* nodes = scratch ? scratch + (size_t)layer * (g.ncell + 1)
-                            : reinterpret_cast<double*>(hdr + kPedStages * kPedTile);
-    const int nb = g.ncell + 2 * g.cut_off + 2;
-    double* bins = a.pedbin + (size_t)layer * nb;
+    double* smem_tail = reinterpret_cast<double*>(hdr + kPedStages * kPedTile);
+    double* out_bins = a.pedbin + (size_t)layer * nb;
+    double* nodes = scratch ? scratch + (size_t)layer * (g.ncell + 1) : smem_tail;
+    double* bins = scratch ? out_bins : smem_tail + (g.ncell + 1);
     for (int c = lane; c <= g.ncell; c += 32) nodes[c] = 0.;
     for (int b = lane; b < nb; b += 32) bins[b] = 0.;
     __syncwarp();
@@ -175,14 +345,20 @@ pedestal_chain_kernel(const PedArgs a, const double* __restrict__ terms, double*
         const int cnt = (n - first < kPedTile) ? n - first : kPedTile;
         const double* rows = ring + (size_t)stage * kPedTile * wpad;
         const int4* cells = hdr + stage * kPedTile;
-        for (int l = 0; l < cnt; ++l)
+        const int my_cb = cells[lane < cnt ? lane : cnt - 1].x;
+        int l = 0;
+        while (l < cnt)
         {
-            const int cb = cells[l].x;
+            // Run = maximal stretch of lines l, l+1, ... with the same window cell.
+            const int cb = __shfl_sync(0xffffffffu, my_cb, l);
+            const unsigned differ = __ballot_sync(0xffffffffu, lane >= l && (lane >= cnt || my_cb != cb));
+            const int run = (differ ? __ffs(differ) - 1 : 32) - l;
             if (!st.have || cb != st.cb)
             {
                 const PedWindow w = ped_window(cb, g);
                 if (w.skip)
                 {
+                    l += run;
                     continue;
                 }
                 ped_lane_flush(st, g, lane, nodes, bins);
@@ -190,11 +366,58 @@ pedestal_chain_kernel(const PedArgs a, const double* __restrict__ terms, double*
                 ped_lane_reload(st, g, lane, cb, w, nodes);
                 __syncwarp();
             }
-            ped_lane_line(st, lane, rows + (size_t)l * wpad);
+            const double* row0 = rows + (size_t)l * wpad;
+            double pedsum = 0.;
+            if (run <= 2)
+            {
+                // Short run: every lane does the same two-node update (no shuffles).
+                for (int m = 0; m < run; ++m)
+                {
+                    const double fs = row0[(size_t)m * wpad + st.w.s_slot];
+                    const double fe = row0[(size_t)m * wpad + st.w.e_slot];
+                    pedsum += ped_line_value(st.ks, st.ke, fs, fe, st.ks, st.ke);
+                }
+            }
+            else
+            {
+                // Lane m takes line m of the run: d before it = d0 + sum_{j<m} (fs_j - fe_j).
+                const bool mine = lane < run;
+                const double fs = mine ? row0[(size_t)lane * wpad + st.w.s_slot] : 0.;
+                const double fe = mine ? row0[(size_t)lane * wpad + st.w.e_slot] : 0.;
+                const double diff = fs - fe;
+                double scan = diff;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1)
+                {
+                    const double up = shfl_up_f64(scan, o);
+                    if (lane >= o) scan += up;
+                }
+                const double d_prev = (st.ks - st.ke) + (scan - diff);
+                const double ks_prev = (lane == 0) ? st.ks : fmax(d_prev, 0.);
+                const double ke_prev = (lane == 0) ? st.ke : fmax(-d_prev, 0.);
+                double ks_new, ke_new;
+                double ped = ped_line_value(ks_prev, ke_prev, fs, fe, ks_new, ke_new);
+                if (!mine) ped = 0.;
+                pedsum = ped;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1)
+                {
+                    pedsum += __shfl_xor_sync(0xffffffffu, pedsum, o);
+                }
+                st.ks = __shfl_sync(0xffffffffu, ks_new, run - 1);
+                st.ke = __shfl_sync(0xffffffffu, ke_new, run - 1);
+            }
+            ped_lane_slots(st, lane, row0, wpad, run, pedsum);
+            l += run;
         }
         __syncwarp();
     }
     ped_lane_flush(st, g, lane, nodes, bins);
+    __syncwarp();
+    if (!scratch)
+    {
+        for (int b = lane; b < nb; b += 32) out_bins[b] = bins[b];
+    }
 }
 
 // K4a.  One thread per (layer, cell): the pedestal seen by the cell's points.

@@ -131,8 +131,17 @@ template <int P>
 LBL_HD void plain_range(const FarAB* __restrict__ ab, const double* __restrict__ cc, int jb, int je,
                         const double (&v)[P], double (&acc)[P])
 {
-#pragma unroll 2
-    for (int j = jb; j < je; ++j)
+    // Lines are taken two at a time so that each pair shares one reciprocal (far_terms_pair).
+    int j = jb;
+    for (; j + 1 < je; j += 2)
+    {
+        const double2 l1 = LBL_LDG(reinterpret_cast<const double2*>(ab + j));
+        const double2 l2 = LBL_LDG(reinterpret_cast<const double2*>(ab + j + 1));
+        const double c1 = LBL_LDG(cc + j);
+        const double c2 = LBL_LDG(cc + j + 1);
+        far_terms_pair<P>(v, l1.x, l1.y, c1, l2.x, l2.y, c2, acc);
+    }
+    if (j < je)
     {
         const double2 l = LBL_LDG(reinterpret_cast<const double2*>(ab + j));
         const double c = LBL_LDG(cc + j);
@@ -236,6 +245,21 @@ LBL_HD void sum_thread(const SumArgs& a, int layer, int tid)
 // about as wide as a near zone.  Adds into the spectrum K2 wrote (same stream, no atomics:
 // each point still has exactly one owner).
 // ---------------------------------------------------------------------------------------
+// Candidate range of K2b's near loop for grid points [t_first, t_last] (same reach as
+// find_segments uses for its checked middle segment).
+LBL_HD void near_candidates(const LinesView& lines, const GridSpec& g, const LayerIn& ly,
+                            int t_first, int t_last, int& jlo, int& jhi)
+{
+    const double base = (double)g.v0;
+    const double v_first = base + (double)t_first * g.dv;
+    const double v_last = base + (double)t_last * g.dv;
+    const double reach = (ly.kappa < 0.5)
+        ? (ly.kappa * fabs(v_last) / (1.0 - ly.kappa)) * (1.0 + 0x1p-20) + ly.slack + 3.0 * g.dv
+        : 1.0e300;
+    jlo = lower_bound(lines.nu, lines.n, v_first - reach);
+    jhi = lower_bound(lines.nu, lines.n, v_last + reach);
+}
+
 template <int T>
 LBL_HD void fixup_thread(const SumArgs& a, int tile, int layer_group, int lane)
 {
@@ -259,16 +283,10 @@ LBL_HD void fixup_thread(const SumArgs& a, int tile, int layer_group, int lane)
     const bool is_node = (i - cell * g.n_per_v) == 0;
     double acc = 0.;
 
-    // (1) near zone: every line whose [nlo, nhi] contains i (same reach as find_segments).
+    // (1) near zone: every line whose [nlo, nhi] contains i.
     {
-        const double base = (double)g.v0;
-        const double v_first = base + (double)t_first * g.dv;
-        const double v_last = base + (double)t_last * g.dv;
-        const double reach = (ly.kappa < 0.5)
-            ? (ly.kappa * fabs(v_last) / (1.0 - ly.kappa)) * (1.0 + 0x1p-20) + ly.slack + 3.0 * g.dv
-            : 1.0e300;
-        const int jlo = lower_bound(a.lines.nu, a.lines.n, v_first - reach);
-        const int jhi = lower_bound(a.lines.nu, a.lines.n, v_last + reach);
+        int jlo, jhi;
+        near_candidates(a.lines, g, ly, t_first, t_last, jlo, jhi);
         for (int j = jlo; j < jhi; ++j)
         {
             const int4 ck = LBL_LDG(reinterpret_cast<const int4*>(chk + j));
@@ -285,7 +303,8 @@ LBL_HD void fixup_thread(const SumArgs& a, int tile, int layer_group, int lane)
             }
             const double2 g0 = LBL_LDG(reinterpret_cast<const double2*>(gen + j));
             const double2 g1 = LBL_LDG(reinterpret_cast<const double2*>(gen + j) + 1);
-            acc += voigt_general(v, g0.x, g0.y, g1.x, g1.y);
+            const double2 g2 = LBL_LDG(reinterpret_cast<const double2*>(gen + j) + 2);
+            acc += voigt_general(v, g0.x, g0.y, g1.x, g1.y, g2.x, g2.y);
         }
     }
     // (2) node terms: lines with cb == cell-cut-1 reach exactly the cell's first point.
@@ -396,19 +415,66 @@ LBL_HD double pedestal_term(const PedArgs& a, int layer, int r, int t)
     return line_point(grid_point(g.v0, g.dv, i), i, a.rec.ab[o], a.rec.cc[o], chk, a.rec.gen[o]);
 }
 
-// K3b: per-lane state of the sequential chain.  While consecutive lines share the same cb
-// the window does not move, so each lane keeps its K slots -- and a private copy of the two
-// nodes k[s], k[e] that decide the pedestal -- in registers; the node array is only touched
-// when cb changes.
+// K3a, warp form: the 32 lanes of a warp take the slots lane, lane+32, ... of row r, so the
+// per-line work (record loads, window) is warp-uniform and the stores are coalesced.
+template <int K>
+LBL_HD void pedestal_terms_row(const PedArgs& a, int layer, int r, int lane, double* row)
+{
+    const GridSpec& g = a.grid;
+    const int j = a.lines.db_to_sorted ? LBL_LDG(a.lines.db_to_sorted + r) : r;
+    const size_t o = (size_t)layer * a.lines.n + j;
+    const int4 ck = LBL_LDG(reinterpret_cast<const int4*>(a.rec.chk + o));
+    const PedWindow w = ped_window(ck.x, g);
+    if (w.skip)
+    {
+#pragma unroll
+        for (int k = 0; k < K; ++k) row[lane + 32 * k] = 0.;
+        return;
+    }
+    const double2 l = LBL_LDG(reinterpret_cast<const double2*>(a.rec.ab + o));
+    const double c = LBL_LDG(a.rec.cc + o);
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+    {
+        const int idx = ped_slot_index(w, g, lane + 32 * k);
+        double val = 0.;
+        if (idx >= 0)
+        {
+            const int i = (idx == g.ncell) ? g.n - 1 : idx * g.n_per_v;
+            const double v = grid_point(g.v0, g.dv, i);
+            if (i >= ck.y && i <= ck.z)
+            {
+                const LineGen gen = a.rec.gen[o];
+                val = voigt_general(v, gen.nu, gen.repwid, gen.y, gen.cof, gen.xlim0, gen.xlim1);
+            }
+            else
+            {
+                val = far_term(v, l.x, l.y, c, 0.);
+            }
+        }
+        row[lane + 32 * k] = val;
+    }
+}
+
+// K3b: the sequential chain, organised in RUNS of consecutive lines that share one window
+// cell cb (in a nu-sorted database a run is all lines of one integer-wavenumber bin).
+// Inside a run the window does not move, and after the first line one of the two deciding
+// nodes k[s], k[e] is exactly zero (the pedestal just removed it), so with d = k[s] - k[e]
+//     k[s] = max(d, 0),  k[e] = max(-d, 0),  d_l = d_(l-1) + (f_l[s] - f_l[e]):
+// the recurrence over the run is a prefix sum.  Lanes take one line each for the pedestals
+// (warp scan), then one slot each for the node updates
+//     node += sum_l f_l[slot] - sum_l pedestal_l.
+// Sums are re-associated relative to the reference's line-by-line order (rounding-level
+// differences, ~1e-16 of the node values).
 template <int K>
 struct PedLane
 {
     int cb;
     bool have;
     PedWindow w;
-    double own[K];
-    double ks, ke;
-    double binsum;
+    double own[K];   // this lane's slots of the current window
+    double ks, ke;   // k[s], k[e] of the current window (same value in every lane)
+    double binsum;   // pedestal accumulated for the current cb (same value in every lane)
 };
 
 template <int K>
@@ -461,24 +527,42 @@ LBL_HD void ped_lane_reload(PedLane<K>& st, const GridSpec& g, int lane, int cb,
     st.ke = nodes[ped_slot_index(w, g, w.e_slot)];
 }
 
-// Per line: k[s..e] += f ; pedestal = min(k[s], k[e]) ; k[s..e] -= pedestal (spectra.c:65-77).
-// `row` holds the line's K3a terms, one per slot.
-template <int K>
-LBL_HD void ped_lane_line(PedLane<K>& st, int lane, const double* row)
+// One line: k[s] += f[s]; k[e] += f[e]; pedestal = min(k[s], k[e]); both -= pedestal
+// (spectra.c:65-77 restricted to the two nodes that decide the pedestal).
+LBL_HD double ped_line_value(double ks_prev, double ke_prev, double fs, double fe, double& ks_new,
+                             double& ke_new)
 {
-    double f[K];
+    const double ks1 = ks_prev + fs;
+    const double ke1 = ke_prev + fe;
+    const double pedestal = (ke1 < ks1) ? ke1 : ks1;  // spectra.c:68-72
+    ks_new = ks1 - pedestal;
+    ke_new = ke1 - pedestal;
+    return pedestal;
+}
+
+// Node update of one run: own += sum over the run's R lines of their terms - their pedestals.
+template <int K>
+LBL_HD void ped_lane_slots(PedLane<K>& st, int lane, const double* row0, int wpad, int run,
+                           double pedsum)
+{
 #pragma unroll
-    for (int k = 0; k < K; ++k) f[k] = row[lane + 32 * k];
-    const double fs = row[st.w.s_slot];
-    const double fe = row[st.w.e_slot];
-    st.ks += fs;
-    st.ke += fe;
-    const double pedestal = (st.ke < st.ks) ? st.ke : st.ks;  // spectra.c:68-72
-    st.ks -= pedestal;
-    st.ke -= pedestal;
-    st.binsum += pedestal;
-#pragma unroll
-    for (int k = 0; k < K; ++k) st.own[k] = (st.own[k] + f[k]) - pedestal;
+    for (int k = 0; k < K; ++k)
+    {
+        const double* col = row0 + lane + 32 * k;
+        double s0 = 0., s1 = 0.;
+        int m = 0;
+        for (; m + 1 < run; m += 2)
+        {
+            s0 += col[(size_t)m * wpad];
+            s1 += col[(size_t)(m + 1) * wpad];
+        }
+        if (m < run)
+        {
+            s0 += col[(size_t)m * wpad];
+        }
+        st.own[k] += (s0 + s1) - pedsum;
+    }
+    st.binsum += pedsum;
 }
 
 // Generic (slow) form of the whole recurrence for one layer, used when the window is wider

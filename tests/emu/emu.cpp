@@ -5,6 +5,7 @@
 // check the gather logic (window membership, segment search, near/far split, pedestal
 // recurrence) against the oracle without a GPU.  The product never loads this file; the
 // MUFU reciprocal seed is emulated (see rcp_seed in lbl_core.cuh).
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -50,7 +51,7 @@ static void run_fixup(const SumArgs& a, int n_layers)
     }
 }
 
-// The register-resident chain of K3b with its 32 lanes run phase by phase.
+// The run-organised chain of K3b: 32 emulated lanes, warp collectives done sequentially.
 template <int K>
 static void run_chain(const PedArgs& pa, int layer, double* nodes)
 {
@@ -62,20 +63,66 @@ static void run_chain(const PedArgs& pa, int layer, double* nodes)
     for (int b = 0; b < nb; ++b) bins[b] = 0.;
     std::vector<PedLane<K>> lanes(32);
     for (auto& st : lanes) ped_lane_init(st);
-    std::vector<double> row(wpad);
-    for (int r = 0; r < pa.lines.n; ++r)
+    const int n = pa.lines.n;
+    std::vector<int> cells(n);
+    for (int r = 0; r < n; ++r)
     {
         const int j = pa.lines.db_to_sorted ? pa.lines.db_to_sorted[r] : r;
-        const int cb = pa.rec.chk[(size_t)layer * pa.lines.n + j].cb;
-        if (!lanes[0].have || cb != lanes[0].cb)
+        cells[r] = pa.rec.chk[(size_t)layer * n + j].cb;
+    }
+    std::vector<double> rows((size_t)32 * wpad);
+    for (int first = 0; first < n; first += 32)   // tiles of 32 lines, as staged by cp.async
+    {
+        const int cnt = std::min(32, n - first);
+        for (int m = 0; m < cnt; ++m)
+            for (int lane = 0; lane < 32; ++lane)
+                pedestal_terms_row<K>(pa, layer, first + m, lane, rows.data() + (size_t)m * wpad);
+        int l = 0;
+        while (l < cnt)
         {
-            const PedWindow w = ped_window(cb, g);
-            if (w.skip) continue;
-            for (int lane = 0; lane < 32; ++lane) ped_lane_flush(lanes[lane], g, lane, nodes, bins);
-            for (int lane = 0; lane < 32; ++lane) ped_lane_reload(lanes[lane], g, lane, cb, w, nodes);
+            const int cb = cells[first + l];
+            int run = 1;
+            while (l + run < cnt && cells[first + l + run] == cb) ++run;
+            if (!lanes[0].have || cb != lanes[0].cb)
+            {
+                const PedWindow w = ped_window(cb, g);
+                if (w.skip) { l += run; continue; }
+                for (int lane = 0; lane < 32; ++lane) ped_lane_flush(lanes[lane], g, lane, nodes, bins);
+                for (int lane = 0; lane < 32; ++lane) ped_lane_reload(lanes[lane], g, lane, cb, w, nodes);
+            }
+            const double* row0 = rows.data() + (size_t)l * wpad;
+            PedLane<K>& u = lanes[0];
+            double pedsum = 0., ks = u.ks, ke = u.ke;
+            if (run <= 2)
+            {
+                for (int m = 0; m < run; ++m)
+                    pedsum += ped_line_value(ks, ke, row0[(size_t)m * wpad + u.w.s_slot],
+                                             row0[(size_t)m * wpad + u.w.e_slot], ks, ke);
+            }
+            else
+            {
+                double scan = 0., ks_end = ks, ke_end = ke;
+                for (int m = 0; m < run; ++m)   // lane m
+                {
+                    const double fs = row0[(size_t)m * wpad + u.w.s_slot];
+                    const double fe = row0[(size_t)m * wpad + u.w.e_slot];
+                    const double d_prev = (ks - ke) + scan;   // exclusive prefix
+                    const double ks_prev = (m == 0) ? ks : fmax(d_prev, 0.);
+                    const double ke_prev = (m == 0) ? ke : fmax(-d_prev, 0.);
+                    pedsum += ped_line_value(ks_prev, ke_prev, fs, fe, ks_end, ke_end);
+                    scan += fs - fe;
+                }
+                ks = ks_end;
+                ke = ke_end;
+            }
+            for (int lane = 0; lane < 32; ++lane)
+            {
+                lanes[lane].ks = ks;
+                lanes[lane].ke = ke;
+                ped_lane_slots(lanes[lane], lane, row0, wpad, run, pedsum);
+            }
+            l += run;
         }
-        for (int t = 0; t < wpad; ++t) row[t] = pedestal_term(pa, layer, r, t);
-        for (int lane = 0; lane < 32; ++lane) ped_lane_line(lanes[lane], lane, row.data());
     }
     for (int lane = 0; lane < 32; ++lane) ped_lane_flush(lanes[lane], g, lane, nodes, bins);
 }

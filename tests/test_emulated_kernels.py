@@ -46,7 +46,7 @@ def run(emu, gas, t, p, x, bounds, ped, cut=25, points=None):
     t, p, x = (np.ascontiguousarray(a, dtype=np.float64) for a in (t, p, x))
     k = np.zeros(t.size * n)
     if points is None:
-        points = [q for q in (10, 8, 5, 4, 2, 1) if npv % q == 0][0]
+        points = [q for q in (5, 4, 8, 10, 2, 1) if npv % q == 0][0]
     evals = c_longlong(0)
     rc = emu.emu_absorption(t.size, p, t, x, v0, vn, npv, k, d["nu"].size, d["nu"], d["sw"],
                             d["gamma_air"], d["gamma_self"], d["n_air"], d["elower"],

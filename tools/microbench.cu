@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(256) rcp_kernel(double* out, int iters)
 }
 
 // far_term with P accumulators per thread and per-"line" operands read through L1 like K2.
-template <int P, bool STAGED>
+template <int P, int STAGED>
 __global__ void __launch_bounds__(128) far_kernel(const double2* __restrict__ ab,
                                                   const double* __restrict__ cc, int n_lines,
                                                   double* out)
@@ -65,6 +65,18 @@ __global__ void __launch_bounds__(128) far_kernel(const double2* __restrict__ ab
         v[p] = 1000.0 + (blockIdx.x * 128 + threadIdx.x) * P * 0.01 + p * 0.01;
         acc[p] = 0.;
     }
+    if (STAGED == 2)
+    {
+        for (int j = 0; j + 1 < n_lines; j += 2)
+        {
+            const double2 l1 = __ldg(ab + j);
+            const double c1 = __ldg(cc + j);
+            const double2 l2 = __ldg(ab + j + 1);
+            const double c2 = __ldg(cc + j + 1);
+            lbl::far_terms_pair<P>(v, l1.x, l1.y, c1, l2.x, l2.y, c2, acc);
+        }
+    }
+    else
 #pragma unroll 2
     for (int j = 0; j < n_lines; ++j)
     {
@@ -121,7 +133,7 @@ static float time_ms(F launch, int reps)
     return best;
 }
 
-template <int P, bool STAGED>
+template <int P, int STAGED>
 static void bench_far(const double2* ab, const double* cc, int n_lines, double* out, int sms)
 {
     const int blocks = sms * 16;
@@ -177,18 +189,24 @@ int main()
         CHECK(cudaMalloc(&d_cc, sizeof(double) * n_lines));
         CHECK(cudaMemcpy(d_ab, ab.data(), sizeof(double2) * n_lines, cudaMemcpyHostToDevice));
         CHECK(cudaMemcpy(d_cc, cc.data(), sizeof(double) * n_lines, cudaMemcpyHostToDevice));
-        bench_far<1, false>(d_ab, d_cc, n_lines, out, sms);
-        bench_far<1, true>(d_ab, d_cc, n_lines, out, sms);
-        bench_far<2, false>(d_ab, d_cc, n_lines, out, sms);
-        bench_far<2, true>(d_ab, d_cc, n_lines, out, sms);
-        bench_far<4, false>(d_ab, d_cc, n_lines, out, sms);
-        bench_far<4, true>(d_ab, d_cc, n_lines, out, sms);
-        bench_far<5, false>(d_ab, d_cc, n_lines, out, sms);
-        bench_far<5, true>(d_ab, d_cc, n_lines, out, sms);
-        bench_far<8, false>(d_ab, d_cc, n_lines, out, sms);
-        bench_far<8, true>(d_ab, d_cc, n_lines, out, sms);
-        bench_far<10, false>(d_ab, d_cc, n_lines, out, sms);
-        bench_far<10, true>(d_ab, d_cc, n_lines, out, sms);
+        bench_far<1, 0>(d_ab, d_cc, n_lines, out, sms);
+        bench_far<1, 1>(d_ab, d_cc, n_lines, out, sms);
+        bench_far<1, 2>(d_ab, d_cc, n_lines, out, sms);
+        bench_far<2, 0>(d_ab, d_cc, n_lines, out, sms);
+        bench_far<2, 1>(d_ab, d_cc, n_lines, out, sms);
+        bench_far<2, 2>(d_ab, d_cc, n_lines, out, sms);
+        bench_far<4, 0>(d_ab, d_cc, n_lines, out, sms);
+        bench_far<4, 1>(d_ab, d_cc, n_lines, out, sms);
+        bench_far<4, 2>(d_ab, d_cc, n_lines, out, sms);
+        bench_far<5, 0>(d_ab, d_cc, n_lines, out, sms);
+        bench_far<5, 1>(d_ab, d_cc, n_lines, out, sms);
+        bench_far<5, 2>(d_ab, d_cc, n_lines, out, sms);
+        bench_far<8, 0>(d_ab, d_cc, n_lines, out, sms);
+        bench_far<8, 1>(d_ab, d_cc, n_lines, out, sms);
+        bench_far<8, 2>(d_ab, d_cc, n_lines, out, sms);
+        bench_far<10, 0>(d_ab, d_cc, n_lines, out, sms);
+        bench_far<10, 1>(d_ab, d_cc, n_lines, out, sms);
+        bench_far<10, 2>(d_ab, d_cc, n_lines, out, sms);
     }
     {
         const int n = 1 << 20;
