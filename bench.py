@@ -310,8 +310,10 @@ def run_ours(args, rank, local_rank, world, dist):
     sum_ms = 0.0
     sum_launches = 0
     launches = 0
+    points = 0
     for _ in range(args.steps):
         for s in step_resident():
+            points = s["points_per_thread"]
             evals += s["evals"]
             sum_ms += s["sum_ms"]
             sum_launches += s["sum_launches"]
@@ -356,7 +358,7 @@ def run_ours(args, rank, local_rank, world, dist):
     flops = FLOP_PER_EVAL * evals                       # this rank, timed region
     achieved = flops / (sum_ms * 1e-3) / 1e12 if sum_ms > 0 else 0.0
     roofline = {
-        "bound": "fp64", "kernel": "lbl::sum_kernel<10>", "achieved": achieved,
+        "bound": "fp64", "kernel": f"lbl::sum_kernel<{points}>", "achieved": achieved,
         "peak": peak.value, "unit": "TFLOP/s",
         "frac": achieved / peak.value if peak.value else None, "traffic": None,
         "flop_per_eval": FLOP_PER_EVAL,

@@ -335,9 +335,9 @@ cudaError_t launch_chain(const PedArgs& pa, double* terms, double* scratch, int 
 {
     cudaError_t e = cudaSuccess;
     {
-        const int rows_per_block = (256 / 32) * kTermRowsPerWarp;
-        dim3 tg((pa.lines.n + rows_per_block - 1) / rows_per_block, n_layers);
-        pedestal_terms_kernel<K><<<tg, 256, 0, s>>>(pa, terms);
+        const int tiles = (pa.lines.n + kPedTileRows - 1) / kPedTileRows;
+        dim3 tg((tiles + 3) / 4, n_layers);
+        pedestal_terms_kernel<K><<<tg, 128, 0, s>>>(pa, terms);
     }
     if (smem > 48 * 1024)
     {
@@ -666,7 +666,8 @@ int lbl_gas_submit(lbl_gas* g, int n_layers, const double* pressure, const doubl
 
     // ---- chunking over layers ------------------------------------------------------
     // Pedestal chain: K slots per lane cover the 2*cut+3 tracked points of a line window.
-    const int ped_k = (2 * cut_off + 3 + 31) / 32;
+    // (+2 spare slots per row for the bare f[s], f[e] of each line.)
+    const int ped_k = (2 * cut_off + 5 + 31) / 32;
     const bool ped_chain = remove_pedestal && ped_k <= 4;
     const int ped_wpad = 32 * ped_k;
     const size_t rec_per_layer = (size_t)plan.n_active *
@@ -677,14 +678,18 @@ int lbl_gas_submit(lbl_gas* g, int n_layers, const double* pressure, const doubl
     long long chunk = std::min<long long>(n_layers,
                                           std::max<long long>(1, (long long)(budget / rec_per_layer)));
     chunk = std::min<long long>(chunk, std::max<long long>(1, (long long)(budget / out_per_layer)));
-    if (g_chunk_layers > 0)
+    int chunk_override = g_chunk_layers;
+    if (const char* env = getenv("PYLBL_B200_CHUNK_LAYERS")) chunk_override = atoi(env);
+    if (chunk_override > 0)
     {
-        chunk = std::min<long long>(chunk, g_chunk_layers);
+        chunk = std::min<long long>(chunk, chunk_override);
     }
-    else if (k_host && n_layers >= 8)
+    else if (k_host && n_layers >= 16)
     {
-        // Four or more groups so the device->host copy of one overlaps the next one's kernels.
-        chunk = std::min<long long>(chunk, (n_layers + 3) / 4);
+        // Two groups so the device->host copy of the first overlaps the second one's kernels
+        // (more groups lengthen the critical path: the pedestal chain is latency-bound and
+        // takes as long for 15 layers as for 60).
+        chunk = std::min<long long>(chunk, (n_layers + 1) / 2);
     }
     const int n_chunks = (int)((n_layers + chunk - 1) / chunk);
 

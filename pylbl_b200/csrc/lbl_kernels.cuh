@@ -232,27 +232,21 @@ pedestal_kernel(const PedArgs a, double* scratch)
     pedestal_layer(a, blockIdx.x, threadIdx.x, 32, nodes, WarpSync());
 }
 
-// K3a.  terms[layer][row r][slot t], 32*K slots per row (zero beyond the window).
-// grid = (ceil(n / (8 warps * 4 rows)), layers), block = 256.
-constexpr int kTermRowsPerWarp = 4;
+// K3a.  terms[layer][row r][slot t], 32*K slots per row; one warp per tile of 32 rows.
+// grid = (ceil(tiles / 4), layers), block = 128.
 template <int K>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 pedestal_terms_kernel(const PedArgs a, double* __restrict__ terms)
 {
     const int layer = blockIdx.y;
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    const int first = warp * kTermRowsPerWarp;
-    double* base = terms + (size_t)layer * a.lines.n * (32 * K);
-#pragma unroll
-    for (int m = 0; m < kTermRowsPerWarp; ++m)
+    if (tile * kPedTileRows >= a.lines.n)
     {
-        const int r = first + m;
-        if (r < a.lines.n)
-        {
-            pedestal_terms_row<K>(a, layer, r, lane, base + (size_t)r * (32 * K));
-        }
+        return;
     }
+    double* rows = terms + ((size_t)layer * a.lines.n + (size_t)tile * kPedTileRows) * (32 * K);
+    pedestal_terms_tile<K>(a, layer, tile, lane, rows);
 }
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
@@ -270,7 +264,7 @@ __device__ __forceinline__ void cp_async_wait()
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-constexpr int kPedTile = 32;    // lines per staged tile
+constexpr int kPedTile = kPedTileRows;    // lines per staged tile (= K3a's tile)
 constexpr int kPedStages = 4;   // cp.async ring depth
 
 __device__ __forceinline__ double shfl_up_f64(double x, int delta)
@@ -367,14 +361,15 @@ pedestal_chain_kernel(const PedArgs a, const double* __restrict__ terms, double*
                 __syncwarp();
             }
             const double* row0 = rows + (size_t)l * wpad;
+            const int spare = 2 * g.cut_off + 3;   // f[s], f[e] of each line (K3a)
             double pedsum = 0.;
             if (run <= 2)
             {
                 // Short run: every lane does the same two-node update (no shuffles).
                 for (int m = 0; m < run; ++m)
                 {
-                    const double fs = row0[(size_t)m * wpad + st.w.s_slot];
-                    const double fe = row0[(size_t)m * wpad + st.w.e_slot];
+                    const double fs = row0[(size_t)m * wpad + spare];
+                    const double fe = row0[(size_t)m * wpad + spare + 1];
                     pedsum += ped_line_value(st.ks, st.ke, fs, fe, st.ks, st.ke);
                 }
             }
@@ -382,8 +377,8 @@ pedestal_chain_kernel(const PedArgs a, const double* __restrict__ terms, double*
             {
                 // Lane m takes line m of the run: d before it = d0 + sum_{j<m} (fs_j - fe_j).
                 const bool mine = lane < run;
-                const double fs = mine ? row0[(size_t)lane * wpad + st.w.s_slot] : 0.;
-                const double fe = mine ? row0[(size_t)lane * wpad + st.w.e_slot] : 0.;
+                const double fs = mine ? row0[(size_t)lane * wpad + spare] : 0.;
+                const double fe = mine ? row0[(size_t)lane * wpad + spare + 1] : 0.;
                 const double diff = fs - fe;
                 double scan = diff;
 #pragma unroll
@@ -407,7 +402,7 @@ pedestal_chain_kernel(const PedArgs a, const double* __restrict__ terms, double*
                 st.ks = __shfl_sync(0xffffffffu, ks_new, run - 1);
                 st.ke = __shfl_sync(0xffffffffu, ke_new, run - 1);
             }
-            ped_lane_slots(st, lane, row0, wpad, run, pedsum);
+            ped_lane_slots(st, lane, row0 + (size_t)(run - 1) * wpad, pedsum);
             l += run;
         }
         __syncwarp();

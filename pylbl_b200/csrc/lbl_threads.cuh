@@ -415,44 +415,74 @@ LBL_HD double pedestal_term(const PedArgs& a, int layer, int r, int t)
     return line_point(grid_point(g.v0, g.dv, i), i, a.rec.ab[o], a.rec.cc[o], chk, a.rec.gen[o]);
 }
 
-// K3a, warp form: the 32 lanes of a warp take the slots lane, lane+32, ... of row r, so the
-// per-line work (record loads, window) is warp-uniform and the stores are coalesced.
+// K3a, warp form.  A warp takes one TILE of 32 consecutive database rows; its 32 lanes take
+// the slots lane, lane+32, ... of every row, so the per-line work (record loads, window) is
+// warp-uniform and the stores are coalesced.  What is stored for row l is not the bare term
+// but the RUN-LOCAL PREFIX: the sum of the terms of rows l', l'+1, ..., l that precede it in
+// the same run (maximal stretch of equal window cell cb inside the tile).  K3b then needs
+// one row per run -- the last -- for its node update.  The bare terms at the two nodes that
+// decide the pedestal, f[s] and f[e], go to the two spare slots 2*cut+3 and 2*cut+4.
+constexpr int kPedTileRows = 32;
+
 template <int K>
-LBL_HD void pedestal_terms_row(const PedArgs& a, int layer, int r, int lane, double* row)
+LBL_HD void pedestal_terms_tile(const PedArgs& a, int layer, int tile, int lane, double* rows)
 {
     const GridSpec& g = a.grid;
-    const int j = a.lines.db_to_sorted ? LBL_LDG(a.lines.db_to_sorted + r) : r;
-    const size_t o = (size_t)layer * a.lines.n + j;
-    const int4 ck = LBL_LDG(reinterpret_cast<const int4*>(a.rec.chk + o));
-    const PedWindow w = ped_window(ck.x, g);
-    if (w.skip)
+    constexpr int wpad = 32 * K;
+    const int spare = 2 * g.cut_off + 3;
+    const int first = tile * kPedTileRows;
+    const int cnt = (a.lines.n - first < kPedTileRows) ? a.lines.n - first : kPedTileRows;
+    double run_sum[K];
+    int prev_cb = 0;
+    for (int m = 0; m < cnt; ++m)
     {
-#pragma unroll
-        for (int k = 0; k < K; ++k) row[lane + 32 * k] = 0.;
-        return;
-    }
-    const double2 l = LBL_LDG(reinterpret_cast<const double2*>(a.rec.ab + o));
-    const double c = LBL_LDG(a.rec.cc + o);
-#pragma unroll
-    for (int k = 0; k < K; ++k)
-    {
-        const int idx = ped_slot_index(w, g, lane + 32 * k);
-        double val = 0.;
-        if (idx >= 0)
+        const int r = first + m;
+        const int j = a.lines.db_to_sorted ? LBL_LDG(a.lines.db_to_sorted + r) : r;
+        const size_t o = (size_t)layer * a.lines.n + j;
+        const int4 ck = LBL_LDG(reinterpret_cast<const int4*>(a.rec.chk + o));
+        if (m == 0 || ck.x != prev_cb)
         {
-            const int i = (idx == g.ncell) ? g.n - 1 : idx * g.n_per_v;
-            const double v = grid_point(g.v0, g.dv, i);
-            if (i >= ck.y && i <= ck.z)
+#pragma unroll
+            for (int k = 0; k < K; ++k) run_sum[k] = 0.;
+        }
+        prev_cb = ck.x;
+        double* row = rows + (size_t)m * wpad;
+        const PedWindow w = ped_window(ck.x, g);
+        if (!w.skip)
+        {
+            const double2 l = LBL_LDG(reinterpret_cast<const double2*>(a.rec.ab + o));
+            const double c = LBL_LDG(a.rec.cc + o);
+#pragma unroll
+            for (int k = 0; k < K; ++k)
             {
-                const LineGen gen = a.rec.gen[o];
-                val = voigt_general(v, gen.nu, gen.repwid, gen.y, gen.cof, gen.xlim0, gen.xlim1);
-            }
-            else
-            {
-                val = far_term(v, l.x, l.y, c, 0.);
+                const int t = lane + 32 * k;
+                const int idx = ped_slot_index(w, g, t);
+                if (idx >= 0)
+                {
+                    const int i = (idx == g.ncell) ? g.n - 1 : idx * g.n_per_v;
+                    const double v = grid_point(g.v0, g.dv, i);
+                    double val;
+                    if (i >= ck.y && i <= ck.z)
+                    {
+                        const LineGen gen = a.rec.gen[o];
+                        val = voigt_general(v, gen.nu, gen.repwid, gen.y, gen.cof, gen.xlim0, gen.xlim1);
+                    }
+                    else
+                    {
+                        val = far_term(v, l.x, l.y, c, 0.);
+                    }
+                    run_sum[k] += val;
+                    if (t == w.s_slot) row[spare] = val;
+                    if (t == w.e_slot) row[spare + 1] = val;
+                }
             }
         }
-        row[lane + 32 * k] = val;
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+        {
+            const int t = lane + 32 * k;
+            if (t != spare && t != spare + 1) row[t] = run_sum[k];
+        }
     }
 }
 
@@ -540,27 +570,15 @@ LBL_HD double ped_line_value(double ks_prev, double ke_prev, double fs, double f
     return pedestal;
 }
 
-// Node update of one run: own += sum over the run's R lines of their terms - their pedestals.
+// Node update of one run: own += (sum of the run's terms, = K3a's prefix in the run's last
+// row) - (sum of the run's pedestals).
 template <int K>
-LBL_HD void ped_lane_slots(PedLane<K>& st, int lane, const double* row0, int wpad, int run,
-                           double pedsum)
+LBL_HD void ped_lane_slots(PedLane<K>& st, int lane, const double* last_row, double pedsum)
 {
 #pragma unroll
     for (int k = 0; k < K; ++k)
     {
-        const double* col = row0 + lane + 32 * k;
-        double s0 = 0., s1 = 0.;
-        int m = 0;
-        for (; m + 1 < run; m += 2)
-        {
-            s0 += col[(size_t)m * wpad];
-            s1 += col[(size_t)(m + 1) * wpad];
-        }
-        if (m < run)
-        {
-            s0 += col[(size_t)m * wpad];
-        }
-        st.own[k] += (s0 + s1) - pedsum;
+        st.own[k] += last_row[lane + 32 * k] - pedsum;
     }
     st.binsum += pedsum;
 }

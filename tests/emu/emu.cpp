@@ -74,9 +74,8 @@ static void run_chain(const PedArgs& pa, int layer, double* nodes)
     for (int first = 0; first < n; first += 32)   // tiles of 32 lines, as staged by cp.async
     {
         const int cnt = std::min(32, n - first);
-        for (int m = 0; m < cnt; ++m)
-            for (int lane = 0; lane < 32; ++lane)
-                pedestal_terms_row<K>(pa, layer, first + m, lane, rows.data() + (size_t)m * wpad);
+        for (int lane = 0; lane < 32; ++lane)
+            pedestal_terms_tile<K>(pa, layer, first / 32, lane, rows.data());
         int l = 0;
         while (l < cnt)
         {
@@ -91,21 +90,22 @@ static void run_chain(const PedArgs& pa, int layer, double* nodes)
                 for (int lane = 0; lane < 32; ++lane) ped_lane_reload(lanes[lane], g, lane, cb, w, nodes);
             }
             const double* row0 = rows.data() + (size_t)l * wpad;
+            const int spare = 2 * g.cut_off + 3;
             PedLane<K>& u = lanes[0];
             double pedsum = 0., ks = u.ks, ke = u.ke;
             if (run <= 2)
             {
                 for (int m = 0; m < run; ++m)
-                    pedsum += ped_line_value(ks, ke, row0[(size_t)m * wpad + u.w.s_slot],
-                                             row0[(size_t)m * wpad + u.w.e_slot], ks, ke);
+                    pedsum += ped_line_value(ks, ke, row0[(size_t)m * wpad + spare],
+                                             row0[(size_t)m * wpad + spare + 1], ks, ke);
             }
             else
             {
                 double scan = 0., ks_end = ks, ke_end = ke;
                 for (int m = 0; m < run; ++m)   // lane m
                 {
-                    const double fs = row0[(size_t)m * wpad + u.w.s_slot];
-                    const double fe = row0[(size_t)m * wpad + u.w.e_slot];
+                    const double fs = row0[(size_t)m * wpad + spare];
+                    const double fe = row0[(size_t)m * wpad + spare + 1];
                     const double d_prev = (ks - ke) + scan;   // exclusive prefix
                     const double ks_prev = (m == 0) ? ks : fmax(d_prev, 0.);
                     const double ke_prev = (m == 0) ? ke : fmax(-d_prev, 0.);
@@ -119,7 +119,7 @@ static void run_chain(const PedArgs& pa, int layer, double* nodes)
             {
                 lanes[lane].ks = ks;
                 lanes[lane].ke = ke;
-                ped_lane_slots(lanes[lane], lane, row0, wpad, run, pedsum);
+                ped_lane_slots(lanes[lane], lane, row0 + (size_t)(run - 1) * wpad, pedsum);
             }
             l += run;
         }
@@ -244,7 +244,7 @@ extern "C" int emu_absorption(int n_layers, const double* pressure, const double
         pa.pedbin = pedbin.data();
         for (int l = 0; l < n_layers; ++l)
         {
-            switch ((2 * cut_off + 3 + 31) / 32)
+            switch ((2 * cut_off + 5 + 31) / 32)
             {
                 case 1: run_chain<1>(pa, l, nodes.data()); break;
                 case 2: run_chain<2>(pa, l, nodes.data()); break;
