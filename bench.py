@@ -228,6 +228,40 @@ def run_reference_arm(args, rank, world):
 
 
 # --------------------------------------------------------------------------------------
+# rank plumbing (the data path has no collective: ranks only agree on timing and totals)
+# --------------------------------------------------------------------------------------
+class Ranks(object):
+    """barrier / max / sum over the ranks of a torch.distributed job (or a single process)."""
+
+    def __init__(self, dist=None, device="cpu"):
+        self.dist = dist
+        self.device = device
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+
+    def _reduce(self, x, op):
+        if self.dist is None:
+            return float(x)
+        import torch
+        t = torch.tensor([float(x)], dtype=torch.float64, device=self.device)
+        self.dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    def max(self, x):
+        return self._reduce(x, None if self.dist is None else self.dist.ReduceOp.MAX)
+
+    def sum(self, x):
+        return self._reduce(x, None if self.dist is None else self.dist.ReduceOp.SUM)
+
+
+def rank_column(rank):
+    """Weak scaling: rank r computes its own 60-layer column r."""
+    return synth.standard_column(N_LAYERS, column=rank)
+
+
+# --------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------
 def run_ours(args, rank, local_rank, world, dist):
@@ -236,30 +270,14 @@ def run_ours(args, rank, local_rank, world, dist):
 
     torch.cuda.set_device(local_rank)
     lib = _lib.library()
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-
-    def max_over_ranks(x):
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local_rank}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def sum_over_ranks(x):
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local_rank}")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+    ranks = Ranks(dist, f"cuda:{local_rank}")
+    barrier, max_over_ranks, sum_over_ranks = ranks.barrier, ranks.max, ranks.sum
 
     db = database_path(local_rank, barrier)
     bounds = synth.config_grid(CONFIG)
     v0, vn, npv = bounds
     n = (vn - v0) * npv
-    column = synth.standard_column(N_LAYERS, column=rank)
+    column = rank_column(rank)
     gases = {f: Gas(db, f, devices=[local_rank]) for f in GASES}
 
     peak = ctypes.c_double(0.)

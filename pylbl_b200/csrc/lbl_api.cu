@@ -381,6 +381,14 @@ int lbl_device_count(int* count)
 {
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
+    if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver)
+    {
+        // A machine without a usable GPU has zero devices; that is an answer, not a failure.
+        cudaGetLastError();
+        g_last_error = std::string("Error: CUDA: ") + cudaGetErrorString(e);
+        *count = 0;
+        return 0;
+    }
     if (e != cudaSuccess)
     {
         *count = 0;
@@ -497,7 +505,10 @@ int lbl_gas_open(const char* database, const char* formula, int device, lbl_gas*
     *out = nullptr;
     int ndev = 0;
     if (lbl_device_count(&ndev)) return 1;
-    if (ndev == 0) return fail("Error: no CUDA device (this library has no CPU path).");
+    if (ndev == 0)
+    {
+        return fail("Error: no CUDA device (" + g_last_error + "); this library has no CPU path.");
+    }
     if (device < 0 || device >= ndev) return fail("Error: CUDA device index out of range.");
     std::unique_ptr<lbl_gas> g(new lbl_gas);
     g->device = device;
