@@ -133,7 +133,7 @@ struct lbl_gas
 
     cudaStream_t s_compute = nullptr, s_side = nullptr, s_copy = nullptr;
     DevBuf rec_ab, rec_cc, rec_chk, rec_gen, layers_dev, evals_dev, pedbin, pedcorr, pednodes,
-        pedterms;
+        pedterms, rec_f32, amp_max;
     DevBuf out[2];
     LayerIn* layers_host = nullptr;  // pinned
     size_t layers_host_cap = 0;
@@ -286,23 +286,30 @@ int pick_points_per_thread(int n_per_v)
 }
 
 template <int P>
-void launch_sum(const SumArgs& a, int n_layers, cudaStream_t s)
+void launch_sum(const SumArgs& a, int n_layers, bool fp32, cudaStream_t s)
 {
     const int threads = (a.grid.n + P - 1) / P;
     dim3 grid((threads + kSumBlock - 1) / kSumBlock, n_layers);
-    sum_kernel<P><<<grid, kSumBlock, 0, s>>>(a);
+    if (fp32)
+    {
+        sum32_kernel<P><<<grid, kSumBlock, 0, s>>>(a);
+    }
+    else
+    {
+        sum_kernel<P><<<grid, kSumBlock, 0, s>>>(a);
+    }
 }
 
-void launch_sum_dispatch(int P, const SumArgs& a, int n_layers, cudaStream_t s)
+void launch_sum_dispatch(int P, const SumArgs& a, int n_layers, bool fp32, cudaStream_t s)
 {
     switch (P)
     {
-        case 10: launch_sum<10>(a, n_layers, s); break;
-        case 8: launch_sum<8>(a, n_layers, s); break;
-        case 5: launch_sum<5>(a, n_layers, s); break;
-        case 4: launch_sum<4>(a, n_layers, s); break;
-        case 2: launch_sum<2>(a, n_layers, s); break;
-        default: launch_sum<1>(a, n_layers, s); break;
+        case 10: launch_sum<10>(a, n_layers, fp32, s); break;
+        case 8: launch_sum<8>(a, n_layers, fp32, s); break;
+        case 5: launch_sum<5>(a, n_layers, fp32, s); break;
+        case 4: launch_sum<4>(a, n_layers, fp32, s); break;
+        case 2: launch_sum<2>(a, n_layers, fp32, s); break;
+        default: launch_sum<1>(a, n_layers, fp32, s); break;
     }
 }
 
@@ -561,7 +568,7 @@ int lbl_gas_close(lbl_gas* g)
     g->plan.own.release();
     for (DevBuf* b : {&g->tips_t, &g->tips_q, &g->rec_ab, &g->rec_cc, &g->rec_chk, &g->rec_gen,
                       &g->layers_dev, &g->evals_dev, &g->pedbin, &g->pedcorr, &g->pednodes,
-                      &g->pedterms,
+                      &g->pedterms, &g->rec_f32, &g->amp_max,
                       &g->out[0], &g->out[1]})
     {
         b->release();
@@ -589,10 +596,11 @@ int lbl_gas_submit(lbl_gas* g, int n_layers, const double* pressure, const doubl
 {
     if (!g) return fail("Error: null handle.");
     if (g->pending && lbl_gas_wait(g)) return 1;
-    if (precision != LBL_PRECISION_FP64)
+    if (precision != LBL_PRECISION_FP64 && precision != LBL_PRECISION_FP32)
     {
         return fail("Error: unsupported precision mode.");
     }
+    const bool fp32 = precision == LBL_PRECISION_FP32;
     if (n_layers < 0 || n_per_v < 1 || vn <= v0 || cut_off < 0)
     {
         return fail("Error: invalid grid or layer count.");
@@ -683,7 +691,7 @@ int lbl_gas_submit(lbl_gas* g, int n_layers, const double* pressure, const doubl
     const int ped_wpad = 32 * ped_k;
     const size_t rec_per_layer = (size_t)plan.n_active *
         (sizeof(FarAB) + sizeof(double) + sizeof(LineChk) + sizeof(LineGen) +
-         (ped_chain ? sizeof(double) * ped_wpad : 0));
+         (ped_chain ? sizeof(double) * ped_wpad : 0) + (fp32 ? sizeof(Far32) : 0));
     const size_t out_per_layer = sizeof(double) * (size_t)grid.n;
     const size_t budget = (size_t)6 << 30;
     long long chunk = std::min<long long>(n_layers,
@@ -709,6 +717,11 @@ int lbl_gas_submit(lbl_gas* g, int n_layers, const double* pressure, const doubl
     LBL_CUDA(g->rec_cc.reserve(sizeof(double) * (size_t)plan.n_active * chunk));
     LBL_CUDA(g->rec_chk.reserve(sizeof(LineChk) * (size_t)plan.n_active * chunk));
     LBL_CUDA(g->rec_gen.reserve(sizeof(LineGen) * (size_t)plan.n_active * chunk));
+    if (fp32)
+    {
+        LBL_CUDA(g->rec_f32.reserve(sizeof(Far32) * (size_t)plan.n_active * chunk));
+        LBL_CUDA(g->amp_max.reserve(sizeof(unsigned long long) * (size_t)n_layers));
+    }
     LBL_CUDA(g->layers_dev.reserve(sizeof(LayerIn) * (size_t)n_layers));
     LBL_CUDA(g->evals_dev.reserve(sizeof(unsigned long long) * (size_t)n_layers));
     LBL_CUDA(g->out[0].reserve(out_per_layer * chunk));
@@ -785,6 +798,10 @@ int lbl_gas_submit(lbl_gas* g, int n_layers, const double* pressure, const doubl
     LBL_CUDA(cudaMemcpyAsync(g->layers_dev.p, g->layers_host, sizeof(LayerIn) * n_layers,
                              cudaMemcpyHostToDevice, sc));
     LBL_CUDA(cudaMemsetAsync(g->evals_dev.p, 0, sizeof(unsigned long long) * n_layers, sc));
+    if (fp32)
+    {
+        LBL_CUDA(cudaMemsetAsync(g->amp_max.p, 0, sizeof(unsigned long long) * n_layers, sc));
+    }
     st.h2d_bytes += (long long)(sizeof(LayerIn) * n_layers);
 
     Records rec;
@@ -792,6 +809,8 @@ int lbl_gas_submit(lbl_gas* g, int n_layers, const double* pressure, const doubl
     rec.cc = g->rec_cc.as<double>();
     rec.chk = g->rec_chk.as<LineChk>();
     rec.gen = g->rec_gen.as<LineGen>();
+    rec.f32 = fp32 ? g->rec_f32.as<Far32>() : nullptr;
+    rec.amp_max = nullptr;
 
     for (int c = 0; c < n_chunks; ++c)
     {
@@ -816,13 +835,19 @@ int lbl_gas_submit(lbl_gas* g, int n_layers, const double* pressure, const doubl
             g->out_busy[slot] = false;
         }
 
-        // K1
+        // K1 (+ K1f in FP32 mode)
         LBL_CUDA(cudaEventRecord(ev.k1_begin, sc));
         {
+            rec.amp_max = fp32 ? g->amp_max.as<unsigned long long>() + first : nullptr;
             dim3 grid1((plan.n_active + kScaleBlock - 1) / kScaleBlock, nl);
             scale_kernel<<<grid1, kScaleBlock, 0, sc>>>(lines, tips, layers_c, grid, rec,
                                                         g->evals_dev.as<unsigned long long>() + first);
             st.total_launches++;
+            if (fp32)
+            {
+                far32_kernel<<<grid1, kScaleBlock, 0, sc>>>(rec, plan.n_active);
+                st.total_launches++;
+            }
         }
         LBL_CUDA(cudaEventRecord(ev.k1_end, sc));
 
@@ -870,7 +895,7 @@ int lbl_gas_submit(lbl_gas* g, int n_layers, const double* pressure, const doubl
         sa.out = g->out[slot].as<double>();
         sa.n_layers = nl;
         LBL_CUDA(cudaEventRecord(ev.k2_begin, sc));
-        launch_sum_dispatch(P, sa, nl, sc);
+        launch_sum_dispatch(P, sa, nl, fp32, sc);
         LBL_CUDA(cudaEventRecord(ev.k2_end, sc));
         launch_fixup_dispatch(pick_fixup_tile(n_per_v), sa, nl, sc);
         LBL_CUDA(cudaEventRecord(ev.k2b_end, sc));

@@ -20,6 +20,7 @@
 // Plain-C++ stand-ins for the CUDA vector types (CPU emulation build only).
 struct alignas(16) double2 { double x, y; };
 struct alignas(16) int4 { int x, y, z, w; };
+struct alignas(16) float4 { float x, y, z, w; };
 #endif
 
 namespace lbl
@@ -58,6 +59,14 @@ struct alignas(16) LineGen  // operands of the full profile (voigt.c:13-15,34-43
     double cof;     // sw*rsqrpi*repwid
     double xlim0;   // sqrt(15100 + y*(40 - 3.6*y))                  voigt.c:34
     double xlim1;   // y >= 8.425 ? 0 : sqrt(164 - y*(4.3 + 1.8*y))  voigt.c:36-43
+};
+
+struct alignas(16) Far32  // FP32-mode operands of one (layer, line): term = amp/((v-nu')^2 + g2)
+{
+    float cbf;   // floor(nu') - v0 as a float (exact below 2^24)
+    float frac;  // nu' - floor(nu') in [0, 1)
+    float g2;    // gamma^2
+    float amp;   // A * 2^shift(layer), A = sw'*gamma/pi   (0 masks the line)
 };
 
 struct LayerIn
@@ -253,6 +262,63 @@ LBL_HD void far_terms_pair(const double (&v)[P], double a1, double b1, double c1
     for (int p = 0; p < P; ++p)
     {
         acc[p] = fma_(s[p], m[p], acc[p]);
+    }
+}
+
+// ---- opt-in FP32 far-wing arithmetic ----------------------------------------------------------
+// A wavenumber difference cannot be formed in FP32 from absolute wavenumbers (ulp(5000) =
+// 5e-4 cm-1), so positions are split into an integer cell and a fraction: for a point in
+// cell `cellf` at fraction `fp`, and a line in cell `cbf` at fraction `frac`,
+//     v - nu' = ((cellf - cbf) - frac) + fp
+// where the first bracket is exact (small integers) and the absolute error of the whole is
+// <= 2e-6 cm-1 -- against a far-zone distance of at least ~0.1 cm-1.  Amplitudes carry a
+// per-layer power-of-two scale so that they sit mid-range in FP32.
+LBL_HD float rcp_f32(float x)
+{
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return 1.0f / x;
+#endif
+}
+
+LBL_HD float fmaf_(float a, float b, float c)
+{
+#if defined(__CUDA_ARCH__)
+    return __fmaf_rn(a, b, c);
+#else
+    return fmaf(a, b, c);
+#endif
+}
+
+// Two lines at P points: amp1/q1 + amp2/q2 = (amp1*q2 + amp2*q1)/(q1*q2): 8 FP32 + 1 MUFU.
+template <int P>
+LBL_HD void far32_pair(const float (&fp)[P], float t1, float g1, float a1, float t2, float g2,
+                       float a2, float (&acc)[P])
+{
+#pragma unroll
+    for (int p = 0; p < P; ++p)
+    {
+        const float u1 = t1 + fp[p];
+        const float u2 = t2 + fp[p];
+        const float q1 = fmaf_(u1, u1, g1);
+        const float q2 = fmaf_(u2, u2, g2);
+        const float m = q1 * q2;
+        const float n = fmaf_(a2, q1, a1 * q2);
+        acc[p] = fmaf_(n, rcp_f32(m), acc[p]);
+    }
+}
+
+template <int P>
+LBL_HD void far32_one(const float (&fp)[P], float t1, float g1, float a1, float (&acc)[P])
+{
+#pragma unroll
+    for (int p = 0; p < P; ++p)
+    {
+        const float u1 = t1 + fp[p];
+        acc[p] = fmaf_(a1, rcp_f32(fmaf_(u1, u1, g1)), acc[p]);
     }
 }
 

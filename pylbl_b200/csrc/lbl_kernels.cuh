@@ -27,18 +27,36 @@ scale_kernel(LinesView ln, TipsView tips, const LayerIn* __restrict__ layers, Gr
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const int layer = blockIdx.y;
     long long w = 0;
+    double amp = 0.;
     if (j < ln.n)
     {
-        w = scale_thread(ln, tips, layers, g, rec, layer, j);
+        w = scale_thread(ln, tips, layers, g, rec, layer, j, amp);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1)
     {
         w += __shfl_down_sync(0xffffffffu, w, o);
+        amp = fmax(amp, __shfl_down_sync(0xffffffffu, amp, o));
     }
-    if ((threadIdx.x & 31) == 0 && w != 0)
+    if ((threadIdx.x & 31) == 0)
     {
-        atomicAdd(evals + layer, (unsigned long long)w);
+        if (w != 0) atomicAdd(evals + layer, (unsigned long long)w);
+        // FP32 mode: largest amplitude of the layer (non-negative doubles order like integers).
+        if (rec.amp_max && amp > 0.)
+        {
+            atomicMax(rec.amp_max + layer, (unsigned long long)__double_as_longlong(amp));
+        }
+    }
+}
+
+// K1f (FP32 mode).  Thread per (layer, line): FP32 operands from the FP64 records.
+__global__ void __launch_bounds__(kScaleBlock)
+far32_kernel(Records rec, int n_lines)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n_lines)
+    {
+        far32_thread(rec, n_lines, blockIdx.y, j);
     }
 }
 
@@ -48,6 +66,14 @@ __global__ void __launch_bounds__(kSumBlock)
 sum_kernel(const SumArgs a)
 {
     sum_thread<P>(a, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x);
+}
+
+// K2, FP32 mode (opt-in).
+template <int P>
+__global__ void __launch_bounds__(kSumBlock)
+sum32_kernel(const SumArgs a)
+{
+    sum32_thread<P>(a, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x);
 }
 
 // K2b.  One warp per tile of T points x 32/T layers; grid = (ceil(tiles/4), ceil(layers/(32/T))).

@@ -43,6 +43,8 @@ struct Records
     double* cc;    // [layer][line]
     LineChk* chk;  // [layer][line]
     LineGen* gen;  // [layer][line]
+    Far32* f32;    // [layer][line], FP32 mode only (else nullptr)
+    unsigned long long* amp_max;  // [layer] bit pattern of the largest amplitude A (FP32 mode)
 };
 
 struct GridSpec
@@ -53,12 +55,19 @@ struct GridSpec
     double dv;  // 1./n_per_v
 };
 
+// Lorentz amplitude A = sw'*gamma/pi of a record (0 for a dropped line).
+LBL_HD double record_amplitude(const FarAB& ab)
+{
+    return (ab.a > 0.) ? 1. / (ab.a * ab.a) : 0.;
+}
+
 // ---------------------------------------------------------------------------------------
 // K1: scaling of one (layer, line).  Returns the line's window size (e - s + 1, the
 // reference's count of grid evaluations, spectra.c:48-62) for the eval counter.
 // ---------------------------------------------------------------------------------------
 LBL_HD long long scale_thread(const LinesView& ln, const TipsView& tips, const LayerIn* layers,
-                              const GridSpec& g, const Records& rec, int layer, int j)
+                              const GridSpec& g, const Records& rec, int layer, int j,
+                              double& amplitude)
 {
     const LayerIn ly = layers[layer];
     LineIn in;
@@ -86,6 +95,7 @@ LBL_HD long long scale_thread(const LinesView& ln, const TipsView& tips, const L
     rec.cc[o] = cc;
     rec.chk[o] = chk;
     rec.gen[o] = gen;
+    amplitude = record_amplitude(ab);
 
     // Reference window (spectra.c:48-62) for the evaluation count.
     long long s = (long long)(chk.cb - g.cut_off) * g.n_per_v;
@@ -103,6 +113,47 @@ LBL_HD long long scale_thread(const LinesView& ln, const TipsView& tips, const L
         e = g.n - 1;
     }
     return (e >= s) ? (e - s + 1) : 0;
+}
+
+// Per-layer power-of-two scale of the FP32 amplitudes: the largest amplitude maps to ~2^40.
+LBL_HD int amp_shift(unsigned long long amp_max_bits)
+{
+    union { unsigned long long u; double d; } x;
+    x.u = amp_max_bits;
+    if (!(x.d > 0.))
+    {
+        return 0;
+    }
+    int e;
+    frexp(x.d, &e);
+    return 40 - e;
+}
+
+// K1f: FP32 operands of one (layer, line) from its FP64 records.
+LBL_HD void far32_thread(const Records& rec, int n_lines, int layer, int j)
+{
+    const size_t o = (size_t)layer * n_lines + j;
+    const FarAB ab = rec.ab[o];
+    const double amp = record_amplitude(ab);
+    Far32 f;
+    if (amp > 0.)
+    {
+        const double nu = rec.gen[o].nu;
+        const int shift = amp_shift(rec.amp_max[layer]);
+        f.cbf = (float)rec.chk[o].cb;
+        f.frac = (float)(nu - floor(nu));
+        f.g2 = (float)(rec.cc[o] * amp);
+        f.amp = (float)ldexp(amp, shift);
+        if (!(f.g2 > 0.f)) f.g2 = 1.0e-30f;
+    }
+    else
+    {
+        f.cbf = 0.f;
+        f.frac = 0.f;
+        f.g2 = 1.f;
+        f.amp = 0.f;
+    }
+    rec.f32[o] = f;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -234,6 +285,150 @@ LBL_HD void sum_thread(const SumArgs& a, int layer, int tid)
         for (int p = 0; p < P; ++p)
         {
             o[p] = acc[p];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// K2 (FP32 mode): same ranges, same masks, same ownership as sum_thread; the far-wing terms
+// are evaluated in FP32 (far32_pair) and flushed into FP64 accumulators every kF32Flush
+// lines so that the FP32 running sums stay short.  Near zone, node terms and the pedestal
+// remain FP64 (K2b, K3).  Stated tolerance of the mode: 1e-4 (tests/helpers.py: FP32_TOL).
+// ---------------------------------------------------------------------------------------
+constexpr int kF32Flush = 64;
+
+template <int P>
+LBL_HD void flush32(float (&acc32)[P], double (&acc)[P])
+{
+#pragma unroll
+    for (int p = 0; p < P; ++p)
+    {
+        acc[p] += (double)acc32[p];
+        acc32[p] = 0.f;
+    }
+}
+
+template <int P>
+LBL_HD void plain_range32(const Far32* __restrict__ f32, int jb, int je, float cellf,
+                          const float (&fp)[P], float (&acc32)[P], double (&acc)[P])
+{
+    int j = jb;
+    while (j < je)
+    {
+        const int stop = (je - j > kF32Flush) ? j + kF32Flush : je;
+        for (; j + 1 < stop; j += 2)
+        {
+            const float4 l1 = LBL_LDG(reinterpret_cast<const float4*>(f32 + j));
+            const float4 l2 = LBL_LDG(reinterpret_cast<const float4*>(f32 + j + 1));
+            far32_pair<P>(fp, (cellf - l1.x) - l1.y, l1.z, l1.w, (cellf - l2.x) - l2.y, l2.z, l2.w,
+                          acc32);
+        }
+        if (j < stop)
+        {
+            const float4 l1 = LBL_LDG(reinterpret_cast<const float4*>(f32 + j));
+            far32_one<P>(fp, (cellf - l1.x) - l1.y, l1.z, l1.w, acc32);
+            ++j;
+        }
+        flush32<P>(acc32, acc);
+    }
+}
+
+template <int P>
+LBL_HD void masked_range32(const Far32* __restrict__ f32, const LineChk* __restrict__ chk, int jb,
+                           int je, int i_first, int cell, int cut_off, float cellf,
+                           const float (&fp)[P], float (&acc32)[P], double (&acc)[P])
+{
+    const int cmin = cell - cut_off;
+    const int cmax = cell + cut_off;
+    const int i_last = i_first + P - 1;
+    int since_flush = 0;
+    for (int j = jb; j < je; ++j)
+    {
+        const int4 ck = LBL_LDG(reinterpret_cast<const int4*>(chk + j));
+        if (ck.x < cmin || ck.x > cmax)
+        {
+            continue;
+        }
+        const float4 l = LBL_LDG(reinterpret_cast<const float4*>(f32 + j));
+        const float t = (cellf - l.x) - l.y;
+        if (ck.y > i_last || ck.z < i_first)
+        {
+            far32_one<P>(fp, t, l.z, l.w, acc32);
+        }
+        else
+        {
+#pragma unroll
+            for (int p = 0; p < P; ++p)
+            {
+                const int i = i_first + p;
+                const float ap = (i >= ck.y && i <= ck.z) ? 0.f : l.w;
+                const float u = t + fp[p];
+                acc32[p] = fmaf_(ap, rcp_f32(fmaf_(u, u, l.z)), acc32[p]);
+            }
+        }
+        if (++since_flush == kF32Flush)
+        {
+            flush32<P>(acc32, acc);
+            since_flush = 0;
+        }
+    }
+    flush32<P>(acc32, acc);
+}
+
+template <int P>
+LBL_HD void sum32_thread(const SumArgs& a, int layer, int tid)
+{
+    const GridSpec& g = a.grid;
+    const int warp_first = (tid & ~31) * P;
+    if (warp_first >= g.n)
+    {
+        return;
+    }
+    int warp_last = warp_first + 32 * P - 1;
+    if (warp_last > g.n - 1)
+    {
+        warp_last = g.n - 1;
+    }
+    const LayerIn ly = a.layers[layer];
+    const Segments seg = find_segments(a.lines.nu, a.lines.n, g.v0, g.n_per_v, g.dv, g.cut_off,
+                                       warp_first, warp_last, ly.slack, ly.kappa);
+    int i_first = tid * P;
+    const bool valid = i_first < g.n;
+    if (!valid)
+    {
+        i_first = g.n - P;
+    }
+    const int cell = i_first / g.n_per_v;
+    const float cellf = (float)cell;
+    const double cell_origin = (double)g.v0 + (double)cell;
+
+    float fp[P], acc32[P];
+    double acc[P];
+#pragma unroll
+    for (int p = 0; p < P; ++p)
+    {
+        fp[p] = (float)(grid_point(g.v0, g.dv, i_first + p) - cell_origin);
+        acc32[p] = 0.f;
+        acc[p] = 0.;
+    }
+    const size_t off = (size_t)layer * a.lines.n;
+    const Far32* f32 = a.rec.f32 + off;
+    const LineChk* chk = a.rec.chk + off;
+
+    masked_range32<P>(f32, chk, seg.j[0], seg.j[1], i_first, cell, g.cut_off, cellf, fp, acc32, acc);
+    plain_range32<P>(f32, seg.j[1], seg.j[2], cellf, fp, acc32, acc);
+    masked_range32<P>(f32, chk, seg.j[2], seg.j[3], i_first, cell, g.cut_off, cellf, fp, acc32, acc);
+    plain_range32<P>(f32, seg.j[3], seg.j[4], cellf, fp, acc32, acc);
+    masked_range32<P>(f32, chk, seg.j[4], seg.j[5], i_first, cell, g.cut_off, cellf, fp, acc32, acc);
+
+    if (valid)
+    {
+        const double unscale = ldexp(1.0, -amp_shift(a.rec.amp_max[layer]));
+        double* o = a.out + (size_t)layer * g.n + i_first;
+#pragma unroll
+        for (int p = 0; p < P; ++p)
+        {
+            o[p] = acc[p] * unscale;
         }
     }
 }

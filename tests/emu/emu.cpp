@@ -15,7 +15,7 @@
 using namespace lbl;
 
 template <int P>
-static void run_sum(const SumArgs& a, int n_layers)
+static void run_sum(const SumArgs& a, int n_layers, bool fp32)
 {
     const int threads = (a.grid.n + P - 1) / P;
     const int padded = (threads + 127) / 128 * 128;
@@ -23,7 +23,14 @@ static void run_sum(const SumArgs& a, int n_layers)
     {
         for (int tid = 0; tid < padded; ++tid)
         {
-            sum_thread<P>(a, layer, tid);
+            if (fp32)
+            {
+                sum32_thread<P>(a, layer, tid);
+            }
+            else
+            {
+                sum_thread<P>(a, layer, tid);
+            }
         }
     }
 }
@@ -134,7 +141,8 @@ extern "C" int emu_absorption(int n_layers, const double* pressure, const double
                               const double* n_air, const double* elower, const double* delta_air,
                               const int* local_iso_id, const double* iso_mass, int num_iso,
                               int num_t, const double* tips_t, const double* tips_q, int cut_off,
-                              int remove_pedestal, int points_per_thread, long long* n_evals)
+                              int remove_pedestal, int points_per_thread, int precision,
+                              long long* n_evals)
 {
     GridSpec g;
     g.v0 = v0;
@@ -202,13 +210,26 @@ extern "C" int emu_absorption(int n_layers, const double* pressure, const double
     std::vector<double> cc((size_t)na * n_layers);
     std::vector<LineChk> chk((size_t)na * n_layers);
     std::vector<LineGen> gen((size_t)na * n_layers);
-    Records rec{ab.data(), cc.data(), chk.data(), gen.data()};
+    const bool fp32 = precision == 1;
+    std::vector<Far32> f32(fp32 ? (size_t)na * n_layers : 0);
+    std::vector<unsigned long long> amp_max(n_layers, 0ull);
+    Records rec{ab.data(), cc.data(), chk.data(), gen.data(), fp32 ? f32.data() : nullptr,
+                fp32 ? amp_max.data() : nullptr};
     for (int l = 0; l < n_layers; ++l)
     {
         for (int j = 0; j < na; ++j)
         {
-            *n_evals += scale_thread(ln, tips, layers.data(), g, rec, l, j);
+            double amp = 0.;
+            *n_evals += scale_thread(ln, tips, layers.data(), g, rec, l, j, amp);
+            union { double d; unsigned long long u; } bits;
+            bits.d = amp;
+            if (amp > 0. && bits.u > amp_max[l]) amp_max[l] = bits.u;
         }
+    }
+    if (fp32)
+    {
+        for (int l = 0; l < n_layers; ++l)
+            for (int j = 0; j < na; ++j) far32_thread(rec, na, l, j);
     }
     SumArgs sa;
     sa.lines = ln;
@@ -219,12 +240,12 @@ extern "C" int emu_absorption(int n_layers, const double* pressure, const double
     sa.n_layers = n_layers;
     switch (points_per_thread)
     {
-        case 10: run_sum<10>(sa, n_layers); break;
-        case 8: run_sum<8>(sa, n_layers); break;
-        case 5: run_sum<5>(sa, n_layers); break;
-        case 4: run_sum<4>(sa, n_layers); break;
-        case 2: run_sum<2>(sa, n_layers); break;
-        case 1: run_sum<1>(sa, n_layers); break;
+        case 10: run_sum<10>(sa, n_layers, fp32); break;
+        case 8: run_sum<8>(sa, n_layers, fp32); break;
+        case 5: run_sum<5>(sa, n_layers, fp32); break;
+        case 4: run_sum<4>(sa, n_layers, fp32); break;
+        case 2: run_sum<2>(sa, n_layers, fp32); break;
+        case 1: run_sum<1>(sa, n_layers, fp32); break;
         default: return 1;
     }
     // K2b: same tile rule as pick_fixup_tile() in lbl_api.cu.

@@ -17,7 +17,7 @@ from numpy.ctypeslib import ndpointer
 from oracle import OracleGas
 from pylbl_b200 import synth
 
-from helpers import FP64_TOL, relative_error, scaled_error
+from helpers import FP32_TOL, FP64_TOL, relative_error, scaled_error
 
 EMU_DIR = Path(__file__).resolve().parent / "emu"
 
@@ -34,12 +34,12 @@ def emu():
     f64 = ndpointer(np.float64, flags="C_CONTIGUOUS")
     i32 = ndpointer(np.int32, flags="C_CONTIGUOUS")
     lib.emu_absorption.argtypes = [c_int, f64, f64, f64, c_int, c_int, c_int, f64, c_int] + \
-        [f64] * 7 + [i32, f64, c_int, c_int, f64, f64, c_int, c_int, c_int, POINTER(c_longlong)]
+        [f64] * 7 + [i32, f64, c_int, c_int, f64, f64, c_int, c_int, c_int, c_int, POINTER(c_longlong)]
     lib.emu_absorption.restype = c_int
     return lib
 
 
-def run(emu, gas, t, p, x, bounds, ped, cut=25, points=None):
+def run(emu, gas, t, p, x, bounds, ped, cut=25, points=None, fp32=False):
     d = gas.data
     v0, vn, npv = bounds
     n = (vn - v0) * npv
@@ -52,7 +52,7 @@ def run(emu, gas, t, p, x, bounds, ped, cut=25, points=None):
                             d["gamma_air"], d["gamma_self"], d["n_air"], d["elower"],
                             d["delta_air"], d["local_iso_id"], d["mass"], d["num_iso"],
                             d["num_t"], d["tips_t"], d["tips_q"], cut, int(ped), points,
-                            ctypes.byref(evals))
+                            1 if fp32 else 0, ctypes.byref(evals))
     assert rc == 0
     return k.reshape(t.size, n), int(evals.value)
 
@@ -137,3 +137,30 @@ def test_large_pressure_shift_near_integer_boundaries(emu, tmp_path):
             total += gas.last_evals
             assert scaled_error(k[layer], k_ref, 20) <= FP64_TOL
         assert evals == total
+
+
+@pytest.mark.parametrize("bounds", [(1, 601, 10), (1, 301, 100), (1, 500, 4), (1, 41, 1000)])
+@pytest.mark.parametrize("ped", [0, 1])
+def test_fp32_mode_within_stated_tolerance(emu, small_db, atmosphere, bounds, ped):
+    """Opt-in FP32 far-wing arithmetic: 1e-4 of the local scale (and pointwise without the
+    pedestal); windows and evaluation counts stay exact."""
+    worst = 0.0
+    for formula in ("H2O", "CO2"):
+        gas = OracleGas(small_db, formula)
+        k, evals = run(emu, gas, atmosphere.t, atmosphere.p, atmosphere.vmr[formula], bounds, ped,
+                       fp32=True)
+        total = 0
+        for layer in range(atmosphere.t.size):
+            k_ref = gas.absorption(atmosphere.t[layer], atmosphere.p[layer],
+                                   atmosphere.vmr[formula][layer], *bounds, ped)
+            total += gas.last_evals
+            if not np.any(k_ref):
+                assert not np.any(k[layer])
+                continue
+            err = scaled_error(k[layer], k_ref, bounds[2])
+            worst = max(worst, err)
+            assert err <= FP32_TOL
+            if not ped:
+                assert relative_error(k[layer], k_ref) <= FP32_TOL
+        assert evals == total
+    assert worst > 1e-12   # it really is the FP32 path

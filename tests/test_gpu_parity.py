@@ -10,7 +10,7 @@ from oracle import OracleGas, oracle_scale_line, oracle_tips
 from pylbl_b200 import Gas, synth
 from pylbl_b200 import _lib
 
-from helpers import FP64_TOL, relative_error, scaled_error
+from helpers import FP32_TOL, FP64_TOL, relative_error, scaled_error
 
 pytestmark = pytest.mark.gpu
 
@@ -212,3 +212,32 @@ def test_many_layers_chunked(small_db):
         ref.absorption(col.t[layer], col.p[layer], col.vmr["H2O"][layer], *bounds, True)
         total += ref.last_evals
     assert gas.last_stats[0]["evals"] == total
+
+
+@pytest.mark.parametrize("bounds", [(1, 1201, 10), (1, 601, 100), (1, 500, 4), (1, 41, 1000)])
+@pytest.mark.parametrize("remove_pedestal", [False, True])
+def test_fp32_mode(small_db, atmosphere, bounds, remove_pedestal):
+    """Opt-in FP32 mode, stated tolerance 1e-4; window bookkeeping stays bit-exact."""
+    worst = 0.0
+    for formula in ("H2O", "CO2", "O3"):
+        gas = Gas(small_db, formula, precision="fp32")
+        ref = OracleGas(small_db, formula)
+        k = gas.absorption_coefficients(atmosphere.t, atmosphere.p, atmosphere.vmr[formula],
+                                        bounds=bounds, remove_pedestal=remove_pedestal)
+        total = 0
+        for layer in range(atmosphere.t.size):
+            k_ref = ref.absorption(atmosphere.t[layer], atmosphere.p[layer],
+                                   atmosphere.vmr[formula][layer], *bounds, remove_pedestal,
+                                   windows=True)
+            total += ref.last_evals
+            if not np.any(k_ref):
+                assert not np.any(k[layer])
+                continue
+            err = scaled_error(k[layer], k_ref, bounds[2])
+            worst = max(worst, err)
+            assert err <= FP32_TOL
+            if not remove_pedestal:
+                assert relative_error(k[layer], k_ref) <= FP32_TOL
+            assert np.array_equal(gas.windows(layer), ref.last_windows[:ref.last_active])
+        assert gas.last_stats[0]["evals"] == total
+    assert worst > 1e-12
