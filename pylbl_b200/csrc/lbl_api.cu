@@ -686,7 +686,8 @@ int lbl_gas_submit(lbl_gas* g, int n_layers, const double* pressure, const doubl
     // ---- chunking over layers ------------------------------------------------------
     // Pedestal chain: K slots per lane cover the 2*cut+3 tracked points of a line window.
     // (+2 spare slots per row for the bare f[s], f[e] of each line.)
-    const int ped_k = (2 * cut_off + 5 + 31) / 32;
+    int ped_k = (2 * cut_off + 5 + 31) / 32;
+    if (ped_k == 3) ped_k = 4;   // the node ring is indexed with a power-of-two mask
     const bool ped_chain = remove_pedestal && ped_k <= 4;
     const int ped_wpad = 32 * ped_k;
     const size_t rec_per_layer = (size_t)plan.n_active *
@@ -869,7 +870,6 @@ int lbl_gas_submit(lbl_gas* g, int n_layers, const double* pressure, const doubl
                 {
                     case 1: ce = launch_chain<1>(pa, g->pedterms.as<double>(), scratch, nl, ped_smem, g->s_side); break;
                     case 2: ce = launch_chain<2>(pa, g->pedterms.as<double>(), scratch, nl, ped_smem, g->s_side); break;
-                    case 3: ce = launch_chain<3>(pa, g->pedterms.as<double>(), scratch, nl, ped_smem, g->s_side); break;
                     default: ce = launch_chain<4>(pa, g->pedterms.as<double>(), scratch, nl, ped_smem, g->s_side); break;
                 }
                 LBL_CUDA(ce);

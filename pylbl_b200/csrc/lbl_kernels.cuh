@@ -381,10 +381,11 @@ pedestal_chain_kernel(const PedArgs a, const double* __restrict__ terms, double*
                     l += run;
                     continue;
                 }
-                ped_lane_flush(st, g, lane, nodes, bins);
-                __syncwarp();
-                ped_lane_reload(st, g, lane, cb, w, nodes);
-                __syncwarp();
+                ped_lane_move(st, g, lane, cb, w, nodes, bins);
+                // k[s], k[e]: broadcast from the lanes that hold them.
+                const int cs = ped_s_index(w), ce = ped_e_index(w, g);
+                st.ks = __shfl_sync(0xffffffffu, ped_lane_value(st, cs), cs & 31);
+                st.ke = __shfl_sync(0xffffffffu, ped_lane_value(st, ce), ce & 31);
             }
             const double* row0 = rows + (size_t)l * wpad;
             const int spare = 2 * g.cut_off + 3;   // f[s], f[e] of each line (K3a)
@@ -428,12 +429,12 @@ pedestal_chain_kernel(const PedArgs a, const double* __restrict__ terms, double*
                 st.ks = __shfl_sync(0xffffffffu, ks_new, run - 1);
                 st.ke = __shfl_sync(0xffffffffu, ke_new, run - 1);
             }
-            ped_lane_slots(st, lane, row0 + (size_t)(run - 1) * wpad, pedsum);
+            ped_lane_slots(st, row0 + (size_t)(run - 1) * wpad, pedsum);
             l += run;
         }
         __syncwarp();
     }
-    ped_lane_flush(st, g, lane, nodes, bins);
+    ped_lane_finish(st, g, lane, bins);
     __syncwarp();
     if (!scratch)
     {

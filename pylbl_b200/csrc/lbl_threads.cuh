@@ -691,13 +691,22 @@ LBL_HD void pedestal_terms_tile(const PedArgs& a, int layer, int tile, int lane,
 //     node += sum_l f_l[slot] - sum_l pedestal_l.
 // Sums are re-associated relative to the reference's line-by-line order (rounding-level
 // differences, ~1e-16 of the node values).
+//
+// Node storage.  Tracked points have storage indices 0..ncell-1 (nodes) and ncell (the last
+// grid point).  Index c always lives in the same register of the same lane:
+// lane = c mod 32, register k = (c div 32) mod K -- a ring of 32*K indices that follows the
+// window.  When the window moves a lane swaps, per register, the index that left the ring
+// for the one that entered, through a backing array; because an index is only ever touched
+// by its own (lane, register), no synchronisation is needed.
 template <int K>
 struct PedLane
 {
     int cb;
     bool have;
     PedWindow w;
-    double own[K];   // this lane's slots of the current window
+    int idx[K];      // storage index currently held in own[k] (-1: none)
+    int slot[K];     // K3a row slot of idx[k] in the current window (-1: outside the window)
+    double own[K];   // running spectrum at idx[k]
     double ks, ke;   // k[s], k[e] of the current window (same value in every lane)
     double binsum;   // pedestal accumulated for the current cb (same value in every lane)
 };
@@ -710,46 +719,66 @@ LBL_HD void ped_lane_init(PedLane<K>& st)
     st.binsum = 0.;
     st.ks = st.ke = 0.;
 #pragma unroll
-    for (int k = 0; k < K; ++k) st.own[k] = 0.;
-}
-
-// Phase 1 of a window move: write the lane's slots back (and the finished bin's pedestal).
-template <int K>
-LBL_HD void ped_lane_flush(PedLane<K>& st, const GridSpec& g, int lane, double* nodes, double* bins)
-{
-    if (!st.have)
-    {
-        return;
-    }
-#pragma unroll
     for (int k = 0; k < K; ++k)
     {
-        const int idx = ped_slot_index(st.w, g, lane + 32 * k);
-        if (idx >= 0) nodes[idx] = st.own[k];
+        st.own[k] = 0.;
+        st.idx[k] = -1;
+        st.slot[k] = -1;
     }
-    if (lane == 0)
+}
+
+// Storage indices of the window's two deciding points k[s], k[e].
+LBL_HD int ped_s_index(const PedWindow& w)
+{
+    return w.s_node;
+}
+LBL_HD int ped_e_index(const PedWindow& w, const GridSpec& g)
+{
+    return w.tail ? g.ncell : w.e_node;
+}
+
+// Window move, lane-local part: re-map the ring onto the new window, swapping values with
+// the backing array where the held index changes.
+template <int K>
+LBL_HD void ped_lane_move(PedLane<K>& st, const GridSpec& g, int lane, int cb, const PedWindow& w,
+                          double* backing, double* bins)
+{
+    if (st.have && lane == 0)
     {
         bins[st.cb + g.cut_off + 1] += st.binsum;
     }
-}
-
-// Phase 2 (after a barrier): load the slots of the new window.
-template <int K>
-LBL_HD void ped_lane_reload(PedLane<K>& st, const GridSpec& g, int lane, int cb, const PedWindow& w,
-                            const double* nodes)
-{
     st.cb = cb;
     st.have = true;
     st.w = w;
     st.binsum = 0.;
+    const int lo = ped_s_index(w);
+    const int hi = ped_e_index(w, g);
 #pragma unroll
     for (int k = 0; k < K; ++k)
     {
-        const int idx = ped_slot_index(w, g, lane + 32 * k);
-        st.own[k] = (idx >= 0) ? nodes[idx] : 0.;
+        // the unique index in [lo, lo + 32K) congruent to lane + 32k
+        const int c = lo + ((lane + 32 * k - lo) & (32 * K - 1));
+        if (c != st.idx[k])
+        {
+            if (st.idx[k] >= 0 && st.idx[k] <= g.ncell) backing[st.idx[k]] = st.own[k];
+            st.own[k] = (c <= g.ncell) ? backing[c] : 0.;
+            st.idx[k] = c;
+        }
+        st.slot[k] = (c > hi) ? -1 : ((c == g.ncell && w.tail) ? 2 * g.cut_off + 2 : c - w.base);
     }
-    st.ks = nodes[ped_slot_index(w, g, w.s_slot)];
-    st.ke = nodes[ped_slot_index(w, g, w.e_slot)];
+}
+
+// The value this lane holds for storage index c (0 if it does not hold it).
+template <int K>
+LBL_HD double ped_lane_value(const PedLane<K>& st, int c)
+{
+    double v = 0.;
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+    {
+        if (st.idx[k] == c) v = st.own[k];
+    }
+    return v;
 }
 
 // One line: k[s] += f[s]; k[e] += f[e]; pedestal = min(k[s], k[e]); both -= pedestal
@@ -768,14 +797,24 @@ LBL_HD double ped_line_value(double ks_prev, double ke_prev, double fs, double f
 // Node update of one run: own += (sum of the run's terms, = K3a's prefix in the run's last
 // row) - (sum of the run's pedestals).
 template <int K>
-LBL_HD void ped_lane_slots(PedLane<K>& st, int lane, const double* last_row, double pedsum)
+LBL_HD void ped_lane_slots(PedLane<K>& st, const double* last_row, double pedsum)
 {
 #pragma unroll
     for (int k = 0; k < K; ++k)
     {
-        st.own[k] += last_row[lane + 32 * k] - pedsum;
+        if (st.slot[k] >= 0) st.own[k] += last_row[st.slot[k]] - pedsum;
     }
     st.binsum += pedsum;
+}
+
+// End of the layer: the last bin's pedestal.
+template <int K>
+LBL_HD void ped_lane_finish(PedLane<K>& st, const GridSpec& g, int lane, double* bins)
+{
+    if (st.have && lane == 0)
+    {
+        bins[st.cb + g.cut_off + 1] += st.binsum;
+    }
 }
 
 // Generic (slow) form of the whole recurrence for one layer, used when the window is wider

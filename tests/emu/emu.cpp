@@ -93,8 +93,11 @@ static void run_chain(const PedArgs& pa, int layer, double* nodes)
             {
                 const PedWindow w = ped_window(cb, g);
                 if (w.skip) { l += run; continue; }
-                for (int lane = 0; lane < 32; ++lane) ped_lane_flush(lanes[lane], g, lane, nodes, bins);
-                for (int lane = 0; lane < 32; ++lane) ped_lane_reload(lanes[lane], g, lane, cb, w, nodes);
+                for (int lane = 0; lane < 32; ++lane) ped_lane_move(lanes[lane], g, lane, cb, w, nodes, bins);
+                const int cs = ped_s_index(w), ce = ped_e_index(w, g);
+                const double ks0 = ped_lane_value(lanes[cs & 31], cs);
+                const double ke0 = ped_lane_value(lanes[ce & 31], ce);
+                for (int lane = 0; lane < 32; ++lane) { lanes[lane].ks = ks0; lanes[lane].ke = ke0; }
             }
             const double* row0 = rows.data() + (size_t)l * wpad;
             const int spare = 2 * g.cut_off + 3;
@@ -126,12 +129,12 @@ static void run_chain(const PedArgs& pa, int layer, double* nodes)
             {
                 lanes[lane].ks = ks;
                 lanes[lane].ke = ke;
-                ped_lane_slots(lanes[lane], lane, row0 + (size_t)(run - 1) * wpad, pedsum);
+                ped_lane_slots(lanes[lane], row0 + (size_t)(run - 1) * wpad, pedsum);
             }
             l += run;
         }
     }
-    for (int lane = 0; lane < 32; ++lane) ped_lane_flush(lanes[lane], g, lane, nodes, bins);
+    for (int lane = 0; lane < 32; ++lane) ped_lane_finish(lanes[lane], g, lane, bins);
 }
 
 extern "C" int emu_absorption(int n_layers, const double* pressure, const double* temperature,
@@ -269,7 +272,7 @@ extern "C" int emu_absorption(int n_layers, const double* pressure, const double
             {
                 case 1: run_chain<1>(pa, l, nodes.data()); break;
                 case 2: run_chain<2>(pa, l, nodes.data()); break;
-                case 3: run_chain<3>(pa, l, nodes.data()); break;
+                case 3:
                 case 4: run_chain<4>(pa, l, nodes.data()); break;
                 default: pedestal_layer(pa, l, 0, 1, nodes.data(), NoSync()); break;
             }
