@@ -285,11 +285,23 @@ int pick_points_per_thread(int n_per_v)
     return 1;
 }
 
+// Threads of a warp that share a layer: as many as keep the warp within about two
+// integer-wavenumber cells (a wider warp wastes work on window edges), but no more layers per
+// warp than there are layers.
+int pick_threads_per_layer(int n_per_v, int P, int n_layers)
+{
+    int tpw = 32;
+    while (tpw > 1 && tpw * P > 2 * n_per_v) tpw >>= 1;
+    while (tpw < 32 && (32 / tpw) > n_layers) tpw <<= 1;
+    return tpw;
+}
+
 template <int P>
 void launch_sum(const SumArgs& a, int n_layers, bool fp32, cudaStream_t s)
 {
-    const int threads = (a.grid.n + P - 1) / P;
-    dim3 grid((threads + kSumBlock - 1) / kSumBlock, n_layers);
+    const int tiles = (a.grid.n + a.tpw * P - 1) / (a.tpw * P);   // one warp each
+    const int lp = 32 / a.tpw;
+    dim3 grid((tiles + kSumBlock / 32 - 1) / (kSumBlock / 32), (n_layers + lp - 1) / lp);
     if (fp32)
     {
         sum32_kernel<P><<<grid, kSumBlock, 0, s>>>(a);
@@ -894,6 +906,7 @@ int lbl_gas_submit(lbl_gas* g, int n_layers, const double* pressure, const doubl
         sa.grid = grid;
         sa.out = g->out[slot].as<double>();
         sa.n_layers = nl;
+        sa.tpw = pick_threads_per_layer(n_per_v, P, nl);
         LBL_CUDA(cudaEventRecord(ev.k2_begin, sc));
         launch_sum_dispatch(P, sa, nl, fp32, sc);
         LBL_CUDA(cudaEventRecord(ev.k2_end, sc));

@@ -60,12 +60,13 @@ far32_kernel(Records rec, int n_lines)
     }
 }
 
-// K2.  grid = (ceil(n/(P*128)), layers), block = 128 threads = 4 independent warps.
+// K2.  block = 128 threads = 4 independent warps; warp w of the grid's x dimension covers
+// tpw*P points (tile w) of the 32/tpw layers of layer group blockIdx.y.
 template <int P>
 __global__ void __launch_bounds__(kSumBlock)
 sum_kernel(const SumArgs a)
 {
-    sum_thread<P>(a, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x);
+    sum_thread<P>(a, blockIdx.y, (blockIdx.x * blockDim.x + threadIdx.x) >> 5, threadIdx.x & 31);
 }
 
 // K2, FP32 mode (opt-in).
@@ -73,7 +74,7 @@ template <int P>
 __global__ void __launch_bounds__(kSumBlock)
 sum32_kernel(const SumArgs a)
 {
-    sum32_thread<P>(a, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x);
+    sum32_thread<P>(a, blockIdx.y, (blockIdx.x * blockDim.x + threadIdx.x) >> 5, threadIdx.x & 31);
 }
 
 // K2b.  One warp per tile of T points x 32/T layers; grid = (ceil(tiles/4), ceil(layers/(32/T))).

@@ -176,6 +176,8 @@ struct SumArgs
     GridSpec grid;
     double* out;  // [layer][n]
     int n_layers;
+    int tpw;      // K2: threads of one warp that share a layer (power of two); a warp covers
+                  // tpw*P consecutive points of 32/tpw consecutive layers
 };
 
 template <int P>
@@ -235,29 +237,53 @@ LBL_HD void masked_range(const FarAB* __restrict__ ab, const double* __restrict_
     }
 }
 
+// Which layer and which points a lane of K2 owns.  On fine grids a warp is 32 threads of one
+// layer (tpw = 32).  On coarse grids (few points per cell) that warp would span many cells
+// and most of each line window would be edge; there the warp is folded: tpw threads along
+// the points, 32/tpw consecutive layers.
+struct SumLane
+{
+    int layer;
+    int i_first;
+    int group_first, group_last;  // points of this lane's layer that the warp covers
+    bool valid;                   // owns real points (stores its result)
+    bool any;                     // false: the whole warp is past the end of the grid
+};
+
 template <int P>
-LBL_HD void sum_thread(const SumArgs& a, int layer, int tid)
+LBL_HD SumLane sum_lane(const SumArgs& a, int layer_group, int tile, int lane)
 {
     const GridSpec& g = a.grid;
-    const int warp_first = (tid & ~31) * P;
-    if (warp_first >= g.n)
+    SumLane s;
+    const int lp = 32 / a.tpw;
+    s.layer = layer_group * lp + lane / a.tpw;
+    const bool layer_ok = s.layer < a.n_layers;
+    if (!layer_ok) s.layer = a.n_layers - 1;
+    s.group_first = tile * a.tpw * P;
+    s.any = s.group_first < g.n;
+    s.group_last = s.group_first + a.tpw * P - 1;
+    if (s.group_last > g.n - 1) s.group_last = g.n - 1;
+    s.i_first = s.group_first + (lane % a.tpw) * P;
+    s.valid = layer_ok && s.i_first < g.n;
+    if (s.i_first >= g.n) s.i_first = g.n - P;  // idle lanes shadow a real thread, store nothing
+    return s;
+}
+
+template <int P>
+LBL_HD void sum_thread(const SumArgs& a, int layer_group, int tile, int lane)
+{
+    const GridSpec& g = a.grid;
+    const SumLane sl = sum_lane<P>(a, layer_group, tile, lane);
+    if (!sl.any)
     {
         return;
     }
-    int warp_last = warp_first + 32 * P - 1;
-    if (warp_last > g.n - 1)
-    {
-        warp_last = g.n - 1;
-    }
+    const int layer = sl.layer;
+    const int i_first = sl.i_first;
+    const bool valid = sl.valid;
     const LayerIn ly = a.layers[layer];
     const Segments seg = find_segments(a.lines.nu, a.lines.n, g.v0, g.n_per_v, g.dv, g.cut_off,
-                                       warp_first, warp_last, ly.slack, ly.kappa);
-    int i_first = tid * P;
-    const bool valid = i_first < g.n;
-    if (!valid)
-    {
-        i_first = g.n - P;  // idle lanes of the last warp shadow a real thread, store nothing
-    }
+                                       sl.group_first, sl.group_last, ly.slack, ly.kappa);
     const int cell = i_first / g.n_per_v;
 
     double v[P], acc[P];
@@ -376,28 +402,20 @@ LBL_HD void masked_range32(const Far32* __restrict__ f32, const LineChk* __restr
 }
 
 template <int P>
-LBL_HD void sum32_thread(const SumArgs& a, int layer, int tid)
+LBL_HD void sum32_thread(const SumArgs& a, int layer_group, int tile, int lane)
 {
     const GridSpec& g = a.grid;
-    const int warp_first = (tid & ~31) * P;
-    if (warp_first >= g.n)
+    const SumLane sl = sum_lane<P>(a, layer_group, tile, lane);
+    if (!sl.any)
     {
         return;
     }
-    int warp_last = warp_first + 32 * P - 1;
-    if (warp_last > g.n - 1)
-    {
-        warp_last = g.n - 1;
-    }
+    const int layer = sl.layer;
+    const int i_first = sl.i_first;
+    const bool valid = sl.valid;
     const LayerIn ly = a.layers[layer];
     const Segments seg = find_segments(a.lines.nu, a.lines.n, g.v0, g.n_per_v, g.dv, g.cut_off,
-                                       warp_first, warp_last, ly.slack, ly.kappa);
-    int i_first = tid * P;
-    const bool valid = i_first < g.n;
-    if (!valid)
-    {
-        i_first = g.n - P;
-    }
+                                       sl.group_first, sl.group_last, ly.slack, ly.kappa);
     const int cell = i_first / g.n_per_v;
     const float cellf = (float)cell;
     const double cell_origin = (double)g.v0 + (double)cell;

@@ -17,19 +17,22 @@ using namespace lbl;
 template <int P>
 static void run_sum(const SumArgs& a, int n_layers, bool fp32)
 {
-    const int threads = (a.grid.n + P - 1) / P;
-    const int padded = (threads + 127) / 128 * 128;
-    for (int layer = 0; layer < n_layers; ++layer)
+    const int tiles = (a.grid.n + a.tpw * P - 1) / (a.tpw * P) + 3;   // + idle warps of the last block
+    const int lp = 32 / a.tpw;
+    for (int group = 0; group < (n_layers + lp - 1) / lp; ++group)
     {
-        for (int tid = 0; tid < padded; ++tid)
+        for (int tile = 0; tile < tiles; ++tile)
         {
-            if (fp32)
+            for (int lane = 0; lane < 32; ++lane)
             {
-                sum32_thread<P>(a, layer, tid);
-            }
-            else
-            {
-                sum_thread<P>(a, layer, tid);
+                if (fp32)
+                {
+                    sum32_thread<P>(a, group, tile, lane);
+                }
+                else
+                {
+                    sum_thread<P>(a, group, tile, lane);
+                }
             }
         }
     }
@@ -241,6 +244,13 @@ extern "C" int emu_absorption(int n_layers, const double* pressure, const double
     sa.grid = g;
     sa.out = k;
     sa.n_layers = n_layers;
+    {
+        // same rule as pick_threads_per_layer() in lbl_api.cu
+        int tpw = 32;
+        while (tpw > 1 && tpw * points_per_thread > 2 * n_per_v) tpw >>= 1;
+        while (tpw < 32 && (32 / tpw) > n_layers) tpw <<= 1;
+        sa.tpw = tpw;
+    }
     switch (points_per_thread)
     {
         case 10: run_sum<10>(sa, n_layers, fp32); break;
