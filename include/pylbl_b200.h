@@ -38,6 +38,8 @@ typedef struct lbl_gas lbl_gas;
 typedef struct lbl_stats
 {
     long long evals;        /* sum over layers and processed lines of (e-s+1), spectra.c:48-62 */
+    long long executed;     /* far-wing evaluations the summation kernel actually performed (the
+                               far-field interpolation makes this smaller than `evals`) */
     long long h2d_bytes;    /* bytes copied host->device by the call (layer states, first-use packing) */
     long long d2h_bytes;    /* bytes copied device->host by the call (spectra) */
     int n_lines;            /* transition rows of the molecule */

@@ -26,7 +26,8 @@ PRECISION_FP32 = 1
 class Stats(Structure):
     """struct lbl_stats (include/pylbl_b200.h)."""
     _fields_ = [
-        ("evals", c_longlong), ("h2d_bytes", c_longlong), ("d2h_bytes", c_longlong),
+        ("evals", c_longlong), ("executed", c_longlong), ("h2d_bytes", c_longlong),
+        ("d2h_bytes", c_longlong),
         ("n_lines", c_int), ("n_active", c_int), ("n_layers", c_int), ("n_points", c_int),
         ("points_per_thread", c_int), ("sum_launches", c_int), ("total_launches", c_int),
         ("scale_ms", c_float), ("sum_ms", c_float), ("fixup_ms", c_float),

@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "../../include/pylbl_b200.h"
+#include "lbl_cheb.h"
 #include "lbl_db.h"
 #include "lbl_kernels.cuh"
 
@@ -133,7 +134,9 @@ struct lbl_gas
 
     cudaStream_t s_compute = nullptr, s_side = nullptr, s_copy = nullptr;
     DevBuf rec_ab, rec_cc, rec_chk, rec_gen, layers_dev, evals_dev, pedbin, pedcorr, pednodes,
-        pedterms, rec_f32, amp_max;
+        pedterms, rec_f32, amp_max, cheb_nodes, cheb_weights, executed_dev;
+    int cheb_npv = 0;
+    unsigned long long* executed_host = nullptr;  // pinned
     DevBuf out[2];
     LayerIn* layers_host = nullptr;  // pinned
     size_t layers_host_cap = 0;
@@ -153,6 +156,7 @@ struct lbl_gas
     cudaEvent_t ev_out_ready[2] = {nullptr, nullptr}, ev_out_free[2] = {nullptr, nullptr};
     bool out_busy[2] = {false, false};
     bool pending = false;
+    bool farfield_last = false;
     lbl_stats stats{};
     // what is resident after the last call (for windows/scaled/device_result)
     GridSpec last_grid{};
@@ -368,6 +372,24 @@ cudaError_t launch_chain(const PedArgs& pa, double* terms, double* scratch, int 
     return cudaGetLastError();
 }
 
+// Interpolation tables of K2c for one grid resolution: Chebyshev nodes of the first kind on
+// the cell interval [0, (n_per_v-1)/n_per_v] and the Lagrange basis of those nodes at the
+// grid offsets r/n_per_v (barycentric form, evaluated in long double).
+int ensure_cheb_tables(lbl_gas* g, int n_per_v)
+{
+    if (g->cheb_npv == n_per_v) return 0;
+    std::vector<double> nodes, weights;
+    build_cheb_tables(kNodes, n_per_v, nodes, weights);
+    size_t bytes = 0;
+    if (upload(g->cheb_nodes, nodes.data(), sizeof(double) * kNodes, g->s_compute, bytes)) return 1;
+    if (upload(g->cheb_weights, weights.data(), sizeof(double) * weights.size(), g->s_compute, bytes))
+        return 1;
+    LBL_CUDA(cudaStreamSynchronize(g->s_compute));   // the host vectors go out of scope
+    g->open_h2d += bytes;
+    g->cheb_npv = n_per_v;
+    return 0;
+}
+
 int set_device(lbl_gas* g)
 {
     LBL_CUDA(cudaSetDevice(g->device));
@@ -580,13 +602,15 @@ int lbl_gas_close(lbl_gas* g)
     g->plan.own.release();
     for (DevBuf* b : {&g->tips_t, &g->tips_q, &g->rec_ab, &g->rec_cc, &g->rec_chk, &g->rec_gen,
                       &g->layers_dev, &g->evals_dev, &g->pedbin, &g->pedcorr, &g->pednodes,
-                      &g->pedterms, &g->rec_f32, &g->amp_max,
+                      &g->pedterms, &g->rec_f32, &g->amp_max, &g->cheb_nodes, &g->cheb_weights,
+                      &g->executed_dev,
                       &g->out[0], &g->out[1]})
     {
         b->release();
     }
     if (g->layers_host) cudaFreeHost(g->layers_host);
     if (g->evals_host) cudaFreeHost(g->evals_host);
+    if (g->executed_host) cudaFreeHost(g->executed_host);
     for (cudaEvent_t e : g->ev_pool) cudaEventDestroy(e);
     if (g->ev_call_begin) cudaEventDestroy(g->ev_call_begin);
     if (g->ev_call_end) cudaEventDestroy(g->ev_call_end);
@@ -660,7 +684,11 @@ int lbl_gas_submit(lbl_gas* g, int n_layers, const double* pressure, const doubl
     st.h2d_bytes += (long long)(g->open_h2d - h2d_before);
     const Plan& plan = g->plan;
     st.n_active = plan.n_active;
-    const int P = pick_points_per_thread(n_per_v);
+    // Fine grids use the cell-tiled kernel with the polynomial far field (K2c); coarse grids
+    // (a cell holds fewer points than the 32 interpolation nodes would cost) use K2.
+    bool farfield = !fp32 && n_per_v >= 64;
+    if (const char* env = getenv("PYLBL_B200_FARFIELD")) farfield = farfield && atoi(env) != 0;
+    const int P = farfield ? kCellP : pick_points_per_thread(n_per_v);
     st.points_per_thread = P;
 
     // The reference indexes the TIPS table without a bounds check
@@ -779,6 +807,18 @@ int lbl_gas_submit(lbl_gas* g, int n_layers, const double* pressure, const doubl
                                cudaHostAllocDefault));
         g->layers_host_cap = n_layers;
     }
+    if (farfield)
+    {
+        const size_t h2d0 = g->open_h2d;
+        if (ensure_cheb_tables(g, n_per_v)) return 1;
+        st.h2d_bytes += (long long)(g->open_h2d - h2d0);
+        LBL_CUDA(g->executed_dev.reserve(sizeof(unsigned long long)));
+        if (!g->executed_host)
+        {
+            LBL_CUDA(cudaHostAlloc((void**)&g->executed_host, sizeof(unsigned long long),
+                                   cudaHostAllocDefault));
+        }
+    }
     if (g->evals_host_cap < (size_t)n_layers)
     {
         if (g->evals_host) cudaFreeHost(g->evals_host);
@@ -811,6 +851,11 @@ int lbl_gas_submit(lbl_gas* g, int n_layers, const double* pressure, const doubl
     LBL_CUDA(cudaMemcpyAsync(g->layers_dev.p, g->layers_host, sizeof(LayerIn) * n_layers,
                              cudaMemcpyHostToDevice, sc));
     LBL_CUDA(cudaMemsetAsync(g->evals_dev.p, 0, sizeof(unsigned long long) * n_layers, sc));
+    if (farfield)
+    {
+        LBL_CUDA(cudaMemsetAsync(g->executed_dev.p, 0, sizeof(unsigned long long), sc));
+    }
+    g->farfield_last = farfield;
     if (fp32)
     {
         LBL_CUDA(cudaMemsetAsync(g->amp_max.p, 0, sizeof(unsigned long long) * n_layers, sc));
@@ -908,7 +953,20 @@ int lbl_gas_submit(lbl_gas* g, int n_layers, const double* pressure, const doubl
         sa.n_layers = nl;
         sa.tpw = pick_threads_per_layer(n_per_v, P, nl);
         LBL_CUDA(cudaEventRecord(ev.k2_begin, sc));
-        launch_sum_dispatch(P, sa, nl, fp32, sc);
+        if (farfield)
+        {
+            CellArgs ca;
+            ca.sum = sa;
+            ca.node_offset = g->cheb_nodes.as<double>();
+            ca.weights = g->cheb_weights.as<double>();
+            ca.executed = g->executed_dev.as<unsigned long long>();
+            dim3 gridc((grid.ncell + kSumBlock / 32 - 1) / (kSumBlock / 32), nl);
+            sum_cell_kernel<<<gridc, kSumBlock, 0, sc>>>(ca);
+        }
+        else
+        {
+            launch_sum_dispatch(P, sa, nl, fp32, sc);
+        }
         LBL_CUDA(cudaEventRecord(ev.k2_end, sc));
         launch_fixup_dispatch(pick_fixup_tile(n_per_v), sa, nl, sc);
         LBL_CUDA(cudaEventRecord(ev.k2b_end, sc));
@@ -943,6 +1001,11 @@ int lbl_gas_submit(lbl_gas* g, int n_layers, const double* pressure, const doubl
     }
     LBL_CUDA(cudaMemcpyAsync(g->evals_host, g->evals_dev.p, sizeof(unsigned long long) * n_layers,
                              cudaMemcpyDeviceToHost, sc));
+    if (farfield)
+    {
+        LBL_CUDA(cudaMemcpyAsync(g->executed_host, g->executed_dev.p, sizeof(unsigned long long),
+                                 cudaMemcpyDeviceToHost, sc));
+    }
     if (k_host)
     {
         // The call ends when the last copy has landed.
@@ -965,6 +1028,7 @@ int lbl_gas_wait(lbl_gas* g)
     g->out_busy[0] = g->out_busy[1] = false;
     lbl_stats& st = g->stats;
     for (int l = 0; l < st.n_layers; ++l) st.evals += (long long)g->evals_host[l];
+    st.executed = g->farfield_last ? (long long)*g->executed_host : st.evals;
     float ms = 0.f;
     for (const lbl_gas::ChunkEvents& ev : g->chunk_events)
     {

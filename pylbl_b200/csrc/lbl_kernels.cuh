@@ -69,6 +69,52 @@ sum_kernel(const SumArgs a)
     sum_thread<P>(a, blockIdx.y, (blockIdx.x * blockDim.x + threadIdx.x) >> 5, threadIdx.x & 31);
 }
 
+// K2c.  Cell-tiled summation with the Chebyshev far field (see lbl_threads.cuh).
+// block = 128 threads = 4 independent warps; warp = one cell of layer blockIdx.y.
+__global__ void __launch_bounds__(kSumBlock)
+sum_cell_kernel(const CellArgs a)
+{
+    __shared__ double fields[kSumBlock / 32][kNodes];
+    const GridSpec& g = a.sum.grid;
+    const int cell = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (cell >= g.ncell)
+    {
+        return;
+    }
+    const int lane = threadIdx.x & 31;
+    const int layer = blockIdx.y;
+    const LayerIn ly = a.sum.layers[layer];
+    // six binary searches, one per lane, shared by shuffle
+    int mine = 0;
+    if (lane < 6)
+    {
+        mine = lower_bound(a.sum.lines.nu, a.sum.lines.n, cell_search_key(g, ly, cell, lane));
+    }
+    int found[6];
+#pragma unroll
+    for (int which = 0; which < 6; ++which)
+    {
+        found[which] = __shfl_sync(0xffffffffu, mine, which);
+    }
+    const CellSegments seg = cell_segments_from(found);
+    double* field = fields[threadIdx.x >> 5];
+    field[lane] = cell_far_lane(a, layer, cell, lane, seg);
+    const int chunks = (g.n_per_v + 32 * kCellP - 1) / (32 * kCellP);
+    for (int chunk = 0; chunk < chunks; ++chunk)
+    {
+        cell_direct_lane(a, layer, cell, chunk, lane, seg);
+    }
+    __syncwarp();   // the cell's direct sums are stored, the node sums are in shared memory
+    cell_field_lane(a, layer, cell, lane, 32, field);
+    if (a.executed && lane == 0)
+    {
+        // statistics only: evaluations this warp performed (nodes + direct slots)
+        const unsigned long long far = (unsigned long long)((seg.j[2] - seg.j[0]) + (seg.j[5] - seg.j[3]));
+        const unsigned long long direct = (unsigned long long)(seg.j[3] - seg.j[2]);
+        atomicAdd(a.executed, far * kNodes + direct * (unsigned long long)(chunks * 32 * kCellP));
+    }
+}
+
 // K2, FP32 mode (opt-in).
 template <int P>
 __global__ void __launch_bounds__(kSumBlock)

@@ -452,6 +452,218 @@ LBL_HD void sum32_thread(const SumArgs& a, int layer_group, int tile, int lane)
 }
 
 // ---------------------------------------------------------------------------------------
+// K2c: cell-tiled summation with a polynomial far field (fine grids, n_per_v >= 64).
+//
+// A warp owns ONE integer-wavenumber cell of one layer: all its points (r > 0) share the
+// same line window [cell-cut, cell+cut], so there are no window edges inside the tile.
+// Lines are split by distance from the cell:
+//   direct : centre within `reach` (>= 0.4 cm-1) of the cell.  Evaluated at every grid point
+//            exactly as in K2 (P consecutive points per thread, near-zone masks for K2b).
+//   far    : the rest of the window, ~96 % of the lines.  Their sum is smooth on the cell:
+//            each line's poles sit >= 1.8 half-widths a from the cell centre, i.e. on or
+//            outside the Bernstein ellipse rho = 1.8 + sqrt(1.8^2 - 1) = 3.3 of the cell, so
+//            the degree-31 Chebyshev interpolant of the sum through kNodes = 32 nodes is exact
+//            to ~rho^-32 ~ 1e-16 of the line's size on the cell.
+//            Lane k evaluates every far line at node k only -- 32 evaluations per (cell,
+//            line) instead of n_per_v -- and the cell's points get  sum_k W[r][k] * F[k].
+// The interpolation matrix W (Lagrange basis of the nodes at the grid offsets r/n_per_v) is
+// the same for every cell and layer; it is built once per n_per_v on the host.
+// ---------------------------------------------------------------------------------------
+constexpr int kNodes = 32;
+constexpr int kCellP = 4;       // points per thread in the direct part
+constexpr double kFarMin = 0.4; // cm-1 beyond the cell edges where the far field starts
+
+struct CellArgs
+{
+    SumArgs sum;
+    const double* node_offset;   // [kNodes] node position relative to the cell origin v0+cell
+    const double* weights;       // [kNodes][n_per_v] interpolation matrix W (node-major)
+    unsigned long long* executed;  // statistics: evaluations actually performed (or nullptr)
+};
+
+struct CellSegments
+{
+    int j[6];   // [j0,j1) far+window test | [j1,j2) far | [j2,j3) direct | [j3,j4) far | [j4,j5) far+test
+};
+
+// The six search keys of a cell's line ranges (one binary search each; the kernel gives one
+// key to each of six lanes): window start/end with and without the shift slack, and the
+// direct range.
+LBL_HD double cell_search_key(const GridSpec& g, const LayerIn& ly, int cell, int which)
+{
+    const double lo = (double)g.v0 + (double)cell;            // first point of the cell
+    const double hi = lo + (double)(g.n_per_v - 1) * g.dv;    // last point of the cell
+    const double near = (ly.kappa < 0.5)
+        ? (ly.kappa * fabs(hi) / (1.0 - ly.kappa)) * (1.0 + 0x1p-20) + 3.0 * g.dv
+        : 1.0e300;
+    const double reach = (near > kFarMin ? near : kFarMin) + ly.slack;
+    switch (which)
+    {
+        case 0: return lo - (double)g.cut_off - ly.slack;        // first line that can be in the window
+        case 1: return lo - (double)g.cut_off + ly.slack;        // first line certainly in it
+        case 2: return lo - reach;                               // direct range
+        case 3: return hi + reach;
+        case 4: return lo + (double)(g.cut_off + 1) - ly.slack;  // end of the certain part
+        default: return lo + (double)(g.cut_off + 1) + ly.slack; // end of the window
+    }
+}
+
+LBL_HD CellSegments cell_segments_from(const int (&found)[6])
+{
+    CellSegments s;
+    s.j[0] = found[0];
+    s.j[5] = found[5];
+    int core_lo = found[1];
+    int core_hi = found[4];
+    if (core_lo < s.j[0]) core_lo = s.j[0];
+    if (core_hi > s.j[5]) core_hi = s.j[5];
+    if (core_hi < core_lo) core_hi = core_lo;
+    int d_lo = found[2];
+    int d_hi = found[3];
+    // The direct range may reach into (or beyond) the window edges when cut_off is tiny.
+    if (d_lo < s.j[0]) d_lo = s.j[0];
+    if (d_hi > s.j[5]) d_hi = s.j[5];
+    if (d_hi < d_lo) d_hi = d_lo;
+    s.j[2] = d_lo;
+    s.j[3] = d_hi;
+    s.j[1] = core_lo < d_lo ? core_lo : d_lo;
+    s.j[4] = core_hi > d_hi ? core_hi : d_hi;
+    if (s.j[1] < s.j[0]) s.j[1] = s.j[0];
+    if (s.j[4] > s.j[5]) s.j[4] = s.j[5];
+    return s;
+}
+
+LBL_HD CellSegments cell_segments(const LinesView& lines, const GridSpec& g, const LayerIn& ly,
+                                  int cell)
+{
+    int found[6];
+    for (int which = 0; which < 6; ++which)
+    {
+        found[which] = lower_bound(lines.nu, lines.n, cell_search_key(g, ly, cell, which));
+    }
+    return cell_segments_from(found);
+}
+
+// Far lines of [jb, je) at ONE point v (this lane's node), no tests: pairs share a reciprocal,
+// four independent accumulators keep the FP64 pipe busy with a single point per lane.
+LBL_HD double node_plain(const FarAB* __restrict__ ab, const double* __restrict__ cc, int jb, int je,
+                         double v)
+{
+    double acc[4] = {0., 0., 0., 0.};
+    const double vv[1] = {v};
+    int j = jb;
+    for (; j + 7 < je; j += 8)
+    {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+        {
+            const double2 l1 = LBL_LDG(reinterpret_cast<const double2*>(ab + j + 2 * u));
+            const double2 l2 = LBL_LDG(reinterpret_cast<const double2*>(ab + j + 2 * u + 1));
+            const double c1 = LBL_LDG(cc + j + 2 * u);
+            const double c2 = LBL_LDG(cc + j + 2 * u + 1);
+            double one[1] = {acc[u]};
+            far_terms_pair<1>(vv, l1.x, l1.y, c1, l2.x, l2.y, c2, one);
+            acc[u] = one[0];
+        }
+    }
+    for (; j < je; ++j)
+    {
+        const double2 l = LBL_LDG(reinterpret_cast<const double2*>(ab + j));
+        acc[0] = far_term(v, l.x, l.y, LBL_LDG(cc + j), acc[0]);
+    }
+    return (acc[0] + acc[1]) + (acc[2] + acc[3]);
+}
+
+// Far lines next to a window edge: the window test decides (cb within [cell-cut, cell+cut]).
+LBL_HD double node_tested(const FarAB* __restrict__ ab, const double* __restrict__ cc,
+                          const LineChk* __restrict__ chk, int jb, int je, int cell, int cut_off,
+                          double v)
+{
+    double acc = 0.;
+    for (int j = jb; j < je; ++j)
+    {
+        const int cb = LBL_LDG(reinterpret_cast<const int4*>(chk + j)).x;
+        if (cb < cell - cut_off || cb > cell + cut_off)
+        {
+            continue;
+        }
+        const double2 l = LBL_LDG(reinterpret_cast<const double2*>(ab + j));
+        acc = far_term(v, l.x, l.y, LBL_LDG(cc + j), acc);
+    }
+    return acc;
+}
+
+// Phase 1, lane = node: sum of the far lines at this lane's node.
+LBL_HD double cell_far_lane(const CellArgs& a, int layer, int cell, int lane, const CellSegments& seg)
+{
+    const GridSpec& g = a.sum.grid;
+    const size_t off = (size_t)layer * a.sum.lines.n;
+    const FarAB* ab = a.sum.rec.ab + off;
+    const double* cc = a.sum.rec.cc + off;
+    const LineChk* chk = a.sum.rec.chk + off;
+    const double v = ((double)g.v0 + (double)cell) + a.node_offset[lane];
+    double f = node_tested(ab, cc, chk, seg.j[0], seg.j[1], cell, g.cut_off, v);
+    f += node_plain(ab, cc, seg.j[1], seg.j[2], v);
+    f += node_plain(ab, cc, seg.j[3], seg.j[4], v);
+    f += node_tested(ab, cc, chk, seg.j[4], seg.j[5], cell, g.cut_off, v);
+    return f;
+}
+
+// Phase 2, lane = kCellP consecutive points of chunk `chunk` of the cell: the direct lines.
+LBL_HD void cell_direct_lane(const CellArgs& a, int layer, int cell, int chunk, int lane,
+                             const CellSegments& seg)
+{
+    const GridSpec& g = a.sum.grid;
+    constexpr int P = kCellP;
+    int r_first = (chunk * 32 + lane) * P;          // offset inside the cell
+    const bool valid = r_first < g.n_per_v;
+    if (!valid) r_first = 0;
+    int count = g.n_per_v - r_first;                // points this thread really owns
+    if (count > P) count = P;
+    const int i_first = cell * g.n_per_v + r_first;
+    double v[P], acc[P];
+#pragma unroll
+    for (int p = 0; p < P; ++p)
+    {
+        // a thread at the end of the cell shadows the cell's last point with its spare slots
+        const int r = (p < count) ? r_first + p : g.n_per_v - 1;
+        v[p] = grid_point(g.v0, g.dv, cell * g.n_per_v + r);
+        acc[p] = 0.;
+    }
+    const size_t off = (size_t)layer * a.sum.lines.n;
+    masked_range<P>(a.sum.rec.ab + off, a.sum.rec.cc + off, a.sum.rec.chk + off, seg.j[2], seg.j[3],
+                    i_first, cell, g.cut_off, v, acc);
+    if (valid)
+    {
+        double* o = a.sum.out + (size_t)layer * g.n + i_first;
+#pragma unroll
+        for (int p = 0; p < P; ++p)
+        {
+            if (p < count) o[p] = acc[p];
+        }
+    }
+}
+
+// Phase 3, lane = points lane, lane+32, ... of the cell: add the interpolated far field
+// sum_k W[k][r] * field[k].  W is stored node-major so that a warp reads consecutive r.
+LBL_HD void cell_field_lane(const CellArgs& a, int layer, int cell, int lane, int nlanes,
+                            const double* field)
+{
+    const GridSpec& g = a.sum.grid;
+    double* o = a.sum.out + (size_t)layer * g.n + (size_t)cell * g.n_per_v;
+    for (int r = lane; r < g.n_per_v; r += nlanes)
+    {
+        double far = 0.;
+#pragma unroll 8
+        for (int k = 0; k < kNodes; ++k)
+        {
+            far = fma_(LBL_LDG(a.weights + (size_t)k * g.n_per_v + r), field[k], far);
+        }
+        o[r] += far;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // K2b: near-zone and node terms, one grid point per lane (dense in the near zone, where K2's
 // P-points-per-thread layout would leave most lanes idle).  A warp covers T consecutive
 // points of 32/T consecutive layers; T shrinks with the grid resolution so that a tile stays

@@ -10,6 +10,7 @@
 #include <cstring>
 #include <vector>
 
+#include "../../pylbl_b200/csrc/lbl_cheb.h"
 #include "../../pylbl_b200/csrc/lbl_threads.cuh"
 
 using namespace lbl;
@@ -251,7 +252,33 @@ extern "C" int emu_absorption(int n_layers, const double* pressure, const double
         while (tpw < 32 && (32 / tpw) > n_layers) tpw <<= 1;
         sa.tpw = tpw;
     }
-    switch (points_per_thread)
+    if (points_per_thread == 0)
+    {
+        // K2c: cell-tiled summation with the Chebyshev far field, one emulated warp per cell
+        std::vector<double> nodes, weights, field(kNodes);
+        build_cheb_tables(kNodes, n_per_v, nodes, weights);
+        CellArgs ca;
+        ca.sum = sa;
+        ca.node_offset = nodes.data();
+        ca.weights = weights.data();
+        ca.executed = nullptr;
+        const int chunks = (n_per_v + 32 * kCellP - 1) / (32 * kCellP);
+        for (int layer = 0; layer < n_layers; ++layer)
+        {
+            for (int cell = 0; cell < g.ncell; ++cell)
+            {
+                const CellSegments seg = cell_segments(ln, g, layers[layer], cell);
+                for (int lane = 0; lane < 32; ++lane)
+                    field[lane] = cell_far_lane(ca, layer, cell, lane, seg);
+                for (int chunk = 0; chunk < chunks; ++chunk)
+                    for (int lane = 0; lane < 32; ++lane)
+                        cell_direct_lane(ca, layer, cell, chunk, lane, seg);
+                for (int lane = 0; lane < 32; ++lane)
+                    cell_field_lane(ca, layer, cell, lane, 32, field.data());
+            }
+        }
+    }
+    else switch (points_per_thread)
     {
         case 10: run_sum<10>(sa, n_layers, fp32); break;
         case 8: run_sum<8>(sa, n_layers, fp32); break;

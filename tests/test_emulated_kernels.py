@@ -46,7 +46,8 @@ def run(emu, gas, t, p, x, bounds, ped, cut=25, points=None, fp32=False):
     t, p, x = (np.ascontiguousarray(a, dtype=np.float64) for a in (t, p, x))
     k = np.zeros(t.size * n)
     if points is None:
-        points = [q for q in (5, 4, 8, 10, 2, 1) if npv % q == 0][0]
+        # the library's choice: cell-tiled far-field kernel (coded 0 here) on fine grids
+        points = 0 if (npv >= 64 and not fp32) else [q for q in (5, 4, 8, 10, 2, 1) if npv % q == 0][0]
     evals = c_longlong(0)
     rc = emu.emu_absorption(t.size, p, t, x, v0, vn, npv, k, d["nu"].size, d["nu"], d["sw"],
                             d["gamma_air"], d["gamma_self"], d["n_air"], d["elower"],
@@ -58,7 +59,8 @@ def run(emu, gas, t, p, x, bounds, ped, cut=25, points=None, fp32=False):
 
 
 @pytest.mark.parametrize("bounds", [(1, 601, 10), (1, 301, 100), (1, 900, 1), (1, 500, 4),
-                                    (1, 400, 7), (1, 201, 8), (100, 161, 1000)])
+                                    (1, 400, 7), (1, 201, 8), (100, 161, 1000), (1, 121, 64),
+                                    (1, 81, 250), (1, 31, 2000)])
 @pytest.mark.parametrize("ped", [0, 1])
 def test_emulated_vs_oracle(emu, small_db, atmosphere, bounds, ped):
     for formula in ("H2O", "O3"):
@@ -164,3 +166,16 @@ def test_fp32_mode_within_stated_tolerance(emu, small_db, atmosphere, bounds, pe
                 assert relative_error(k[layer], k_ref) <= FP32_TOL
         assert evals == total
     assert worst > 1e-12   # it really is the FP32 path
+
+
+def test_far_field_kernel_against_direct_kernel(emu, small_db, atmosphere):
+    """The cell-tiled kernel's polynomial far field reproduces the direct summation far below
+    the parity tolerance (the interpolant of each far line is exact to ~1e-16 of the line)."""
+    gas = OracleGas(small_db, "CO2")
+    for bounds in ((1, 201, 100), (600, 640, 500)):
+        for ped in (0, 1):
+            fast, _ = run(emu, gas, atmosphere.t, atmosphere.p, atmosphere.vmr["CO2"], bounds, ped, points=0)
+            direct, _ = run(emu, gas, atmosphere.t, atmosphere.p, atmosphere.vmr["CO2"], bounds, ped, points=5)
+            for layer in range(4):
+                if np.any(direct[layer]):
+                    assert scaled_error(fast[layer], direct[layer], bounds[2]) <= 1e-11
