@@ -960,8 +960,18 @@ int lbl_gas_submit(lbl_gas* g, int n_layers, const double* pressure, const doubl
             ca.node_offset = g->cheb_nodes.as<double>();
             ca.weights = g->cheb_weights.as<double>();
             ca.executed = g->executed_dev.as<unsigned long long>();
-            dim3 gridc((grid.ncell + kSumBlock / 32 - 1) / (kSumBlock / 32), nl);
-            sum_cell_kernel<<<gridc, kSumBlock, 0, sc>>>(ca);
+            // cells per warp: more cells amortise the loads of the line operands over more
+            // node evaluations, fewer keep the (per-cell) direct range short
+            int cells_per_warp = (n_per_v <= 256) ? 2 : 1;
+            if (const char* env = getenv("PYLBL_B200_CELLS")) cells_per_warp = atoi(env);
+            const int groups = (grid.ncell + cells_per_warp - 1) / cells_per_warp;
+            dim3 gridc((groups + kSumBlock / 32 - 1) / (kSumBlock / 32), nl);
+            switch (cells_per_warp)
+            {
+                case 1: sum_cell_kernel<1><<<gridc, kSumBlock, 0, sc>>>(ca); break;
+                case 2: sum_cell_kernel<2><<<gridc, kSumBlock, 0, sc>>>(ca); break;
+                default: sum_cell_kernel<4><<<gridc, kSumBlock, 0, sc>>>(ca); break;
+            }
         }
         else
         {

@@ -70,13 +70,14 @@ sum_kernel(const SumArgs a)
 }
 
 // K2c.  Cell-tiled summation with the Chebyshev far field (see lbl_threads.cuh).
-// block = 128 threads = 4 independent warps; warp = one cell of layer blockIdx.y.
+// block = 128 threads = 4 independent warps; warp = G consecutive cells of layer blockIdx.y.
+template <int G>
 __global__ void __launch_bounds__(kSumBlock)
 sum_cell_kernel(const CellArgs a)
 {
-    __shared__ double fields[kSumBlock / 32][kNodes];
+    __shared__ double fields[kSumBlock / 32][G][kNodes];
     const GridSpec& g = a.sum.grid;
-    const int cell = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int cell = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * G;
     if (cell >= g.ncell)
     {
         return;
@@ -88,7 +89,7 @@ sum_cell_kernel(const CellArgs a)
     int mine = 0;
     if (lane < 6)
     {
-        mine = lower_bound(a.sum.lines.nu, a.sum.lines.n, cell_search_key(g, ly, cell, lane));
+        mine = lower_bound(a.sum.lines.nu, a.sum.lines.n, cell_search_key(g, ly, cell, G, lane));
     }
     int found[6];
 #pragma unroll
@@ -97,21 +98,33 @@ sum_cell_kernel(const CellArgs a)
         found[which] = __shfl_sync(0xffffffffu, mine, which);
     }
     const CellSegments seg = cell_segments_from(found);
-    double* field = fields[threadIdx.x >> 5];
-    field[lane] = cell_far_lane(a, layer, cell, lane, seg);
+    double f[G];
+    cell_far_lane<G>(a, layer, cell, lane, seg, f);
+    double (*field)[kNodes] = fields[threadIdx.x >> 5];
+#pragma unroll
+    for (int q = 0; q < G; ++q) field[q][lane] = f[q];
     const int chunks = (g.n_per_v + 32 * kCellP - 1) / (32 * kCellP);
-    for (int chunk = 0; chunk < chunks; ++chunk)
+    int cells = g.ncell - cell;
+    if (cells > G) cells = G;
+    for (int q = 0; q < cells; ++q)
     {
-        cell_direct_lane(a, layer, cell, chunk, lane, seg);
+        for (int chunk = 0; chunk < chunks; ++chunk)
+        {
+            cell_direct_lane(a, layer, cell + q, chunk, lane, seg);
+        }
     }
-    __syncwarp();   // the cell's direct sums are stored, the node sums are in shared memory
-    cell_field_lane(a, layer, cell, lane, 32, field);
+    __syncwarp();   // the direct sums are stored, the node sums are in shared memory
+    for (int q = 0; q < cells; ++q)
+    {
+        cell_field_lane(a, layer, cell + q, lane, 32, field[q]);
+    }
     if (a.executed && lane == 0)
     {
         // statistics only: evaluations this warp performed (nodes + direct slots)
         const unsigned long long far = (unsigned long long)((seg.j[2] - seg.j[0]) + (seg.j[5] - seg.j[3]));
         const unsigned long long direct = (unsigned long long)(seg.j[3] - seg.j[2]);
-        atomicAdd(a.executed, far * kNodes + direct * (unsigned long long)(chunks * 32 * kCellP));
+        atomicAdd(a.executed, far * (kNodes * G) +
+                              direct * (unsigned long long)(cells * chunks * 32 * kCellP));
     }
 }
 

@@ -454,9 +454,9 @@ LBL_HD void sum32_thread(const SumArgs& a, int layer_group, int tile, int lane)
 // ---------------------------------------------------------------------------------------
 // K2c: cell-tiled summation with a polynomial far field (fine grids, n_per_v >= 64).
 //
-// A warp owns ONE integer-wavenumber cell of one layer: all its points (r > 0) share the
-// same line window [cell-cut, cell+cut], so there are no window edges inside the tile.
-// Lines are split by distance from the cell:
+// A warp owns a group of G consecutive integer-wavenumber cells of one layer.  All points
+// (r > 0) of a cell share the line window [cell-cut, cell+cut], so there are no window
+// edges inside a cell.  Lines are split by distance from the group:
 //   direct : centre within `reach` (>= 0.4 cm-1) of the cell.  Evaluated at every grid point
 //            exactly as in K2 (P consecutive points per thread, near-zone masks for K2b).
 //   far    : the rest of the window, ~96 % of the lines.  Their sum is smooth on the cell:
@@ -464,8 +464,10 @@ LBL_HD void sum32_thread(const SumArgs& a, int layer_group, int tile, int lane)
 //            outside the Bernstein ellipse rho = 1.8 + sqrt(1.8^2 - 1) = 3.3 of the cell, so
 //            the degree-31 Chebyshev interpolant of the sum through kNodes = 32 nodes is exact
 //            to ~rho^-32 ~ 1e-16 of the line's size on the cell.
-//            Lane k evaluates every far line at node k only -- 32 evaluations per (cell,
-//            line) instead of n_per_v -- and the cell's points get  sum_k W[r][k] * F[k].
+//            Lane k evaluates every far line at node k of each cell only -- 32 evaluations
+//            per (cell, line) instead of n_per_v -- and the cell's points get
+//            sum_k W[r][k] * F[k].  (G cells per warp so that one load of a line's operands
+//            feeds G evaluations: with G = 1 the kernel is bound by load issue.)
 // The interpolation matrix W (Lagrange basis of the nodes at the grid offsets r/n_per_v) is
 // the same for every cell and layer; it is built once per n_per_v on the host.
 // ---------------------------------------------------------------------------------------
@@ -486,25 +488,25 @@ struct CellSegments
     int j[6];   // [j0,j1) far+window test | [j1,j2) far | [j2,j3) direct | [j3,j4) far | [j4,j5) far+test
 };
 
-// The six search keys of a cell's line ranges (one binary search each; the kernel gives one
-// key to each of six lanes): window start/end with and without the shift slack, and the
-// direct range.
-LBL_HD double cell_search_key(const GridSpec& g, const LayerIn& ly, int cell, int which)
+// The six search keys of the line ranges of a GROUP of `cells` consecutive cells starting at
+// `cell` (one binary search each; the kernel gives one key to each of six lanes).
+LBL_HD double cell_search_key(const GridSpec& g, const LayerIn& ly, int cell, int cells, int which)
 {
-    const double lo = (double)g.v0 + (double)cell;            // first point of the cell
-    const double hi = lo + (double)(g.n_per_v - 1) * g.dv;    // last point of the cell
+    const double lo = (double)g.v0 + (double)cell;                       // first point of the group
+    const double lo_last = lo + (double)(cells - 1);                     // first point of its last cell
+    const double hi = lo_last + (double)(g.n_per_v - 1) * g.dv;          // last point of the group
     const double near = (ly.kappa < 0.5)
         ? (ly.kappa * fabs(hi) / (1.0 - ly.kappa)) * (1.0 + 0x1p-20) + 3.0 * g.dv
         : 1.0e300;
     const double reach = (near > kFarMin ? near : kFarMin) + ly.slack;
     switch (which)
     {
-        case 0: return lo - (double)g.cut_off - ly.slack;        // first line that can be in the window
-        case 1: return lo - (double)g.cut_off + ly.slack;        // first line certainly in it
-        case 2: return lo - reach;                               // direct range
+        case 0: return lo - (double)g.cut_off - ly.slack;            // first line in any cell's window
+        case 1: return lo_last - (double)g.cut_off + ly.slack;       // first line certainly in all of them
+        case 2: return lo - reach;                                   // direct range
         case 3: return hi + reach;
-        case 4: return lo + (double)(g.cut_off + 1) - ly.slack;  // end of the certain part
-        default: return lo + (double)(g.cut_off + 1) + ly.slack; // end of the window
+        case 4: return lo + (double)(g.cut_off + 1) - ly.slack;      // end of the certain part
+        default: return lo_last + (double)(g.cut_off + 1) + ly.slack; // end of the last window
     }
 }
 
@@ -534,79 +536,102 @@ LBL_HD CellSegments cell_segments_from(const int (&found)[6])
 }
 
 LBL_HD CellSegments cell_segments(const LinesView& lines, const GridSpec& g, const LayerIn& ly,
-                                  int cell)
+                                  int cell, int cells)
 {
     int found[6];
     for (int which = 0; which < 6; ++which)
     {
-        found[which] = lower_bound(lines.nu, lines.n, cell_search_key(g, ly, cell, which));
+        found[which] = lower_bound(lines.nu, lines.n, cell_search_key(g, ly, cell, cells, which));
     }
     return cell_segments_from(found);
 }
 
-// Far lines of [jb, je) at ONE point v (this lane's node), no tests: pairs share a reciprocal,
-// four independent accumulators keep the FP64 pipe busy with a single point per lane.
-LBL_HD double node_plain(const FarAB* __restrict__ ab, const double* __restrict__ cc, int jb, int je,
-                         double v)
+// Far lines of [jb, je) at this lane's node in each of the G cells, no tests.  Pairs of lines
+// share a reciprocal; U*G independent chains per lane keep the FP64 pipe busy.
+template <int G>
+LBL_HD void node_plain(const FarAB* __restrict__ ab, const double* __restrict__ cc, int jb, int je,
+                       const double (&v)[G], double (&sum)[G])
 {
-    double acc[4] = {0., 0., 0., 0.};
-    const double vv[1] = {v};
+    constexpr int U = (G >= 4) ? 1 : 4 / G;
+    double acc[U][G];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int c = 0; c < G; ++c) acc[u][c] = 0.;
     int j = jb;
-    for (; j + 7 < je; j += 8)
+    for (; j + 2 * U - 1 < je; j += 2 * U)
     {
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < U; ++u)
         {
             const double2 l1 = LBL_LDG(reinterpret_cast<const double2*>(ab + j + 2 * u));
             const double2 l2 = LBL_LDG(reinterpret_cast<const double2*>(ab + j + 2 * u + 1));
             const double c1 = LBL_LDG(cc + j + 2 * u);
             const double c2 = LBL_LDG(cc + j + 2 * u + 1);
-            double one[1] = {acc[u]};
-            far_terms_pair<1>(vv, l1.x, l1.y, c1, l2.x, l2.y, c2, one);
-            acc[u] = one[0];
+            far_terms_pair<G>(v, l1.x, l1.y, c1, l2.x, l2.y, c2, acc[u]);
         }
     }
     for (; j < je; ++j)
     {
         const double2 l = LBL_LDG(reinterpret_cast<const double2*>(ab + j));
-        acc[0] = far_term(v, l.x, l.y, LBL_LDG(cc + j), acc[0]);
+        far_terms<G>(v, l.x, l.y, LBL_LDG(cc + j), acc[0]);
     }
-    return (acc[0] + acc[1]) + (acc[2] + acc[3]);
+#pragma unroll
+    for (int c = 0; c < G; ++c)
+    {
+        double t = 0.;
+#pragma unroll
+        for (int u = 0; u < U; ++u) t += acc[u][c];
+        sum[c] += t;
+    }
 }
 
-// Far lines next to a window edge: the window test decides (cb within [cell-cut, cell+cut]).
-LBL_HD double node_tested(const FarAB* __restrict__ ab, const double* __restrict__ cc,
-                          const LineChk* __restrict__ chk, int jb, int je, int cell, int cut_off,
-                          double v)
+// Far lines next to a window edge: each cell's own window test decides
+// (cb within [cell-cut, cell+cut]); a line outside a cell's window is masked for that cell.
+template <int G>
+LBL_HD void node_tested(const FarAB* __restrict__ ab, const double* __restrict__ cc,
+                        const LineChk* __restrict__ chk, int jb, int je, int cell, int cut_off,
+                        const double (&v)[G], double (&sum)[G])
 {
-    double acc = 0.;
     for (int j = jb; j < je; ++j)
     {
         const int cb = LBL_LDG(reinterpret_cast<const int4*>(chk + j)).x;
-        if (cb < cell - cut_off || cb > cell + cut_off)
+        if (cb < cell - cut_off || cb > cell + G - 1 + cut_off)
         {
             continue;
         }
         const double2 l = LBL_LDG(reinterpret_cast<const double2*>(ab + j));
-        acc = far_term(v, l.x, l.y, LBL_LDG(cc + j), acc);
+        const double c = LBL_LDG(cc + j);
+#pragma unroll
+        for (int q = 0; q < G; ++q)
+        {
+            const bool in = (cb >= cell + q - cut_off) && (cb <= cell + q + cut_off);
+            sum[q] = far_term(v[q], l.x, l.y, in ? c : kBig, sum[q]);
+        }
     }
-    return acc;
 }
 
-// Phase 1, lane = node: sum of the far lines at this lane's node.
-LBL_HD double cell_far_lane(const CellArgs& a, int layer, int cell, int lane, const CellSegments& seg)
+// Phase 1, lane = node: sums of the far lines at this lane's node of each cell of the group.
+template <int G>
+LBL_HD void cell_far_lane(const CellArgs& a, int layer, int cell, int lane, const CellSegments& seg,
+                          double (&f)[G])
 {
     const GridSpec& g = a.sum.grid;
     const size_t off = (size_t)layer * a.sum.lines.n;
     const FarAB* ab = a.sum.rec.ab + off;
     const double* cc = a.sum.rec.cc + off;
     const LineChk* chk = a.sum.rec.chk + off;
-    const double v = ((double)g.v0 + (double)cell) + a.node_offset[lane];
-    double f = node_tested(ab, cc, chk, seg.j[0], seg.j[1], cell, g.cut_off, v);
-    f += node_plain(ab, cc, seg.j[1], seg.j[2], v);
-    f += node_plain(ab, cc, seg.j[3], seg.j[4], v);
-    f += node_tested(ab, cc, chk, seg.j[4], seg.j[5], cell, g.cut_off, v);
-    return f;
+    double v[G];
+#pragma unroll
+    for (int q = 0; q < G; ++q)
+    {
+        v[q] = ((double)g.v0 + (double)(cell + q)) + a.node_offset[lane];
+        f[q] = 0.;
+    }
+    node_tested<G>(ab, cc, chk, seg.j[0], seg.j[1], cell, g.cut_off, v, f);
+    node_plain<G>(ab, cc, seg.j[1], seg.j[2], v, f);
+    node_plain<G>(ab, cc, seg.j[3], seg.j[4], v, f);
+    node_tested<G>(ab, cc, chk, seg.j[4], seg.j[5], cell, g.cut_off, v, f);
 }
 
 // Phase 2, lane = kCellP consecutive points of chunk `chunk` of the cell: the direct lines.

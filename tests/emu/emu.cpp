@@ -263,18 +263,27 @@ extern "C" int emu_absorption(int n_layers, const double* pressure, const double
         ca.weights = weights.data();
         ca.executed = nullptr;
         const int chunks = (n_per_v + 32 * kCellP - 1) / (32 * kCellP);
+        constexpr int G = 2;   // cells per emulated warp (the library uses 2 up to n_per_v = 256, else 1)
+        std::vector<double> fields((size_t)G * kNodes);
         for (int layer = 0; layer < n_layers; ++layer)
         {
-            for (int cell = 0; cell < g.ncell; ++cell)
+            for (int cell = 0; cell < g.ncell; cell += G)
             {
-                const CellSegments seg = cell_segments(ln, g, layers[layer], cell);
+                const CellSegments seg = cell_segments(ln, g, layers[layer], cell, G);
+                const int cells = std::min(G, g.ncell - cell);
                 for (int lane = 0; lane < 32; ++lane)
-                    field[lane] = cell_far_lane(ca, layer, cell, lane, seg);
-                for (int chunk = 0; chunk < chunks; ++chunk)
+                {
+                    double f[G];
+                    cell_far_lane<G>(ca, layer, cell, lane, seg, f);
+                    for (int q = 0; q < G; ++q) fields[(size_t)q * kNodes + lane] = f[q];
+                }
+                for (int q = 0; q < cells; ++q)
+                    for (int chunk = 0; chunk < chunks; ++chunk)
+                        for (int lane = 0; lane < 32; ++lane)
+                            cell_direct_lane(ca, layer, cell + q, chunk, lane, seg);
+                for (int q = 0; q < cells; ++q)
                     for (int lane = 0; lane < 32; ++lane)
-                        cell_direct_lane(ca, layer, cell, chunk, lane, seg);
-                for (int lane = 0; lane < 32; ++lane)
-                    cell_field_lane(ca, layer, cell, lane, 32, field.data());
+                        cell_field_lane(ca, layer, cell + q, lane, 32, fields.data() + (size_t)q * kNodes);
             }
         }
     }
