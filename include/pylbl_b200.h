@@ -47,6 +47,7 @@ typedef struct lbl_stats
     int n_layers;
     int n_points;           /* (vn - v0)*n_per_v */
     int points_per_thread;
+    int cells_per_warp;     /* > 0: the cell-tiled summation kernel with the far-field interpolation ran */
     int sum_launches;       /* launches of the summation kernel */
     int total_launches;     /* all kernel launches */
     float scale_ms;         /* K1, CUDA events on the launching stream */

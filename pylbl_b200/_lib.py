@@ -29,7 +29,8 @@ class Stats(Structure):
         ("evals", c_longlong), ("executed", c_longlong), ("h2d_bytes", c_longlong),
         ("d2h_bytes", c_longlong),
         ("n_lines", c_int), ("n_active", c_int), ("n_layers", c_int), ("n_points", c_int),
-        ("points_per_thread", c_int), ("sum_launches", c_int), ("total_launches", c_int),
+        ("points_per_thread", c_int), ("cells_per_warp", c_int), ("sum_launches", c_int),
+        ("total_launches", c_int),
         ("scale_ms", c_float), ("sum_ms", c_float), ("fixup_ms", c_float),
         ("pedestal_ms", c_float),
         ("total_ms", c_float),

@@ -964,6 +964,7 @@ int lbl_gas_submit(lbl_gas* g, int n_layers, const double* pressure, const doubl
             // node evaluations, fewer keep the (per-cell) direct range short
             int cells_per_warp = (n_per_v <= 256) ? 2 : 1;
             if (const char* env = getenv("PYLBL_B200_CELLS")) cells_per_warp = atoi(env);
+            st.cells_per_warp = cells_per_warp;
             const int groups = (grid.ncell + cells_per_warp - 1) / cells_per_warp;
             dim3 gridc((groups + kSumBlock / 32 - 1) / (kSumBlock / 32), nl);
             switch (cells_per_warp)
@@ -972,13 +973,18 @@ int lbl_gas_submit(lbl_gas* g, int n_layers, const double* pressure, const doubl
                 case 2: sum_cell_kernel<2><<<gridc, kSumBlock, 0, sc>>>(ca); break;
                 default: sum_cell_kernel<4><<<gridc, kSumBlock, 0, sc>>>(ca); break;
             }
+            LBL_CUDA(cudaEventRecord(ev.k2_end, sc));
+            launch_fixup_dispatch(pick_fixup_tile(n_per_v), sa, nl, sc);
         }
         else
         {
             launch_sum_dispatch(P, sa, nl, fp32, sc);
         }
-        LBL_CUDA(cudaEventRecord(ev.k2_end, sc));
-        launch_fixup_dispatch(pick_fixup_tile(n_per_v), sa, nl, sc);
+        if (!farfield)
+        {
+            LBL_CUDA(cudaEventRecord(ev.k2_end, sc));
+            launch_fixup_dispatch(pick_fixup_tile(n_per_v), sa, nl, sc);
+        }
         LBL_CUDA(cudaEventRecord(ev.k2b_end, sc));
         st.sum_launches++;
         st.total_launches += 2;

@@ -71,14 +71,20 @@ sum_kernel(const SumArgs a)
 
 // K2c.  Cell-tiled summation with the Chebyshev far field (see lbl_threads.cuh).
 // block = 128 threads = 4 independent warps; warp = G consecutive cells of layer blockIdx.y.
+//
+// Phase 1  lane = node: the far lines at this lane's node of each cell (cell_far_lane).
+// Phase 2  lane = kCellP consecutive points: the direct lines in Lorentz form, near-zone
+//          points masked (cell_direct_lane); spectra stored.
+// Phase 3  lane = points lane, lane+32, ...: + interpolated far field (cell_field_lane).
+// The near zone and the node terms are added afterwards by K2b (fixup_kernel).
 template <int G>
 __global__ void __launch_bounds__(kSumBlock)
 sum_cell_kernel(const CellArgs a)
 {
     __shared__ double fields[kSumBlock / 32][G][kNodes];
     const GridSpec& g = a.sum.grid;
-    const int cell = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * G;
-    if (cell >= g.ncell)
+    const int cell0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * G;
+    if (cell0 >= g.ncell)
     {
         return;
     }
@@ -89,7 +95,7 @@ sum_cell_kernel(const CellArgs a)
     int mine = 0;
     if (lane < 6)
     {
-        mine = lower_bound(a.sum.lines.nu, a.sum.lines.n, cell_search_key(g, ly, cell, G, lane));
+        mine = lower_bound(a.sum.lines.nu, a.sum.lines.n, cell_search_key(g, ly, cell0, G, lane));
     }
     int found[6];
 #pragma unroll
@@ -98,29 +104,35 @@ sum_cell_kernel(const CellArgs a)
         found[which] = __shfl_sync(0xffffffffu, mine, which);
     }
     const CellSegments seg = cell_segments_from(found);
+    int cells = g.ncell - cell0;
+    if (cells > G) cells = G;
+
+    // ---- phase 1: far field at the nodes ---------------------------------------------------
     double f[G];
-    cell_far_lane<G>(a, layer, cell, lane, seg, f);
+    cell_far_lane<G>(a, layer, cell0, lane, seg, f);
     double (*field)[kNodes] = fields[threadIdx.x >> 5];
 #pragma unroll
     for (int q = 0; q < G; ++q) field[q][lane] = f[q];
+
+    // ---- phase 2: direct lines, Lorentz form ------------------------------------------------
     const int chunks = (g.n_per_v + 32 * kCellP - 1) / (32 * kCellP);
-    int cells = g.ncell - cell;
-    if (cells > G) cells = G;
     for (int q = 0; q < cells; ++q)
     {
         for (int chunk = 0; chunk < chunks; ++chunk)
         {
-            cell_direct_lane(a, layer, cell + q, chunk, lane, seg);
+            cell_direct_lane(a, layer, cell0 + q, chunk, lane, seg);
         }
     }
-    __syncwarp();   // the direct sums are stored, the node sums are in shared memory
+    __syncwarp();   // spectra stored, node sums in shared memory
+
+    // ---- phase 3: + interpolated far field ---------------------------------------------------
     for (int q = 0; q < cells; ++q)
     {
-        cell_field_lane(a, layer, cell + q, lane, 32, field[q]);
+        cell_field_lane(a, layer, cell0 + q, lane, 32, field[q]);
     }
     if (a.executed && lane == 0)
     {
-        // statistics only: evaluations this warp performed (nodes + direct slots)
+        // statistics only: far-wing evaluations this warp performed (nodes + direct slots)
         const unsigned long long far = (unsigned long long)((seg.j[2] - seg.j[0]) + (seg.j[5] - seg.j[3]));
         const unsigned long long direct = (unsigned long long)(seg.j[3] - seg.j[2]);
         atomicAdd(a.executed, far * (kNodes * G) +

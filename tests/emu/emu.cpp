@@ -262,7 +262,6 @@ extern "C" int emu_absorption(int n_layers, const double* pressure, const double
         ca.node_offset = nodes.data();
         ca.weights = weights.data();
         ca.executed = nullptr;
-        const int chunks = (n_per_v + 32 * kCellP - 1) / (32 * kCellP);
         constexpr int G = 2;   // cells per emulated warp (the library uses 2 up to n_per_v = 256, else 1)
         std::vector<double> fields((size_t)G * kNodes);
         for (int layer = 0; layer < n_layers; ++layer)
@@ -277,6 +276,7 @@ extern "C" int emu_absorption(int n_layers, const double* pressure, const double
                     cell_far_lane<G>(ca, layer, cell, lane, seg, f);
                     for (int q = 0; q < G; ++q) fields[(size_t)q * kNodes + lane] = f[q];
                 }
+                const int chunks = (n_per_v + 32 * kCellP - 1) / (32 * kCellP);
                 for (int q = 0; q < cells; ++q)
                     for (int chunk = 0; chunk < chunks; ++chunk)
                         for (int lane = 0; lane < 32; ++lane)
