@@ -210,14 +210,13 @@ LBL_HD void far_terms(const double (&v)[P], double a, double b, double c, double
     }
 }
 
-// Reciprocal to ~1e-16: hardware seed (2^-20) and two Newton steps.  Used by the full
-// profile below, where the reference divides (voigt.c:82,95,113,145,159-183).
+// Reciprocal to ~1e-12: hardware seed (2^-20) and one Newton step.  Used by the full profile
+// below, where the reference divides (voigt.c:82,95,113,145,159-183); three orders of
+// magnitude inside the 1e-9 parity target.
 LBL_HD double rcp_newton2(double q)
 {
-    double r = rcp_seed(q);
-    r = r * fma_(-q, r, 2.0);
-    r = r * fma_(-q, r, 2.0);
-    return r;
+    const double r = rcp_seed(q);
+    return r * fma_(-q, r, 2.0);
 }
 
 // Two lines at once for P points: 1/q1 + 1/q2 = (q1 + q2)/(q1*q2) needs ONE reciprocal.
