@@ -754,8 +754,8 @@ int lbl_gas_submit(lbl_gas* g, int n_layers, const double* pressure, const doubl
     const int n_chunks = (int)((n_layers + chunk - 1) / chunk);
 
     // ---- buffers -------------------------------------------------------------------
-    LBL_CUDA(g->rec_ab.reserve(sizeof(FarAB) * (size_t)plan.n_active * chunk));
-    LBL_CUDA(g->rec_cc.reserve(sizeof(double) * (size_t)plan.n_active * chunk));
+    LBL_CUDA(g->rec_ab.reserve(sizeof(FarAB) * (size_t)plan.n_active * chunk + 64));
+    LBL_CUDA(g->rec_cc.reserve(sizeof(double) * (size_t)plan.n_active * chunk + 64));
     LBL_CUDA(g->rec_chk.reserve(sizeof(LineChk) * (size_t)plan.n_active * chunk));
     LBL_CUDA(g->rec_gen.reserve(sizeof(LineGen) * (size_t)plan.n_active * chunk));
     if (fp32)

@@ -77,23 +77,103 @@ sum_kernel(const SumArgs a)
 //          points masked (cell_direct_lane); spectra stored.
 // Phase 3  lane = points lane, lane+32, ...: + interpolated far field (cell_field_lane).
 // The near zone and the node terms are added afterwards by K2b (fixup_kernel).
+// ---- TMA bulk copy + mbarrier (PTX; SASS: UBLKCP / SYNCS) ------------------------------------
+__device__ __forceinline__ unsigned smem_addr(const void* p)
+{
+    return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, unsigned bytes,
+                                              unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_addr(dst)), "l"(src), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LBL_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LBL_DONE;\n"
+        "bra LBL_WAIT;\n"
+        "LBL_DONE:\n"
+        "}\n" ::"r"(smem_addr(bar)), "r"(parity)
+        : "memory");
+}
+
+constexpr int kStageLines = 256;   // lines per staged chunk (4 KB of (a,b) + 2 KB of c)
+constexpr int kStages = 3;
+
+// Far lines [jb, je) of one staged chunk, operands in shared memory (index j - base).
+template <int G>
+__device__ __forceinline__ void node_plain_staged(const double2* __restrict__ s_ab,
+                                                  const double* __restrict__ s_cc, int base, int jb,
+                                                  int je, const double (&v)[G], double (&sum)[G])
+{
+    constexpr int U = (G >= 4) ? 1 : 4 / G;
+    double acc[U][G];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int c = 0; c < G; ++c) acc[u][c] = 0.;
+    int j = jb - base;
+    const int stop = je - base;
+    for (; j + 2 * U - 1 < stop; j += 2 * U)
+    {
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+        {
+            const double2 l1 = s_ab[j + 2 * u];
+            const double2 l2 = s_ab[j + 2 * u + 1];
+            far_terms_pair<G>(v, l1.x, l1.y, s_cc[j + 2 * u], l2.x, l2.y, s_cc[j + 2 * u + 1], acc[u]);
+        }
+    }
+    for (; j < stop; ++j)
+    {
+        const double2 l = s_ab[j];
+        far_terms<G>(v, l.x, l.y, s_cc[j], acc[0]);
+    }
+#pragma unroll
+    for (int c = 0; c < G; ++c)
+    {
+        double t = 0.;
+#pragma unroll
+        for (int u = 0; u < U; ++u) t += acc[u][c];
+        sum[c] += t;
+    }
+}
+
 template <int G>
 __global__ void __launch_bounds__(kSumBlock)
 sum_cell_kernel(const CellArgs a)
 {
-    __shared__ double fields[kSumBlock / 32][G][kNodes];
+    constexpr int kWarps = kSumBlock / 32;
+    __shared__ double fields[kWarps][G][kNodes];
+    __shared__ alignas(16) double2 s_ab[kStages][kStageLines];
+    __shared__ alignas(16) double s_cc[kStages][kStageLines];
+    __shared__ alignas(8) unsigned long long full[kStages];
+    __shared__ int s_range[kWarps][2];
     const GridSpec& g = a.sum.grid;
-    const int cell0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * G;
-    if (cell0 >= g.ncell)
-    {
-        return;
-    }
+    const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int layer = blockIdx.y;
+    const int cell0 = (blockIdx.x * kWarps + warp) * G;
+    const bool active = cell0 < g.ncell;      // idle warps of the last block still join the barriers
     const LayerIn ly = a.sum.layers[layer];
     // six binary searches, one per lane, shared by shuffle
     int mine = 0;
-    if (lane < 6)
+    if (active && lane < 6)
     {
         mine = lower_bound(a.sum.lines.nu, a.sum.lines.n, cell_search_key(g, ly, cell0, G, lane));
     }
@@ -104,13 +184,86 @@ sum_cell_kernel(const CellArgs a)
         found[which] = __shfl_sync(0xffffffffu, mine, which);
     }
     const CellSegments seg = cell_segments_from(found);
-    int cells = g.ncell - cell0;
+    int cells = active ? g.ncell - cell0 : 0;
     if (cells > G) cells = G;
 
-    // ---- phase 1: far field at the nodes ---------------------------------------------------
-    double f[G];
-    cell_far_lane<G>(a, layer, cell0, lane, seg, f);
-    double (*field)[kNodes] = fields[threadIdx.x >> 5];
+    // ---- phase 1: far field at the nodes -------------------------------------------------
+    // The four warps of a block own neighbouring cell groups, so their far-line ranges
+    // [j1, j2) u [j3, j4) overlap almost entirely.  The block walks the union in chunks that
+    // one thread stages into shared memory with TMA bulk copies (3-deep ring, mbarrier per
+    // stage); each warp takes from a chunk what lies inside its own ranges.
+    if (lane == 0)
+    {
+        s_range[warp][0] = active ? seg.j[1] : 0x7fffffff;
+        s_range[warp][1] = active ? seg.j[4] : 0;
+    }
+    if (threadIdx.x == 0)
+    {
+        for (int st = 0; st < kStages; ++st) mbar_init(&full[st], 1);
+    }
+    __syncthreads();
+    int lo_all = s_range[0][0], hi_all = s_range[0][1];
+#pragma unroll
+    for (int w = 1; w < kWarps; ++w)
+    {
+        lo_all = min(lo_all, s_range[w][0]);
+        hi_all = max(hi_all, s_range[w][1]);
+    }
+    const size_t off = (size_t)layer * a.sum.lines.n;
+    // 16-byte alignment of the c[] source (8-byte elements): the chunk must start at an even
+    // ABSOLUTE element index; at worst this stages one element of the previous layer.
+    lo_all -= (int)((off + (size_t)lo_all) & 1);
+    const FarAB* ab = a.sum.rec.ab + off;
+    const double* cc = a.sum.rec.cc + off;
+    const LineChk* chk = a.sum.rec.chk + off;
+    const int n_chunks = (hi_all > lo_all) ? (hi_all - lo_all + kStageLines - 1) / kStageLines : 0;
+    auto issue = [&](int t) {
+        const int stage = t % kStages;
+        const int first = lo_all + t * kStageLines;
+        int cnt = hi_all - first;
+        if (cnt > kStageLines) cnt = kStageLines;
+        cnt = (cnt + 1) & ~1;   // the copies move multiples of 16 bytes (buffers carry slack)
+        mbar_expect_tx(&full[stage], (unsigned)(cnt * 24));
+        bulk_copy_g2s(&s_ab[stage][0], ab + first, (unsigned)(cnt * 16), &full[stage]);
+        bulk_copy_g2s(&s_cc[stage][0], cc + first, (unsigned)(cnt * 8), &full[stage]);
+    };
+    if (threadIdx.x == 0)
+    {
+        for (int t = 0; t < kStages && t < n_chunks; ++t) issue(t);
+    }
+    double v[G], f[G];
+#pragma unroll
+    for (int q = 0; q < G; ++q)
+    {
+        v[q] = ((double)g.v0 + (double)(cell0 + q)) + a.node_offset[lane];
+        f[q] = 0.;
+    }
+    if (active)
+    {
+        node_tested<G>(ab, cc, chk, seg.j[0], seg.j[1], cell0, g.cut_off, v, f);
+        node_tested<G>(ab, cc, chk, seg.j[4], seg.j[5], cell0, g.cut_off, v, f);
+    }
+    for (int t = 0; t < n_chunks; ++t)
+    {
+        const int stage = t % kStages;
+        mbar_wait(&full[stage], (unsigned)((t / kStages) & 1));
+        const int first = lo_all + t * kStageLines;
+        const int last = min(first + kStageLines, hi_all);
+        if (active)
+        {
+            const int b1 = max(first, seg.j[1]), e1 = min(last, seg.j[2]);
+            if (b1 < e1) node_plain_staged<G>(s_ab[stage], s_cc[stage], first, b1, e1, v, f);
+            const int b2 = max(first, seg.j[3]), e2 = min(last, seg.j[4]);
+            if (b2 < e2) node_plain_staged<G>(s_ab[stage], s_cc[stage], first, b2, e2, v, f);
+        }
+        __syncthreads();   // every warp is done with this stage
+        if (threadIdx.x == 0 && t + kStages < n_chunks) issue(t + kStages);
+    }
+    if (!active)
+    {
+        return;
+    }
+    double (*field)[kNodes] = fields[warp];
 #pragma unroll
     for (int q = 0; q < G; ++q) field[q][lane] = f[q];
 
