@@ -781,7 +781,12 @@ int lbl_gas_submit(lbl_gas* g, int n_layers, const double* pressure, const doubl
         const size_t bins_bytes = ped_chain ? sizeof(double) * (size_t)nb : 0;
         ped_smem = ring_bytes + node_bytes + bins_bytes;
         ped_nodes_in_smem = true;
-        if (ped_smem > 200 * 1024)
+        // With many layers in flight the chain kernel keeps its node and bin arrays in global
+        // memory (they are touched only when the window moves, by the lane that owns the index,
+        // and stay in L1): a one-warp block holding ~150 KB of shared memory would evict the
+        // summation kernel's blocks from its SM for the whole length of the chain.  With few
+        // layers (scalar calls) latency matters more and the arrays stay in shared memory.
+        if ((ped_chain && chunk > 16) || ped_smem > 200 * 1024)
         {
             // Grid too wide for shared memory: the node array goes to global memory.
             LBL_CUDA(g->pednodes.reserve(node_bytes * chunk));

@@ -884,12 +884,44 @@ LBL_HD void pedestal_terms_tile(const PedArgs& a, int layer, int tile, int lane,
     const int cnt = (a.lines.n - first < kPedTileRows) ? a.lines.n - first : kPedTileRows;
     double run_sum[K];
     int prev_cb = 0;
+#if defined(__CUDA_ARCH__)
+    // Lane m fetches the records of the tile's row m once (independent, coalesced loads); the
+    // row loop below gets them by shuffle instead of waiting on memory row after row.
+    int my_j = 0;
+    int4 my_ck = make_int4(0, 0, 0, 0);
+    double2 my_l = make_double2(0., 0.);
+    double my_c = 0.;
+    if (lane < cnt)
+    {
+        my_j = a.lines.db_to_sorted ? LBL_LDG(a.lines.db_to_sorted + first + lane) : first + lane;
+        const size_t mo = (size_t)layer * a.lines.n + my_j;
+        my_ck = LBL_LDG(reinterpret_cast<const int4*>(a.rec.chk + mo));
+        my_l = LBL_LDG(reinterpret_cast<const double2*>(a.rec.ab + mo));
+        my_c = LBL_LDG(a.rec.cc + mo);
+    }
+#endif
     for (int m = 0; m < cnt; ++m)
     {
+#if defined(__CUDA_ARCH__)
+        const int j = __shfl_sync(0xffffffffu, my_j, m);
+        const size_t o = (size_t)layer * a.lines.n + j;
+        int4 ck;
+        ck.x = __shfl_sync(0xffffffffu, my_ck.x, m);
+        ck.y = __shfl_sync(0xffffffffu, my_ck.y, m);
+        ck.z = __shfl_sync(0xffffffffu, my_ck.z, m);
+        ck.w = 0;
+        double2 l;
+        l.x = __shfl_sync(0xffffffffu, my_l.x, m);
+        l.y = __shfl_sync(0xffffffffu, my_l.y, m);
+        const double c = __shfl_sync(0xffffffffu, my_c, m);
+#else
         const int r = first + m;
         const int j = a.lines.db_to_sorted ? LBL_LDG(a.lines.db_to_sorted + r) : r;
         const size_t o = (size_t)layer * a.lines.n + j;
         const int4 ck = LBL_LDG(reinterpret_cast<const int4*>(a.rec.chk + o));
+        const double2 l = LBL_LDG(reinterpret_cast<const double2*>(a.rec.ab + o));
+        const double c = LBL_LDG(a.rec.cc + o);
+#endif
         if (m == 0 || ck.x != prev_cb)
         {
 #pragma unroll
@@ -900,8 +932,6 @@ LBL_HD void pedestal_terms_tile(const PedArgs& a, int layer, int tile, int lane,
         const PedWindow w = ped_window(ck.x, g);
         if (!w.skip)
         {
-            const double2 l = LBL_LDG(reinterpret_cast<const double2*>(a.rec.ab + o));
-            const double c = LBL_LDG(a.rec.cc + o);
 #pragma unroll
             for (int k = 0; k < K; ++k)
             {
