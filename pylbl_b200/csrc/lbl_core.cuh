@@ -350,29 +350,36 @@ LBL_HD double voigt_outer(double abx, double xq, double y, double xlim0)
     return d * y * (a0 + xq);
 }
 
-// Regions 2, 3 and CPF12 (voigt.c:98-186); requires abx < voigt_outer_limit().  Returns K(x,y).
-static LBL_HD_NOINLINE double voigt_core(double xi, double y, double xlim0)
+// W4 region 2 (voigt.c:98-115): |x| in [xlim2, xlim1).  Returns K(x,y).
+LBL_HD double voigt_region2(double xq, double y)
 {
     const double yq = y * y;
+    const double h0 = 0.5625 + yq * (4.5 + yq * (10.5 + yq * (6.0 + yq)));
+    const double h2 = -4.5 + yq * (9.0 + yq * (6.0 + yq * 4.0));
+    const double h4 = 10.5 - yq * (6.0 - yq * 6.0);
+    const double h6 = -6.0 + yq * 4.0;
+    const double e0 = 1.875 + yq * (8.25 + yq * (5.5 + yq));
+    const double e2 = 5.25 + yq * (1.0 + yq * 3.0);
+    const double e4 = 0.75 * h6;
+    const double d = kRsqrPi * rcp_newton2(h0 + xq * (h2 + xq * (h4 + xq * (h6 + xq))));
+    return d * y * (e0 + xq * (e2 + xq * (e4 + xq)));
+}
+
+// voigt.c:44,48-53: lower limit of region 2 (regions 1 and 2 are off for y <= 1e-6).
+LBL_HD double voigt_region2_limit(double y, double xlim0)
+{
+    return (y <= 0.000001) ? xlim0 : 6.8 - y;
+}
+
+// W4 region 3 and CPF12 (voigt.c:116-186): |x| < xlim2.  Returns K(x,y).
+static LBL_HD_NOINLINE double voigt_inner(double xi, double y)
+{
     const double abx = fabs(xi);
     const double xq = abx * abx;
-    const double xlim2 = (y <= 0.000001) ? xlim0 : 6.8 - y;
     const double xlim3 = 2.4 * y;
     const double xlim4 = 18.1 * y + 1.65;
     double buf;
-    if (abx >= xlim2)
-    {
-        const double h0 = 0.5625 + yq * (4.5 + yq * (10.5 + yq * (6.0 + yq)));
-        const double h2 = -4.5 + yq * (9.0 + yq * (6.0 + yq * 4.0));
-        const double h4 = 10.5 - yq * (6.0 - yq * 6.0);
-        const double h6 = -6.0 + yq * 4.0;
-        const double e0 = 1.875 + yq * (8.25 + yq * (5.5 + yq));
-        const double e2 = 5.25 + yq * (1.0 + yq * 3.0);
-        const double e4 = 0.75 * h6;
-        const double d = kRsqrPi * rcp_newton2(h0 + xq * (h2 + xq * (h4 + xq * (h6 + xq))));
-        buf = d * y * (e0 + xq * (e2 + xq * (e4 + xq)));
-    }
-    else if (abx < xlim3)
+    if (abx < xlim3)
     {
         const double z0 = 272.1014 + y * (1280.829 + y * (2802.870 + y * (3764.966
                           + y * (3447.629 + y * (2256.981 + y * (1074.409 + y * (369.1989
@@ -442,6 +449,17 @@ static LBL_HD_NOINLINE double voigt_core(double xi, double y, double xlim0)
         }
     }
     return buf;
+}
+
+// Regions 2, 3 and CPF12 (voigt.c:98-186); requires abx < voigt_outer_limit().  Returns K(x,y).
+LBL_HD double voigt_core(double xi, double y, double xlim0)
+{
+    const double abx = fabs(xi);
+    if (abx >= voigt_region2_limit(y, xlim0))
+    {
+        return voigt_region2(abx * abx, y);
+    }
+    return voigt_inner(xi, y);
 }
 
 // The whole profile for one point: cof*K(x,y)  (voigt.c:76-188).

@@ -327,7 +327,7 @@ __device__ __forceinline__ double fixup_drain(const SumArgs& a, const int* queue
         const double2 g0 = __ldg(reinterpret_cast<const double2*>(gp));
         const double2 g1 = __ldg(reinterpret_cast<const double2*>(gp) + 1);
         const double2 g2 = __ldg(reinterpret_cast<const double2*>(gp) + 2);
-        val = g1.y * voigt_core((v_src - g0.x) * g0.y, g1.x, g2.x);
+        val = g1.y * voigt_inner((v_src - g0.x) * g0.y, g1.x);
     }
     for (int e = 0; e < cnt; ++e)
     {
@@ -396,9 +396,13 @@ __device__ __forceinline__ void fixup_warp(const SumArgs& a, int tile, int layer
                     {
                         acc += g1.y * voigt_outer(abx, abx * abx, g1.x, g2.x);
                     }
+                    else if (abx >= voigt_region2_limit(g1.x, g2.x))
+                    {
+                        acc += g1.y * voigt_region2(abx * abx, g1.x);   // short rational: on the spot
+                    }
                     else
                     {
-                        core = true;
+                        core = true;   // region 3 / CPF12: queued and lane-packed
                     }
                 }
             }
