@@ -134,7 +134,8 @@ struct lbl_gas
 
     cudaStream_t s_compute = nullptr, s_side = nullptr, s_copy = nullptr;
     DevBuf rec_ab, rec_cc, rec_chk, rec_gen, layers_dev, evals_dev, pedbin, pedcorr, pednodes,
-        pedterms, rec_f32, amp_max, cheb_nodes, cheb_weights, executed_dev;
+        pedterms, rec_f32, amp_max, cheb_nodes, cheb_weights, cheb_nodes16, cheb_weights16,
+        executed_dev;
     int cheb_npv = 0;
     unsigned long long* executed_host = nullptr;  // pinned
     DevBuf out[2];
@@ -384,6 +385,11 @@ int ensure_cheb_tables(lbl_gas* g, int n_per_v)
     if (upload(g->cheb_nodes, nodes.data(), sizeof(double) * kNodes, g->s_compute, bytes)) return 1;
     if (upload(g->cheb_weights, weights.data(), sizeof(double) * weights.size(), g->s_compute, bytes))
         return 1;
+    LBL_CUDA(cudaStreamSynchronize(g->s_compute));   // the host vectors are reused
+    build_cheb_tables(kNodes16, n_per_v, nodes, weights);
+    if (upload(g->cheb_nodes16, nodes.data(), sizeof(double) * kNodes16, g->s_compute, bytes)) return 1;
+    if (upload(g->cheb_weights16, weights.data(), sizeof(double) * weights.size(), g->s_compute, bytes))
+        return 1;
     LBL_CUDA(cudaStreamSynchronize(g->s_compute));   // the host vectors go out of scope
     g->open_h2d += bytes;
     g->cheb_npv = n_per_v;
@@ -603,6 +609,7 @@ int lbl_gas_close(lbl_gas* g)
     for (DevBuf* b : {&g->tips_t, &g->tips_q, &g->rec_ab, &g->rec_cc, &g->rec_chk, &g->rec_gen,
                       &g->layers_dev, &g->evals_dev, &g->pedbin, &g->pedcorr, &g->pednodes,
                       &g->pedterms, &g->rec_f32, &g->amp_max, &g->cheb_nodes, &g->cheb_weights,
+                      &g->cheb_nodes16, &g->cheb_weights16,
                       &g->executed_dev,
                       &g->out[0], &g->out[1]})
     {
@@ -964,19 +971,23 @@ int lbl_gas_submit(lbl_gas* g, int n_layers, const double* pressure, const doubl
             ca.sum = sa;
             ca.node_offset = g->cheb_nodes.as<double>();
             ca.weights = g->cheb_weights.as<double>();
+            ca.node_offset16 = g->cheb_nodes16.as<double>();
+            ca.weights16 = g->cheb_weights16.as<double>();
             ca.executed = g->executed_dev.as<unsigned long long>();
             // cells per warp: more cells amortise the loads of the line operands over more
             // node evaluations, fewer keep the (per-cell) direct range short
             int cells_per_warp = (n_per_v <= 256) ? 2 : 1;
-            if (const char* env = getenv("PYLBL_B200_CELLS")) cells_per_warp = atoi(env);
+            if (const char* env = getenv("PYLBL_B200_CELLS")) cells_per_warp = atoi(env) == 1 ? 1 : 2;
             st.cells_per_warp = cells_per_warp;
             const int groups = (grid.ncell + cells_per_warp - 1) / cells_per_warp;
             dim3 gridc((groups + kSumBlock / 32 - 1) / (kSumBlock / 32), nl);
-            switch (cells_per_warp)
+            if (cells_per_warp == 1)
             {
-                case 1: sum_cell_kernel<1><<<gridc, kSumBlock, 0, sc>>>(ca); break;
-                case 2: sum_cell_kernel<2><<<gridc, kSumBlock, 0, sc>>>(ca); break;
-                default: sum_cell_kernel<4><<<gridc, kSumBlock, 0, sc>>>(ca); break;
+                sum_cell_kernel<1><<<gridc, kSumBlock, 0, sc>>>(ca);
+            }
+            else
+            {
+                sum_cell_kernel<2><<<gridc, kSumBlock, 0, sc>>>(ca);
             }
             LBL_CUDA(cudaEventRecord(ev.k2_end, sc));
             launch_fixup_dispatch(pick_fixup_tile(n_per_v), sa, nl, sc);

@@ -115,7 +115,7 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 constexpr int kStageLines = 256;   // lines per staged chunk (4 KB of (a,b) + 2 KB of c)
 constexpr int kStages = 3;
 
-// Far lines [jb, je) of one staged chunk, operands in shared memory (index j - base).
+// Mid lines [jb, je) of one staged chunk, operands in shared memory (index j - base).
 template <int G>
 __device__ __forceinline__ void node_plain_staged(const double2* __restrict__ s_ab,
                                                   const double* __restrict__ s_cc, int base, int jb,
@@ -154,12 +154,54 @@ __device__ __forceinline__ void node_plain_staged(const double2* __restrict__ s_
     }
 }
 
+// Very far lines [jb, je) of one staged chunk at one point per lane (see node16_plain).
+__device__ __forceinline__ double node16_plain_staged(const double2* __restrict__ s_ab,
+                                                      const double* __restrict__ s_cc, int base,
+                                                      int jb, int je, int first, int stride, double v)
+{
+    double acc[4] = {0., 0., 0., 0.};
+    const double vv[1] = {v};
+    const int b = jb - base;
+    const int pairs = (je - jb) >> 1;
+    int p = first;
+    for (; p + 3 * stride < pairs; p += 4 * stride)
+    {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+        {
+            const int j = b + 2 * (p + u * stride);
+            const double2 l1 = s_ab[j];
+            const double2 l2 = s_ab[j + 1];
+            double one[1] = {acc[u]};
+            far_terms_pair<1>(vv, l1.x, l1.y, s_cc[j], l2.x, l2.y, s_cc[j + 1], one);
+            acc[u] = one[0];
+        }
+    }
+    for (; p < pairs; p += stride)
+    {
+        const int j = b + 2 * p;
+        const double2 l1 = s_ab[j];
+        const double2 l2 = s_ab[j + 1];
+        double one[1] = {acc[0]};
+        far_terms_pair<1>(vv, l1.x, l1.y, s_cc[j], l2.x, l2.y, s_cc[j + 1], one);
+        acc[0] = one[0];
+    }
+    if (((je - jb) & 1) && first == 0)
+    {
+        const int j = je - 1 - base;
+        const double2 l = s_ab[j];
+        acc[1] = far_term(v, l.x, l.y, s_cc[j], acc[1]);
+    }
+    return (acc[0] + acc[1]) + (acc[2] + acc[3]);
+}
+
 template <int G>
 __global__ void __launch_bounds__(kSumBlock)
 sum_cell_kernel(const CellArgs a)
 {
     constexpr int kWarps = kSumBlock / 32;
     __shared__ double fields[kWarps][G][kNodes];
+    __shared__ double fields16[kWarps][G][kNodes16];
     __shared__ alignas(16) double2 s_ab[kStages][kStageLines];
     __shared__ alignas(16) double s_cc[kStages][kStageLines];
     __shared__ alignas(8) unsigned long long full[kStages];
@@ -171,15 +213,15 @@ sum_cell_kernel(const CellArgs a)
     const int cell0 = (blockIdx.x * kWarps + warp) * G;
     const bool active = cell0 < g.ncell;      // idle warps of the last block still join the barriers
     const LayerIn ly = a.sum.layers[layer];
-    // six binary searches, one per lane, shared by shuffle
+    // eight binary searches, one per lane, shared by shuffle
     int mine = 0;
-    if (active && lane < 6)
+    if (active && lane < kCellKeys)
     {
         mine = lower_bound(a.sum.lines.nu, a.sum.lines.n, cell_search_key(g, ly, cell0, G, lane));
     }
-    int found[6];
+    int found[kCellKeys];
 #pragma unroll
-    for (int which = 0; which < 6; ++which)
+    for (int which = 0; which < kCellKeys; ++which)
     {
         found[which] = __shfl_sync(0xffffffffu, mine, which);
     }
@@ -187,15 +229,15 @@ sum_cell_kernel(const CellArgs a)
     int cells = active ? g.ncell - cell0 : 0;
     if (cells > G) cells = G;
 
-    // ---- phase 1: far field at the nodes -------------------------------------------------
+    // ---- phase 1: far fields at the nodes ------------------------------------------------
     // The four warps of a block own neighbouring cell groups, so their far-line ranges
-    // [j1, j2) u [j3, j4) overlap almost entirely.  The block walks the union in chunks that
+    // [j1, j3) u [j4, j6) overlap almost entirely.  The block walks the union in chunks that
     // one thread stages into shared memory with TMA bulk copies (3-deep ring, mbarrier per
     // stage); each warp takes from a chunk what lies inside its own ranges.
     if (lane == 0)
     {
         s_range[warp][0] = active ? seg.j[1] : 0x7fffffff;
-        s_range[warp][1] = active ? seg.j[4] : 0;
+        s_range[warp][1] = active ? seg.j[6] : 0;
     }
     if (threadIdx.x == 0)
     {
@@ -231,7 +273,11 @@ sum_cell_kernel(const CellArgs a)
     {
         for (int t = 0; t < kStages && t < n_chunks; ++t) issue(t);
     }
+    const Lane16<G> m16 = lane16<G>(lane);
+    const int my_cell = cell0 + m16.cell_off;
+    const double v16 = ((double)g.v0 + (double)my_cell) + a.node_offset16[m16.node];
     double v[G], f[G];
+    double f16 = 0.;
 #pragma unroll
     for (int q = 0; q < G; ++q)
     {
@@ -240,8 +286,8 @@ sum_cell_kernel(const CellArgs a)
     }
     if (active)
     {
-        node_tested<G>(ab, cc, chk, seg.j[0], seg.j[1], cell0, g.cut_off, v, f);
-        node_tested<G>(ab, cc, chk, seg.j[4], seg.j[5], cell0, g.cut_off, v, f);
+        f16 += node16_tested(ab, cc, chk, seg.j[0], seg.j[1], m16.first, m16.stride, my_cell, g.cut_off, v16);
+        f16 += node16_tested(ab, cc, chk, seg.j[6], seg.j[7], m16.first, m16.stride, my_cell, g.cut_off, v16);
     }
     for (int t = 0; t < n_chunks; ++t)
     {
@@ -251,10 +297,14 @@ sum_cell_kernel(const CellArgs a)
         const int last = min(first + kStageLines, hi_all);
         if (active)
         {
-            const int b1 = max(first, seg.j[1]), e1 = min(last, seg.j[2]);
-            if (b1 < e1) node_plain_staged<G>(s_ab[stage], s_cc[stage], first, b1, e1, v, f);
-            const int b2 = max(first, seg.j[3]), e2 = min(last, seg.j[4]);
-            if (b2 < e2) node_plain_staged<G>(s_ab[stage], s_cc[stage], first, b2, e2, v, f);
+            int b = max(first, seg.j[1]), e = min(last, seg.j[2]);
+            if (b < e) f16 += node16_plain_staged(s_ab[stage], s_cc[stage], first, b, e, m16.first, m16.stride, v16);
+            b = max(first, seg.j[2]); e = min(last, seg.j[3]);
+            if (b < e) node_plain_staged<G>(s_ab[stage], s_cc[stage], first, b, e, v, f);
+            b = max(first, seg.j[4]); e = min(last, seg.j[5]);
+            if (b < e) node_plain_staged<G>(s_ab[stage], s_cc[stage], first, b, e, v, f);
+            b = max(first, seg.j[5]); e = min(last, seg.j[6]);
+            if (b < e) f16 += node16_plain_staged(s_ab[stage], s_cc[stage], first, b, e, m16.first, m16.stride, v16);
         }
         __syncthreads();   // every warp is done with this stage
         if (threadIdx.x == 0 && t + kStages < n_chunks) issue(t + kStages);
@@ -263,9 +313,15 @@ sum_cell_kernel(const CellArgs a)
     {
         return;
     }
+    if (G == 1)
+    {
+        f16 += __shfl_xor_sync(0xffffffffu, f16, 16);   // the half-warps held partial sums
+    }
     double (*field)[kNodes] = fields[warp];
+    double (*field16)[kNodes16] = fields16[warp];
 #pragma unroll
     for (int q = 0; q < G; ++q) field[q][lane] = f[q];
+    if (G >= 2 || lane < 16) field16[m16.cell_off][m16.node] = f16;
 
     // ---- phase 2: direct lines, Lorentz form ------------------------------------------------
     const int chunks = (g.n_per_v + 32 * kCellP - 1) / (32 * kCellP);
@@ -278,17 +334,18 @@ sum_cell_kernel(const CellArgs a)
     }
     __syncwarp();   // spectra stored, node sums in shared memory
 
-    // ---- phase 3: + interpolated far field ---------------------------------------------------
+    // ---- phase 3: + interpolated far fields ---------------------------------------------------
     for (int q = 0; q < cells; ++q)
     {
-        cell_field_lane(a, layer, cell0 + q, lane, 32, field[q]);
+        cell_field_lane(a, layer, cell0 + q, lane, 32, field[q], field16[q]);
     }
     if (a.executed && lane == 0)
     {
-        // statistics only: far-wing evaluations this warp performed (nodes + direct slots)
-        const unsigned long long far = (unsigned long long)((seg.j[2] - seg.j[0]) + (seg.j[5] - seg.j[3]));
-        const unsigned long long direct = (unsigned long long)(seg.j[3] - seg.j[2]);
-        atomicAdd(a.executed, far * (kNodes * G) +
+        // statistics only: Lorentz evaluations this warp performed (nodes + direct slots)
+        const unsigned long long mid = (unsigned long long)((seg.j[3] - seg.j[2]) + (seg.j[5] - seg.j[4]));
+        const unsigned long long vfar = (unsigned long long)((seg.j[2] - seg.j[0]) + (seg.j[7] - seg.j[5]));
+        const unsigned long long direct = (unsigned long long)(seg.j[4] - seg.j[3]);
+        atomicAdd(a.executed, mid * (kNodes * G) + vfar * (kNodes16 * G) +
                               direct * (unsigned long long)(cells * chunks * 32 * kCellP));
     }
 }

@@ -456,40 +456,50 @@ LBL_HD void sum32_thread(const SumArgs& a, int layer_group, int tile, int lane)
 //
 // A warp owns a group of G consecutive integer-wavenumber cells of one layer.  All points
 // (r > 0) of a cell share the line window [cell-cut, cell+cut], so there are no window
-// edges inside a cell.  Lines are split by distance from the group:
-//   direct : centre within `reach` (>= 0.4 cm-1) of the cell.  Evaluated at every grid point
-//            exactly as in K2 (P consecutive points per thread, near-zone masks for K2b).
-//   far    : the rest of the window, ~96 % of the lines.  Their sum is smooth on the cell:
-//            each line's poles sit >= 1.8 half-widths a from the cell centre, i.e. on or
-//            outside the Bernstein ellipse rho = 1.8 + sqrt(1.8^2 - 1) = 3.3 of the cell, so
-//            the degree-31 Chebyshev interpolant of the sum through kNodes = 32 nodes is exact
-//            to ~rho^-32 ~ 1e-16 of the line's size on the cell.
-//            Lane k evaluates every far line at node k of each cell only -- 32 evaluations
-//            per (cell, line) instead of n_per_v -- and the cell's points get
-//            sum_k W[r][k] * F[k].  (G cells per warp so that one load of a line's operands
-//            feeds G evaluations: with G = 1 the kernel is bound by load issue.)
-// The interpolation matrix W (Lagrange basis of the nodes at the grid offsets r/n_per_v) is
-// the same for every cell and layer; it is built once per n_per_v on the host.
+// edges inside a cell.  Lines are split by the distance of their centre from the group:
+//   direct   within `reach` (>= kFarMin = 0.4 cm-1) of the group's cells.  Evaluated at every
+//            grid point exactly as in K2 (kCellP consecutive points per thread, near-zone
+//            points masked for K2b).
+//   mid      up to kVeryFar = 2 cm-1 beyond the cells.  Each pole sits >= 1.8 half-widths a
+//            from a cell centre, i.e. outside the Bernstein ellipse rho = 3.3 of the cell
+//            interval: the Chebyshev interpolant of the lines' sum through kNodes = 32 nodes
+//            is exact to ~rho^-32 ~ 1e-16 of a line's size on the cell.  Lane k evaluates the
+//            mid lines at node k of each cell.
+//   very far the rest of the window (~90 % of the lines): poles >= 5a away, rho = 9.9, and
+//            kNodes16 = 16 nodes do (rho^-16 ~ 1e-16).  A half-warp takes a cell's 16 nodes
+//            (G = 2), or the two half-warps split the lines of the one cell (G = 1): one
+//            evaluation per lane per line.
+// Every point of a cell then receives sum_k W32[k][r] F32[k] + sum_k W16[k][r] F16[k]; the
+// interpolation matrices (Lagrange bases of the nodes at the grid offsets r/n_per_v) are the
+// same for every cell and layer and are built once per n_per_v on the host (lbl_cheb.h).
 // ---------------------------------------------------------------------------------------
 constexpr int kNodes = 32;
-constexpr int kCellP = 4;       // points per thread in the direct part
-constexpr double kFarMin = 0.4; // cm-1 beyond the cell edges where the far field starts
+constexpr int kNodes16 = 16;
+constexpr int kCellP = 4;         // points per thread in the direct part
+constexpr double kFarMin = 0.4;   // cm-1 beyond the cell edges where the 32-node field starts
+constexpr double kVeryFar = 2.0;  // cm-1 beyond the cell edges where the 16-node field starts
 
 struct CellArgs
 {
     SumArgs sum;
-    const double* node_offset;   // [kNodes] node position relative to the cell origin v0+cell
-    const double* weights;       // [kNodes][n_per_v] interpolation matrix W (node-major)
+    const double* node_offset;     // [kNodes] node position relative to the cell origin v0+cell
+    const double* weights;         // [kNodes][n_per_v] interpolation matrix (node-major)
+    const double* node_offset16;   // [kNodes16]
+    const double* weights16;       // [kNodes16][n_per_v]
     unsigned long long* executed;  // statistics: evaluations actually performed (or nullptr)
 };
 
+// Line ranges of a cell group, as indices into the nu-sorted line list:
+//   [j0,j1) very far + window test | [j1,j2) very far | [j2,j3) mid | [j3,j4) direct |
+//   [j4,j5) mid | [j5,j6) very far | [j6,j7) very far + window test
 struct CellSegments
 {
-    int j[6];   // [j0,j1) far+window test | [j1,j2) far | [j2,j3) direct | [j3,j4) far | [j4,j5) far+test
+    int j[8];
 };
+constexpr int kCellKeys = 8;
 
-// The six search keys of the line ranges of a GROUP of `cells` consecutive cells starting at
-// `cell` (one binary search each; the kernel gives one key to each of six lanes).
+// The search keys of those ranges for the group of `cells` consecutive cells starting at
+// `cell` (one binary search each; the kernel gives one key to each of eight lanes).
 LBL_HD double cell_search_key(const GridSpec& g, const LayerIn& ly, int cell, int cells, int which)
 {
     const double lo = (double)g.v0 + (double)cell;                       // first point of the group
@@ -503,51 +513,58 @@ LBL_HD double cell_search_key(const GridSpec& g, const LayerIn& ly, int cell, in
     {
         case 0: return lo - (double)g.cut_off - ly.slack;            // first line in any cell's window
         case 1: return lo_last - (double)g.cut_off + ly.slack;       // first line certainly in all of them
-        case 2: return lo - reach;                                   // direct range
-        case 3: return hi + reach;
-        case 4: return lo + (double)(g.cut_off + 1) - ly.slack;      // end of the certain part
+        case 2: return lo - kVeryFar - ly.slack;                     // 32-node range
+        case 3: return lo - reach;                                   // direct range
+        case 4: return hi + reach;
+        case 5: return hi + kVeryFar + ly.slack;
+        case 6: return lo + (double)(g.cut_off + 1) - ly.slack;      // end of the certain part
         default: return lo_last + (double)(g.cut_off + 1) + ly.slack; // end of the last window
     }
 }
 
-LBL_HD CellSegments cell_segments_from(const int (&found)[6])
+LBL_HD int clamp_int(int x, int lo, int hi)
+{
+    return x < lo ? lo : (x > hi ? hi : x);
+}
+
+LBL_HD CellSegments cell_segments_from(const int (&found)[kCellKeys])
 {
     CellSegments s;
-    s.j[0] = found[0];
-    s.j[5] = found[5];
-    int core_lo = found[1];
-    int core_hi = found[4];
-    if (core_lo < s.j[0]) core_lo = s.j[0];
-    if (core_hi > s.j[5]) core_hi = s.j[5];
-    if (core_hi < core_lo) core_hi = core_lo;
-    int d_lo = found[2];
-    int d_hi = found[3];
-    // The direct range may reach into (or beyond) the window edges when cut_off is tiny.
-    if (d_lo < s.j[0]) d_lo = s.j[0];
-    if (d_hi > s.j[5]) d_hi = s.j[5];
-    if (d_hi < d_lo) d_hi = d_lo;
-    s.j[2] = d_lo;
-    s.j[3] = d_hi;
-    s.j[1] = core_lo < d_lo ? core_lo : d_lo;
-    s.j[4] = core_hi > d_hi ? core_hi : d_hi;
-    if (s.j[1] < s.j[0]) s.j[1] = s.j[0];
-    if (s.j[4] > s.j[5]) s.j[4] = s.j[5];
+    const int w_lo = found[0];
+    const int w_hi = found[7] > w_lo ? found[7] : w_lo;
+    // direct range, clamped to the window (it may reach beyond it when cut_off is tiny)
+    const int d_lo = clamp_int(found[3], w_lo, w_hi);
+    const int d_hi = clamp_int(found[4], d_lo, w_hi);
+    // 32-node range around it
+    const int m_lo = clamp_int(found[2], w_lo, d_lo);
+    const int m_hi = clamp_int(found[5], d_hi, w_hi);
+    // lines certainly inside every cell's window
+    const int c_lo = clamp_int(found[1], w_lo, m_lo);
+    const int c_hi = clamp_int(found[6], m_hi, w_hi);
+    s.j[0] = w_lo;
+    s.j[1] = c_lo;
+    s.j[2] = m_lo;
+    s.j[3] = d_lo;
+    s.j[4] = d_hi;
+    s.j[5] = m_hi;
+    s.j[6] = c_hi;
+    s.j[7] = w_hi;
     return s;
 }
 
 LBL_HD CellSegments cell_segments(const LinesView& lines, const GridSpec& g, const LayerIn& ly,
                                   int cell, int cells)
 {
-    int found[6];
-    for (int which = 0; which < 6; ++which)
+    int found[kCellKeys];
+    for (int which = 0; which < kCellKeys; ++which)
     {
         found[which] = lower_bound(lines.nu, lines.n, cell_search_key(g, ly, cell, cells, which));
     }
     return cell_segments_from(found);
 }
 
-// Far lines of [jb, je) at this lane's node in each of the G cells, no tests.  Pairs of lines
-// share a reciprocal; U*G independent chains per lane keep the FP64 pipe busy.
+// Mid lines of [jb, je) at this lane's node in each of the G cells.  Pairs of lines share a
+// reciprocal; U*G independent chains per lane keep the FP64 pipe busy.
 template <int G>
 LBL_HD void node_plain(const FarAB* __restrict__ ab, const double* __restrict__ cc, int jb, int je,
                        const double (&v)[G], double (&sum)[G])
@@ -586,36 +603,101 @@ LBL_HD void node_plain(const FarAB* __restrict__ ab, const double* __restrict__ 
     }
 }
 
-// Far lines next to a window edge: each cell's own window test decides
-// (cb within [cell-cut, cell+cut]); a line outside a cell's window is masked for that cell.
-template <int G>
-LBL_HD void node_tested(const FarAB* __restrict__ ab, const double* __restrict__ cc,
-                        const LineChk* __restrict__ chk, int jb, int je, int cell, int cut_off,
-                        const double (&v)[G], double (&sum)[G])
+// Very far lines of [jb, je) at ONE point per lane (a 16-node point of the lane's cell).
+// `first`/`stride`: which lines of the range this lane takes (all of them when a half-warp
+// owns a cell; every other pair when the two half-warps share one cell).
+LBL_HD double node16_plain(const FarAB* __restrict__ ab, const double* __restrict__ cc, int jb,
+                           int je, int first, int stride, double v)
 {
-    for (int j = jb; j < je; ++j)
+    double acc[4] = {0., 0., 0., 0.};
+    const double vv[1] = {v};
+    // pairs (jb + 2p, jb + 2p + 1), p = first, first + stride, ...
+    const int pairs = (je - jb) >> 1;
+    int p = first;
+    for (; p + 3 * stride < pairs; p += 4 * stride)
+    {
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+        {
+            const int j = jb + 2 * (p + u * stride);
+            const double2 l1 = LBL_LDG(reinterpret_cast<const double2*>(ab + j));
+            const double2 l2 = LBL_LDG(reinterpret_cast<const double2*>(ab + j + 1));
+            double one[1] = {acc[u]};
+            far_terms_pair<1>(vv, l1.x, l1.y, LBL_LDG(cc + j), l2.x, l2.y, LBL_LDG(cc + j + 1), one);
+            acc[u] = one[0];
+        }
+    }
+    for (; p < pairs; p += stride)
+    {
+        const int j = jb + 2 * p;
+        const double2 l1 = LBL_LDG(reinterpret_cast<const double2*>(ab + j));
+        const double2 l2 = LBL_LDG(reinterpret_cast<const double2*>(ab + j + 1));
+        double one[1] = {acc[0]};
+        far_terms_pair<1>(vv, l1.x, l1.y, LBL_LDG(cc + j), l2.x, l2.y, LBL_LDG(cc + j + 1), one);
+        acc[0] = one[0];
+    }
+    if (((je - jb) & 1) && first == 0)
+    {
+        const int j = je - 1;   // odd line out
+        const double2 l = LBL_LDG(reinterpret_cast<const double2*>(ab + j));
+        acc[1] = far_term(v, l.x, l.y, LBL_LDG(cc + j), acc[1]);
+    }
+    return (acc[0] + acc[1]) + (acc[2] + acc[3]);
+}
+
+// Very far lines next to a window edge: the lane's cell's own window test decides.
+LBL_HD double node16_tested(const FarAB* __restrict__ ab, const double* __restrict__ cc,
+                            const LineChk* __restrict__ chk, int jb, int je, int first, int stride,
+                            int cell, int cut_off, double v)
+{
+    double acc = 0.;
+    for (int j = jb + first; j < je; j += stride)
     {
         const int cb = LBL_LDG(reinterpret_cast<const int4*>(chk + j)).x;
-        if (cb < cell - cut_off || cb > cell + G - 1 + cut_off)
+        if (cb < cell - cut_off || cb > cell + cut_off)
         {
             continue;
         }
         const double2 l = LBL_LDG(reinterpret_cast<const double2*>(ab + j));
-        const double c = LBL_LDG(cc + j);
-#pragma unroll
-        for (int q = 0; q < G; ++q)
-        {
-            const bool in = (cb >= cell + q - cut_off) && (cb <= cell + q + cut_off);
-            sum[q] = far_term(v[q], l.x, l.y, in ? c : kBig, sum[q]);
-        }
+        acc = far_term(v, l.x, l.y, LBL_LDG(cc + j), acc);
     }
+    return acc;
 }
 
-// Phase 1, lane = node: sums of the far lines at this lane's node of each cell of the group.
+// How the 32 lanes map onto 16-node points: (cell offset, node, first line share, stride).
+template <int G>
+struct Lane16
+{
+    int cell_off, node, first, stride;
+};
+template <int G>
+LBL_HD Lane16<G> lane16(int lane)
+{
+    Lane16<G> m;
+    m.node = lane & 15;
+    if (G >= 2)
+    {
+        m.cell_off = lane >> 4;   // a half-warp per cell (G == 2)
+        m.first = 0;
+        m.stride = 1;
+    }
+    else
+    {
+        m.cell_off = 0;           // the half-warps split the lines of the one cell
+        m.first = lane >> 4;
+        m.stride = 2;
+    }
+    return m;
+}
+
+// Phase 1, lane = node: sums of the mid lines at this lane's 32-node point of each cell (f32)
+// and of the very far lines at this lane's 16-node point (f16; for G == 1 the two half-warps
+// hold partial sums of the same 16 points).
 template <int G>
 LBL_HD void cell_far_lane(const CellArgs& a, int layer, int cell, int lane, const CellSegments& seg,
-                          double (&f)[G])
+                          double (&f32)[G], double& f16)
 {
+    static_assert(G == 1 || G == 2, "a warp holds the 16-node points of one or two cells");
     const GridSpec& g = a.sum.grid;
     const size_t off = (size_t)layer * a.sum.lines.n;
     const FarAB* ab = a.sum.rec.ab + off;
@@ -626,12 +708,17 @@ LBL_HD void cell_far_lane(const CellArgs& a, int layer, int cell, int lane, cons
     for (int q = 0; q < G; ++q)
     {
         v[q] = ((double)g.v0 + (double)(cell + q)) + a.node_offset[lane];
-        f[q] = 0.;
+        f32[q] = 0.;
     }
-    node_tested<G>(ab, cc, chk, seg.j[0], seg.j[1], cell, g.cut_off, v, f);
-    node_plain<G>(ab, cc, seg.j[1], seg.j[2], v, f);
-    node_plain<G>(ab, cc, seg.j[3], seg.j[4], v, f);
-    node_tested<G>(ab, cc, chk, seg.j[4], seg.j[5], cell, g.cut_off, v, f);
+    node_plain<G>(ab, cc, seg.j[2], seg.j[3], v, f32);
+    node_plain<G>(ab, cc, seg.j[4], seg.j[5], v, f32);
+    const Lane16<G> m = lane16<G>(lane);
+    const int my_cell = cell + m.cell_off;
+    const double v16 = ((double)g.v0 + (double)my_cell) + a.node_offset16[m.node];
+    f16 = node16_tested(ab, cc, chk, seg.j[0], seg.j[1], m.first, m.stride, my_cell, g.cut_off, v16);
+    f16 += node16_plain(ab, cc, seg.j[1], seg.j[2], m.first, m.stride, v16);
+    f16 += node16_plain(ab, cc, seg.j[5], seg.j[6], m.first, m.stride, v16);
+    f16 += node16_tested(ab, cc, chk, seg.j[6], seg.j[7], m.first, m.stride, my_cell, g.cut_off, v16);
 }
 
 // Phase 2, lane = kCellP consecutive points of chunk `chunk` of the cell: the direct lines.
@@ -656,7 +743,7 @@ LBL_HD void cell_direct_lane(const CellArgs& a, int layer, int cell, int chunk, 
         acc[p] = 0.;
     }
     const size_t off = (size_t)layer * a.sum.lines.n;
-    masked_range<P>(a.sum.rec.ab + off, a.sum.rec.cc + off, a.sum.rec.chk + off, seg.j[2], seg.j[3],
+    masked_range<P>(a.sum.rec.ab + off, a.sum.rec.cc + off, a.sum.rec.chk + off, seg.j[3], seg.j[4],
                     i_first, cell, g.cut_off, v, acc);
     if (valid)
     {
@@ -669,10 +756,11 @@ LBL_HD void cell_direct_lane(const CellArgs& a, int layer, int cell, int chunk, 
     }
 }
 
-// Phase 3, lane = points lane, lane+32, ... of the cell: add the interpolated far field
-// sum_k W[k][r] * field[k].  W is stored node-major so that a warp reads consecutive r.
+// Phase 3, lane = points lane, lane+32, ... of the cell: add the interpolated far fields
+// sum_k W32[k][r] * field32[k] + sum_k W16[k][r] * field16[k].  The matrices are stored
+// node-major so that a warp reads consecutive r.
 LBL_HD void cell_field_lane(const CellArgs& a, int layer, int cell, int lane, int nlanes,
-                            const double* field)
+                            const double* field32, const double* field16)
 {
     const GridSpec& g = a.sum.grid;
     double* o = a.sum.out + (size_t)layer * g.n + (size_t)cell * g.n_per_v;
@@ -682,9 +770,15 @@ LBL_HD void cell_field_lane(const CellArgs& a, int layer, int cell, int lane, in
 #pragma unroll 8
         for (int k = 0; k < kNodes; ++k)
         {
-            far = fma_(LBL_LDG(a.weights + (size_t)k * g.n_per_v + r), field[k], far);
+            far = fma_(LBL_LDG(a.weights + (size_t)k * g.n_per_v + r), field32[k], far);
         }
-        o[r] += far;
+        double far16 = 0.;
+#pragma unroll 8
+        for (int k = 0; k < kNodes16; ++k)
+        {
+            far16 = fma_(LBL_LDG(a.weights16 + (size_t)k * g.n_per_v + r), field16[k], far16);
+        }
+        o[r] += far + far16;
     }
 }
 

@@ -39,6 +39,39 @@ static void run_sum(const SumArgs& a, int n_layers, bool fp32)
     }
 }
 
+template <int G>
+static void run_cells(const CellArgs& ca, const LinesView& ln, const GridSpec& g,
+                      const std::vector<LayerIn>& layers, int n_layers)
+{
+    std::vector<double> fields((size_t)G * kNodes), fields16((size_t)G * kNodes16, 0.);
+    const int chunks = (g.n_per_v + 32 * kCellP - 1) / (32 * kCellP);
+    for (int layer = 0; layer < n_layers; ++layer)
+    {
+        for (int cell = 0; cell < g.ncell; cell += G)
+        {
+            const CellSegments seg = cell_segments(ln, g, layers[layer], cell, G);
+            const int cells = std::min(G, g.ncell - cell);
+            std::fill(fields16.begin(), fields16.end(), 0.);
+            for (int lane = 0; lane < 32; ++lane)
+            {
+                double f32[G], f16;
+                cell_far_lane<G>(ca, layer, cell, lane, seg, f32, f16);
+                for (int q = 0; q < G; ++q) fields[(size_t)q * kNodes + lane] = f32[q];
+                const Lane16<G> m = lane16<G>(lane);
+                fields16[(size_t)m.cell_off * kNodes16 + m.node] += f16;   // G == 1: two partial sums
+            }
+            for (int q = 0; q < cells; ++q)
+                for (int chunk = 0; chunk < chunks; ++chunk)
+                    for (int lane = 0; lane < 32; ++lane)
+                        cell_direct_lane(ca, layer, cell + q, chunk, lane, seg);
+            for (int q = 0; q < cells; ++q)
+                for (int lane = 0; lane < 32; ++lane)
+                    cell_field_lane(ca, layer, cell + q, lane, 32, fields.data() + (size_t)q * kNodes,
+                                    fields16.data() + (size_t)q * kNodes16);
+        }
+    }
+}
+
 struct NoSync
 {
     void operator()() const {}
@@ -254,38 +287,20 @@ extern "C" int emu_absorption(int n_layers, const double* pressure, const double
     }
     if (points_per_thread == 0)
     {
-        // K2c: cell-tiled summation with the Chebyshev far field, one emulated warp per cell
-        std::vector<double> nodes, weights, field(kNodes);
+        // K2c: cell-tiled summation with the two-level Chebyshev far field, one emulated warp
+        // per group of cells (the library uses 2 cells up to n_per_v = 256, else 1)
+        std::vector<double> nodes, weights, nodes16, weights16;
         build_cheb_tables(kNodes, n_per_v, nodes, weights);
+        build_cheb_tables(kNodes16, n_per_v, nodes16, weights16);
         CellArgs ca;
         ca.sum = sa;
         ca.node_offset = nodes.data();
         ca.weights = weights.data();
+        ca.node_offset16 = nodes16.data();
+        ca.weights16 = weights16.data();
         ca.executed = nullptr;
-        constexpr int G = 2;   // cells per emulated warp (the library uses 2 up to n_per_v = 256, else 1)
-        std::vector<double> fields((size_t)G * kNodes);
-        for (int layer = 0; layer < n_layers; ++layer)
-        {
-            for (int cell = 0; cell < g.ncell; cell += G)
-            {
-                const CellSegments seg = cell_segments(ln, g, layers[layer], cell, G);
-                const int cells = std::min(G, g.ncell - cell);
-                for (int lane = 0; lane < 32; ++lane)
-                {
-                    double f[G];
-                    cell_far_lane<G>(ca, layer, cell, lane, seg, f);
-                    for (int q = 0; q < G; ++q) fields[(size_t)q * kNodes + lane] = f[q];
-                }
-                const int chunks = (n_per_v + 32 * kCellP - 1) / (32 * kCellP);
-                for (int q = 0; q < cells; ++q)
-                    for (int chunk = 0; chunk < chunks; ++chunk)
-                        for (int lane = 0; lane < 32; ++lane)
-                            cell_direct_lane(ca, layer, cell + q, chunk, lane, seg);
-                for (int q = 0; q < cells; ++q)
-                    for (int lane = 0; lane < 32; ++lane)
-                        cell_field_lane(ca, layer, cell + q, lane, 32, fields.data() + (size_t)q * kNodes);
-            }
-        }
+        if (n_per_v <= 256) run_cells<2>(ca, ln, g, layers, n_layers);
+        else run_cells<1>(ca, ln, g, layers, n_layers);
     }
     else switch (points_per_thread)
     {
