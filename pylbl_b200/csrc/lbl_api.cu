@@ -964,6 +964,7 @@ int lbl_gas_submit(lbl_gas* g, int n_layers, const double* pressure, const doubl
         sa.out = g->out[slot].as<double>();
         sa.n_layers = nl;
         sa.tpw = pick_threads_per_layer(n_per_v, P, nl);
+        sa.near_masked = farfield ? 0 : 1;
         LBL_CUDA(cudaEventRecord(ev.k2_begin, sc));
         if (farfield)
         {

@@ -449,6 +449,12 @@ __device__ __forceinline__ void fixup_warp(const SumArgs& a, int tile, int layer
                     const double2 g1 = __ldg(reinterpret_cast<const double2*>(gen + j) + 1);
                     const double2 g2 = __ldg(reinterpret_cast<const double2*>(gen + j) + 2);
                     const double abx = fabs((v - g0.x) * g0.y);
+                    if (!a.near_masked)
+                    {
+                        // the summation kernel added the Lorentz form here: take it back
+                        const double2 l = __ldg(reinterpret_cast<const double2*>(a.rec.ab + off + j));
+                        acc -= far_term(v, l.x, l.y, __ldg(a.rec.cc + off + j), 0.);
+                    }
                     if (abx >= voigt_outer_limit(g1.x, g2.x, g2.y))
                     {
                         acc += g1.y * voigt_outer(abx, abx * abx, g1.x, g2.x);

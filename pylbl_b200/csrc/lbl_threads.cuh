@@ -178,6 +178,8 @@ struct SumArgs
     int n_layers;
     int tpw;      // K2: threads of one warp that share a layer (power of two); a warp covers
                   // tpw*P consecutive points of 32/tpw consecutive layers
+    int near_masked;  // 1: the summation kernel left near-zone points out (K2); 0: it added the
+                      // Lorentz form there too (K2c) and K2b must add (profile - Lorentz)
 };
 
 template <int P>
@@ -249,6 +251,26 @@ struct SumLane
     bool valid;                   // owns real points (stores its result)
     bool any;                     // false: the whole warp is past the end of the grid
 };
+
+// Lines [jb, je) at P consecutive points of one cell, Lorentz form everywhere (window test only).
+template <int P>
+LBL_HD void window_range(const FarAB* __restrict__ ab, const double* __restrict__ cc,
+                         const LineChk* __restrict__ chk, int jb, int je, int cell, int cut_off,
+                         const double (&v)[P], double (&acc)[P])
+{
+    const int cmin = cell - cut_off;
+    const int cmax = cell + cut_off;
+    for (int j = jb; j < je; ++j)
+    {
+        const int cb = LBL_LDG(reinterpret_cast<const int4*>(chk + j)).x;
+        if (cb < cmin || cb > cmax)
+        {
+            continue;
+        }
+        const double2 l = LBL_LDG(reinterpret_cast<const double2*>(ab + j));
+        far_terms<P>(v, l.x, l.y, LBL_LDG(cc + j), acc);
+    }
+}
 
 template <int P>
 LBL_HD SumLane sum_lane(const SumArgs& a, int layer_group, int tile, int lane)
@@ -457,9 +479,10 @@ LBL_HD void sum32_thread(const SumArgs& a, int layer_group, int tile, int lane)
 // A warp owns a group of G consecutive integer-wavenumber cells of one layer.  All points
 // (r > 0) of a cell share the line window [cell-cut, cell+cut], so there are no window
 // edges inside a cell.  Lines are split by the distance of their centre from the group:
-//   direct   within `reach` (>= kFarMin = 0.4 cm-1) of the group's cells.  Evaluated at every
-//            grid point exactly as in K2 (kCellP consecutive points per thread, near-zone
-//            points masked for K2b).
+//   direct   within kFarMin = 0.4 cm-1 of the group's cells.  Evaluated at every grid point
+//            (kCellP consecutive points per thread).  Unlike K2, this kernel adds the
+//            Lorentz form at a line's near-zone points too -- a smooth function that the
+//            interpolation handles like any other -- and K2b adds (profile - Lorentz) there.
 //   mid      up to kVeryFar = 2 cm-1 beyond the cells.  Each pole sits >= 1.8 half-widths a
 //            from a cell centre, i.e. outside the Bernstein ellipse rho = 3.3 of the cell
 //            interval: the Chebyshev interpolant of the lines' sum through kNodes = 32 nodes
@@ -505,10 +528,7 @@ LBL_HD double cell_search_key(const GridSpec& g, const LayerIn& ly, int cell, in
     const double lo = (double)g.v0 + (double)cell;                       // first point of the group
     const double lo_last = lo + (double)(cells - 1);                     // first point of its last cell
     const double hi = lo_last + (double)(g.n_per_v - 1) * g.dv;          // last point of the group
-    const double near = (ly.kappa < 0.5)
-        ? (ly.kappa * fabs(hi) / (1.0 - ly.kappa)) * (1.0 + 0x1p-20) + 3.0 * g.dv
-        : 1.0e300;
-    const double reach = (near > kFarMin ? near : kFarMin) + ly.slack;
+    const double reach = kFarMin + ly.slack;
     switch (which)
     {
         case 0: return lo - (double)g.cut_off - ly.slack;            // first line in any cell's window
@@ -743,8 +763,8 @@ LBL_HD void cell_direct_lane(const CellArgs& a, int layer, int cell, int chunk, 
         acc[p] = 0.;
     }
     const size_t off = (size_t)layer * a.sum.lines.n;
-    masked_range<P>(a.sum.rec.ab + off, a.sum.rec.cc + off, a.sum.rec.chk + off, seg.j[3], seg.j[4],
-                    i_first, cell, g.cut_off, v, acc);
+    window_range<P>(a.sum.rec.ab + off, a.sum.rec.cc + off, a.sum.rec.chk + off, seg.j[3], seg.j[4],
+                    cell, g.cut_off, v, acc);
     if (valid)
     {
         double* o = a.sum.out + (size_t)layer * g.n + i_first;
@@ -849,6 +869,11 @@ LBL_HD void fixup_thread(const SumArgs& a, int tile, int layer_group, int lane)
             const double2 g1 = LBL_LDG(reinterpret_cast<const double2*>(gen + j) + 1);
             const double2 g2 = LBL_LDG(reinterpret_cast<const double2*>(gen + j) + 2);
             acc += voigt_general(v, g0.x, g0.y, g1.x, g1.y, g2.x, g2.y);
+            if (!a.near_masked)
+            {
+                const double2 l = LBL_LDG(reinterpret_cast<const double2*>(a.rec.ab + off + j));
+                acc -= far_term(v, l.x, l.y, LBL_LDG(a.rec.cc + off + j), 0.);
+            }
         }
     }
     // (2) node terms: lines with cb == cell-cut-1 reach exactly the cell's first point.

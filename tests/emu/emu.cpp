@@ -278,6 +278,7 @@ extern "C" int emu_absorption(int n_layers, const double* pressure, const double
     sa.grid = g;
     sa.out = k;
     sa.n_layers = n_layers;
+    sa.near_masked = (points_per_thread == 0) ? 0 : 1;
     {
         // same rule as pick_threads_per_layer() in lbl_api.cu
         int tpw = 32;
