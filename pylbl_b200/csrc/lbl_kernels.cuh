@@ -417,6 +417,8 @@ __device__ __forceinline__ void fixup_warp(const SumArgs& a, int tile, int layer
     const double v = grid_point(g.v0, g.dv, i);
     const int cell = i / g.n_per_v;
     const bool is_node = (i - cell * g.n_per_v) == 0;
+    const int cb_min = cell - g.cut_off - (is_node ? 1 : 0);
+    const int cb_max = cell + g.cut_off;
     double acc = 0.;
 
     int jlo, jhi;
@@ -440,10 +442,9 @@ __device__ __forceinline__ void fixup_warp(const SumArgs& a, int tile, int layer
             const int4 ck = __ldg(reinterpret_cast<const int4*>(chk + j));
             if (i >= ck.y && i <= ck.z)
             {
-                // inside the line's window? s <= i <= e, spectra.c:48-62 (unclamped form)
-                const long long s = (long long)(ck.x - g.cut_off) * g.n_per_v;
-                const long long e = (long long)(ck.x + g.cut_off + 1) * g.n_per_v;
-                if ((long long)i >= s && (long long)i <= e)
+                // inside the line's window?  s <= i <= e of spectra.c:48-62 in cell form:
+                // cell-cut <= cb <= cell+cut, plus cb == cell-cut-1 for a cell's first point
+                if (ck.x >= cb_min && ck.x <= cb_max)
                 {
                     const double2 g0 = __ldg(reinterpret_cast<const double2*>(gen + j));
                     const double2 g1 = __ldg(reinterpret_cast<const double2*>(gen + j) + 1);
