@@ -380,7 +380,9 @@ def run_ours(args, rank, local_rank, world, dist):
     # The summation kernel on fine grids interpolates the far field: it PERFORMS `executed`
     # Lorentz evaluations to deliver `evals` reference-equivalent ones.  The roofline counts
     # the work performed; `value` counts the work delivered.
-    flops = FLOP_PER_EVAL * executed                    # this rank, timed region
+    # K2c also spends 2 flop per (point, node) on the interpolation: 48 nodes per point.
+    interp_flops = 2.0 * 48 * n * N_LAYERS * len(GASES) * args.steps if cells else 0.0
+    flops = FLOP_PER_EVAL * executed + interp_flops     # this rank, timed region
     achieved = flops / (sum_ms * 1e-3) / 1e12 if sum_ms > 0 else 0.0
     kernel = f"lbl::sum_cell_kernel<{cells}>" if cells else f"lbl::sum_kernel<{points}>"
     roofline = {
@@ -388,6 +390,7 @@ def run_ours(args, rank, local_rank, world, dist):
         "peak": peak.value, "unit": "TFLOP/s",
         "frac": achieved / peak.value if peak.value else None, "traffic": None,
         "flop_per_eval": FLOP_PER_EVAL,
+        "interpolation_flops_per_launch": interp_flops / max(sum_launches, 1),
         "executed_evals_per_launch": executed / max(sum_launches, 1),
         "reference_evals_per_launch": evals / max(sum_launches, 1),
         "far_field_work_reduction": evals / executed if executed else None,

@@ -643,7 +643,7 @@ int lbl_gas_submit(lbl_gas* g, int n_layers, const double* pressure, const doubl
     {
         return fail("Error: unsupported precision mode.");
     }
-    const bool fp32 = precision == LBL_PRECISION_FP32;
+    const bool fp32_requested = precision == LBL_PRECISION_FP32;
     if (n_layers < 0 || n_per_v < 1 || vn <= v0 || cut_off < 0)
     {
         return fail("Error: invalid grid or layer count.");
@@ -693,8 +693,11 @@ int lbl_gas_submit(lbl_gas* g, int n_layers, const double* pressure, const doubl
     st.n_active = plan.n_active;
     // Fine grids use the cell-tiled kernel with the polynomial far field (K2c); coarse grids
     // (a cell holds fewer points than the 32 interpolation nodes would cost) use K2.
-    bool farfield = !fp32 && n_per_v >= 64;
+    bool farfield = n_per_v >= 64;
     if (const char* env = getenv("PYLBL_B200_FARFIELD")) farfield = farfield && atoi(env) != 0;
+    // The FP32 mode is a mode of the direct kernel K2.  Where K2c runs it is already faster
+    // in FP64 than K2 is in FP32, so the request is honoured with FP64 arithmetic there.
+    const bool fp32 = fp32_requested && !farfield;
     const int P = farfield ? kCellP : pick_points_per_thread(n_per_v);
     st.points_per_thread = P;
 

@@ -141,7 +141,7 @@ def test_large_pressure_shift_near_integer_boundaries(emu, tmp_path):
         assert evals == total
 
 
-@pytest.mark.parametrize("bounds", [(1, 601, 10), (1, 301, 100), (1, 500, 4), (1, 41, 1000)])
+@pytest.mark.parametrize("bounds", [(1, 601, 10), (1, 301, 32), (1, 500, 4), (1, 41, 50)])
 @pytest.mark.parametrize("ped", [0, 1])
 def test_fp32_mode_within_stated_tolerance(emu, small_db, atmosphere, bounds, ped):
     """Opt-in FP32 far-wing arithmetic: 1e-4 of the local scale (and pointwise without the
