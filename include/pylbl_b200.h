@@ -107,6 +107,23 @@ LBL_API int lbl_gas_windows(lbl_gas* gas, int layer, int* s, int* e, int capacit
  * out[4*r + {0,1,2,3}] = nu', alpha, gamma, sw'.  capacity >= n_active. */
 LBL_API int lbl_gas_scaled(lbl_gas* gas, int layer, double* out, int capacity);
 
+/* ---- gas-summed absorption on the device ("next" step after the path) -------------------
+ * Replaces the host-side  beta = n * k[:grid.size]  and the sum over gases of
+ * pyLBL/spectroscopy.py:181-191,225-234 (output_format="total", lines mechanism): the
+ * spectra of several gases stay on the device, are scaled per layer and summed there, and
+ * one array comes back instead of one per gas.
+ *   lbl_mix_open   allocates a zeroed accumulator of n_layers*n doubles on `device`
+ *   lbl_mix_add    acc[L][i] += scale[L] * k_gas[L][i] with the spectra of the gas's last
+ *                  call, which must still be resident on the device (k_host == NULL, one
+ *                  layer group); scale = number density p*x/(kB*T) for beta in m-1
+ *   lbl_mix_download  copies the accumulator to host memory (blocking) */
+typedef struct lbl_mix lbl_mix;
+LBL_API int lbl_mix_open(int device, int n_layers, int n_points, lbl_mix** out);
+LBL_API int lbl_mix_reset(lbl_mix* mix);
+LBL_API int lbl_mix_add(lbl_mix* mix, lbl_gas* gas, const double* scale);
+LBL_API int lbl_mix_download(lbl_mix* mix, double* host);
+LBL_API int lbl_mix_close(lbl_mix* mix);
+
 /* Pinned host memory for k_host (lets the device->host copy run asynchronously). */
 LBL_API int lbl_host_alloc(size_t bytes, void** ptr);
 LBL_API int lbl_host_free(void* ptr);

@@ -45,7 +45,8 @@ EXPORTS = (
     "lbl_gas_wait", "lbl_gas_stats", "lbl_gas_device_result", "lbl_gas_windows",
     "lbl_gas_scaled", "lbl_host_alloc", "lbl_host_free", "lbl_device_count",
     "lbl_set_chunk_layers", "lbl_last_error", "lbl_version", "lbl_timer_start",
-    "lbl_timer_join", "lbl_timer_stop", "lbl_measure_fp64_peak",
+    "lbl_timer_join", "lbl_timer_stop", "lbl_measure_fp64_peak", "lbl_mix_open", "lbl_mix_reset",
+    "lbl_mix_add", "lbl_mix_download", "lbl_mix_close",
 )
 
 _library = None
@@ -93,6 +94,11 @@ def library():
     lib.lbl_timer_join.argtypes = [c_void_p]
     lib.lbl_timer_stop.argtypes = [c_int, POINTER(c_float)]
     lib.lbl_measure_fp64_peak.argtypes = [c_int, POINTER(c_double)]
+    lib.lbl_mix_open.argtypes = [c_int, c_int, c_int, POINTER(c_void_p)]
+    lib.lbl_mix_reset.argtypes = [c_void_p]
+    lib.lbl_mix_add.argtypes = [c_void_p, c_void_p, f64]
+    lib.lbl_mix_download.argtypes = [c_void_p, c_void_p]
+    lib.lbl_mix_close.argtypes = [c_void_p]
     for name in EXPORTS:
         if name not in ("absorption", "lbl_last_error", "lbl_version"):
             getattr(lib, name).restype = check_return_code

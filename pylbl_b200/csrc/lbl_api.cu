@@ -1184,6 +1184,107 @@ int lbl_gas_scaled(lbl_gas* g, int layer, double* out, int capacity)
     return 0;
 }
 
+// ---- gas-summed absorption on the device ----------------------------------------------------
+}  // extern "C"
+
+struct lbl_mix
+{
+    int device = 0;
+    int n_layers = 0, n = 0;
+    cudaStream_t stream = nullptr;
+    DevBuf acc, scale;
+};
+
+extern "C" {
+
+int lbl_mix_open(int device, int n_layers, int n_points, lbl_mix** out)
+{
+    *out = nullptr;
+    if (n_layers <= 0 || n_points <= 0) return fail("Error: invalid accumulator shape.");
+    int ndev = 0;
+    if (lbl_device_count(&ndev)) return 1;
+    if (device < 0 || device >= ndev) return fail("Error: CUDA device index out of range.");
+    std::unique_ptr<lbl_mix> m(new lbl_mix);
+    m->device = device;
+    m->n_layers = n_layers;
+    m->n = n_points;
+    LBL_CUDA(cudaSetDevice(device));
+    LBL_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+    LBL_CUDA(m->acc.reserve(sizeof(double) * (size_t)n_layers * n_points));
+    LBL_CUDA(m->scale.reserve(sizeof(double) * (size_t)n_layers));
+    LBL_CUDA(cudaMemsetAsync(m->acc.p, 0, sizeof(double) * (size_t)n_layers * n_points, m->stream));
+    LBL_CUDA(cudaStreamSynchronize(m->stream));
+    *out = m.release();
+    return 0;
+}
+
+int lbl_mix_reset(lbl_mix* m)
+{
+    if (!m) return fail("Error: null handle.");
+    LBL_CUDA(cudaSetDevice(m->device));
+    LBL_CUDA(cudaMemsetAsync(m->acc.p, 0, sizeof(double) * (size_t)m->n_layers * m->n, m->stream));
+    return 0;
+}
+
+int lbl_mix_add(lbl_mix* m, lbl_gas* g, const double* scale)
+{
+    if (!m || !g) return fail("Error: null handle.");
+    if (g->device != m->device) return fail("Error: gas and accumulator live on different devices.");
+    LBL_CUDA(cudaSetDevice(m->device));
+    if (g->stats.n_layers != m->n_layers || g->last_grid.n != m->n)
+    {
+        return fail("Error: accumulator shape differs from the gas's last call.");
+    }
+    if (g->stats.n_active == 0)
+    {
+        return 0;   // the gas contributed an all-zero spectrum
+    }
+    if (g->last_chunk_first != 0 || g->last_chunk_layers != m->n_layers)
+    {
+        return fail("Error: the gas's spectra are not resident on the device "
+                    "(compute with k_host == NULL and a single layer group).");
+    }
+    // The accumulator's stream waits for the gas's kernels; accumulations of different gases
+    // are ordered on that one stream, so the sum needs no atomics.
+    if (g->pending)
+    {
+        LBL_CUDA(cudaStreamWaitEvent(m->stream, g->ev_call_end, 0));
+    }
+    // scale[] is consumed asynchronously: stage it through the stream in order
+    LBL_CUDA(cudaMemcpyAsync(m->scale.p, scale, sizeof(double) * m->n_layers, cudaMemcpyHostToDevice,
+                             m->stream));
+    const size_t total = (size_t)m->n_layers * m->n;
+    const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
+    mix_add_kernel<<<blocks, 256, 0, m->stream>>>(m->acc.as<double>(),
+                                                  g->out[g->last_slot].as<double>(),
+                                                  m->scale.as<double>(), m->n, m->n_layers);
+    LBL_CUDA(cudaGetLastError());
+    // the gas must not start a new call before its spectra have been consumed
+    LBL_CUDA(cudaStreamSynchronize(m->stream));
+    return 0;
+}
+
+int lbl_mix_download(lbl_mix* m, double* host)
+{
+    if (!m || !host) return fail("Error: null argument.");
+    LBL_CUDA(cudaSetDevice(m->device));
+    LBL_CUDA(cudaMemcpyAsync(host, m->acc.p, sizeof(double) * (size_t)m->n_layers * m->n,
+                             cudaMemcpyDeviceToHost, m->stream));
+    LBL_CUDA(cudaStreamSynchronize(m->stream));
+    return 0;
+}
+
+int lbl_mix_close(lbl_mix* m)
+{
+    if (!m) return 0;
+    cudaSetDevice(m->device);
+    m->acc.release();
+    m->scale.release();
+    if (m->stream) cudaStreamDestroy(m->stream);
+    delete m;
+    return 0;
+}
+
 // ---- the reference's own entry point (absorption.c:19-30) ---------------------------------
 int absorption(double pressure, double temperature, double volume_mixing_ratio, int v0, int vn,
                int n_per_v, double* k, char* database, char* formula, int cut_off,

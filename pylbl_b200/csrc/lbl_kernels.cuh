@@ -766,6 +766,18 @@ __global__ void pedestal_apply_kernel(double* __restrict__ out, const double* __
     }
 }
 
+// Gas-sum epilogue: acc[layer][i] += scale[layer] * k[layer][i]  (spectroscopy.py:181-191).
+__global__ void mix_add_kernel(double* __restrict__ acc, const double* __restrict__ k,
+                               const double* __restrict__ scale, int n, int n_layers)
+{
+    const size_t total = (size_t)n_layers * n;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x)
+    {
+        acc[idx] = fma(scale[idx / n], k[idx], acc[idx]);
+    }
+}
+
 // FP64 peak probe: 8 independent DFMA chains per thread, nothing else in the loop.
 __global__ void __launch_bounds__(256) dfma_probe_kernel(double* out, int iters, double a, double b)
 {

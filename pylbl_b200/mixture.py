@@ -1,0 +1,82 @@
+"""Gas-summed line absorption on the device.
+
+pyLBL's driver turns each gas's cross-sections into absorption coefficients on the host,
+``beta = n * k[:grid.size]`` with ``n = p*x/(kB*T)`` (pyLBL/spectroscopy.py:18-29,181-191),
+and sums the gases when ``output_format="total"`` (:225-234).  With every spectrum coming
+back over PCIe that sum costs seven device-to-host copies per column.  ``Mixture`` keeps the
+per-gas spectra on the GPU, applies the number densities there and returns one array.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import c_void_p
+
+import numpy as np
+
+from . import _lib
+from .gas_optics import Gas, default_device, grid_to_ints
+
+KB = 1.38064852e-23  # Boltzmann constant [J K-1], pyLBL/spectroscopy.py:15
+
+
+def number_density(temperature, pressure, volume_mixing_ratio):
+    """Ideal-gas number density [m-3], pyLBL/spectroscopy.py:18-29."""
+    return pressure * volume_mixing_ratio / (KB * temperature)
+
+
+class Mixture(object):
+    """Several gases of one database on one device, summed on the device."""
+
+    def __init__(self, lines_database, formulas, device=None, precision="fp64"):
+        self.device = default_device() if device is None else int(device)
+        self.gases = {f: Gas(lines_database, f, devices=[self.device], precision=precision)
+                      for f in formulas}
+        self._mix = None
+        self._shape = None
+
+    def close(self):
+        if self._mix is not None:
+            _lib.library().lbl_mix_close(self._mix)
+            self._mix = None
+        for g in self.gases.values():
+            g.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def total_absorption(self, temperature, pressure, volume_mixing_ratio, grid=None,
+                         remove_pedestal=True, cut_off=25, bounds=None, out=None):
+        """sum over gases of n_gas * k_gas [m-1], shape (n_layers, (vn-v0)*n_per_v).
+
+        Args:
+            volume_mixing_ratio: {formula: array over layers}.
+            remove_pedestal: True is what ``Spectroscopy.compute_absorption`` passes with the
+                             MT-CKD continuum backend (pyLBL/spectroscopy.py:163-164).
+        """
+        v0, vn, n_per_v = bounds if bounds is not None else grid_to_ints(grid)
+        t = np.ascontiguousarray(temperature, dtype=np.float64).ravel()
+        p = np.ascontiguousarray(pressure, dtype=np.float64).ravel()
+        n_layers, n = t.size, (vn - v0) * n_per_v
+        lib = _lib.library()
+        if self._shape != (n_layers, n):
+            if self._mix is not None:
+                lib.lbl_mix_close(self._mix)
+            self._mix = c_void_p()
+            lib.lbl_mix_open(self.device, n_layers, n, ctypes.byref(self._mix))
+            self._shape = (n_layers, n)
+        else:
+            lib.lbl_mix_reset(self._mix)
+        for formula, gas in self.gases.items():
+            x = np.ascontiguousarray(volume_mixing_ratio[formula], dtype=np.float64).ravel()
+            gas.absorption_coefficients(t, p, x, bounds=(v0, vn, n_per_v),
+                                        remove_pedestal=remove_pedestal, cut_off=cut_off,
+                                        to_host=False)
+            scale = np.ascontiguousarray(number_density(t, p, x))
+            lib.lbl_mix_add(self._mix, gas._handle(self.device).ptr, scale)
+        if out is None:
+            out = np.empty((n_layers, n))
+        lib.lbl_mix_download(self._mix, out.ctypes.data_as(c_void_p))
+        return out

@@ -246,3 +246,40 @@ def test_fp32_mode(small_db, atmosphere, bounds, remove_pedestal):
         assert worst > 1e-12     # it really was the FP32 arithmetic
     else:
         assert worst <= FP64_TOL
+
+
+def test_mixture_total_absorption(small_db, atmosphere):
+    """Device-side  sum_gas n_gas * k_gas  against the host-side statement of
+    pyLBL/spectroscopy.py:181-191,225-234 built from the oracle."""
+    from pylbl_b200 import Mixture, number_density
+    formulas = ["H2O", "CO2", "O3"]
+    bounds = (1, 801, 100)
+    mix = Mixture(small_db, formulas)
+    total = mix.total_absorption(atmosphere.t, atmosphere.p, atmosphere.vmr, bounds=bounds)
+    again = mix.total_absorption(atmosphere.t, atmosphere.p, atmosphere.vmr, bounds=bounds)
+    assert np.array_equal(total, again)          # the accumulator is reset between calls
+    want = np.zeros_like(total)
+    for f in formulas:
+        ref = OracleGas(small_db, f)
+        for layer in range(atmosphere.t.size):
+            n = number_density(atmosphere.t[layer], atmosphere.p[layer], atmosphere.vmr[f][layer])
+            want[layer] += n * ref.absorption(atmosphere.t[layer], atmosphere.p[layer],
+                                              atmosphere.vmr[f][layer], *bounds, True)
+    for layer in range(atmosphere.t.size):
+        assert scaled_error(total[layer], want[layer], bounds[2]) <= FP64_TOL
+    mix.close()
+
+
+def test_layers_sharded_over_two_devices(small_db):
+    """`Gas(devices=[0, 1])`: contiguous layer shards, one per device, bitwise the same spectra."""
+    if _lib.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    col = synth.standard_column(12)
+    bounds = (1, 401, 100)
+    one = Gas(small_db, "CO2", devices=[0]).absorption_coefficients(
+        col.t, col.p, col.vmr["CO2"], bounds=bounds, remove_pedestal=True)
+    gas = Gas(small_db, "CO2", devices=[0, 1])
+    two = gas.absorption_coefficients(col.t, col.p, col.vmr["CO2"], bounds=bounds,
+                                      remove_pedestal=True)
+    assert np.array_equal(one, two)
+    assert [s["n_layers"] for s in gas.last_stats] == [6, 6]
