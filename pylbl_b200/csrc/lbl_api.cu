@@ -153,7 +153,7 @@ struct lbl_gas
         bool pedestal;
     };
     std::vector<ChunkEvents> chunk_events;
-    cudaEvent_t ev_call_begin = nullptr, ev_call_end = nullptr;
+    cudaEvent_t ev_call_begin = nullptr, ev_call_end = nullptr, ev_compute_end = nullptr;
     cudaEvent_t ev_out_ready[2] = {nullptr, nullptr}, ev_out_free[2] = {nullptr, nullptr};
     bool out_busy[2] = {false, false};
     bool pending = false;
@@ -564,6 +564,8 @@ int lbl_gas_open(const char* database, const char* formula, int device, lbl_gas*
     std::string err;
     if (read_molecule(database, formula, g->mol, err)) return fail(err);
     if (set_device(g.get())) return 1;
+    // Every handle has its own compute stream: while one gas waits for its (latency-bound)
+    // pedestal chain, the kernels of the other gases fill the GPU.
     LBL_CUDA(cudaStreamCreateWithFlags(&g->s_compute, cudaStreamNonBlocking));
     {
         // The pedestal chain is a long, thin dependency chain: give its stream priority so
@@ -575,6 +577,7 @@ int lbl_gas_open(const char* database, const char* formula, int device, lbl_gas*
     LBL_CUDA(cudaStreamCreateWithFlags(&g->s_copy, cudaStreamNonBlocking));
     LBL_CUDA(cudaEventCreate(&g->ev_call_begin));
     LBL_CUDA(cudaEventCreate(&g->ev_call_end));
+    LBL_CUDA(cudaEventCreateWithFlags(&g->ev_compute_end, cudaEventDisableTiming));
     for (int i = 0; i < 2; ++i)
     {
         LBL_CUDA(cudaEventCreateWithFlags(&g->ev_out_ready[i], cudaEventDisableTiming));
@@ -621,6 +624,7 @@ int lbl_gas_close(lbl_gas* g)
     for (cudaEvent_t e : g->ev_pool) cudaEventDestroy(e);
     if (g->ev_call_begin) cudaEventDestroy(g->ev_call_begin);
     if (g->ev_call_end) cudaEventDestroy(g->ev_call_end);
+    if (g->ev_compute_end) cudaEventDestroy(g->ev_compute_end);
     for (int i = 0; i < 2; ++i)
     {
         if (g->ev_out_ready[i]) cudaEventDestroy(g->ev_out_ready[i]);
@@ -1044,10 +1048,16 @@ int lbl_gas_submit(lbl_gas* g, int n_layers, const double* pressure, const doubl
     }
     if (k_host)
     {
-        // The call ends when the last copy has landed.
-        LBL_CUDA(cudaStreamWaitEvent(sc, g->ev_out_free[g->last_slot], 0));
+        // The call ends when the last copy has landed: the end mark goes on the copy stream,
+        // after the kernels' end mark.
+        LBL_CUDA(cudaEventRecord(g->ev_compute_end, sc));
+        LBL_CUDA(cudaStreamWaitEvent(g->s_copy, g->ev_compute_end, 0));
+        LBL_CUDA(cudaEventRecord(g->ev_call_end, g->s_copy));
     }
-    LBL_CUDA(cudaEventRecord(g->ev_call_end, sc));
+    else
+    {
+        LBL_CUDA(cudaEventRecord(g->ev_call_end, sc));
+    }
     g->pending = true;
     return 0;
 }
@@ -1058,9 +1068,9 @@ int lbl_gas_wait(lbl_gas* g)
     if (!g->pending) return 0;
     if (set_device(g)) return 1;
     g->pending = false;
-    LBL_CUDA(cudaStreamSynchronize(g->s_compute));
-    LBL_CUDA(cudaStreamSynchronize(g->s_copy));
-    LBL_CUDA(cudaStreamSynchronize(g->s_side));
+    // ev_call_end closes the call: it follows the last kernel, the last copy (the compute
+    // stream waited for it) and, through the pedestal events, the side stream.
+    LBL_CUDA(cudaEventSynchronize(g->ev_call_end));
     g->out_busy[0] = g->out_busy[1] = false;
     lbl_stats& st = g->stats;
     for (int l = 0; l < st.n_layers; ++l) st.evals += (long long)g->evals_host[l];
