@@ -283,3 +283,64 @@ def test_layers_sharded_over_two_devices(small_db):
                                       remove_pedestal=True)
     assert np.array_equal(one, two)
     assert [s["n_layers"] for s in gas.last_stats] == [6, 6]
+
+
+def test_lines_on_integer_boundaries_with_large_shifts(tmp_path):
+    """Lines sitting on integer wavenumbers with shifts of both signs: the window cell comes
+    from the SHIFTED centre and must match the reference bit for bit (spectra.c:22,48)."""
+    lines = synth.make_line_list("O2", 200, 30.0, 130.0, seed=9)
+    lines["nu"] = np.sort(np.round(lines["nu"]) + np.tile([0.0, 1e-6, -1e-6, 0.5], 50))
+    lines["delta_air"] = np.tile([-0.02, 0.02, 0.0199, -0.0003], 50)
+    path = str(tmp_path / "shift.db")
+    synth.write_database(path, {"O2": lines})
+    gas, ref = Gas(path, "O2"), OracleGas(path, "O2")
+    t = np.array([250.0, 296.0]); p = np.array([101325.0, 5.0e4]); x = np.array([0.209, 0.209])
+    for bounds in ((5, 161, 20), (5, 161, 100)):
+        for ped in (False, True):
+            k = gas.absorption_coefficients(t, p, x, bounds=bounds, remove_pedestal=ped)
+            for layer in range(2):
+                k_ref = ref.absorption(t[layer], p[layer], x[layer], *bounds, ped, windows=True)
+                assert scaled_error(k[layer], k_ref, bounds[2]) <= FP64_TOL
+                assert np.array_equal(gas.windows(layer), ref.last_windows[:ref.last_active])
+
+
+def test_one_handle_many_grids_and_errors(small_db, atmosphere):
+    """A handle is reused across grids (the line plan is rebuilt), and bad inputs fail with the
+    reference's error type instead of reading out of bounds."""
+    gas, ref = Gas(small_db, "H2O"), OracleGas(small_db, "H2O")
+    layer = 1
+    args = (atmosphere.t[layer], atmosphere.p[layer], atmosphere.vmr["H2O"][layer])
+    for bounds in ((1, 301, 100), (1, 2001, 10), (1, 301, 100), (1, 120, 7)):
+        k = gas.absorption_coefficients([args[0]], [args[1]], [args[2]], bounds=bounds)[0]
+        k_ref = ref.absorption(*args, *bounds)
+        assert relative_error(k, k_ref) <= FP64_TOL
+    with pytest.raises(ValueError):        # temperature outside the TIPS table (1..1000 K here)
+        gas.absorption_coefficients([1500.0], [args[1]], [args[2]], bounds=(1, 301, 100))
+    assert "TIPS" in _lib.last_error()
+    with pytest.raises(ValueError):        # vn <= v0
+        gas.absorption_coefficients([args[0]], [args[1]], [args[2]], bounds=(300, 300, 10))
+    # and the handle still works afterwards
+    k = gas.absorption_coefficients([args[0]], [args[1]], [args[2]], bounds=(1, 301, 100))[0]
+    assert relative_error(k, ref.absorption(*args, 1, 301, 100)) <= FP64_TOL
+
+
+def test_two_handles_from_two_threads(small_db, atmosphere):
+    """Different handles may be driven from different host threads."""
+    import threading
+    bounds = (1, 401, 100)
+    results = {}
+
+    def work(formula):
+        gas = Gas(small_db, formula)
+        results[formula] = gas.absorption_coefficients(atmosphere.t, atmosphere.p,
+                                                       atmosphere.vmr[formula], bounds=bounds,
+                                                       remove_pedestal=True)
+    threads = [threading.Thread(target=work, args=(f,)) for f in ("H2O", "CO2", "O3")]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    for f in ("H2O", "CO2", "O3"):
+        ref = OracleGas(small_db, f)
+        k_ref = ref.absorption(atmosphere.t[2], atmosphere.p[2], atmosphere.vmr[f][2], *bounds, True)
+        assert scaled_error(results[f][2], k_ref, 100) <= FP64_TOL
