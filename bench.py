@@ -380,8 +380,11 @@ def run_ours(args, rank, local_rank, world, dist):
     # The summation kernel on fine grids interpolates the far field: it PERFORMS `executed`
     # Lorentz evaluations to deliver `evals` reference-equivalent ones.  The roofline counts
     # the work performed; `value` counts the work delivered.
-    # K2c also spends 2 flop per (point, node) on the interpolation: 48 nodes per point.
-    interp_flops = 2.0 * 48 * n * N_LAYERS * len(GASES) * args.steps if cells else 0.0
+    # K2c also evaluates the two interpolants at every point: Clenshaw, one FMA + one add per
+    # (point, coefficient), 32 + 16 coefficients; and 2*(32^2 + 16^2) flop per cell for the
+    # node-sum -> coefficient transforms.
+    interp_flops = ((3.0 * 48 * n + 2.0 * (32 * 32 + 16 * 16) * (vn - v0))
+                    * N_LAYERS * len(GASES) * args.steps) if cells else 0.0
     flops = FLOP_PER_EVAL * executed + interp_flops     # this rank, timed region
     achieved = flops / (sum_ms * 1e-3) / 1e12 if sum_ms > 0 else 0.0
     kernel = f"lbl::sum_cell_kernel<{cells}>" if cells else f"lbl::sum_kernel<{points}>"

@@ -114,7 +114,6 @@ struct Plan  // which lines a given (v0, vn, cut_off) sees, and where they are o
     std::vector<int> sorted_to_db; // host copy of the permutation (empty = identity)
 };
 
-constexpr int kMaxEvents = 64;
 
 }  // namespace
 }  // namespace lbl
@@ -381,12 +380,14 @@ int ensure_cheb_tables(lbl_gas* g, int n_per_v)
     if (g->cheb_npv == n_per_v) return 0;
     std::vector<double> nodes, weights;
     build_cheb_tables(kNodes, n_per_v, nodes, weights);
+    build_cheb_transform(kNodes, weights);
     size_t bytes = 0;
     if (upload(g->cheb_nodes, nodes.data(), sizeof(double) * kNodes, g->s_compute, bytes)) return 1;
     if (upload(g->cheb_weights, weights.data(), sizeof(double) * weights.size(), g->s_compute, bytes))
         return 1;
     LBL_CUDA(cudaStreamSynchronize(g->s_compute));   // the host vectors are reused
     build_cheb_tables(kNodes16, n_per_v, nodes, weights);
+    build_cheb_transform(kNodes16, weights);
     if (upload(g->cheb_nodes16, nodes.data(), sizeof(double) * kNodes16, g->s_compute, bytes)) return 1;
     if (upload(g->cheb_weights16, weights.data(), sizeof(double) * weights.size(), g->s_compute, bytes))
         return 1;
@@ -978,9 +979,9 @@ int lbl_gas_submit(lbl_gas* g, int n_layers, const double* pressure, const doubl
             CellArgs ca;
             ca.sum = sa;
             ca.node_offset = g->cheb_nodes.as<double>();
-            ca.weights = g->cheb_weights.as<double>();
+            ca.transform = g->cheb_weights.as<double>();
             ca.node_offset16 = g->cheb_nodes16.as<double>();
-            ca.weights16 = g->cheb_weights16.as<double>();
+            ca.transform16 = g->cheb_weights16.as<double>();
             ca.executed = g->executed_dev.as<unsigned long long>();
             // cells per warp: more cells amortise the loads of the line operands over more
             // node evaluations, fewer keep the (per-cell) direct range short

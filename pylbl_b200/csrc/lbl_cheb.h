@@ -58,4 +58,23 @@ inline void build_cheb_tables(int n_nodes, int n_per_v, std::vector<double>& nod
     }
 }
 
+// Values at the n first-kind Chebyshev nodes -> Chebyshev coefficients of the interpolant:
+//   p(s) = sum_j c_j T_j(s),  c_j = sum_k M[k][j] F_k,  M[k][j] = (2 - [j == 0])/n * cos(j theta_k),
+// theta_k = (2k+1) pi / (2n), node k at s_k = cos(theta_k) (the same nodes build_cheb_tables
+// places on the cell interval).  Stored k-major so that lane j reads consecutive addresses.
+inline void build_cheb_transform(int n_nodes, std::vector<double>& m)
+{
+    const long double pi = 3.14159265358979323846264338327950288L;
+    m.assign((size_t)n_nodes * n_nodes, 0.);
+    for (int k = 0; k < n_nodes; ++k)
+    {
+        const long double theta = (2 * k + 1) * pi / (2.0L * n_nodes);
+        for (int j = 0; j < n_nodes; ++j)
+        {
+            const long double scale = (j == 0 ? 1.0L : 2.0L) / n_nodes;
+            m[(size_t)k * n_nodes + j] = (double)(scale * cosl(j * theta));
+        }
+    }
+}
+
 }  // namespace lbl

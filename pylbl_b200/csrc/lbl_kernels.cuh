@@ -335,6 +335,24 @@ sum_cell_kernel(const CellArgs a)
     __syncwarp();   // spectra stored, node sums in shared memory
 
     // ---- phase 3: + interpolated far fields ---------------------------------------------------
+    // node sums -> Chebyshev coefficients (lane = coefficient), in place in shared memory
+    {
+        double c32[G], c16[G];
+#pragma unroll
+        for (int q = 0; q < G; ++q)
+        {
+            c32[q] = cell_coefficient(a.transform, field[q], kNodes, lane);
+            c16[q] = cell_coefficient(a.transform16, field16[q], kNodes16, lane);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < G; ++q)
+        {
+            field[q][lane] = c32[q];
+            if (lane < kNodes16) field16[q][lane] = c16[q];
+        }
+        __syncwarp();
+    }
     for (int q = 0; q < cells; ++q)
     {
         cell_field_lane(a, layer, cell0 + q, lane, 32, field[q], field16[q]);

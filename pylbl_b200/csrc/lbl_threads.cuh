@@ -492,9 +492,9 @@ LBL_HD void sum32_thread(const SumArgs& a, int layer_group, int tile, int lane)
 //            kNodes16 = 16 nodes do (rho^-16 ~ 1e-16).  A half-warp takes a cell's 16 nodes
 //            (G = 2), or the two half-warps split the lines of the one cell (G = 1): one
 //            evaluation per lane per line.
-// Every point of a cell then receives sum_k W32[k][r] F32[k] + sum_k W16[k][r] F16[k]; the
-// interpolation matrices (Lagrange bases of the nodes at the grid offsets r/n_per_v) are the
-// same for every cell and layer and are built once per n_per_v on the host (lbl_cheb.h).
+// Every point of a cell then receives the two interpolants, evaluated from their Chebyshev
+// coefficients (a 32x32 and a 16x16 transform of the node sums, lbl_cheb.h) by Clenshaw's
+// recurrence.
 // ---------------------------------------------------------------------------------------
 constexpr int kNodes = 32;
 constexpr int kNodes16 = 16;
@@ -506,9 +506,9 @@ struct CellArgs
 {
     SumArgs sum;
     const double* node_offset;     // [kNodes] node position relative to the cell origin v0+cell
-    const double* weights;         // [kNodes][n_per_v] interpolation matrix (node-major)
+    const double* transform;       // [kNodes][kNodes] node sums -> Chebyshev coefficients (k-major)
     const double* node_offset16;   // [kNodes16]
-    const double* weights16;       // [kNodes16][n_per_v]
+    const double* transform16;     // [kNodes16][kNodes16]
     unsigned long long* executed;  // statistics: evaluations actually performed (or nullptr)
 };
 
@@ -763,8 +763,17 @@ LBL_HD void cell_direct_lane(const CellArgs& a, int layer, int cell, int chunk, 
         acc[p] = 0.;
     }
     const size_t off = (size_t)layer * a.sum.lines.n;
-    window_range<P>(a.sum.rec.ab + off, a.sum.rec.cc + off, a.sum.rec.chk + off, seg.j[3], seg.j[4],
-                    cell, g.cut_off, v, acc);
+    if (g.cut_off >= 4)
+    {
+        // Direct lines lie within kFarMin of the (at most 2-cell) group: their window cell is
+        // within 2 of this cell, inside any window with cut_off >= 4 -- no per-line test.
+        plain_range<P>(a.sum.rec.ab + off, a.sum.rec.cc + off, seg.j[3], seg.j[4], v, acc);
+    }
+    else
+    {
+        window_range<P>(a.sum.rec.ab + off, a.sum.rec.cc + off, a.sum.rec.chk + off, seg.j[3],
+                        seg.j[4], cell, g.cut_off, v, acc);
+    }
     if (valid)
     {
         double* o = a.sum.out + (size_t)layer * g.n + i_first;
@@ -776,29 +785,78 @@ LBL_HD void cell_direct_lane(const CellArgs& a, int layer, int cell, int chunk, 
     }
 }
 
-// Phase 3, lane = points lane, lane+32, ... of the cell: add the interpolated far fields
-// sum_k W32[k][r] * field32[k] + sum_k W16[k][r] * field16[k].  The matrices are stored
-// node-major so that a warp reads consecutive r.
+// Phase 3a, lane = coefficient index: node sums -> Chebyshev coefficients of the interpolant
+// (c_j = sum_k M[k][j] F_k, lbl_cheb.h).  `nodes` is 32 or 16; lanes >= nodes return 0.
+LBL_HD double cell_coefficient(const double* transform, const double* field, int nodes, int lane)
+{
+    double c = 0.;
+    if (lane < nodes)
+    {
+        for (int k = 0; k < nodes; ++k)
+        {
+            c = fma_(LBL_LDG(transform + (size_t)k * nodes + lane), field[k], c);
+        }
+    }
+    return c;
+}
+
+// Phase 3b, lane = points lane, lane+32, ... of the cell: add the two interpolated far fields,
+// evaluated from their Chebyshev coefficients by Clenshaw's recurrence
+//   b_j = c_j + 2 s b_(j+1) - b_(j+2),   p(s) = c_0 + s b_1 - b_2,
+// with s in [-1, 1] the point's position on the cell interval.  (A stored 48 x n_per_v
+// interpolation matrix would cost one cache read per point and node -- on this grid that is
+// more L1 traffic than the rest of the kernel together; the recurrence costs two FP64
+// operations per point and coefficient and reads only the coefficients, by broadcast.)
 LBL_HD void cell_field_lane(const CellArgs& a, int layer, int cell, int lane, int nlanes,
-                            const double* field32, const double* field16)
+                            const double* coef32, const double* coef16)
 {
     const GridSpec& g = a.sum.grid;
     double* o = a.sum.out + (size_t)layer * g.n + (size_t)cell * g.n_per_v;
-    for (int r = lane; r < g.n_per_v; r += nlanes)
+    constexpr int R = 4;   // points per lane in flight: independent recurrences hide the latency
+    const double to_s = 2.0 / (double)(g.n_per_v - 1);
+    for (int r0 = lane; r0 < g.n_per_v; r0 += R * nlanes)
     {
-        double far = 0.;
-#pragma unroll 8
-        for (int k = 0; k < kNodes; ++k)
+        double s2[R], b1[R], b2[R], d1[R], d2[R];
+#pragma unroll
+        for (int u = 0; u < R; ++u)
         {
-            far = fma_(LBL_LDG(a.weights + (size_t)k * g.n_per_v + r), field32[k], far);
+            int r = r0 + u * nlanes;
+            if (r >= g.n_per_v) r = g.n_per_v - 1;   // spare slots shadow the last point
+            s2[u] = 2.0 * fma_((double)r, to_s, -1.0);
+            b1[u] = b2[u] = d1[u] = d2[u] = 0.;
         }
-        double far16 = 0.;
-#pragma unroll 8
-        for (int k = 0; k < kNodes16; ++k)
+        for (int j = kNodes - 1; j >= 1; --j)
         {
-            far16 = fma_(LBL_LDG(a.weights16 + (size_t)k * g.n_per_v + r), field16[k], far16);
+            const double c = coef32[j];
+#pragma unroll
+            for (int u = 0; u < R; ++u)
+            {
+                const double t = fma_(s2[u], b1[u], c - b2[u]);
+                b2[u] = b1[u];
+                b1[u] = t;
+            }
         }
-        o[r] += far + far16;
+        for (int j = kNodes16 - 1; j >= 1; --j)
+        {
+            const double c = coef16[j];
+#pragma unroll
+            for (int u = 0; u < R; ++u)
+            {
+                const double t = fma_(s2[u], d1[u], c - d2[u]);
+                d2[u] = d1[u];
+                d1[u] = t;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < R; ++u)
+        {
+            const int r = r0 + u * nlanes;
+            if (r < g.n_per_v)
+            {
+                const double s = 0.5 * s2[u];
+                o[r] += (fma_(s, b1[u], coef32[0]) - b2[u]) + (fma_(s, d1[u], coef16[0]) - d2[u]);
+            }
+        }
     }
 }
 

@@ -64,10 +64,20 @@ static void run_cells(const CellArgs& ca, const LinesView& ln, const GridSpec& g
                 for (int chunk = 0; chunk < chunks; ++chunk)
                     for (int lane = 0; lane < 32; ++lane)
                         cell_direct_lane(ca, layer, cell + q, chunk, lane, seg);
+            std::vector<double> coef((size_t)G * kNodes), coef16((size_t)G * kNodes16);
+            for (int q = 0; q < G; ++q)
+                for (int lane = 0; lane < 32; ++lane)
+                {
+                    coef[(size_t)q * kNodes + lane] =
+                        cell_coefficient(ca.transform, fields.data() + (size_t)q * kNodes, kNodes, lane);
+                    if (lane < kNodes16)
+                        coef16[(size_t)q * kNodes16 + lane] = cell_coefficient(
+                            ca.transform16, fields16.data() + (size_t)q * kNodes16, kNodes16, lane);
+                }
             for (int q = 0; q < cells; ++q)
                 for (int lane = 0; lane < 32; ++lane)
-                    cell_field_lane(ca, layer, cell + q, lane, 32, fields.data() + (size_t)q * kNodes,
-                                    fields16.data() + (size_t)q * kNodes16);
+                    cell_field_lane(ca, layer, cell + q, lane, 32, coef.data() + (size_t)q * kNodes,
+                                    coef16.data() + (size_t)q * kNodes16);
         }
     }
 }
@@ -293,12 +303,14 @@ extern "C" int emu_absorption(int n_layers, const double* pressure, const double
         std::vector<double> nodes, weights, nodes16, weights16;
         build_cheb_tables(kNodes, n_per_v, nodes, weights);
         build_cheb_tables(kNodes16, n_per_v, nodes16, weights16);
+        build_cheb_transform(kNodes, weights);
+        build_cheb_transform(kNodes16, weights16);
         CellArgs ca;
         ca.sum = sa;
         ca.node_offset = nodes.data();
-        ca.weights = weights.data();
+        ca.transform = weights.data();
         ca.node_offset16 = nodes16.data();
-        ca.weights16 = weights16.data();
+        ca.transform16 = weights16.data();
         ca.executed = nullptr;
         if (n_per_v <= 256) run_cells<2>(ca, ln, g, layers, n_layers);
         else run_cells<1>(ca, ln, g, layers, n_layers);
