@@ -112,6 +112,8 @@ struct Plan  // which lines a given (v0, vn, cut_off) sees, and where they are o
     bool valid = false;
     DeviceLines own;               // used only when the database rows are not nu-sorted
     std::vector<int> sorted_to_db; // host copy of the permutation (empty = identity)
+    DevBuf cell_first;             // per-wavenumber index of the sorted active lines (LinesView)
+    int cell_w0 = 0, cell_n = 0;
 };
 
 
@@ -257,6 +259,25 @@ int make_plan(lbl_gas* g, int v0, int vn, int cut_off)
         std::stable_sort(p.sorted_to_db.begin(), p.sorted_to_db.end(),
                          [&](int a, int b) { return nu[a] < nu[b]; });
         if (pack_lines(g, p.own, p.sorted_to_db, p.n_active)) return 1;
+    }
+    // Per-wavenumber index (LinesView::cell_first).  Every active line lies within
+    // [v0-(cut+1), vn+cut+1] (active_prefix), inside the table's [w0, w0+n-1].
+    {
+        const std::vector<double>& nu = g->mol.nu;
+        p.cell_w0 = v0 - cut_off - 3;
+        p.cell_n = (vn - v0) + 2 * cut_off + 7;
+        std::vector<int> first((size_t)p.cell_n);
+        int j = 0;
+        for (int k = 0; k < p.cell_n; ++k)
+        {
+            const double w = (double)p.cell_w0 + (double)k;
+            while (j < p.n_active && nu[p.sorted_to_db.empty() ? j : p.sorted_to_db[j]] < w) ++j;
+            first[k] = j;
+        }
+        size_t bytes = 0;
+        if (upload(p.cell_first, first.data(), sizeof(int) * first.size(), g->s_compute, bytes)) return 1;
+        LBL_CUDA(cudaStreamSynchronize(g->s_compute));   // `first` goes out of scope
+        g->open_h2d += bytes;
     }
     p.valid = true;
     return 0;
@@ -610,6 +631,7 @@ int lbl_gas_close(lbl_gas* g)
     if (g->pending) lbl_gas_wait(g);
     g->base.release();
     g->plan.own.release();
+    g->plan.cell_first.release();
     for (DevBuf* b : {&g->tips_t, &g->tips_q, &g->rec_ab, &g->rec_cc, &g->rec_chk, &g->rec_gen,
                       &g->layers_dev, &g->evals_dev, &g->pedbin, &g->pedcorr, &g->pednodes,
                       &g->pedterms, &g->rec_f32, &g->amp_max, &g->cheb_nodes, &g->cheb_weights,
@@ -731,7 +753,10 @@ int lbl_gas_submit(lbl_gas* g, int n_layers, const double* pressure, const doubl
         return 0;
     }
     const DeviceLines& dl = g->mol.sorted ? g->base : plan.own;
-    const LinesView lines = dl.view(plan.n_active);
+    LinesView lines = dl.view(plan.n_active);
+    lines.cell_first = plan.cell_first.as<int>();
+    lines.cell_w0 = plan.cell_w0;
+    lines.cell_n = plan.cell_n;
     TipsView tips;
     tips.num_iso = g->mol.num_iso;
     tips.num_t = g->mol.num_t;

@@ -217,7 +217,7 @@ sum_cell_kernel(const CellArgs a)
     int mine = 0;
     if (active && lane < kCellKeys)
     {
-        mine = lower_bound(a.sum.lines.nu, a.sum.lines.n, cell_search_key(g, ly, cell0, G, lane));
+        mine = first_line_at(a.sum.lines, cell_search_key(g, ly, cell0, G, lane));
     }
     int found[kCellKeys];
 #pragma unroll
@@ -520,8 +520,8 @@ __device__ __forceinline__ void fixup_warp(const SumArgs& a, int tile, int layer
     if (is_node)
     {
         const double key = (double)g.v0 + (double)(cell - g.cut_off - 1);
-        const int nlo = lower_bound(a.lines.nu, a.lines.n, key - ly.slack);
-        const int nhi = lower_bound(a.lines.nu, a.lines.n, key + 1.0 + ly.slack);
+        const int nlo = first_line_at(a.lines, key - ly.slack);
+        const int nhi = first_line_at(a.lines, key + 1.0 + ly.slack);
         const FarAB* ab = a.rec.ab + off;
         const double* cc = a.rec.cc + off;
         for (int j = nlo; j < nhi; ++j)
@@ -541,12 +541,163 @@ __device__ __forceinline__ void fixup_warp(const SumArgs& a, int tile, int layer
     }
 }
 
+// The T = 32 form (one layer per warp; every grid with at least 64 points per cm-1): the
+// candidate lines are the same for all lanes, so the warp first derives their NearLine
+// records lane-parallel -- lane m tests line jlo+m against the tile and, if it can touch it,
+// loads its records and writes the derived constants to shared memory -- and then walks the
+// compacted list with broadcast reads.  No global-memory latency and no per-line setup sits
+// in the evaluation loop.
+__device__ __forceinline__ void fixup_warp_staged(const SumArgs& a, int tile, int layer, int lane,
+                                                  int* queue, NearLine* slots)
+{
+    const GridSpec& g = a.grid;
+    int i = tile * 32 + lane;
+    const bool valid = i < g.n;
+    if (i >= g.n) i = g.n - 1;
+    const int t_first = tile * 32;
+    int t_last = t_first + 31;
+    if (t_last > g.n - 1) t_last = g.n - 1;
+
+    const LayerIn ly = a.layers[layer];
+    const size_t off = (size_t)layer * a.lines.n;
+    const LineChk* chk = a.rec.chk + off;
+    const LineGen* gen = a.rec.gen + off;
+    const double v = grid_point(g.v0, g.dv, i);
+    const int cell = i / g.n_per_v;
+    const bool is_node = (i - cell * g.n_per_v) == 0;
+    const int cb_min = cell - g.cut_off - (is_node ? 1 : 0);
+    const int cb_max = cell + g.cut_off;
+    const int tile_cb_min = t_first / g.n_per_v - g.cut_off - 1;
+    const int tile_cb_max = t_last / g.n_per_v + g.cut_off;
+    const unsigned below = (1u << lane) - 1u;
+    double acc = 0.;
+
+    int jlo, jhi;
+    near_candidates(a.lines, g, ly, t_first, t_last, jlo, jhi);
+    int qn = 0;
+    for (int base = jlo; base < jhi; base += 32)
+    {
+        const int j = base + lane;
+        bool touches = false;
+        int4 ck = make_int4(0, 0, 0, 0);
+        if (j < jhi)
+        {
+            ck = __ldg(reinterpret_cast<const int4*>(chk + j));
+            touches = ck.z >= t_first && ck.y <= t_last && ck.x >= tile_cb_min && ck.x <= tile_cb_max;
+        }
+        const unsigned listed = __ballot_sync(0xffffffffu, touches);
+        if (listed == 0)
+        {
+            continue;
+        }
+        if (touches)
+        {
+            LineGen gn;
+            const double2 g0 = __ldg(reinterpret_cast<const double2*>(gen + j));
+            const double2 g1 = __ldg(reinterpret_cast<const double2*>(gen + j) + 1);
+            const double2 g2 = __ldg(reinterpret_cast<const double2*>(gen + j) + 2);
+            gn.nu = g0.x; gn.repwid = g0.y; gn.y = g1.x; gn.cof = g1.y; gn.xlim0 = g2.x; gn.xlim1 = g2.y;
+            const double2 l = __ldg(reinterpret_cast<const double2*>(a.rec.ab + off + j));
+            FarAB ab;
+            ab.a = l.x; ab.b = l.y;
+            slots[__popc(listed & below)] =
+                near_line(ck, j, gn, ab, __ldg(a.rec.cc + off + j), a.near_masked != 0);
+        }
+        __syncwarp();
+        const int n_listed = __popc(listed);
+        for (int s = 0; s < n_listed; ++s)
+        {
+            const NearLine& nl = slots[s];
+            const int4 hd = *reinterpret_cast<const int4*>(&nl);
+            bool core = false;
+            if (i >= hd.x && i <= hd.y && hd.z >= cb_min && hd.z <= cb_max)
+            {
+                acc += near_point(nl, v, core);   // region 3 / CPF12 left over: queued below
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, core);
+            if (m)
+            {
+                if (core)
+                {
+                    queue[qn + __popc(m & below)] = ((hd.w >> 1) << 5) | lane;
+                }
+                qn += __popc(m);
+                __syncwarp();
+                if (qn >= 32)
+                {
+                    acc = fixup_drain<32>(a, queue, 32, lane, layer, v, acc);
+                    __syncwarp();
+                    const int keep = qn - 32;
+                    const int moved = (lane < keep) ? queue[32 + lane] : 0;
+                    __syncwarp();
+                    if (lane < keep) queue[lane] = moved;
+                    qn = keep;
+                    __syncwarp();
+                }
+            }
+        }
+        __syncwarp();   // the slots are rewritten by the next batch
+    }
+    if (qn > 0)
+    {
+        acc = fixup_drain<32>(a, queue, qn, lane, layer, v, acc);
+    }
+
+    // node terms: lines with cb == cell-cut-1 reach exactly the cell's first point.  The lanes
+    // share the lines of that cell and the owner of the point collects the sum.
+    unsigned node_lanes = __ballot_sync(0xffffffffu, is_node);
+    while (node_lanes)
+    {
+        const int src = __ffs(node_lanes) - 1;
+        node_lanes &= node_lanes - 1;
+        const int cb_node = __shfl_sync(0xffffffffu, cell, src) - g.cut_off - 1;
+        const int i_node = __shfl_sync(0xffffffffu, i, src);
+        const double v_node = __shfl_sync(0xffffffffu, v, src);
+        const double key = (double)g.v0 + (double)cb_node;
+        const int nlo = first_line_at(a.lines, key - ly.slack);
+        const int nhi = first_line_at(a.lines, key + 1.0 + ly.slack);
+        const FarAB* ab = a.rec.ab + off;
+        const double* cc = a.rec.cc + off;
+        double part = 0.;
+        for (int j = nlo + lane; j < nhi; j += 32)
+        {
+            const int4 ck = __ldg(reinterpret_cast<const int4*>(chk + j));
+            if (ck.x == cb_node && !(i_node >= ck.y && i_node <= ck.z))   // else: the near loop's
+            {
+                const double2 l = __ldg(reinterpret_cast<const double2*>(ab + j));
+                part = far_term(v_node, l.x, l.y, __ldg(cc + j), part);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+        {
+            part += __shfl_xor_sync(0xffffffffu, part, o);
+        }
+        if (lane == src) acc += part;
+    }
+    if (valid)
+    {
+        a.out[(size_t)layer * g.n + i] += acc;
+    }
+}
+
 template <int T>
 __global__ void __launch_bounds__(128)
 fixup_kernel(const SumArgs a)
 {
     __shared__ int queues[4][kFixQueue];
     const int tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (T == 32)
+    {
+        __shared__ __align__(16) NearLine slots[4][32];
+        if (tile * 32 >= a.grid.n)
+        {
+            return;
+        }
+        fixup_warp_staged(a, tile, blockIdx.y, threadIdx.x & 31, queues[threadIdx.x >> 5],
+                          slots[threadIdx.x >> 5]);
+        return;
+    }
     if (tile * T >= a.grid.n)
     {
         return;

@@ -244,6 +244,16 @@ extern "C" int emu_absorption(int n_layers, const double* pressure, const double
     ln.gamma_self = c_gs.data(); ln.n_air = c_na.data(); ln.elower = c_el.data();
     ln.delta_air = c_da.data(); ln.mass = c_m.data(); ln.iso = c_iso.data();
     ln.db_to_sorted = inv.data();
+    // per-wavenumber index, as make_plan builds it
+    std::vector<int> cell_first((size_t)((vn - v0) + 2 * cut_off + 7));
+    ln.cell_w0 = v0 - cut_off - 3;
+    ln.cell_n = (int)cell_first.size();
+    for (int k = 0, j = 0; k < ln.cell_n; ++k)
+    {
+        while (j < na && c_nu[j] < (double)ln.cell_w0 + (double)k) ++j;
+        cell_first[k] = j;
+    }
+    ln.cell_first = cell_first.data();
     TipsView tips{num_iso, num_t, tips_t, tips_q};
 
     std::vector<LayerIn> layers(n_layers);
