@@ -52,6 +52,12 @@ CONFIG = 2
 FLOP_PER_EVAL = 7.0  # algorithmic flops of one Lorentz-form evaluation
                      # (the only kind the summation kernel performs; regions 1-3/CPF12 are K2b's)
 GASES = ["H2O", "CO2", "O3", "N2O", "CO", "CH4", "O2"]
+# Order in which a step submits the gases: fewest lines first.  Every gas returns the same
+# number of bytes, so the short ones go first and their copies to the host are under way
+# while the long ones compute (two-stage flow shop, Johnson's rule).
+SUBMIT_ORDER = sorted(GASES, key=lambda f: synth.CONFIG2_SHARES[f])
+if os.environ.get("BENCH_GAS_ORDER"):
+    SUBMIT_ORDER = os.environ["BENCH_GAS_ORDER"].split(",")
 N_LAYERS = 60
 REMOVE_PEDESTAL = True
 CUT_OFF = 25
@@ -284,38 +290,35 @@ def run_ours(args, rank, local_rank, world, dist):
     peak = ctypes.c_double(0.)
     lib.lbl_measure_fp64_peak(local_rank, ctypes.byref(peak))
 
-    def step_resident():
-        """All gases, spectra left on the device.  Gases run one after another so that the
-        per-launch CUDA-event durations of the summation kernel are not inflated by overlap."""
-        stats = []
-        for f in GASES:
-            gases[f].absorption_coefficients(column.t, column.p, column.vmr[f], bounds=bounds,
-                                             remove_pedestal=REMOVE_PEDESTAL, cut_off=CUT_OFF,
-                                             to_host=False)
-            stats.append(gases[f].last_stats[0])
-        return stats
-
-    pinned = {f: _lib.PinnedArray((N_LAYERS, n)) for f in GASES}
-
-    def step_e2e():
-        """Public API with host buffers: submit every gas (each on its own CUDA streams), then
-        wait; inputs go up and every spectrum comes back to pinned host memory."""
+    def submit_all(destinations):
+        """Submits every gas of the column (each handle has its own CUDA streams, the
+        summation kernels share the device's main stream in submission order), then waits."""
         handles = []
-        stats = []
-        for f in GASES:
-            g = gases[f]
-            h = g._handle(local_rank)
+        for f in SUBMIT_ORDER:
+            h = gases[f]._handle(local_rank)
             t = np.ascontiguousarray(column.t)
             p = np.ascontiguousarray(column.p)
             x = np.ascontiguousarray(column.vmr[f])
+            dst = destinations[f].array.ctypes.data_as(ctypes.c_void_p) if destinations else None
             lib.lbl_gas_submit(h.ptr, N_LAYERS, p, t, x, v0, vn, npv, CUT_OFF,
-                               1 if REMOVE_PEDESTAL else 0, 0,
-                               pinned[f].array.ctypes.data_as(ctypes.c_void_p))
+                               1 if REMOVE_PEDESTAL else 0, 0, dst)
             handles.append(h)
+        stats = []
         for h in handles:
             lib.lbl_gas_wait(h.ptr)
             stats.append(h.stats())
         return stats
+
+    def step_resident():
+        """All gases, spectra left on the device."""
+        return submit_all(None)
+
+    pinned = {f: _lib.PinnedArray((N_LAYERS, n)) for f in GASES}
+
+    def step_e2e():
+        """Public API with host buffers: inputs go up and every spectrum comes back to pinned
+        host memory."""
+        return submit_all(pinned)
 
     # ---- device-resident throughput ("value") ------------------------------------------
     for _ in range(args.warmup):

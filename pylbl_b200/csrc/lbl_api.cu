@@ -150,9 +150,14 @@ struct lbl_gas
     int ev_used = 0;
     struct ChunkEvents
     {
-        cudaEvent_t k1_begin, k1_end, k2_begin, k2_end, k2b_end, ped_begin, ped_end;
+        cudaEvent_t k1_begin, k1_end, ped_begin, ped_end;
         bool pedestal;
     };
+    struct SumEvents   // one per launch of the summation kernel + K2b
+    {
+        cudaEvent_t k2_begin, k2_end, k2b_end;
+    };
+    std::vector<SumEvents> sum_events;
     std::vector<ChunkEvents> chunk_events;
     cudaEvent_t ev_call_begin = nullptr, ev_call_end = nullptr, ev_compute_end = nullptr;
     cudaEvent_t ev_out_ready[2] = {nullptr, nullptr}, ev_out_free[2] = {nullptr, nullptr};
@@ -393,6 +398,28 @@ cudaError_t launch_chain(const PedArgs& pa, double* terms, double* scratch, int 
     return cudaGetLastError();
 }
 
+// The summation kernels of every handle on a device go through ONE stream per device, in
+// submission order: each gas then finishes (and starts copying out) while the next one
+// computes, instead of all gases sharing the GPU and finishing together at the end.  The
+// small kernels either side (scaling, pedestal, apply) stay on the handle's own priority
+// streams, so the next gas's line records and pedestal chain are ready before its turn.
+std::mutex g_main_mu;
+cudaStream_t g_main_stream[64] = {};
+
+int main_stream(int device, cudaStream_t* out)
+{
+    if (device < 0 || device >= 64) return fail("Error: device index out of range.");
+    std::lock_guard<std::mutex> lock(g_main_mu);
+    if (!g_main_stream[device])
+    {
+        int least = 0, greatest = 0;
+        LBL_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        LBL_CUDA(cudaStreamCreateWithPriority(&g_main_stream[device], cudaStreamNonBlocking, least));
+    }
+    *out = g_main_stream[device];
+    return 0;
+}
+
 // Interpolation tables of K2c for one grid resolution: Chebyshev nodes of the first kind on
 // the cell interval [0, (n_per_v-1)/n_per_v] and the Lagrange basis of those nodes at the
 // grid offsets r/n_per_v (barycentric form, evaluated in long double).
@@ -586,14 +613,13 @@ int lbl_gas_open(const char* database, const char* formula, int device, lbl_gas*
     std::string err;
     if (read_molecule(database, formula, g->mol, err)) return fail(err);
     if (set_device(g.get())) return 1;
-    // Every handle has its own compute stream: while one gas waits for its (latency-bound)
-    // pedestal chain, the kernels of the other gases fill the GPU.
-    LBL_CUDA(cudaStreamCreateWithFlags(&g->s_compute, cudaStreamNonBlocking));
     {
-        // The pedestal chain is a long, thin dependency chain: give its stream priority so
-        // that its blocks are placed ahead of the summation kernel's backlog.
+        // The pedestal chain is a long, thin dependency chain, and the scaling and apply
+        // kernels are short: their streams have priority so that their blocks are placed
+        // ahead of the summation kernels' backlog (which runs on the device's main stream).
         int least = 0, greatest = 0;
         LBL_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        LBL_CUDA(cudaStreamCreateWithPriority(&g->s_compute, cudaStreamNonBlocking, greatest));
         LBL_CUDA(cudaStreamCreateWithPriority(&g->s_side, cudaStreamNonBlocking, greatest));
     }
     LBL_CUDA(cudaStreamCreateWithFlags(&g->s_copy, cudaStreamNonBlocking));
@@ -697,6 +723,7 @@ int lbl_gas_submit(lbl_gas* g, int n_layers, const double* pressure, const doubl
     st.n_layers = n_layers;
     st.n_points = grid.n;
     g->chunk_events.clear();
+    g->sum_events.clear();
     g->ev_used = 0;
     g->last_chunk_layers = 0;
     g->last_grid = grid;
@@ -783,13 +810,6 @@ int lbl_gas_submit(lbl_gas* g, int n_layers, const double* pressure, const doubl
     if (chunk_override > 0)
     {
         chunk = std::min<long long>(chunk, chunk_override);
-    }
-    else if (k_host && n_layers >= 16)
-    {
-        // Two groups so the device->host copy of the first overlaps the second one's kernels
-        // (more groups lengthen the critical path: the pedestal chain is latency-bound and
-        // takes as long for 15 layers as for 60).
-        chunk = std::min<long long>(chunk, (n_layers + 1) / 2);
     }
     const int n_chunks = (int)((n_layers + chunk - 1) / chunk);
 
@@ -892,6 +912,8 @@ int lbl_gas_submit(lbl_gas* g, int n_layers, const double* pressure, const doubl
     }
 
     cudaStream_t sc = g->s_compute;
+    cudaStream_t sm = nullptr;
+    if (main_stream(g->device, &sm)) return 1;
     LBL_CUDA(cudaEventRecord(g->ev_call_begin, sc));
     LBL_CUDA(cudaMemcpyAsync(g->layers_dev.p, g->layers_host, sizeof(LayerIn) * n_layers,
                              cudaMemcpyHostToDevice, sc));
@@ -925,9 +947,6 @@ int lbl_gas_submit(lbl_gas* g, int n_layers, const double* pressure, const doubl
         ev.pedestal = remove_pedestal != 0;
         ev.k1_begin = next_event(g);
         ev.k1_end = next_event(g);
-        ev.k2_begin = next_event(g);
-        ev.k2_end = next_event(g);
-        ev.k2b_end = next_event(g);
         ev.ped_begin = next_event(g);
         ev.ped_end = next_event(g);
 
@@ -995,14 +1014,12 @@ int lbl_gas_submit(lbl_gas* g, int n_layers, const double* pressure, const doubl
         sa.layers = layers_c;
         sa.grid = grid;
         sa.out = g->out[slot].as<double>();
-        sa.n_layers = nl;
         sa.tpw = pick_threads_per_layer(n_per_v, P, nl);
         sa.near_masked = farfield ? 0 : 1;
-        LBL_CUDA(cudaEventRecord(ev.k2_begin, sc));
+        CellArgs ca;
+        int cells_per_warp = 0;
         if (farfield)
         {
-            CellArgs ca;
-            ca.sum = sa;
             ca.node_offset = g->cheb_nodes.as<double>();
             ca.transform = g->cheb_weights.as<double>();
             ca.node_offset16 = g->cheb_nodes16.as<double>();
@@ -1010,56 +1027,87 @@ int lbl_gas_submit(lbl_gas* g, int n_layers, const double* pressure, const doubl
             ca.executed = g->executed_dev.as<unsigned long long>();
             // cells per warp: more cells amortise the loads of the line operands over more
             // node evaluations, fewer keep the (per-cell) direct range short
-            int cells_per_warp = (n_per_v <= 256) ? 2 : 1;
+            cells_per_warp = (n_per_v <= 256) ? 2 : 1;
             if (const char* env = getenv("PYLBL_B200_CELLS")) cells_per_warp = atoi(env) == 1 ? 1 : 2;
             st.cells_per_warp = cells_per_warp;
-            const int groups = (grid.ncell + cells_per_warp - 1) / cells_per_warp;
-            dim3 gridc((groups + kSumBlock / 32 - 1) / (kSumBlock / 32), nl);
-            if (cells_per_warp == 1)
+        }
+        // Layer groups of this chunk: each is summed (main stream), corrected and copied out
+        // while the next one computes, so that only the last group's copy is exposed.  The
+        // records and the pedestal chain are per chunk (the chain takes as long for 15 layers
+        // as for 60).
+        int n_groups = 1;
+        if (farfield && k_host)
+        {
+            n_groups = 1;   // splitting costs a kernel tail per group: off unless asked for
+            if (const char* env = getenv("PYLBL_B200_COPY_GROUPS")) n_groups = std::max(1, std::min(atoi(env), nl));
+        }
+        LBL_CUDA(cudaStreamWaitEvent(sm, ev.k1_end, 0));   // also orders sm after out_free[slot]
+        for (int q = 0; q < n_groups; ++q)
+        {
+            const int q0 = (int)((long long)nl * q / n_groups);
+            const int q1 = (int)((long long)nl * (q + 1) / n_groups);
+            lbl_gas::SumEvents se;
+            se.k2_begin = next_event(g);
+            se.k2_end = next_event(g);
+            se.k2b_end = next_event(g);
+            sa.layer0 = q0;
+            sa.n_layers = q1;
+            LBL_CUDA(cudaEventRecord(se.k2_begin, sm));
+            if (farfield)
             {
-                sum_cell_kernel<1><<<gridc, kSumBlock, 0, sc>>>(ca);
+                ca.sum = sa;
+                const int groups = (grid.ncell + cells_per_warp - 1) / cells_per_warp;
+                dim3 gridc((groups + kSumBlock / 32 - 1) / (kSumBlock / 32), q1 - q0);
+                if (cells_per_warp == 1)
+                {
+                    sum_cell_kernel<1><<<gridc, kSumBlock, 0, sm>>>(ca);
+                }
+                else
+                {
+                    sum_cell_kernel<2><<<gridc, kSumBlock, 0, sm>>>(ca);
+                }
             }
             else
             {
-                sum_cell_kernel<2><<<gridc, kSumBlock, 0, sc>>>(ca);
+                launch_sum_dispatch(P, sa, nl, fp32, sm);
             }
-            LBL_CUDA(cudaEventRecord(ev.k2_end, sc));
-            launch_fixup_dispatch(pick_fixup_tile(n_per_v), sa, nl, sc);
-        }
-        else
-        {
-            launch_sum_dispatch(P, sa, nl, fp32, sc);
-        }
-        if (!farfield)
-        {
-            LBL_CUDA(cudaEventRecord(ev.k2_end, sc));
-            launch_fixup_dispatch(pick_fixup_tile(n_per_v), sa, nl, sc);
-        }
-        LBL_CUDA(cudaEventRecord(ev.k2b_end, sc));
-        st.sum_launches++;
-        st.total_launches += 2;
+            LBL_CUDA(cudaEventRecord(se.k2_end, sm));
+            launch_fixup_dispatch(pick_fixup_tile(n_per_v), sa, q1 - q0, sm);
+            LBL_CUDA(cudaEventRecord(se.k2b_end, sm));
+            st.sum_launches++;
+            st.total_launches += 2;
+            g->sum_events.push_back(se);
+            // Back on the handle's stream (the next chunk's scaling kernel rewrites the records
+            // the summation kernels are reading).
+            LBL_CUDA(cudaStreamWaitEvent(sc, se.k2b_end, 0));
 
-        if (remove_pedestal)
-        {
-            LBL_CUDA(cudaStreamWaitEvent(sc, ev.ped_end, 0));
-            const size_t total = (size_t)nl * grid.n;
-            const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
-            pedestal_apply_kernel<<<blocks, 256, 0, sc>>>(g->out[slot].as<double>(),
-                                                          g->pedcorr.as<double>(), grid, nl);
-            st.total_launches++;
+            if (remove_pedestal)
+            {
+                if (q == 0) LBL_CUDA(cudaStreamWaitEvent(sc, ev.ped_end, 0));
+                const size_t total = (size_t)(q1 - q0) * grid.n;
+                const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
+                pedestal_apply_kernel<<<blocks, 256, 0, sc>>>(
+                    g->out[slot].as<double>() + (size_t)q0 * grid.n,
+                    g->pedcorr.as<double>() + 2 * (size_t)q0 * grid.ncell, grid, q1 - q0);
+                st.total_launches++;
+            }
+            LBL_CUDA(cudaGetLastError());
+
+            if (k_host)
+            {
+                LBL_CUDA(cudaEventRecord(g->ev_out_ready[slot], sc));
+                LBL_CUDA(cudaStreamWaitEvent(g->s_copy, g->ev_out_ready[slot], 0));
+                LBL_CUDA(cudaMemcpyAsync(k_host + (size_t)(first + q0) * grid.n,
+                                         g->out[slot].as<double>() + (size_t)q0 * grid.n,
+                                         out_per_layer * (q1 - q0), cudaMemcpyDeviceToHost, g->s_copy));
+                st.d2h_bytes += (long long)(out_per_layer * (q1 - q0));
+            }
         }
-        LBL_CUDA(cudaGetLastError());
         g->chunk_events.push_back(ev);
-
         if (k_host)
         {
-            LBL_CUDA(cudaEventRecord(g->ev_out_ready[slot], sc));
-            LBL_CUDA(cudaStreamWaitEvent(g->s_copy, g->ev_out_ready[slot], 0));
-            LBL_CUDA(cudaMemcpyAsync(k_host + (size_t)first * grid.n, g->out[slot].p,
-                                     out_per_layer * nl, cudaMemcpyDeviceToHost, g->s_copy));
             LBL_CUDA(cudaEventRecord(g->ev_out_free[slot], g->s_copy));
             g->out_busy[slot] = true;
-            st.d2h_bytes += (long long)(out_per_layer * nl);
         }
         g->last_chunk_first = first;
         g->last_chunk_layers = nl;
@@ -1106,15 +1154,18 @@ int lbl_gas_wait(lbl_gas* g)
     {
         LBL_CUDA(cudaEventElapsedTime(&ms, ev.k1_begin, ev.k1_end));
         st.scale_ms += ms;
-        LBL_CUDA(cudaEventElapsedTime(&ms, ev.k2_begin, ev.k2_end));
-        st.sum_ms += ms;
-        LBL_CUDA(cudaEventElapsedTime(&ms, ev.k2_end, ev.k2b_end));
-        st.fixup_ms += ms;
         if (ev.pedestal)
         {
             LBL_CUDA(cudaEventElapsedTime(&ms, ev.ped_begin, ev.ped_end));
             st.pedestal_ms += ms;
         }
+    }
+    for (const lbl_gas::SumEvents& se : g->sum_events)
+    {
+        LBL_CUDA(cudaEventElapsedTime(&ms, se.k2_begin, se.k2_end));
+        st.sum_ms += ms;
+        LBL_CUDA(cudaEventElapsedTime(&ms, se.k2_end, se.k2b_end));
+        st.fixup_ms += ms;
     }
     LBL_CUDA(cudaEventElapsedTime(&ms, g->ev_call_begin, g->ev_call_end));
     st.total_ms = ms;

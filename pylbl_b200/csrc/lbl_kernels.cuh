@@ -209,7 +209,7 @@ sum_cell_kernel(const CellArgs a)
     const GridSpec& g = a.sum.grid;
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int layer = blockIdx.y;
+    const int layer = blockIdx.y + a.sum.layer0;
     const int cell0 = (blockIdx.x * kWarps + warp) * G;
     const bool active = cell0 < g.ncell;      // idle warps of the last block still join the barriers
     const LayerIn ly = a.sum.layers[layer];
@@ -694,7 +694,7 @@ fixup_kernel(const SumArgs a)
         {
             return;
         }
-        fixup_warp_staged(a, tile, blockIdx.y, threadIdx.x & 31, queues[threadIdx.x >> 5],
+        fixup_warp_staged(a, tile, blockIdx.y + a.layer0, threadIdx.x & 31, queues[threadIdx.x >> 5],
                           slots[threadIdx.x >> 5]);
         return;
     }

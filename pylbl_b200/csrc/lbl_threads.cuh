@@ -219,6 +219,9 @@ struct SumArgs
                   // tpw*P consecutive points of 32/tpw consecutive layers
     int near_masked;  // 1: the summation kernel left near-zone points out (K2); 0: it added the
                       // Lorentz form there too (K2c) and K2b must add (profile - Lorentz)
+    int layer0 = 0;   // K2c and K2b<32>: first layer of this launch (grid.y counts from here;
+                      // n_layers stays the end bound), so that a group of layers can be summed,
+                      // corrected and copied out while the next group computes
 };
 
 template <int P>
