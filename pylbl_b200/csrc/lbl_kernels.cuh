@@ -720,12 +720,32 @@ pedestal_kernel(const PedArgs a, double* scratch)
     pedestal_layer(a, blockIdx.x, threadIdx.x, 32, nodes, WarpSync());
 }
 
+// One database row of a K3a tile, prepared by the lane that owns the row.
+struct __align__(16) PedRow
+{
+    double a, b, c;            // Lorentz operands (far_term)
+    double near_v0, near_v1;   // full-profile values at the (up to two) tracked points inside
+                               // the line's near zone
+    int base, t_lo, t_hi;      // node of slot 0; slots of the first and last node in the window
+    int flags;                 // 1: k[e] is grid point n-1 (slot 2*cut+2); 2: more than two
+                               // tracked points in the near zone (generic path for this row)
+    int s_slot, e_slot;        // slots of k[s], k[e]
+    int near_t0, near_t1;      // slots of near_v0, near_v1 (-1: none)
+    int cb, j, nlo, nhi;
+};
+
 // K3a.  terms[layer][row r][slot t], 32*K slots per row; one warp per tile of 32 rows.
 // grid = (ceil(tiles / 4), layers), block = 128.
+// Row m of the tile is prepared by lane m: window, slots, and the full profile at the tracked
+// points that fall inside the line's near zone (about every second line has one) -- dense over
+// the rows -- and parked in shared memory; the row loop then reads it by broadcast and every
+// lane evaluates the Lorentz form at its K slots.
 template <int K>
 __global__ void __launch_bounds__(128)
 pedestal_terms_kernel(const PedArgs a, double* __restrict__ terms)
 {
+    __shared__ PedRow tile_rows[4][kPedTileRows];
+    const GridSpec& g = a.grid;
     const int layer = blockIdx.y;
     const int tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -733,8 +753,129 @@ pedestal_terms_kernel(const PedArgs a, double* __restrict__ terms)
     {
         return;
     }
-    double* rows = terms + ((size_t)layer * a.lines.n + (size_t)tile * kPedTileRows) * (32 * K);
-    pedestal_terms_tile<K>(a, layer, tile, lane, rows);
+    constexpr int wpad = 32 * K;
+    double* rows = terms + ((size_t)layer * a.lines.n + (size_t)tile * kPedTileRows) * wpad;
+    PedRow* mine = tile_rows[threadIdx.x >> 5];
+    const int spare = 2 * g.cut_off + 3;
+    const int tail_slot = 2 * g.cut_off + 2;
+    const int first = tile * kPedTileRows;
+    const int cnt = min(a.lines.n - first, kPedTileRows);
+
+    if (lane < cnt)
+    {
+        PedRow pr;
+        pr.j = a.lines.db_to_sorted ? __ldg(a.lines.db_to_sorted + first + lane) : first + lane;
+        const size_t o = (size_t)layer * a.lines.n + pr.j;
+        const int4 ck = __ldg(reinterpret_cast<const int4*>(a.rec.chk + o));
+        const double2 l = __ldg(reinterpret_cast<const double2*>(a.rec.ab + o));
+        pr.a = l.x;
+        pr.b = l.y;
+        pr.c = __ldg(a.rec.cc + o);
+        pr.cb = ck.x;
+        pr.nlo = ck.y;
+        pr.nhi = ck.z;
+        const PedWindow w = ped_window(ck.x, g);
+        pr.base = w.base;
+        pr.t_lo = w.skip ? 1 : w.s_node - w.base;
+        pr.t_hi = w.skip ? 0 : w.e_node - w.base;
+        pr.flags = (!w.skip && w.tail) ? 1 : 0;
+        pr.s_slot = w.skip ? -1 : w.s_slot;
+        pr.e_slot = w.skip ? -1 : w.e_slot;
+        pr.near_t0 = pr.near_t1 = -1;
+        pr.near_v0 = pr.near_v1 = 0.;
+        if (!w.skip && ck.y <= ck.z)
+        {
+            // tracked points inside [nlo, nhi]: nodes idx*n_per_v, and grid point n-1 (tail)
+            int lo_idx = ck.y <= 0 ? 0 : (ck.y + g.n_per_v - 1) / g.n_per_v;
+            int hi_idx = ck.z < 0 ? -1 : ck.z / g.n_per_v;
+            lo_idx = max(lo_idx, w.s_node);
+            hi_idx = min(hi_idx, w.e_node);
+            const bool tail_near = w.tail && g.n - 1 >= ck.y && g.n - 1 <= ck.z;
+            const int n_near = max(hi_idx - lo_idx + 1, 0) + (tail_near ? 1 : 0);
+            if (n_near > 2)
+            {
+                pr.flags |= 2;
+            }
+            else if (n_near > 0)
+            {
+                const LineGen gen = a.rec.gen[o];
+                int filled = 0;
+                for (int idx = lo_idx; idx <= hi_idx; ++idx)
+                {
+                    const double val = voigt_general(grid_point(g.v0, g.dv, idx * g.n_per_v), gen.nu,
+                                                     gen.repwid, gen.y, gen.cof, gen.xlim0, gen.xlim1);
+                    if (filled == 0) { pr.near_t0 = idx - w.base; pr.near_v0 = val; }
+                    else { pr.near_t1 = idx - w.base; pr.near_v1 = val; }
+                    ++filled;
+                }
+                if (tail_near)
+                {
+                    const double val = voigt_general(grid_point(g.v0, g.dv, g.n - 1), gen.nu, gen.repwid,
+                                                     gen.y, gen.cof, gen.xlim0, gen.xlim1);
+                    if (filled == 0) { pr.near_t0 = tail_slot; pr.near_v0 = val; }
+                    else { pr.near_t1 = tail_slot; pr.near_v1 = val; }
+                }
+            }
+        }
+        mine[lane] = pr;
+    }
+    __syncwarp();
+
+    double run_sum[K];
+    int prev_cb = 0;
+    for (int m = 0; m < cnt; ++m)
+    {
+        const PedRow& pr = mine[m];
+        const int cb = pr.cb;
+        if (m == 0 || cb != prev_cb)
+        {
+#pragma unroll
+            for (int k = 0; k < K; ++k) run_sum[k] = 0.;
+        }
+        prev_cb = cb;
+        double* row = rows + (size_t)m * wpad;
+        const int flags = pr.flags;
+        const int t_lo = pr.t_lo, t_hi = pr.t_hi;
+        if (t_lo <= t_hi)   // else: the reference does not process this line on this grid
+        {
+            const double la = pr.a, lb = pr.b, lc = pr.c;
+            const int base = pr.base;
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+            {
+                const int t = lane + 32 * k;
+                const bool is_tail = (flags & 1) && t == tail_slot;
+                if ((t >= t_lo && t <= t_hi) || is_tail)
+                {
+                    const int i = is_tail ? g.n - 1 : (base + t) * g.n_per_v;
+                    const double v = grid_point(g.v0, g.dv, i);
+                    double val = far_term(v, la, lb, lc, 0.);
+                    if (flags & 2)
+                    {
+                        if (i >= pr.nlo && i <= pr.nhi)
+                        {
+                            const LineGen gen = a.rec.gen[(size_t)layer * a.lines.n + pr.j];
+                            val = voigt_general(v, gen.nu, gen.repwid, gen.y, gen.cof, gen.xlim0, gen.xlim1);
+                        }
+                    }
+                    else
+                    {
+                        if (t == pr.near_t0) val = pr.near_v0;
+                        if (t == pr.near_t1) val = pr.near_v1;
+                    }
+                    run_sum[k] += val;
+                    if (t == pr.s_slot) row[spare] = val;
+                    if (t == pr.e_slot) row[spare + 1] = val;
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k)
+        {
+            const int t = lane + 32 * k;
+            if (t != spare && t != spare + 1) row[t] = run_sum[k];
+        }
+    }
 }
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
