@@ -196,7 +196,7 @@ __device__ __forceinline__ double node16_plain_staged(const double2* __restrict_
 }
 
 template <int G>
-__global__ void __launch_bounds__(kSumBlock)
+__global__ void __launch_bounds__(kSumBlock, 5)
 sum_cell_kernel(const CellArgs a)
 {
     constexpr int kWarps = kSumBlock / 32;
@@ -548,7 +548,7 @@ __device__ __forceinline__ void fixup_warp(const SumArgs& a, int tile, int layer
 // compacted list with broadcast reads.  No global-memory latency and no per-line setup sits
 // in the evaluation loop.
 __device__ __forceinline__ void fixup_warp_staged(const SumArgs& a, int tile, int layer, int lane,
-                                                  int* queue, NearLine* slots)
+                                                  int* queue, NearLine* slots, unsigned* masks)
 {
     const GridSpec& g = a.grid;
     int i = tile * 32 + lane;
@@ -565,10 +565,12 @@ __device__ __forceinline__ void fixup_warp_staged(const SumArgs& a, int tile, in
     const double v = grid_point(g.v0, g.dv, i);
     const int cell = i / g.n_per_v;
     const bool is_node = (i - cell * g.n_per_v) == 0;
-    const int cb_min = cell - g.cut_off - (is_node ? 1 : 0);
-    const int cb_max = cell + g.cut_off;
-    const int tile_cb_min = t_first / g.n_per_v - g.cut_off - 1;
-    const int tile_cb_max = t_last / g.n_per_v + g.cut_off;
+    // The tile spans at most two cells (n_per_v >= 32): lanes [0, split) lie in cell_a, the
+    // rest in cell_a + 1; lane 0 (if t_first is a node) and lane `split` are first points.
+    const int cell_a = t_first / g.n_per_v;
+    const int split = min((cell_a + 1) * g.n_per_v - t_first, 32);
+    const unsigned lanes_a = split >= 32 ? 0xffffffffu : ((1u << split) - 1u);
+    const bool first_is_node = cell_a * g.n_per_v == t_first;
     const unsigned below = (1u << lane) - 1u;
     double acc = 0.;
 
@@ -577,20 +579,36 @@ __device__ __forceinline__ void fixup_warp_staged(const SumArgs& a, int tile, in
     int qn = 0;
     for (int base = jlo; base < jhi; base += 32)
     {
+        // Lane m: which points of the tile does line base+m touch?  Bit l of `mine` = point
+        // t_first+l lies in the line's near zone [nlo, nhi] and inside its window
+        // (cell-cut <= cb <= cell+cut, plus cb == cell-cut-1 for a cell's first point:
+        // s <= i <= e of spectra.c:48-62 in cell form).
         const int j = base + lane;
-        bool touches = false;
+        unsigned mine = 0;
         int4 ck = make_int4(0, 0, 0, 0);
         if (j < jhi)
         {
             ck = __ldg(reinterpret_cast<const int4*>(chk + j));
-            touches = ck.z >= t_first && ck.y <= t_last && ck.x >= tile_cb_min && ck.x <= tile_cb_max;
+            const int lo = max(ck.y - t_first, 0);
+            const int hi = min(ck.z - t_first, t_last - t_first);
+            if (lo <= hi)
+            {
+                const unsigned span = (0xffffffffu >> (31 - (hi - lo))) << lo;
+                const int da = ck.x - cell_a;
+                unsigned win = 0;
+                if (da >= -g.cut_off && da <= g.cut_off) win |= lanes_a;
+                if (da - 1 >= -g.cut_off && da - 1 <= g.cut_off) win |= ~lanes_a;
+                if (first_is_node && da == -g.cut_off - 1) win |= 1u;
+                if (split < 32 && da - 1 == -g.cut_off - 1) win |= 1u << split;
+                mine = span & win;
+            }
         }
-        const unsigned listed = __ballot_sync(0xffffffffu, touches);
+        const unsigned listed = __ballot_sync(0xffffffffu, mine != 0);
         if (listed == 0)
         {
             continue;
         }
-        if (touches)
+        if (mine != 0)
         {
             LineGen gn;
             const double2 g0 = __ldg(reinterpret_cast<const double2*>(gen + j));
@@ -600,40 +618,45 @@ __device__ __forceinline__ void fixup_warp_staged(const SumArgs& a, int tile, in
             const double2 l = __ldg(reinterpret_cast<const double2*>(a.rec.ab + off + j));
             FarAB ab;
             ab.a = l.x; ab.b = l.y;
-            slots[__popc(listed & below)] =
-                near_line(ck, j, gn, ab, __ldg(a.rec.cc + off + j), a.near_masked != 0);
+            const int slot = __popc(listed & below);
+            slots[slot] = near_line(ck, j, gn, ab, __ldg(a.rec.cc + off + j), a.near_masked != 0);
+            masks[slot] = mine;
         }
         __syncwarp();
         const int n_listed = __popc(listed);
+        unsigned cores = 0;   // bit s: slot s leaves this lane a region-3 / CPF12 evaluation
         for (int s = 0; s < n_listed; ++s)
         {
-            const NearLine& nl = slots[s];
-            const int4 hd = *reinterpret_cast<const int4*>(&nl);
-            bool core = false;
-            if (i >= hd.x && i <= hd.y && hd.z >= cb_min && hd.z <= cb_max)
+            if ((masks[s] >> lane) & 1u)
             {
-                acc += near_point(nl, v, core);   // region 3 / CPF12 left over: queued below
+                bool core;
+                acc += near_point(slots[s], v, core);
+                if (core) cores |= 1u << s;
             }
-            const unsigned m = __ballot_sync(0xffffffffu, core);
-            if (m)
+        }
+        // queue the left-over evaluations, lane-packed
+        while (__any_sync(0xffffffffu, cores != 0))
+        {
+            const bool has = cores != 0;
+            const int s = has ? __ffs(cores) - 1 : 0;
+            cores &= cores - 1u;
+            const unsigned m = __ballot_sync(0xffffffffu, has);
+            if (has)
             {
-                if (core)
-                {
-                    queue[qn + __popc(m & below)] = ((hd.w >> 1) << 5) | lane;
-                }
-                qn += __popc(m);
+                queue[qn + __popc(m & below)] = ((slots[s].tag >> 1) << 5) | lane;
+            }
+            qn += __popc(m);
+            __syncwarp();
+            if (qn >= 32)
+            {
+                acc = fixup_drain<32>(a, queue, 32, lane, layer, v, acc);
                 __syncwarp();
-                if (qn >= 32)
-                {
-                    acc = fixup_drain<32>(a, queue, 32, lane, layer, v, acc);
-                    __syncwarp();
-                    const int keep = qn - 32;
-                    const int moved = (lane < keep) ? queue[32 + lane] : 0;
-                    __syncwarp();
-                    if (lane < keep) queue[lane] = moved;
-                    qn = keep;
-                    __syncwarp();
-                }
+                const int keep = qn - 32;
+                const int moved = (lane < keep) ? queue[32 + lane] : 0;
+                __syncwarp();
+                if (lane < keep) queue[lane] = moved;
+                qn = keep;
+                __syncwarp();
             }
         }
         __syncwarp();   // the slots are rewritten by the next batch
@@ -682,7 +705,7 @@ __device__ __forceinline__ void fixup_warp_staged(const SumArgs& a, int tile, in
 }
 
 template <int T>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 10)
 fixup_kernel(const SumArgs a)
 {
     __shared__ int queues[4][kFixQueue];
@@ -690,12 +713,13 @@ fixup_kernel(const SumArgs a)
     if (T == 32)
     {
         __shared__ __align__(16) NearLine slots[4][32];
+        __shared__ unsigned masks[4][32];
         if (tile * 32 >= a.grid.n)
         {
             return;
         }
         fixup_warp_staged(a, tile, blockIdx.y + a.layer0, threadIdx.x & 31, queues[threadIdx.x >> 5],
-                          slots[threadIdx.x >> 5]);
+                          slots[threadIdx.x >> 5], masks[threadIdx.x >> 5]);
         return;
     }
     if (tile * T >= a.grid.n)

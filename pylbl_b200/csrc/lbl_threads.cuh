@@ -936,7 +936,8 @@ struct NearLine
     double ax, d0, d2, n0;
     double yq, lim_r2, y, cof;
     double a, b, c;               // the summation kernel's operands (far_term)
-    double pad;                   // 144 B: a multiple of 16 (the header is read as one int4)
+    double pad;                   // 144 B: a multiple of 16, and as a shared-memory stride free of
+                                  // bank conflicts for the 16-byte stores of 8 lanes (128 B is not)
 };
 
 LBL_HD NearLine near_line(const int4& ck, int j, const LineGen& gen, const FarAB& ab, double cc,
