@@ -686,9 +686,9 @@ int lbl_gas_close(lbl_gas* g)
     return 0;
 }
 
-int lbl_gas_submit(lbl_gas* g, int n_layers, const double* pressure, const double* temperature,
-                   const double* vmr, int v0, int vn, int n_per_v, int cut_off,
-                   int remove_pedestal, int precision, double* k_host)
+static int submit_call(lbl_gas* g, bool blocking, int n_layers, const double* pressure,
+                       const double* temperature, const double* vmr, int v0, int vn, int n_per_v,
+                       int cut_off, int remove_pedestal, int precision, double* k_host)
 {
     if (!g) return fail("Error: null handle.");
     if (g->pending && lbl_gas_wait(g)) return 1;
@@ -1038,7 +1038,10 @@ int lbl_gas_submit(lbl_gas* g, int n_layers, const double* pressure, const doubl
         int n_groups = 1;
         if (farfield && k_host)
         {
-            n_groups = 1;   // splitting costs a kernel tail per group: off unless asked for
+            // Splitting costs a kernel tail per group.  It pays when the caller blocks on this
+            // call (nothing else would hide the copy); with several calls in flight the copy of
+            // one gas hides behind the kernels of the next and one group is best.
+            n_groups = (blocking && nl >= 16) ? 2 : 1;
             if (const char* env = getenv("PYLBL_B200_COPY_GROUPS")) n_groups = std::max(1, std::min(atoi(env), nl));
         }
         LBL_CUDA(cudaStreamWaitEvent(sm, ev.k1_end, 0));   // also orders sm after out_free[slot]
@@ -1172,12 +1175,20 @@ int lbl_gas_wait(lbl_gas* g)
     return 0;
 }
 
+int lbl_gas_submit(lbl_gas* g, int n_layers, const double* pressure, const double* temperature,
+                   const double* vmr, int v0, int vn, int n_per_v, int cut_off,
+                   int remove_pedestal, int precision, double* k_host)
+{
+    return submit_call(g, false, n_layers, pressure, temperature, vmr, v0, vn, n_per_v, cut_off,
+                       remove_pedestal, precision, k_host);
+}
+
 int lbl_gas_compute(lbl_gas* g, int n_layers, const double* pressure, const double* temperature,
                     const double* vmr, int v0, int vn, int n_per_v, int cut_off,
                     int remove_pedestal, int precision, double* k_host)
 {
-    if (lbl_gas_submit(g, n_layers, pressure, temperature, vmr, v0, vn, n_per_v, cut_off,
-                       remove_pedestal, precision, k_host))
+    if (submit_call(g, true, n_layers, pressure, temperature, vmr, v0, vn, n_per_v, cut_off,
+                    remove_pedestal, precision, k_host))
     {
         return 1;
     }

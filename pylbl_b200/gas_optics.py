@@ -169,23 +169,24 @@ class Gas(object):
         submitted = []
         errors = []
 
-        def submit(d):
+        def submit(d, blocking=False):
             lo, hi = int(edges[d]), int(edges[d + 1])
             h = self._handle(self.devices[d])
             dst = out[lo:hi].ctypes.data_as(c_void_p) if to_host else None
-            lib.lbl_gas_submit(h.ptr, hi - lo, p[lo:hi], t[lo:hi], x[lo:hi], v0, vn, n_per_v,
-                               int(cut_off), ped, self.precision, dst)
+            # The blocking entry point copies the spectra out in layer groups while later groups
+            # compute; submit + wait leaves that overlap to the calls queued behind this one.
+            call = lib.lbl_gas_compute if blocking else lib.lbl_gas_submit
+            call(h.ptr, hi - lo, p[lo:hi], t[lo:hi], x[lo:hi], v0, vn, n_per_v,
+                 int(cut_off), ped, self.precision, dst)
             return h
 
         if ndev == 1:
-            submitted.append(submit(0))
+            submitted.append(submit(0, blocking=True))
         else:
             # One host thread per device: pageable destinations make the copies synchronous.
             def work(d):
                 try:
-                    h = submit(d)
-                    lib.lbl_gas_wait(h.ptr)
-                    submitted.append(h)
+                    submitted.append(submit(d, blocking=True))
                 except Exception as exc:  # re-raised below
                     errors.append(exc)
             threads = [threading.Thread(target=work, args=(d,)) for d in range(ndev)]
