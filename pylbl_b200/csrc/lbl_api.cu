@@ -135,7 +135,7 @@ struct lbl_gas
 
     cudaStream_t s_compute = nullptr, s_side = nullptr, s_copy = nullptr;
     DevBuf rec_ab, rec_cc, rec_chk, rec_gen, layers_dev, evals_dev, pedbin, pedcorr, pednodes,
-        pedterms, rec_f32, amp_max, cheb_nodes, cheb_weights, cheb_nodes16, cheb_weights16,
+        pedterms, rec_f32, amp_max, cheb_nodes, cheb_weights, cheb_nodes16, cheb_weights16, cheb_nodes8, cheb_weights8,
         executed_dev;
     int cheb_npv = 0;
     unsigned long long* executed_host = nullptr;  // pinned
@@ -371,7 +371,11 @@ void launch_fixup_dispatch(int T, const SumArgs& a, int n_layers, cudaStream_t s
     dim3 grid((tiles + 3) / 4, (n_layers + lp - 1) / lp);
     switch (T)
     {
-        case 32: fixup_kernel<32><<<grid, 128, 0, s>>>(a); break;
+        case 32:
+            cudaFuncSetAttribute(fixup_kernel<32>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 cudaSharedmemCarveoutMaxShared);   // 10 blocks x 21 KB per SM
+            fixup_kernel<32><<<grid, 128, 0, s>>>(a);
+            break;
         case 16: fixup_kernel<16><<<grid, 128, 0, s>>>(a); break;
         case 8: fixup_kernel<8><<<grid, 128, 0, s>>>(a); break;
         default: fixup_kernel<4><<<grid, 128, 0, s>>>(a); break;
@@ -420,26 +424,27 @@ int main_stream(int device, cudaStream_t* out)
     return 0;
 }
 
-// Interpolation tables of K2c for one grid resolution: Chebyshev nodes of the first kind on
-// the cell interval [0, (n_per_v-1)/n_per_v] and the Lagrange basis of those nodes at the
-// grid offsets r/n_per_v (barycentric form, evaluated in long double).
+// Interpolation tables of K2c for one grid resolution: for each of the three far fields
+// (32, 16 and 8 nodes) the Chebyshev nodes of the first kind on the cell interval
+// [0, (n_per_v-1)/n_per_v] and the node-values -> coefficients transform (lbl_cheb.h).
 int ensure_cheb_tables(lbl_gas* g, int n_per_v)
 {
     if (g->cheb_npv == n_per_v) return 0;
-    std::vector<double> nodes, weights;
-    build_cheb_tables(kNodes, n_per_v, nodes, weights);
-    build_cheb_transform(kNodes, weights);
+    struct Field { int n; DevBuf* nodes; DevBuf* transform; };
+    const Field fields[3] = {{kNodes, &g->cheb_nodes, &g->cheb_weights},
+                             {kNodes16, &g->cheb_nodes16, &g->cheb_weights16},
+                             {kNodes8, &g->cheb_nodes8, &g->cheb_weights8}};
     size_t bytes = 0;
-    if (upload(g->cheb_nodes, nodes.data(), sizeof(double) * kNodes, g->s_compute, bytes)) return 1;
-    if (upload(g->cheb_weights, weights.data(), sizeof(double) * weights.size(), g->s_compute, bytes))
-        return 1;
-    LBL_CUDA(cudaStreamSynchronize(g->s_compute));   // the host vectors are reused
-    build_cheb_tables(kNodes16, n_per_v, nodes, weights);
-    build_cheb_transform(kNodes16, weights);
-    if (upload(g->cheb_nodes16, nodes.data(), sizeof(double) * kNodes16, g->s_compute, bytes)) return 1;
-    if (upload(g->cheb_weights16, weights.data(), sizeof(double) * weights.size(), g->s_compute, bytes))
-        return 1;
-    LBL_CUDA(cudaStreamSynchronize(g->s_compute));   // the host vectors go out of scope
+    for (const Field& f : fields)
+    {
+        std::vector<double> nodes, transform;
+        build_cheb_nodes(f.n, n_per_v, nodes);
+        build_cheb_transform(f.n, transform);
+        if (upload(*f.nodes, nodes.data(), sizeof(double) * nodes.size(), g->s_compute, bytes)) return 1;
+        if (upload(*f.transform, transform.data(), sizeof(double) * transform.size(), g->s_compute, bytes))
+            return 1;
+        LBL_CUDA(cudaStreamSynchronize(g->s_compute));   // the host vectors go out of scope
+    }
     g->open_h2d += bytes;
     g->cheb_npv = n_per_v;
     return 0;
@@ -661,7 +666,7 @@ int lbl_gas_close(lbl_gas* g)
     for (DevBuf* b : {&g->tips_t, &g->tips_q, &g->rec_ab, &g->rec_cc, &g->rec_chk, &g->rec_gen,
                       &g->layers_dev, &g->evals_dev, &g->pedbin, &g->pedcorr, &g->pednodes,
                       &g->pedterms, &g->rec_f32, &g->amp_max, &g->cheb_nodes, &g->cheb_weights,
-                      &g->cheb_nodes16, &g->cheb_weights16,
+                      &g->cheb_nodes16, &g->cheb_weights16, &g->cheb_nodes8, &g->cheb_weights8,
                       &g->executed_dev,
                       &g->out[0], &g->out[1]})
     {
@@ -1024,11 +1029,14 @@ static int submit_call(lbl_gas* g, bool blocking, int n_layers, const double* pr
             ca.transform = g->cheb_weights.as<double>();
             ca.node_offset16 = g->cheb_nodes16.as<double>();
             ca.transform16 = g->cheb_weights16.as<double>();
+            ca.node_offset8 = g->cheb_nodes8.as<double>();
+            ca.transform8 = g->cheb_weights8.as<double>();
             ca.executed = g->executed_dev.as<unsigned long long>();
-            // cells per warp: more cells amortise the loads of the line operands over more
-            // node evaluations, fewer keep the (per-cell) direct range short
-            cells_per_warp = (n_per_v <= 256) ? 2 : 1;
-            if (const char* env = getenv("PYLBL_B200_CELLS")) cells_per_warp = atoi(env) == 1 ? 1 : 2;
+            // cells per warp: two cells share the loads of the 32-node lines, but one cell per
+            // warp needs fewer registers (8 resident blocks per SM) and has no per-cell window
+            // edges inside the group; measured faster on every BASELINE grid
+            cells_per_warp = 1;
+            if (const char* env = getenv("PYLBL_B200_CELLS")) cells_per_warp = atoi(env) == 2 ? 2 : 1;
             st.cells_per_warp = cells_per_warp;
         }
         // Layer groups of this chunk: each is summed (main stream), corrected and copied out
@@ -1061,12 +1069,20 @@ static int submit_call(lbl_gas* g, bool blocking, int n_layers, const double* pr
                 ca.sum = sa;
                 const int groups = (grid.ncell + cells_per_warp - 1) / cells_per_warp;
                 dim3 gridc((groups + kSumBlock / 32 - 1) / (kSumBlock / 32), q1 - q0);
+                // 23 KB of static shared memory per block: ask for the large carve-out so that
+                // shared memory does not cap the resident blocks below the register limit.
                 if (cells_per_warp == 1)
                 {
+                    LBL_CUDA(cudaFuncSetAttribute(sum_cell_kernel<1>,
+                                                  cudaFuncAttributePreferredSharedMemoryCarveout,
+                                                  cudaSharedmemCarveoutMaxShared));
                     sum_cell_kernel<1><<<gridc, kSumBlock, 0, sm>>>(ca);
                 }
                 else
                 {
+                    LBL_CUDA(cudaFuncSetAttribute(sum_cell_kernel<2>,
+                                                  cudaFuncAttributePreferredSharedMemoryCarveout,
+                                                  cudaSharedmemCarveoutMaxShared));
                     sum_cell_kernel<2><<<gridc, kSumBlock, 0, sm>>>(ca);
                 }
             }

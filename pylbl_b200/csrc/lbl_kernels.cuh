@@ -196,12 +196,13 @@ __device__ __forceinline__ double node16_plain_staged(const double2* __restrict_
 }
 
 template <int G>
-__global__ void __launch_bounds__(kSumBlock, 5)
+__global__ void __launch_bounds__(kSumBlock, 8)
 sum_cell_kernel(const CellArgs a)
 {
     constexpr int kWarps = kSumBlock / 32;
     __shared__ double fields[kWarps][G][kNodes];
     __shared__ double fields16[kWarps][G][kNodes16];
+    __shared__ double fields8[kWarps][G][kNodes8];
     __shared__ alignas(16) double2 s_ab[kStages][kStageLines];
     __shared__ alignas(16) double s_cc[kStages][kStageLines];
     __shared__ alignas(8) unsigned long long full[kStages];
@@ -213,7 +214,7 @@ sum_cell_kernel(const CellArgs a)
     const int cell0 = (blockIdx.x * kWarps + warp) * G;
     const bool active = cell0 < g.ncell;      // idle warps of the last block still join the barriers
     const LayerIn ly = a.sum.layers[layer];
-    // eight binary searches, one per lane, shared by shuffle
+    // ten searches, one per lane, shared by shuffle
     int mine = 0;
     if (active && lane < kCellKeys)
     {
@@ -231,13 +232,13 @@ sum_cell_kernel(const CellArgs a)
 
     // ---- phase 1: far fields at the nodes ------------------------------------------------
     // The four warps of a block own neighbouring cell groups, so their far-line ranges
-    // [j1, j3) u [j4, j6) overlap almost entirely.  The block walks the union in chunks that
+    // [j1, j4) u [j5, j8) overlap almost entirely.  The block walks the union in chunks that
     // one thread stages into shared memory with TMA bulk copies (3-deep ring, mbarrier per
     // stage); each warp takes from a chunk what lies inside its own ranges.
     if (lane == 0)
     {
         s_range[warp][0] = active ? seg.j[1] : 0x7fffffff;
-        s_range[warp][1] = active ? seg.j[6] : 0;
+        s_range[warp][1] = active ? seg.j[8] : 0;
     }
     if (threadIdx.x == 0)
     {
@@ -276,8 +277,10 @@ sum_cell_kernel(const CellArgs a)
     const Lane16<G> m16 = lane16<G>(lane);
     const int my_cell = cell0 + m16.cell_off;
     const double v16 = ((double)g.v0 + (double)my_cell) + a.node_offset16[m16.node];
+    const Lane16<G> m8 = lane8<G>(lane);
+    const double v8 = ((double)g.v0 + (double)(cell0 + m8.cell_off)) + a.node_offset8[m8.node];
     double v[G], f[G];
-    double f16 = 0.;
+    double f16 = 0., f8 = 0.;
 #pragma unroll
     for (int q = 0; q < G; ++q)
     {
@@ -287,7 +290,7 @@ sum_cell_kernel(const CellArgs a)
     if (active)
     {
         f16 += node16_tested(ab, cc, chk, seg.j[0], seg.j[1], m16.first, m16.stride, my_cell, g.cut_off, v16);
-        f16 += node16_tested(ab, cc, chk, seg.j[6], seg.j[7], m16.first, m16.stride, my_cell, g.cut_off, v16);
+        f16 += node16_tested(ab, cc, chk, seg.j[8], seg.j[9], m16.first, m16.stride, my_cell, g.cut_off, v16);
     }
     for (int t = 0; t < n_chunks; ++t)
     {
@@ -298,13 +301,17 @@ sum_cell_kernel(const CellArgs a)
         if (active)
         {
             int b = max(first, seg.j[1]), e = min(last, seg.j[2]);
-            if (b < e) f16 += node16_plain_staged(s_ab[stage], s_cc[stage], first, b, e, m16.first, m16.stride, v16);
+            if (b < e) f8 += node16_plain_staged(s_ab[stage], s_cc[stage], first, b, e, m8.first, m8.stride, v8);
             b = max(first, seg.j[2]); e = min(last, seg.j[3]);
-            if (b < e) node_plain_staged<G>(s_ab[stage], s_cc[stage], first, b, e, v, f);
-            b = max(first, seg.j[4]); e = min(last, seg.j[5]);
+            if (b < e) f16 += node16_plain_staged(s_ab[stage], s_cc[stage], first, b, e, m16.first, m16.stride, v16);
+            b = max(first, seg.j[3]); e = min(last, seg.j[4]);
             if (b < e) node_plain_staged<G>(s_ab[stage], s_cc[stage], first, b, e, v, f);
             b = max(first, seg.j[5]); e = min(last, seg.j[6]);
+            if (b < e) node_plain_staged<G>(s_ab[stage], s_cc[stage], first, b, e, v, f);
+            b = max(first, seg.j[6]); e = min(last, seg.j[7]);
             if (b < e) f16 += node16_plain_staged(s_ab[stage], s_cc[stage], first, b, e, m16.first, m16.stride, v16);
+            b = max(first, seg.j[7]); e = min(last, seg.j[8]);
+            if (b < e) f8 += node16_plain_staged(s_ab[stage], s_cc[stage], first, b, e, m8.first, m8.stride, v8);
         }
         __syncthreads();   // every warp is done with this stage
         if (threadIdx.x == 0 && t + kStages < n_chunks) issue(t + kStages);
@@ -317,11 +324,19 @@ sum_cell_kernel(const CellArgs a)
     {
         f16 += __shfl_xor_sync(0xffffffffu, f16, 16);   // the half-warps held partial sums
     }
+    // the lanes that shared the lines of an 8-node point add up
+    f8 += __shfl_xor_sync(0xffffffffu, f8, 8);
+    if (G == 1)
+    {
+        f8 += __shfl_xor_sync(0xffffffffu, f8, 16);
+    }
     double (*field)[kNodes] = fields[warp];
     double (*field16)[kNodes16] = fields16[warp];
+    double (*field8)[kNodes8] = fields8[warp];
 #pragma unroll
     for (int q = 0; q < G; ++q) field[q][lane] = f[q];
     if (G >= 2 || lane < 16) field16[m16.cell_off][m16.node] = f16;
+    if ((lane & 8) == 0 && (G >= 2 || lane < 8)) field8[m8.cell_off][m8.node] = f8;
 
     // ---- phase 2: direct lines, Lorentz form ------------------------------------------------
     const int chunks = (g.n_per_v + 32 * kCellP - 1) / (32 * kCellP);
@@ -337,12 +352,13 @@ sum_cell_kernel(const CellArgs a)
     // ---- phase 3: + interpolated far fields ---------------------------------------------------
     // node sums -> Chebyshev coefficients (lane = coefficient), in place in shared memory
     {
-        double c32[G], c16[G];
+        double c32[G], c16[G], c8[G];
 #pragma unroll
         for (int q = 0; q < G; ++q)
         {
             c32[q] = cell_coefficient(a.transform, field[q], kNodes, lane);
             c16[q] = cell_coefficient(a.transform16, field16[q], kNodes16, lane);
+            c8[q] = cell_coefficient(a.transform8, field8[q], kNodes8, lane);
         }
         __syncwarp();
 #pragma unroll
@@ -350,20 +366,23 @@ sum_cell_kernel(const CellArgs a)
         {
             field[q][lane] = c32[q];
             if (lane < kNodes16) field16[q][lane] = c16[q];
+            if (lane < kNodes8) field8[q][lane] = c8[q];
         }
         __syncwarp();
     }
     for (int q = 0; q < cells; ++q)
     {
-        cell_field_lane(a, layer, cell0 + q, lane, 32, field[q], field16[q]);
+        cell_field_lane(a, layer, cell0 + q, lane, 32, field[q], field16[q], field8[q]);
     }
     if (a.executed && lane == 0)
     {
         // statistics only: Lorentz evaluations this warp performed (nodes + direct slots)
-        const unsigned long long mid = (unsigned long long)((seg.j[3] - seg.j[2]) + (seg.j[5] - seg.j[4]));
-        const unsigned long long vfar = (unsigned long long)((seg.j[2] - seg.j[0]) + (seg.j[7] - seg.j[5]));
-        const unsigned long long direct = (unsigned long long)(seg.j[4] - seg.j[3]);
-        atomicAdd(a.executed, mid * (kNodes * G) + vfar * (kNodes16 * G) +
+        const unsigned long long mid = (unsigned long long)((seg.j[4] - seg.j[3]) + (seg.j[6] - seg.j[5]));
+        const unsigned long long vfar = (unsigned long long)((seg.j[1] - seg.j[0]) + (seg.j[3] - seg.j[2]) +
+                                                             (seg.j[7] - seg.j[6]) + (seg.j[9] - seg.j[8]));
+        const unsigned long long far8 = (unsigned long long)((seg.j[2] - seg.j[1]) + (seg.j[8] - seg.j[7]));
+        const unsigned long long direct = (unsigned long long)(seg.j[5] - seg.j[4]);
+        atomicAdd(a.executed, mid * (kNodes * G) + vfar * (kNodes16 * G) + far8 * (kNodes8 * G) +
                               direct * (unsigned long long)(cells * chunks * 32 * kCellP));
     }
 }

@@ -540,9 +540,11 @@ LBL_HD void sum32_thread(const SumArgs& a, int layer_group, int tile, int lane)
 // ---------------------------------------------------------------------------------------
 constexpr int kNodes = 32;
 constexpr int kNodes16 = 16;
+constexpr int kNodes8 = 8;
 constexpr int kCellP = 4;         // points per thread in the direct part
 constexpr double kFarMin = 0.4;   // cm-1 beyond the cell edges where the 32-node field starts
 constexpr double kVeryFar = 2.0;  // cm-1 beyond the cell edges where the 16-node field starts
+constexpr double kFar8 = 8.0;     // cm-1 beyond the cell edges where the 8-node field starts
 
 struct CellArgs
 {
@@ -551,20 +553,23 @@ struct CellArgs
     const double* transform;       // [kNodes][kNodes] node sums -> Chebyshev coefficients (k-major)
     const double* node_offset16;   // [kNodes16]
     const double* transform16;     // [kNodes16][kNodes16]
+    const double* node_offset8;    // [kNodes8]
+    const double* transform8;      // [kNodes8][kNodes8]
     unsigned long long* executed;  // statistics: evaluations actually performed (or nullptr)
 };
 
-// Line ranges of a cell group, as indices into the nu-sorted line list:
-//   [j0,j1) very far + window test | [j1,j2) very far | [j2,j3) mid | [j3,j4) direct |
-//   [j4,j5) mid | [j5,j6) very far | [j6,j7) very far + window test
+// Line ranges of a cell group, as indices into the nu-sorted line list, from below:
+//   [j0,j1) window edge, tested per cell (16 nodes) | [j1,j2) 8-node | [j2,j3) 16-node |
+//   [j3,j4) 32-node | [j4,j5) direct | [j5,j6) 32-node | [j6,j7) 16-node | [j7,j8) 8-node |
+//   [j8,j9) window edge, tested per cell (16 nodes)
 struct CellSegments
 {
-    int j[8];
+    int j[10];
 };
-constexpr int kCellKeys = 8;
+constexpr int kCellKeys = 10;
 
 // The search keys of those ranges for the group of `cells` consecutive cells starting at
-// `cell` (one binary search each; the kernel gives one key to each of eight lanes).
+// `cell` (one search each; the kernel gives one key to each of ten lanes).
 LBL_HD double cell_search_key(const GridSpec& g, const LayerIn& ly, int cell, int cells, int which)
 {
     const double lo = (double)g.v0 + (double)cell;                       // first point of the group
@@ -575,11 +580,13 @@ LBL_HD double cell_search_key(const GridSpec& g, const LayerIn& ly, int cell, in
     {
         case 0: return lo - (double)g.cut_off - ly.slack;            // first line in any cell's window
         case 1: return lo_last - (double)g.cut_off + ly.slack;       // first line certainly in all of them
-        case 2: return lo - kVeryFar - ly.slack;                     // 32-node range
-        case 3: return lo - reach;                                   // direct range
-        case 4: return hi + reach;
-        case 5: return hi + kVeryFar + ly.slack;
-        case 6: return lo + (double)(g.cut_off + 1) - ly.slack;      // end of the certain part
+        case 2: return lo - kFar8 - ly.slack;                        // end of the lower 8-node range
+        case 3: return lo - kVeryFar - ly.slack;                     // 32-node range
+        case 4: return lo - reach;                                   // direct range
+        case 5: return hi + reach;
+        case 6: return hi + kVeryFar + ly.slack;
+        case 7: return hi + kFar8 + ly.slack;                        // start of the upper 8-node range
+        case 8: return lo + (double)(g.cut_off + 1) - ly.slack;      // end of the certain part
         default: return lo_last + (double)(g.cut_off + 1) + ly.slack; // end of the last window
     }
 }
@@ -593,24 +600,29 @@ LBL_HD CellSegments cell_segments_from(const int (&found)[kCellKeys])
 {
     CellSegments s;
     const int w_lo = found[0];
-    const int w_hi = found[7] > w_lo ? found[7] : w_lo;
+    const int w_hi = found[9] > w_lo ? found[9] : w_lo;
     // direct range, clamped to the window (it may reach beyond it when cut_off is tiny)
-    const int d_lo = clamp_int(found[3], w_lo, w_hi);
-    const int d_hi = clamp_int(found[4], d_lo, w_hi);
+    const int d_lo = clamp_int(found[4], w_lo, w_hi);
+    const int d_hi = clamp_int(found[5], d_lo, w_hi);
     // 32-node range around it
-    const int m_lo = clamp_int(found[2], w_lo, d_lo);
-    const int m_hi = clamp_int(found[5], d_hi, w_hi);
+    const int m_lo = clamp_int(found[3], w_lo, d_lo);
+    const int m_hi = clamp_int(found[6], d_hi, w_hi);
     // lines certainly inside every cell's window
     const int c_lo = clamp_int(found[1], w_lo, m_lo);
-    const int c_hi = clamp_int(found[6], m_hi, w_hi);
+    const int c_hi = clamp_int(found[8], m_hi, w_hi);
+    // 8-node ranges: the outer part of the certain lines
+    const int e_lo = clamp_int(found[2], c_lo, m_lo);
+    const int e_hi = clamp_int(found[7], m_hi, c_hi);
     s.j[0] = w_lo;
     s.j[1] = c_lo;
-    s.j[2] = m_lo;
-    s.j[3] = d_lo;
-    s.j[4] = d_hi;
-    s.j[5] = m_hi;
-    s.j[6] = c_hi;
-    s.j[7] = w_hi;
+    s.j[2] = e_lo;
+    s.j[3] = m_lo;
+    s.j[4] = d_lo;
+    s.j[5] = d_hi;
+    s.j[6] = m_hi;
+    s.j[7] = e_hi;
+    s.j[8] = c_hi;
+    s.j[9] = w_hi;
     return s;
 }
 
@@ -752,12 +764,34 @@ LBL_HD Lane16<G> lane16(int lane)
     return m;
 }
 
+// How the 32 lanes map onto 8-node points: each cell's lanes split its lines 2 ways (G == 2,
+// a half-warp per cell) or 4 ways (G == 1); the shares are added up by shuffle.
+template <int G>
+LBL_HD Lane16<G> lane8(int lane)
+{
+    Lane16<G> m;
+    m.node = lane & 7;
+    if (G >= 2)
+    {
+        m.cell_off = lane >> 4;
+        m.first = (lane >> 3) & 1;
+        m.stride = 2;
+    }
+    else
+    {
+        m.cell_off = 0;
+        m.first = lane >> 3;
+        m.stride = 4;
+    }
+    return m;
+}
+
 // Phase 1, lane = node: sums of the mid lines at this lane's 32-node point of each cell (f32)
 // and of the very far lines at this lane's 16-node point (f16; for G == 1 the two half-warps
 // hold partial sums of the same 16 points).
 template <int G>
 LBL_HD void cell_far_lane(const CellArgs& a, int layer, int cell, int lane, const CellSegments& seg,
-                          double (&f32)[G], double& f16)
+                          double (&f32)[G], double& f16, double& f8)
 {
     static_assert(G == 1 || G == 2, "a warp holds the 16-node points of one or two cells");
     const GridSpec& g = a.sum.grid;
@@ -772,15 +806,19 @@ LBL_HD void cell_far_lane(const CellArgs& a, int layer, int cell, int lane, cons
         v[q] = ((double)g.v0 + (double)(cell + q)) + a.node_offset[lane];
         f32[q] = 0.;
     }
-    node_plain<G>(ab, cc, seg.j[2], seg.j[3], v, f32);
-    node_plain<G>(ab, cc, seg.j[4], seg.j[5], v, f32);
+    node_plain<G>(ab, cc, seg.j[3], seg.j[4], v, f32);
+    node_plain<G>(ab, cc, seg.j[5], seg.j[6], v, f32);
     const Lane16<G> m = lane16<G>(lane);
     const int my_cell = cell + m.cell_off;
     const double v16 = ((double)g.v0 + (double)my_cell) + a.node_offset16[m.node];
     f16 = node16_tested(ab, cc, chk, seg.j[0], seg.j[1], m.first, m.stride, my_cell, g.cut_off, v16);
-    f16 += node16_plain(ab, cc, seg.j[1], seg.j[2], m.first, m.stride, v16);
-    f16 += node16_plain(ab, cc, seg.j[5], seg.j[6], m.first, m.stride, v16);
-    f16 += node16_tested(ab, cc, chk, seg.j[6], seg.j[7], m.first, m.stride, my_cell, g.cut_off, v16);
+    f16 += node16_plain(ab, cc, seg.j[2], seg.j[3], m.first, m.stride, v16);
+    f16 += node16_plain(ab, cc, seg.j[6], seg.j[7], m.first, m.stride, v16);
+    f16 += node16_tested(ab, cc, chk, seg.j[8], seg.j[9], m.first, m.stride, my_cell, g.cut_off, v16);
+    const Lane16<G> m8 = lane8<G>(lane);
+    const double v8 = ((double)g.v0 + (double)(cell + m8.cell_off)) + a.node_offset8[m8.node];
+    f8 = node16_plain(ab, cc, seg.j[1], seg.j[2], m8.first, m8.stride, v8);
+    f8 += node16_plain(ab, cc, seg.j[7], seg.j[8], m8.first, m8.stride, v8);
 }
 
 // Phase 2, lane = kCellP consecutive points of chunk `chunk` of the cell: the direct lines.
@@ -809,12 +847,12 @@ LBL_HD void cell_direct_lane(const CellArgs& a, int layer, int cell, int chunk, 
     {
         // Direct lines lie within kFarMin of the (at most 2-cell) group: their window cell is
         // within 2 of this cell, inside any window with cut_off >= 4 -- no per-line test.
-        plain_range<P>(a.sum.rec.ab + off, a.sum.rec.cc + off, seg.j[3], seg.j[4], v, acc);
+        plain_range<P>(a.sum.rec.ab + off, a.sum.rec.cc + off, seg.j[4], seg.j[5], v, acc);
     }
     else
     {
-        window_range<P>(a.sum.rec.ab + off, a.sum.rec.cc + off, a.sum.rec.chk + off, seg.j[3],
-                        seg.j[4], cell, g.cut_off, v, acc);
+        window_range<P>(a.sum.rec.ab + off, a.sum.rec.cc + off, a.sum.rec.chk + off, seg.j[4],
+                        seg.j[5], cell, g.cut_off, v, acc);
     }
     if (valid)
     {
@@ -842,7 +880,7 @@ LBL_HD double cell_coefficient(const double* transform, const double* field, int
     return c;
 }
 
-// Phase 3b, lane = points lane, lane+32, ... of the cell: add the two interpolated far fields,
+// Phase 3b, lane = points lane, lane+32, ... of the cell: add the three interpolated far fields,
 // evaluated from their Chebyshev coefficients by Clenshaw's recurrence
 //   b_j = c_j + 2 s b_(j+1) - b_(j+2),   p(s) = c_0 + s b_1 - b_2,
 // with s in [-1, 1] the point's position on the cell interval.  (A stored 48 x n_per_v
@@ -850,43 +888,48 @@ LBL_HD double cell_coefficient(const double* transform, const double* field, int
 // more L1 traffic than the rest of the kernel together; the recurrence costs two FP64
 // operations per point and coefficient and reads only the coefficients, by broadcast.)
 LBL_HD void cell_field_lane(const CellArgs& a, int layer, int cell, int lane, int nlanes,
-                            const double* coef32, const double* coef16)
+                            const double* coef32, const double* coef16, const double* coef8)
 {
     const GridSpec& g = a.sum.grid;
     double* o = a.sum.out + (size_t)layer * g.n + (size_t)cell * g.n_per_v;
     constexpr int R = 4;   // points per lane in flight: independent recurrences hide the latency
     const double to_s = 2.0 / (double)(g.n_per_v - 1);
+    const double* coef[3] = {coef32, coef16, coef8};
+    const int order[3] = {kNodes, kNodes16, kNodes8};
     for (int r0 = lane; r0 < g.n_per_v; r0 += R * nlanes)
     {
-        double s2[R], b1[R], b2[R], d1[R], d2[R];
+        double s2[R], total[R];
 #pragma unroll
         for (int u = 0; u < R; ++u)
         {
             int r = r0 + u * nlanes;
             if (r >= g.n_per_v) r = g.n_per_v - 1;   // spare slots shadow the last point
             s2[u] = 2.0 * fma_((double)r, to_s, -1.0);
-            b1[u] = b2[u] = d1[u] = d2[u] = 0.;
+            total[u] = 0.;
         }
-        for (int j = kNodes - 1; j >= 1; --j)
-        {
-            const double c = coef32[j];
 #pragma unroll
-            for (int u = 0; u < R; ++u)
+        for (int f = 0; f < 3; ++f)   // one field after the other: three live arrays, not seven
+        {
+            const double* c = coef[f];
+            double b1[R], b2[R];
+#pragma unroll
+            for (int u = 0; u < R; ++u) b1[u] = b2[u] = 0.;
+            for (int j = order[f] - 1; j >= 1; --j)
             {
-                const double t = fma_(s2[u], b1[u], c - b2[u]);
-                b2[u] = b1[u];
-                b1[u] = t;
+                const double cj = c[j];
+#pragma unroll
+                for (int u = 0; u < R; ++u)
+                {
+                    const double t = fma_(s2[u], b1[u], cj - b2[u]);
+                    b2[u] = b1[u];
+                    b1[u] = t;
+                }
             }
-        }
-        for (int j = kNodes16 - 1; j >= 1; --j)
-        {
-            const double c = coef16[j];
+            const double c0 = c[0];
 #pragma unroll
             for (int u = 0; u < R; ++u)
             {
-                const double t = fma_(s2[u], d1[u], c - d2[u]);
-                d2[u] = d1[u];
-                d1[u] = t;
+                total[u] += fma_(0.5 * s2[u], b1[u], c0) - b2[u];
             }
         }
 #pragma unroll
@@ -895,8 +938,7 @@ LBL_HD void cell_field_lane(const CellArgs& a, int layer, int cell, int lane, in
             const int r = r0 + u * nlanes;
             if (r < g.n_per_v)
             {
-                const double s = 0.5 * s2[u];
-                o[r] += (fma_(s, b1[u], coef32[0]) - b2[u]) + (fma_(s, d1[u], coef16[0]) - d2[u]);
+                o[r] += total[u];
             }
         }
     }

@@ -44,6 +44,7 @@ static void run_cells(const CellArgs& ca, const LinesView& ln, const GridSpec& g
                       const std::vector<LayerIn>& layers, int n_layers)
 {
     std::vector<double> fields((size_t)G * kNodes), fields16((size_t)G * kNodes16, 0.);
+    std::vector<double> fields8((size_t)G * kNodes8, 0.);
     const int chunks = (g.n_per_v + 32 * kCellP - 1) / (32 * kCellP);
     for (int layer = 0; layer < n_layers; ++layer)
     {
@@ -52,19 +53,23 @@ static void run_cells(const CellArgs& ca, const LinesView& ln, const GridSpec& g
             const CellSegments seg = cell_segments(ln, g, layers[layer], cell, G);
             const int cells = std::min(G, g.ncell - cell);
             std::fill(fields16.begin(), fields16.end(), 0.);
+            std::fill(fields8.begin(), fields8.end(), 0.);
             for (int lane = 0; lane < 32; ++lane)
             {
-                double f32[G], f16;
-                cell_far_lane<G>(ca, layer, cell, lane, seg, f32, f16);
+                double f32[G], f16, f8;
+                cell_far_lane<G>(ca, layer, cell, lane, seg, f32, f16, f8);
                 for (int q = 0; q < G; ++q) fields[(size_t)q * kNodes + lane] = f32[q];
                 const Lane16<G> m = lane16<G>(lane);
                 fields16[(size_t)m.cell_off * kNodes16 + m.node] += f16;   // G == 1: two partial sums
+                const Lane16<G> m8 = lane8<G>(lane);
+                fields8[(size_t)m8.cell_off * kNodes8 + m8.node] += f8;    // 2 or 4 partial sums
             }
             for (int q = 0; q < cells; ++q)
                 for (int chunk = 0; chunk < chunks; ++chunk)
                     for (int lane = 0; lane < 32; ++lane)
                         cell_direct_lane(ca, layer, cell + q, chunk, lane, seg);
             std::vector<double> coef((size_t)G * kNodes), coef16((size_t)G * kNodes16);
+            std::vector<double> coef8((size_t)G * kNodes8);
             for (int q = 0; q < G; ++q)
                 for (int lane = 0; lane < 32; ++lane)
                 {
@@ -73,11 +78,14 @@ static void run_cells(const CellArgs& ca, const LinesView& ln, const GridSpec& g
                     if (lane < kNodes16)
                         coef16[(size_t)q * kNodes16 + lane] = cell_coefficient(
                             ca.transform16, fields16.data() + (size_t)q * kNodes16, kNodes16, lane);
+                    if (lane < kNodes8)
+                        coef8[(size_t)q * kNodes8 + lane] = cell_coefficient(
+                            ca.transform8, fields8.data() + (size_t)q * kNodes8, kNodes8, lane);
                 }
             for (int q = 0; q < cells; ++q)
                 for (int lane = 0; lane < 32; ++lane)
                     cell_field_lane(ca, layer, cell + q, lane, 32, coef.data() + (size_t)q * kNodes,
-                                    coef16.data() + (size_t)q * kNodes16);
+                                    coef16.data() + (size_t)q * kNodes16, coef8.data() + (size_t)q * kNodes8);
         }
     }
 }
@@ -310,17 +318,21 @@ extern "C" int emu_absorption(int n_layers, const double* pressure, const double
     {
         // K2c: cell-tiled summation with the two-level Chebyshev far field, one emulated warp
         // per group of cells (the library uses 2 cells up to n_per_v = 256, else 1)
-        std::vector<double> nodes, weights, nodes16, weights16;
-        build_cheb_tables(kNodes, n_per_v, nodes, weights);
-        build_cheb_tables(kNodes16, n_per_v, nodes16, weights16);
+        std::vector<double> nodes, weights, nodes16, weights16, nodes8, weights8;
+        build_cheb_nodes(kNodes, n_per_v, nodes);
+        build_cheb_nodes(kNodes16, n_per_v, nodes16);
+        build_cheb_nodes(kNodes8, n_per_v, nodes8);
         build_cheb_transform(kNodes, weights);
         build_cheb_transform(kNodes16, weights16);
+        build_cheb_transform(kNodes8, weights8);
         CellArgs ca;
         ca.sum = sa;
         ca.node_offset = nodes.data();
         ca.transform = weights.data();
         ca.node_offset16 = nodes16.data();
         ca.transform16 = weights16.data();
+        ca.node_offset8 = nodes8.data();
+        ca.transform8 = weights8.data();
         ca.executed = nullptr;
         if (n_per_v <= 256) run_cells<2>(ca, ln, g, layers, n_layers);
         else run_cells<1>(ca, ln, g, layers, n_layers);
