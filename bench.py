@@ -353,7 +353,7 @@ def run_ours(args, rank, local_rank, world, dist):
     value = total_evals / seconds
 
     # ---- end to end through the public API with host buffers ---------------------------
-    for _ in range(max(1, args.warmup // 2)):
+    for _ in range(args.warmup):
         step_e2e()
     torch.cuda.synchronize()
     barrier()
@@ -369,6 +369,20 @@ def run_ours(args, rank, local_rank, world, dist):
     e2e_seconds = max_over_ranks(time.perf_counter() - t0)
     barrier()
     e2e_value = sum_over_ranks(float(e2e_evals)) / e2e_seconds
+    # ---- the summation kernel alone (untimed extra pass) ---------------------------------
+    # In the step above the launches of one gas share the SMs with the scaling and pedestal
+    # kernels of the gases queued behind it, which stretches their CUDA-event durations.  One
+    # more pass with the gases run one at a time gives the kernel's own duration.
+    isolated_ms = 0.0
+    isolated_launches = 0
+    for f in SUBMIT_ORDER:
+        gases[f].absorption_coefficients(column.t, column.p, column.vmr[f], bounds=bounds,
+                                         remove_pedestal=REMOVE_PEDESTAL, cut_off=CUT_OFF,
+                                         to_host=False)
+        st = gases[f].last_stats[0]
+        isolated_ms += st["sum_ms"]
+        isolated_launches += st["sum_launches"]
+
     # parity spot check of what came back (one spectrum, against the oracle)
     check = None
     if rank == 0 and not args.no_check:
@@ -383,24 +397,41 @@ def run_ours(args, rank, local_rank, world, dist):
     # The summation kernel on fine grids interpolates the far field: it PERFORMS `executed`
     # Lorentz evaluations to deliver `evals` reference-equivalent ones.  The roofline counts
     # the work performed; `value` counts the work delivered.
-    # K2c also evaluates the two interpolants at every point: Clenshaw, one FMA + one add per
-    # (point, coefficient), 32 + 16 coefficients; and 2*(32^2 + 16^2) flop per cell for the
-    # node-sum -> coefficient transforms.
-    interp_flops = ((3.0 * 48 * n + 2.0 * (32 * 32 + 16 * 16) * (vn - v0))
+    # K2c also evaluates the three interpolants at every point: Clenshaw, one FMA + one add per
+    # (point, coefficient), 32 + 16 + 8 coefficients; and 2*(32^2 + 16^2 + 8^2) flop per cell
+    # for the node-sum -> coefficient transforms.
+    interp_flops = ((3.0 * 56 * n + 2.0 * (32 * 32 + 16 * 16 + 8 * 8) * (vn - v0))
                     * N_LAYERS * len(GASES) * args.steps) if cells else 0.0
     flops = FLOP_PER_EVAL * executed + interp_flops     # this rank, timed region
     achieved = flops / (sum_ms * 1e-3) / 1e12 if sum_ms > 0 else 0.0
     kernel = f"lbl::sum_cell_kernel<{cells}>" if cells else f"lbl::sum_kernel<{points}>"
+    # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture
+    # (profiles/r1_sum_cell_dram.json, written by tools/ncu_dram.py), or null.
+    traffic = None
+    dram_file = ROOT / "profiles" / "r1_sum_cell_dram.json"
+    if cells and dram_file.exists():
+        traffic = json.loads(dram_file.read_text()).get("dram_bytes_per_launch")
     roofline = {
         "bound": "fp64", "kernel": kernel, "achieved": achieved,
         "peak": peak.value, "unit": "TFLOP/s",
-        "frac": achieved / peak.value if peak.value else None, "traffic": None,
+        "frac": achieved / peak.value if peak.value else None, "traffic": traffic,
         "flop_per_eval": FLOP_PER_EVAL,
+        # SURVEY 8(d)'s figure: 7.3 flop x reference-equivalent evaluations DELIVERED by the
+        # launches / their time.  Above the FP64 peak because the polynomial far field
+        # delivers several evaluations per evaluation performed (far_field_work_reduction);
+        # `achieved`/`frac` above count only the arithmetic the kernel really executes.
+        "achieved_reference_equivalent": 7.3 * evals / (sum_ms * 1e-3) / 1e12 if sum_ms > 0 else None,
+        "frac_reference_equivalent": (7.3 * evals / (sum_ms * 1e-3) / 1e12) / peak.value
+        if sum_ms > 0 and peak.value else None,
         "interpolation_flops_per_launch": interp_flops / max(sum_launches, 1),
         "executed_evals_per_launch": executed / max(sum_launches, 1),
         "reference_evals_per_launch": evals / max(sum_launches, 1),
         "far_field_work_reduction": evals / executed if executed else None,
         "avg_launch_ms": sum_ms / max(sum_launches, 1),
+        # the same launches with nothing else on the GPU (one gas at a time, untimed pass)
+        "isolated_avg_launch_ms": isolated_ms / max(isolated_launches, 1),
+        "frac_isolated": (flops / args.steps / (isolated_ms * 1e-3) / 1e12) / peak.value
+        if isolated_ms > 0 and peak.value else None,
         "kernel_share_of_step": sum_ms / (ms.value if ms.value else 1.0),
         "peak_source": "FP64 FMA peak measured live on this GPU (independent DFMA chains, "
                        "lbl_measure_fp64_peak); MEASURED_PEAKS.json carries no FP64 figure",
