@@ -78,6 +78,22 @@ LBL_API int absorption(double pressure, double temperature, double volume_mixing
 LBL_API int lbl_gas_open(const char* database, const char* formula, int device, lbl_gas** out);
 LBL_API int lbl_gas_close(lbl_gas* gas);
 
+/* Packed line-list cache.  The reference re-reads the sqlite file on
+ * every absorption() call (absorption.c:45-79); lbl_gas_open reads it once per handle;
+ * lbl_pack_database writes what that read produced -- TIPS table, isotopologue masses and the
+ * transition rows in DATABASE ROW ORDER (the early break absorption.c:80-83 and the pedestal
+ * spectra.c:66-78 depend on it) -- to one flat, checksummed binary file, and
+ * lbl_gas_open_pack opens a handle from such a file without touching sqlite.  Spectra from
+ * either kind of handle are bit-identical.  lbl_pack_database and lbl_pack_info need no GPU.
+ * lbl_pack_info: any output pointer may be NULL; source_size/source_mtime are the size and
+ * modification time of the sqlite file the pack was made from (for staleness checks).
+ */
+LBL_API int lbl_pack_database(const char* database, const char* formula, const char* pack_path);
+LBL_API int lbl_pack_info(const char* pack_path, char* formula, int formula_capacity,
+                          long long* n_lines, int* num_iso, int* num_t, int* sorted,
+                          long long* source_size, long long* source_mtime);
+LBL_API int lbl_gas_open_pack(const char* pack_path, int device, lbl_gas** out);
+
 /* Layer-batched absorption(): for layer L, k_host[L*n .. L*n+n) receives what the
  * reference's absorption(pressure[L], temperature[L], vmr[L], v0, vn, n_per_v, ...) writes
  * to k.  n = (vn-v0)*n_per_v.  k_host may be pageable or pinned (lbl_host_alloc) memory; it

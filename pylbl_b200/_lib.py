@@ -46,7 +46,8 @@ EXPORTS = (
     "lbl_gas_scaled", "lbl_host_alloc", "lbl_host_free", "lbl_device_count",
     "lbl_set_chunk_layers", "lbl_last_error", "lbl_version", "lbl_timer_start",
     "lbl_timer_join", "lbl_timer_stop", "lbl_measure_fp64_peak", "lbl_mix_open", "lbl_mix_reset",
-    "lbl_mix_add", "lbl_mix_download", "lbl_mix_close",
+    "lbl_mix_add", "lbl_mix_download", "lbl_mix_close", "lbl_pack_database", "lbl_pack_info",
+    "lbl_gas_open_pack",
 )
 
 _library = None
@@ -78,6 +79,11 @@ def library():
 
     lib.lbl_gas_open.argtypes = [c_char_p, c_char_p, c_int, POINTER(c_void_p)]
     lib.lbl_gas_close.argtypes = [c_void_p]
+    lib.lbl_pack_database.argtypes = [c_char_p, c_char_p, c_char_p]
+    lib.lbl_pack_info.argtypes = [c_char_p, c_char_p, c_int, POINTER(c_longlong), POINTER(c_int),
+                                  POINTER(c_int), POINTER(c_int), POINTER(c_longlong),
+                                  POINTER(c_longlong)]
+    lib.lbl_gas_open_pack.argtypes = [c_char_p, c_int, POINTER(c_void_p)]
     batched = [c_void_p, c_int, f64, f64, f64] + 6 * [c_int] + [c_void_p]
     lib.lbl_gas_compute.argtypes = batched
     lib.lbl_gas_submit.argtypes = batched

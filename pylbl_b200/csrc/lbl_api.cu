@@ -4,6 +4,7 @@
 // (gas, layer) call) -- batched over layers, with the database read hoisted into
 // lbl_gas_open().  Citations are relative to /root/reference/pyLBL/c_lib/.
 #include <cuda_runtime.h>
+#include <sys/stat.h>
 
 #include <algorithm>
 #include <cmath>
@@ -601,9 +602,83 @@ int lbl_host_free(void* ptr)
     return 0;
 }
 
+// Size and modification time of a file (0, 0 when it cannot be examined).
+static void file_stamp(const char* path, long long* size, long long* mtime)
+{
+    struct stat st;
+    *size = *mtime = 0;
+    if (stat(path, &st) == 0)
+    {
+        *size = (long long)st.st_size;
+        *mtime = (long long)st.st_mtime;
+    }
+}
+
+int lbl_pack_database(const char* database, const char* formula, const char* pack_path)
+{
+    if (!database || !formula || !pack_path) return fail("Error: null argument.");
+    MoleculeData mol;
+    std::string err;
+    if (read_molecule(database, formula, mol, err)) return fail(err);
+    long long size = 0, mtime = 0;
+    file_stamp(database, &size, &mtime);
+    if (write_pack(pack_path, formula, mol, size, mtime, err)) return fail(err);
+    return 0;
+}
+
+int lbl_pack_info(const char* pack_path, char* formula, int formula_capacity, long long* n_lines,
+                  int* num_iso, int* num_t, int* sorted, long long* source_size,
+                  long long* source_mtime)
+{
+    if (!pack_path) return fail("Error: null argument.");
+    MoleculeData unused;
+    PackInfo info;
+    std::string err;
+    if (read_pack(pack_path, unused, info, true, err)) return fail(err);
+    if (formula && formula_capacity > 0)
+    {
+        strncpy(formula, info.formula.c_str(), (size_t)formula_capacity - 1);
+        formula[formula_capacity - 1] = 0;
+    }
+    if (n_lines) *n_lines = info.n_lines;
+    if (num_iso) *num_iso = info.num_iso;
+    if (num_t) *num_t = info.num_t;
+    if (sorted) *sorted = info.sorted ? 1 : 0;
+    if (source_size) *source_size = info.source_size;
+    if (source_mtime) *source_mtime = info.source_mtime;
+    return 0;
+}
+
+static int open_handle(std::unique_ptr<lbl_gas>& g, int device, lbl_gas** out);
+
 int lbl_gas_open(const char* database, const char* formula, int device, lbl_gas** out)
 {
     *out = nullptr;
+    if (!database || !formula) return fail("Error: null argument.");
+    std::unique_ptr<lbl_gas> g(new lbl_gas);
+    g->database = database;
+    g->formula = formula;
+    std::string err;
+    if (read_molecule(database, formula, g->mol, err)) return fail(err);
+    return open_handle(g, device, out);
+}
+
+int lbl_gas_open_pack(const char* pack_path, int device, lbl_gas** out)
+{
+    *out = nullptr;
+    if (!pack_path) return fail("Error: null argument.");
+    std::unique_ptr<lbl_gas> g(new lbl_gas);
+    PackInfo info;
+    std::string err;
+    if (read_pack(pack_path, g->mol, info, false, err)) return fail(err);
+    g->database = pack_path;
+    g->formula = info.formula;
+    return open_handle(g, device, out);
+}
+
+// The device side of opening: streams, events, TIPS table and (for sorted rows) the lines.
+static int open_handle(std::unique_ptr<lbl_gas>& g, int device, lbl_gas** out)
+{
     int ndev = 0;
     if (lbl_device_count(&ndev)) return 1;
     if (ndev == 0)
@@ -611,12 +686,7 @@ int lbl_gas_open(const char* database, const char* formula, int device, lbl_gas*
         return fail("Error: no CUDA device (" + g_last_error + "); this library has no CPU path.");
     }
     if (device < 0 || device >= ndev) return fail("Error: CUDA device index out of range.");
-    std::unique_ptr<lbl_gas> g(new lbl_gas);
     g->device = device;
-    g->database = database;
-    g->formula = formula;
-    std::string err;
-    if (read_molecule(database, formula, g->mol, err)) return fail(err);
     if (set_device(g.get())) return 1;
     {
         // The pedestal chain is a long, thin dependency chain, and the scaling and apply

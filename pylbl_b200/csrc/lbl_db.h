@@ -29,4 +29,20 @@ struct MoleculeData
 // Returns 0 on success, 1 on error (message in err), like the reference's helpers.
 int read_molecule(const char* path, const char* formula, MoleculeData& out, std::string& err);
 
+// ---- packed line-list cache (lbl_pack.cpp) -------------------------------------------------
+struct PackInfo
+{
+    std::string formula;
+    long long n_lines = 0;
+    int num_iso = 0, num_t = 0;
+    bool sorted = true, has_tips = false;
+    long long source_size = 0, source_mtime = 0;
+};
+
+// Writes everything read_molecule() produced to one flat binary file (atomically).
+int write_pack(const char* path, const char* formula, const MoleculeData& m, long long source_size,
+               long long source_mtime, std::string& err);
+// Reads it back (header_only: just `info`); verifies magic, version and checksum.
+int read_pack(const char* path, MoleculeData& out, PackInfo& info, bool header_only, std::string& err);
+
 }  // namespace lbl

@@ -39,15 +39,58 @@ def default_device() -> int:
     return 0
 
 
+def pack_info(pack_path):
+    """Header of a packed line-list file (no GPU needed)."""
+    formula = ctypes.create_string_buffer(64)
+    n_lines, size, mtime = c_longlong(0), c_longlong(0), c_longlong(0)
+    num_iso, num_t, is_sorted = c_int(0), c_int(0), c_int(0)
+    _lib.library().lbl_pack_info(os.fsencode(pack_path), formula, 64, ctypes.byref(n_lines),
+                                 ctypes.byref(num_iso), ctypes.byref(num_t),
+                                 ctypes.byref(is_sorted), ctypes.byref(size), ctypes.byref(mtime))
+    return {"formula": formula.value.decode(), "n_lines": n_lines.value, "num_iso": num_iso.value,
+            "num_t": num_t.value, "sorted": bool(is_sorted.value), "source_size": size.value,
+            "source_mtime": mtime.value}
+
+
+def pack_database(database, formula, pack_path):
+    """Writes the packed line-list cache of one molecule (no GPU needed): what the reference
+    re-reads from sqlite on every call (pyLBL/c_lib/absorption.c:45-79), once, as one flat
+    binary file.  Returns ``pack_path``."""
+    _lib.library().lbl_pack_database(os.fsencode(getattr(database, "path", database)),
+                                     formula.encode("utf-8"), os.fsencode(pack_path))
+    return pack_path
+
+
+def cached_pack(database, formula, cache_dir):
+    """Path of the pack of (database, formula) under ``cache_dir``, written or rewritten when
+    it is missing, unreadable, or older than the sqlite file."""
+    database = getattr(database, "path", database)
+    os.makedirs(cache_dir, exist_ok=True)
+    stem = os.path.basename(database)
+    path = os.path.join(cache_dir, f"{stem}.{formula}.lblpack")
+    st = os.stat(database)
+    try:
+        info = pack_info(path) if os.path.exists(path) else None
+    except ValueError:
+        info = None
+    if (info is None or info["formula"] != formula or info["source_size"] != st.st_size
+            or info["source_mtime"] != int(st.st_mtime)):
+        pack_database(database, formula, path)
+    return path
+
+
 class _Handle(object):
     """Owns one lbl_gas* (one molecule packed on one device)."""
 
-    def __init__(self, database, formula, device):
+    def __init__(self, database, formula, device, pack=None):
         self.ptr = c_void_p()
         self.device = device
-        _lib.library().lbl_gas_open(bytes(database, encoding="utf-8"),
-                                    bytes(formula, encoding="utf-8"), int(device),
-                                    ctypes.byref(self.ptr))
+        if pack is not None:
+            _lib.library().lbl_gas_open_pack(os.fsencode(pack), int(device), ctypes.byref(self.ptr))
+        else:
+            _lib.library().lbl_gas_open(bytes(database, encoding="utf-8"),
+                                        bytes(formula, encoding="utf-8"), int(device),
+                                        ctypes.byref(self.ptr))
 
     def close(self):
         ptr, self.ptr = self.ptr, None
@@ -76,7 +119,7 @@ class Gas(object):
         precision: "fp64" (default) or "fp32".
     """
 
-    def __init__(self, lines_database, formula, devices=None, precision="fp64"):
+    def __init__(self, lines_database, formula, devices=None, precision="fp64", cache_dir=None):
         """Initializes the object.
 
         Args:
@@ -85,6 +128,9 @@ class Gas(object):
             formula: String chemical formula.
             devices: int, list of ints, or None (see default_device()).
             precision: "fp64" or "fp32".
+            cache_dir: directory for the packed line-list cache (default: the environment
+                       variable PYLBL_B200_CACHE, else no cache).  With a cache the sqlite file
+                       is read once per (database, formula) ever, not once per process.
         """
         self.database = getattr(lines_database, "path", lines_database)
         self.formula = formula
@@ -97,11 +143,14 @@ class Gas(object):
         self._handles = {}
         self._cache = {}
         self.last_stats = []
+        if cache_dir is None:
+            cache_dir = os.environ.get("PYLBL_B200_CACHE") or None
+        self.pack = cached_pack(self.database, formula, cache_dir) if cache_dir else None
 
     # -- handles -----------------------------------------------------------------------
     def _handle(self, device):
         if device not in self._handles:
-            self._handles[device] = _Handle(self.database, self.formula, device)
+            self._handles[device] = _Handle(self.database, self.formula, device, pack=self.pack)
         return self._handles[device]
 
     def close(self):
