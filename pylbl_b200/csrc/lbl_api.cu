@@ -876,7 +876,17 @@ static int submit_call(lbl_gas* g, bool blocking, int n_layers, const double* pr
         (sizeof(FarAB) + sizeof(double) + sizeof(LineChk) + sizeof(LineGen) +
          (ped_chain ? sizeof(double) * ped_wpad : 0) + (fp32 ? sizeof(Far32) : 0));
     const size_t out_per_layer = sizeof(double) * (size_t)grid.n;
-    const size_t budget = (size_t)6 << 30;
+    // Memory budget of one layer group (records + pedestal terms, and one output slab): a
+    // quarter of what is free on the device now, between 6 and 48 GB.  Fewer, larger groups
+    // matter with the pedestal on: the chain takes as long for 10 layers as for 60.
+    size_t budget = (size_t)6 << 30;
+    {
+        size_t free_bytes = 0, total_bytes = 0;
+        if (cudaMemGetInfo(&free_bytes, &total_bytes) == cudaSuccess)
+        {
+            budget = std::min<size_t>(std::max<size_t>(free_bytes / 4, budget), (size_t)48 << 30);
+        }
+    }
     long long chunk = std::min<long long>(n_layers,
                                           std::max<long long>(1, (long long)(budget / rec_per_layer)));
     chunk = std::min<long long>(chunk, std::max<long long>(1, (long long)(budget / out_per_layer)));
