@@ -10,6 +10,7 @@ runs the line-by-line calculation on the GPU with everything else unchanged
 """
 from .gas_optics import Gas, grid_to_ints, pack_database, pack_info  # noqa: F401
 from .mixture import Mixture, number_density  # noqa: F401
+from .spectroscopy import Spectroscopy  # noqa: F401
 
 BACKEND_NAME = "b200"
 

@@ -344,3 +344,56 @@ def test_two_handles_from_two_threads(small_db, atmosphere):
         ref = OracleGas(small_db, f)
         k_ref = ref.absorption(atmosphere.t[2], atmosphere.p[2], atmosphere.vmr[f][2], *bounds, True)
         assert scaled_error(results[f][2], k_ref, 100) <= FP64_TOL
+
+
+def test_spectroscopy_adapter_matches_the_reference_driver_loop(small_db, atmosphere):
+    """`pylbl_b200.Spectroscopy.compute_absorption` against a replica of the reference driver
+    (pyLBL/spectroscopy.py:161-191: flat loop over the atmosphere, beta = n*k[:grid.size])
+    run over the oracle, for a 2-D atmosphere and all three output formats; a gas the database
+    does not hold stays zero (gas = None, spectroscopy.py:53-57)."""
+    from pylbl_b200 import Spectroscopy, number_density
+
+    class Member(object):          # stands in for an xarray DataArray: only .data is read
+        def __init__(self, data):
+            self.data = data
+
+    class Atmosphere(object):
+        pass
+
+    shape = (2, 2)
+    names = ["H2O", "CO2", "XeF6"]
+    atm = Atmosphere()
+    atm.temperature = Member(atmosphere.t.reshape(shape))
+    atm.pressure = Member(atmosphere.p.reshape(shape))
+    atm.gases = {n: Member((atmosphere.vmr[n] if n in atmosphere.vmr else
+                            np.full(4, 1e-9)).reshape(shape)) for n in names}
+    grid = synth.grid_from_bounds(1, 401, 100)
+    s = Spectroscopy(atm, grid, Db(small_db))
+
+    want = {}
+    for n in names[:2]:
+        ref = OracleGas(small_db, n)
+        beta = np.zeros(shape + (grid.size,))
+        for i in range(4):
+            j = np.unravel_index(i, shape)
+            t, p, x = atmosphere.t[i], atmosphere.p[i], atmosphere.vmr[n][i]
+            k = ref.absorption(t, p, x, 1, 401, 100, True)
+            beta[j] = number_density(t, p, x) * k[:grid.size]
+        want[n] = beta
+
+    allv = s.compute_absorption(output_format="all")
+    assert allv["mechanism"] == ["lines", "continuum", "cross_section"]
+    gasv = s.compute_absorption(output_format="gas")
+    total = s.compute_absorption(output_format="total")["absorption"]
+    assert total.shape == shape + (grid.size,)
+    for n in names[:2]:
+        a = allv[f"{n}_absorption"]
+        assert a.shape == shape + (3, grid.size)
+        assert not a[..., 1:, :].any()
+        assert np.array_equal(a[..., 0, :], gasv[f"{n}_absorption"])
+        for j in np.ndindex(shape):
+            assert scaled_error(a[j][0], want[n][j], 100) <= FP64_TOL
+    assert not allv["XeF6_absorption"].any() and not gasv["XeF6_absorption"].any()
+    for j in np.ndindex(shape):
+        assert scaled_error(total[j], want["H2O"][j] + want["CO2"][j], 100) <= FP64_TOL
+    s.close()
