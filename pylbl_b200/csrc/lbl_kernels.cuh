@@ -350,29 +350,25 @@ sum_cell_kernel(const CellArgs a)
     __syncwarp();   // spectra stored, node sums in shared memory
 
     // ---- phase 3: + interpolated far fields ---------------------------------------------------
-    // node sums -> Chebyshev coefficients (lane = coefficient), in place in shared memory
+    // node sums -> Chebyshev coefficients (lane = coefficient index); the three series live
+    // on the same interval, so their coefficients add up to one series of kNodes terms
     {
-        double c32[G], c16[G], c8[G];
+        double c[G];
 #pragma unroll
         for (int q = 0; q < G; ++q)
         {
-            c32[q] = cell_coefficient(a.transform, field[q], kNodes, lane);
-            c16[q] = cell_coefficient(a.transform16, field16[q], kNodes16, lane);
-            c8[q] = cell_coefficient(a.transform8, field8[q], kNodes8, lane);
+            c[q] = cell_coefficient(a.transform, field[q], kNodes, lane) +
+                   cell_coefficient(a.transform16, field16[q], kNodes16, lane) +
+                   cell_coefficient(a.transform8, field8[q], kNodes8, lane);
         }
         __syncwarp();
 #pragma unroll
-        for (int q = 0; q < G; ++q)
-        {
-            field[q][lane] = c32[q];
-            if (lane < kNodes16) field16[q][lane] = c16[q];
-            if (lane < kNodes8) field8[q][lane] = c8[q];
-        }
+        for (int q = 0; q < G; ++q) field[q][lane] = c[q];
         __syncwarp();
     }
     for (int q = 0; q < cells; ++q)
     {
-        cell_field_lane(a, layer, cell0 + q, lane, 32, field[q], field16[q], field8[q]);
+        cell_field_lane(a, layer, cell0 + q, lane, 32, field[q]);
     }
     if (a.executed && lane == 0)
     {

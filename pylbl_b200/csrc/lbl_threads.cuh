@@ -880,65 +880,53 @@ LBL_HD double cell_coefficient(const double* transform, const double* field, int
     return c;
 }
 
-// Phase 3b, lane = points lane, lane+32, ... of the cell: add the three interpolated far fields,
-// evaluated from their Chebyshev coefficients by Clenshaw's recurrence
+// Phase 3b, lane = points lane, lane+32, ... of the cell: add the interpolated far field,
+// evaluated from its Chebyshev coefficients by Clenshaw's recurrence
 //   b_j = c_j + 2 s b_(j+1) - b_(j+2),   p(s) = c_0 + s b_1 - b_2,
-// with s in [-1, 1] the point's position on the cell interval.  (A stored 48 x n_per_v
-// interpolation matrix would cost one cache read per point and node -- on this grid that is
-// more L1 traffic than the rest of the kernel together; the recurrence costs two FP64
-// operations per point and coefficient and reads only the coefficients, by broadcast.)
+// with s in [-1, 1] the point's position on the cell interval.  `coef` holds the SUM of the
+// three fields' coefficients (they are Chebyshev series on the same interval: kNodes terms,
+// the 16- and 8-node fields contributing to the first 16 and 8).  (A stored interpolation
+// matrix would cost one cache read per point and node -- on this grid more L1 traffic than
+// the rest of the kernel together; the recurrence costs two FP64 operations per point and
+// coefficient and reads only the coefficients, by broadcast.)
 LBL_HD void cell_field_lane(const CellArgs& a, int layer, int cell, int lane, int nlanes,
-                            const double* coef32, const double* coef16, const double* coef8)
+                            const double* coef)
 {
     const GridSpec& g = a.sum.grid;
     double* o = a.sum.out + (size_t)layer * g.n + (size_t)cell * g.n_per_v;
     constexpr int R = 4;   // points per lane in flight: independent recurrences hide the latency
     const double to_s = 2.0 / (double)(g.n_per_v - 1);
-    const double* coef[3] = {coef32, coef16, coef8};
-    const int order[3] = {kNodes, kNodes16, kNodes8};
     for (int r0 = lane; r0 < g.n_per_v; r0 += R * nlanes)
     {
-        double s2[R], total[R];
+        double s2[R], b1[R], b2[R];
 #pragma unroll
         for (int u = 0; u < R; ++u)
         {
             int r = r0 + u * nlanes;
             if (r >= g.n_per_v) r = g.n_per_v - 1;   // spare slots shadow the last point
             s2[u] = 2.0 * fma_((double)r, to_s, -1.0);
-            total[u] = 0.;
+            b1[u] = b2[u] = 0.;
         }
-#pragma unroll
-        for (int f = 0; f < 3; ++f)   // one field after the other: three live arrays, not seven
+#pragma unroll 2
+        for (int j = kNodes - 1; j >= 1; --j)
         {
-            const double* c = coef[f];
-            double b1[R], b2[R];
-#pragma unroll
-            for (int u = 0; u < R; ++u) b1[u] = b2[u] = 0.;
-            for (int j = order[f] - 1; j >= 1; --j)
-            {
-                const double cj = c[j];
-#pragma unroll
-                for (int u = 0; u < R; ++u)
-                {
-                    const double t = fma_(s2[u], b1[u], cj - b2[u]);
-                    b2[u] = b1[u];
-                    b1[u] = t;
-                }
-            }
-            const double c0 = c[0];
+            const double cj = coef[j];
 #pragma unroll
             for (int u = 0; u < R; ++u)
             {
-                total[u] += fma_(0.5 * s2[u], b1[u], c0) - b2[u];
+                const double t = fma_(s2[u], b1[u], cj - b2[u]);
+                b2[u] = b1[u];
+                b1[u] = t;
             }
         }
+        const double c0 = coef[0];
 #pragma unroll
         for (int u = 0; u < R; ++u)
         {
             const int r = r0 + u * nlanes;
             if (r < g.n_per_v)
             {
-                o[r] += total[u];
+                o[r] += fma_(0.5 * s2[u], b1[u], c0) - b2[u];
             }
         }
     }

@@ -68,24 +68,16 @@ static void run_cells(const CellArgs& ca, const LinesView& ln, const GridSpec& g
                 for (int chunk = 0; chunk < chunks; ++chunk)
                     for (int lane = 0; lane < 32; ++lane)
                         cell_direct_lane(ca, layer, cell + q, chunk, lane, seg);
-            std::vector<double> coef((size_t)G * kNodes), coef16((size_t)G * kNodes16);
-            std::vector<double> coef8((size_t)G * kNodes8);
+            std::vector<double> coef((size_t)G * kNodes);
             for (int q = 0; q < G; ++q)
                 for (int lane = 0; lane < 32; ++lane)
-                {
                     coef[(size_t)q * kNodes + lane] =
-                        cell_coefficient(ca.transform, fields.data() + (size_t)q * kNodes, kNodes, lane);
-                    if (lane < kNodes16)
-                        coef16[(size_t)q * kNodes16 + lane] = cell_coefficient(
-                            ca.transform16, fields16.data() + (size_t)q * kNodes16, kNodes16, lane);
-                    if (lane < kNodes8)
-                        coef8[(size_t)q * kNodes8 + lane] = cell_coefficient(
-                            ca.transform8, fields8.data() + (size_t)q * kNodes8, kNodes8, lane);
-                }
+                        cell_coefficient(ca.transform, fields.data() + (size_t)q * kNodes, kNodes, lane) +
+                        cell_coefficient(ca.transform16, fields16.data() + (size_t)q * kNodes16, kNodes16, lane) +
+                        cell_coefficient(ca.transform8, fields8.data() + (size_t)q * kNodes8, kNodes8, lane);
             for (int q = 0; q < cells; ++q)
                 for (int lane = 0; lane < 32; ++lane)
-                    cell_field_lane(ca, layer, cell + q, lane, 32, coef.data() + (size_t)q * kNodes,
-                                    coef16.data() + (size_t)q * kNodes16, coef8.data() + (size_t)q * kNodes8);
+                    cell_field_lane(ca, layer, cell + q, lane, 32, coef.data() + (size_t)q * kNodes);
         }
     }
 }
