@@ -365,6 +365,32 @@ int pick_fixup_tile(int n_per_v)
     return 4;
 }
 
+// K2b, line-major form: valid when a point inside a line's near zone is always inside the
+// line's window, i.e. cut_off >= reach + 1 cm-1 (reach: as near_candidates() computes it).
+bool near_block_applies(const SumArgs& a, const std::vector<LayerIn>& layers, int first, int count)
+{
+    if (a.grid.n_per_v < 64) return false;
+    if (const char* env = getenv("PYLBL_B200_NEARBLOCK")) { if (atoi(env) == 0) return false; }
+    const double v_abs = std::max(std::fabs((double)a.grid.v0), std::fabs((double)a.grid.vn));
+    for (int l = first; l < first + count; ++l)
+    {
+        const LayerIn& ly = layers[l];
+        if (!(ly.kappa < 0.5)) return false;
+        const double reach = (ly.kappa * v_abs / (1.0 - ly.kappa)) * (1.0 + 0x1p-20) + ly.slack +
+                             3.0 * a.grid.dv;
+        if (!((double)a.grid.cut_off >= reach + 1.0)) return false;
+    }
+    return true;
+}
+
+void launch_near_block(const SumArgs& a, int n_layers, cudaStream_t s)
+{
+    cudaFuncSetAttribute(near_block_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         cudaSharedmemCarveoutMaxShared);   // 8 blocks x 28 KB per SM
+    dim3 grid((a.grid.n + kNbSpan - 1) / kNbSpan, n_layers);
+    near_block_kernel<<<grid, 128, 0, s>>>(a);
+}
+
 void launch_fixup_dispatch(int T, const SumArgs& a, int n_layers, cudaStream_t s)
 {
     const int tiles = (a.grid.n + T - 1) / T;
@@ -1171,7 +1197,14 @@ static int submit_call(lbl_gas* g, bool blocking, int n_layers, const double* pr
                 launch_sum_dispatch(P, sa, nl, fp32, sm);
             }
             LBL_CUDA(cudaEventRecord(se.k2_end, sm));
-            launch_fixup_dispatch(pick_fixup_tile(n_per_v), sa, q1 - q0, sm);
+            if (near_block_applies(sa, g->last_layers, first, nl))
+            {
+                launch_near_block(sa, q1 - q0, sm);
+            }
+            else
+            {
+                launch_fixup_dispatch(pick_fixup_tile(n_per_v), sa, q1 - q0, sm);
+            }
             LBL_CUDA(cudaEventRecord(se.k2b_end, sm));
             st.sum_launches++;
             st.total_launches += 2;

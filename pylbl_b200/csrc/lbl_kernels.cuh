@@ -719,6 +719,212 @@ __device__ __forceinline__ void fixup_warp_staged(const SumArgs& a, int tile, in
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// K2b, line-major form (fine grids).  A block owns kNbSpan consecutive points of one layer
+// and keeps four private accumulator stripes in shared memory, one per warp.  The lines whose
+// near zone meets the span are staged kNbBatch at a time (NearLine records, as in the T = 32
+// form); warp w then takes the staged lines w, w+4, ... and walks each line's zone 32 points
+// at a time, so every lane holds a point INSIDE the zone (a tile-major warp finds 19 of its 32
+// points inside on average), and the per-tile search and set-up is paid once per span.
+// Region 3 / CPF12 points are queued per warp and evaluated 32 at a time.  At the end the
+// stripes are added in a fixed order -- no atomics, the result does not depend on timing.
+// Requires cut_off >= reach + 1 cm-1 (checked by the host): then a point inside a line's near
+// zone is always inside the line's window, and no (line, point) pair needs a window test.
+// ---------------------------------------------------------------------------------------
+constexpr int kNbSpan = 512;
+constexpr int kNbBatch = 64;
+
+__device__ __forceinline__ void near_block_drain(const SumArgs& a, const int* q, int cnt, int lane,
+                                                 int layer, int p0, double* mine)
+{
+    const GridSpec& g = a.grid;
+    const int e = lane < cnt ? lane : 0;
+    const int jj = q[2 * e];
+    const int i = q[2 * e + 1];
+    double val = 0.;
+    bool pending = lane < cnt;
+    if (pending)
+    {
+        const LineGen* gp = a.rec.gen + (size_t)layer * a.lines.n + jj;
+        const double2 g0 = __ldg(reinterpret_cast<const double2*>(gp));
+        const double2 g1 = __ldg(reinterpret_cast<const double2*>(gp) + 1);
+        val = g1.y * voigt_inner((grid_point(g.v0, g.dv, i) - g0.x) * g0.y, g1.x);
+    }
+    // Two entries may name the same point (two lines' cores overlapping): the lowest lane of
+    // each group of equal points goes first, the others in later rounds.
+    while (true)
+    {
+        const unsigned todo = __ballot_sync(0xffffffffu, pending);
+        if (todo == 0)
+        {
+            break;
+        }
+        if (pending)
+        {
+            const unsigned peers = __match_any_sync(todo, i);
+            if (lane == __ffs(peers) - 1)
+            {
+                mine[i - p0] += val;
+                pending = false;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(128, 8)
+near_block_kernel(const SumArgs a)
+{
+    __shared__ double acc[4][kNbSpan];
+    __shared__ __align__(16) NearLine slots[kNbBatch];
+    __shared__ int queues[4][2 * kFixQueue];
+    __shared__ int batch_count[2];
+    const GridSpec& g = a.grid;
+    const int layer = blockIdx.y + a.layer0;
+    const int p0 = blockIdx.x * kNbSpan;
+    const int p1 = min(p0 + kNbSpan, g.n) - 1;
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const unsigned below = (1u << lane) - 1u;
+    for (int k = threadIdx.x; k < 4 * kNbSpan; k += 128) (&acc[0][0])[k] = 0.;
+    __syncthreads();
+
+    const LayerIn ly = a.layers[layer];
+    const size_t off = (size_t)layer * a.lines.n;
+    const LineChk* chk = a.rec.chk + off;
+    const LineGen* gen = a.rec.gen + off;
+    double* mine = acc[warp];
+    int* q = queues[warp];
+    int qn = 0;
+
+    int jlo, jhi;
+    near_candidates(a.lines, g, ly, p0, p1, jlo, jhi);
+    for (int jb = jlo; jb < jhi; jb += kNbBatch)
+    {
+        __syncthreads();   // the previous batch is consumed
+        const int j = jb + threadIdx.x;
+        int4 ck = make_int4(0, 0, 0, 0);
+        bool touches = false;
+        if (threadIdx.x < kNbBatch && j < jhi)
+        {
+            ck = __ldg(reinterpret_cast<const int4*>(chk + j));
+            touches = ck.z >= p0 && ck.y <= p1;
+        }
+        const unsigned listed = __ballot_sync(0xffffffffu, touches);
+        if (lane == 0 && warp < 2) batch_count[warp] = __popc(listed);
+        __syncthreads();
+        if (touches)
+        {
+            LineGen gn;
+            const double2 g0 = __ldg(reinterpret_cast<const double2*>(gen + j));
+            const double2 g1 = __ldg(reinterpret_cast<const double2*>(gen + j) + 1);
+            const double2 g2 = __ldg(reinterpret_cast<const double2*>(gen + j) + 2);
+            gn.nu = g0.x; gn.repwid = g0.y; gn.y = g1.x; gn.cof = g1.y; gn.xlim0 = g2.x; gn.xlim1 = g2.y;
+            const double2 l = __ldg(reinterpret_cast<const double2*>(a.rec.ab + off + j));
+            FarAB ab;
+            ab.a = l.x; ab.b = l.y;
+            NearLine nl = near_line(ck, j, gn, ab, __ldg(a.rec.cc + off + j), a.near_masked != 0);
+            nl.nlo = max(ck.y, p0);   // the zone, clipped to the span
+            nl.nhi = min(ck.z, p1);
+            slots[__popc(listed & below) + (warp == 1 ? batch_count[0] : 0)] = nl;
+        }
+        __syncthreads();
+        const int n_listed = batch_count[0] + batch_count[1];
+        for (int s = warp; s < n_listed; s += 4)
+        {
+            const NearLine& nl = slots[s];
+            const int zhi = nl.nhi;
+            for (int i0 = nl.nlo; i0 <= zhi; i0 += 32)
+            {
+                const int i = i0 + lane;
+                bool core = false;
+                if (i <= zhi)
+                {
+                    mine[i - p0] += near_point(nl, grid_point(g.v0, g.dv, i), core);
+                }
+                const unsigned mc = __ballot_sync(0xffffffffu, core);
+                if (mc)
+                {
+                    if (core)
+                    {
+                        const int e = qn + __popc(mc & below);
+                        q[2 * e] = nl.tag >> 1;
+                        q[2 * e + 1] = i;
+                    }
+                    qn += __popc(mc);
+                    __syncwarp();
+                    if (qn >= 32)
+                    {
+                        near_block_drain(a, q, 32, lane, layer, p0, mine);
+                        __syncwarp();
+                        const int keep = qn - 32;
+                        int m0 = 0, m1 = 0;
+                        if (lane < keep) { m0 = q[64 + 2 * lane]; m1 = q[64 + 2 * lane + 1]; }
+                        __syncwarp();
+                        if (lane < keep) { q[2 * lane] = m0; q[2 * lane + 1] = m1; }
+                        qn = keep;
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+    }
+    if (qn > 0)
+    {
+        near_block_drain(a, q, qn, lane, layer, p0, mine);
+    }
+
+    // node terms: lines with cb == cell-cut-1 reach exactly the cell's first point.  Warp w
+    // takes every fourth node of the span; its lanes share the lines of that cell.
+    {
+        const int c_first = (p0 + g.n_per_v - 1) / g.n_per_v;
+        const FarAB* ab = a.rec.ab + off;
+        const double* cc = a.rec.cc + off;
+        for (int c = c_first + warp; (long long)c * g.n_per_v <= p1; c += 4)
+        {
+            const int i_node = c * g.n_per_v;
+            const int cb_node = c - g.cut_off - 1;
+            const double v_node = grid_point(g.v0, g.dv, i_node);
+            const double key = (double)g.v0 + (double)cb_node;
+            const int nlo = first_line_at(a.lines, key - ly.slack);
+            const int nhi = first_line_at(a.lines, key + 1.0 + ly.slack);
+            double part = 0.;
+            for (int j = nlo + lane; j < nhi; j += 32)
+            {
+                const int4 ck = __ldg(reinterpret_cast<const int4*>(chk + j));
+                if (ck.x == cb_node)
+                {
+                    if (i_node >= ck.y && i_node <= ck.z)   // near zone 26 cm-1 out: never with
+                    {                                       // the host's cut_off condition
+                        const LineGen gn = gen[j];
+                        part += voigt_general(v_node, gn.nu, gn.repwid, gn.y, gn.cof, gn.xlim0, gn.xlim1);
+                    }
+                    else
+                    {
+                        const double2 l = __ldg(reinterpret_cast<const double2*>(ab + j));
+                        part = far_term(v_node, l.x, l.y, __ldg(cc + j), part);
+                    }
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+            {
+                part += __shfl_xor_sync(0xffffffffu, part, o);
+            }
+            if (lane == 0) mine[i_node - p0] += part;
+        }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; p0 + k <= p1; k += 128)
+    {
+        const double total = (acc[0][k] + acc[1][k]) + (acc[2][k] + acc[3][k]);
+        if (total != 0.)
+        {
+            a.out[(size_t)layer * g.n + p0 + k] += total;
+        }
+    }
+}
+
 template <int T>
 __global__ void __launch_bounds__(128, 10)
 fixup_kernel(const SumArgs a)
