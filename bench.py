@@ -26,6 +26,8 @@ Prints ONE JSON line (rank 0).  Keys beyond the base contract:
 """
 from __future__ import annotations
 
+import os
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # before any CUDA context: see pylbl_b200/_lib.py
 import argparse
 import ctypes
 import json
@@ -59,7 +61,7 @@ SUBMIT_ORDER = sorted(GASES, key=lambda f: synth.CONFIG2_SHARES[f])
 if os.environ.get("BENCH_GAS_ORDER"):
     SUBMIT_ORDER = os.environ["BENCH_GAS_ORDER"].split(",")
 N_LAYERS = 60
-REMOVE_PEDESTAL = True
+REMOVE_PEDESTAL = os.environ.get("BENCH_PEDESTAL", "1") != "0"   # BASELINE: pedestal on (the knob is for experiments)
 CUT_OFF = 25
 
 
@@ -105,13 +107,14 @@ class ClockSampler(object):
     def __init__(self, index):
         self.index = index
         self.proc = None
-        self.lines = []
+        self.lines = []      # (arrival time, csv line)
+        self.window = None   # (begin, end) of the timed region, time.perf_counter()
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "200"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -119,7 +122,13 @@ class ClockSampler(object):
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def mark_begin(self):
+        self.window = (time.perf_counter(), None)
+
+    def mark_end(self):
+        self.window = (self.window[0], time.perf_counter())
 
     def stop(self):
         if self.proc is None:
@@ -128,7 +137,11 @@ class ClockSampler(object):
         self.proc.terminate()
         sm, smax, power, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.lines:
+        # nvidia-smi is started well before the timed region (attaching to the driver stalls the
+        # GPU for tens of milliseconds); only the samples that arrived during the region count.
+        lo, hi = self.window if self.window and self.window[1] else (0., float("inf"))
+        inside = [text for (t, text) in self.lines if lo <= t <= hi + 0.12]
+        for line in (inside or [text for (_, text) in self.lines[-3:]]):
             parts = [x.strip() for x in line.split(",")]
             if len(parts) < 7:
                 continue
@@ -324,6 +337,8 @@ def run_ours(args, rank, local_rank, world, dist):
     # Settle first: on a fresh box the first steps run slow (allocations, clocks and power
     # state ramping up); repeat untimed steps until two in a row agree within 3 %, at most 20.
     # The W warm-up steps asked for come after that.
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     previous = None
     for _ in range(20):
         lib.lbl_timer_start(local_rank)
@@ -332,14 +347,15 @@ def run_ours(args, rank, local_rank, world, dist):
         lib.lbl_timer_stop(local_rank, ctypes.byref(t_step))
         settled = previous is not None and abs(t_step.value - previous) <= 0.03 * previous
         previous = t_step.value
+        if os.environ.get("BENCH_DEBUG"):
+            print(f"settle step: {t_step.value:.2f} ms", file=sys.stderr)
         if ranks.max(0.0 if settled else 1.0) == 0.0:
             break
     for _ in range(args.warmup):
         step_resident()
     torch.cuda.synchronize()
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler.mark_begin()
     lib.lbl_timer_start(local_rank)
     evals = 0
     executed = 0
@@ -348,7 +364,13 @@ def run_ours(args, rank, local_rank, world, dist):
     launches = 0
     points = cells = 0
     for _ in range(args.steps):
-        for s in step_resident():
+        if os.environ.get("BENCH_DEBUG"):
+            _t0 = time.perf_counter()
+            _st = step_resident()
+            print(f"timed step: {(time.perf_counter() - _t0) * 1e3:.2f} ms wall", file=sys.stderr)
+        else:
+            _st = step_resident()
+        for s in _st:
             points = s["points_per_thread"]
             cells = s["cells_per_warp"]
             executed += s["executed"]
@@ -358,6 +380,7 @@ def run_ours(args, rank, local_rank, world, dist):
             launches += s["total_launches"]
     ms = ctypes.c_float(0.)
     lib.lbl_timer_stop(local_rank, ctypes.byref(ms))
+    sampler.mark_end()
     torch.cuda.synchronize()
     barrier()
     clocks = sampler.stop()
@@ -374,7 +397,13 @@ def run_ours(args, rank, local_rank, world, dist):
     e2e_evals = 0
     h2d = d2h = 0
     for _ in range(args.steps):
-        for s in step_e2e():
+        _t0 = time.perf_counter()
+        if os.environ.get("BENCH_DEBUG"):
+            lib.lbl_timer_start(local_rank)   # origin of PYLBL_B200_TIMELINE's printout
+        _st = step_e2e()
+        if os.environ.get("BENCH_DEBUG"):
+            print(f"e2e step: {(time.perf_counter() - _t0) * 1e3:.2f} ms wall", file=sys.stderr)
+        for s in _st:
             e2e_evals += s["evals"]
             h2d += s["h2d_bytes"]
             d2h += s["d2h_bytes"]
@@ -490,8 +519,8 @@ def run_ours(args, rank, local_rank, world, dist):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-check", action="store_true")

@@ -10,6 +10,7 @@ There is no fallback: if the shared object is missing this module raises at firs
 from __future__ import annotations
 
 import ctypes
+import os
 from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_longlong, \
     c_size_t, c_void_p
 from pathlib import Path
@@ -51,6 +52,11 @@ EXPORTS = (
 )
 
 _library = None
+
+# The library runs a handful of CUDA streams per device (pylbl_b200/csrc/lbl_api.cu,
+# DeviceStreams); the default of 8 hardware work queues per context makes some of them share a
+# queue, and work then waits for unrelated work.  Only effective before the CUDA context exists.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 
 def check_return_code(value):

@@ -121,6 +121,14 @@ struct Plan  // which lines a given (v0, vn, cut_off) sees, and where they are o
 }  // namespace
 }  // namespace lbl
 
+namespace lbl
+{
+namespace
+{
+struct DeviceStreams;
+}
+}  // namespace lbl
+
 using namespace lbl;
 
 struct lbl_gas
@@ -134,7 +142,10 @@ struct lbl_gas
     size_t open_h2d = 0;
     bool open_h2d_reported = false;
 
-    cudaStream_t s_compute = nullptr, s_side = nullptr, s_copy = nullptr;
+    // the device's shared streams (DeviceStreams); s_compute = early
+    cudaStream_t s_compute = nullptr, s_late = nullptr, s_copy = nullptr, s_main = nullptr;
+    DeviceStreams* streams = nullptr;
+    size_t group_budget = (size_t)6 << 30;   // bytes per layer group, see lbl_gas_submit
     DevBuf rec_ab, rec_cc, rec_chk, rec_gen, layers_dev, evals_dev, pedbin, pedcorr, pednodes,
         pedterms, rec_f32, amp_max, cheb_nodes, cheb_weights, cheb_nodes16, cheb_weights16, cheb_nodes8, cheb_weights8,
         executed_dev;
@@ -151,7 +162,7 @@ struct lbl_gas
     int ev_used = 0;
     struct ChunkEvents
     {
-        cudaEvent_t k1_begin, k1_end, ped_begin, ped_end;
+        cudaEvent_t k1_begin, k1_end, ped_begin, ped_end, applied;
         bool pedestal;
     };
     struct SumEvents   // one per launch of the summation kernel + K2b
@@ -429,26 +440,56 @@ cudaError_t launch_chain(const PedArgs& pa, double* terms, double* scratch, int 
     return cudaGetLastError();
 }
 
-// The summation kernels of every handle on a device go through ONE stream per device, in
-// submission order: each gas then finishes (and starts copying out) while the next one
-// computes, instead of all gases sharing the GPU and finishing together at the end.  The
-// small kernels either side (scaling, pedestal, apply) stay on the handle's own priority
-// streams, so the next gas's line records and pedestal chain are ready before its turn.
-std::mutex g_main_mu;
-cudaStream_t g_main_stream[64] = {};
+// All handles of a device share one small set of streams.  A GPU context has few hardware
+// work queues (8 by default, CUDA_DEVICE_MAX_CONNECTIONS); with three private streams per
+// handle, seven gases in flight alias their streams onto those queues, and an operation then
+// waits for unrelated work that happens to share its queue (measured: the same step took
+// 31 ms or 70 ms from one process to the next).  The shared set, in submission order on each:
+//   early  scaling kernels (and the uploads) of every call: short, prioritised, never waits
+//   side[] pedestal terms + chain, round-robin over kSideStreams streams: long, thin,
+//          prioritised, so that several gases' chains run side by side
+//   main   the summation kernels (K2/K2c + K2b), low priority, gas after gas: each gas
+//          finishes, and starts copying out, while the next one computes
+//   late   pedestal apply and the small statistics copies: waits for main and side
+//   copy   the device-to-host copies of the spectra
+constexpr int kSideStreams = 4;
+struct DeviceStreams
+{
+    cudaStream_t main = nullptr, early = nullptr, late = nullptr, copy = nullptr;
+    cudaStream_t side[kSideStreams] = {};
+    unsigned next_side = 0;
+    bool ready = false;
+};
+std::mutex g_streams_mu;
+DeviceStreams g_streams[64];
 
-int main_stream(int device, cudaStream_t* out)
+int device_streams(int device, DeviceStreams** out)
 {
     if (device < 0 || device >= 64) return fail("Error: device index out of range.");
-    std::lock_guard<std::mutex> lock(g_main_mu);
-    if (!g_main_stream[device])
+    std::lock_guard<std::mutex> lock(g_streams_mu);
+    DeviceStreams& d = g_streams[device];
+    if (!d.ready)
     {
         int least = 0, greatest = 0;
         LBL_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
-        LBL_CUDA(cudaStreamCreateWithPriority(&g_main_stream[device], cudaStreamNonBlocking, least));
+        LBL_CUDA(cudaStreamCreateWithPriority(&d.main, cudaStreamNonBlocking, least));
+        LBL_CUDA(cudaStreamCreateWithPriority(&d.early, cudaStreamNonBlocking, greatest));
+        LBL_CUDA(cudaStreamCreateWithPriority(&d.late, cudaStreamNonBlocking, greatest));
+        LBL_CUDA(cudaStreamCreateWithFlags(&d.copy, cudaStreamNonBlocking));
+        for (int i = 0; i < kSideStreams; ++i)
+        {
+            LBL_CUDA(cudaStreamCreateWithPriority(&d.side[i], cudaStreamNonBlocking, greatest));
+        }
+        d.ready = true;
     }
-    *out = g_main_stream[device];
+    *out = &d;
     return 0;
+}
+
+cudaStream_t next_side_stream(DeviceStreams* d)
+{
+    std::lock_guard<std::mutex> lock(g_streams_mu);
+    return d->side[d->next_side++ % kSideStreams];
 }
 
 // Interpolation tables of K2c for one grid resolution: for each of the three far fields
@@ -715,15 +756,18 @@ static int open_handle(std::unique_ptr<lbl_gas>& g, int device, lbl_gas** out)
     g->device = device;
     if (set_device(g.get())) return 1;
     {
-        // The pedestal chain is a long, thin dependency chain, and the scaling and apply
-        // kernels are short: their streams have priority so that their blocks are placed
-        // ahead of the summation kernels' backlog (which runs on the device's main stream).
-        int least = 0, greatest = 0;
-        LBL_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
-        LBL_CUDA(cudaStreamCreateWithPriority(&g->s_compute, cudaStreamNonBlocking, greatest));
-        LBL_CUDA(cudaStreamCreateWithPriority(&g->s_side, cudaStreamNonBlocking, greatest));
+        size_t free_bytes = 0, total_bytes = 0;
+        if (cudaMemGetInfo(&free_bytes, &total_bytes) == cudaSuccess)
+        {
+            g->group_budget = std::min<size_t>(std::max<size_t>(free_bytes / 4, g->group_budget),
+                                               (size_t)48 << 30);
+        }
     }
-    LBL_CUDA(cudaStreamCreateWithFlags(&g->s_copy, cudaStreamNonBlocking));
+    if (device_streams(device, &g->streams)) return 1;
+    g->s_compute = g->streams->early;
+    g->s_late = g->streams->late;
+    g->s_copy = g->streams->copy;
+    g->s_main = g->streams->main;
     LBL_CUDA(cudaEventCreate(&g->ev_call_begin));
     LBL_CUDA(cudaEventCreate(&g->ev_call_end));
     LBL_CUDA(cudaEventCreateWithFlags(&g->ev_compute_end, cudaEventDisableTiming));
@@ -780,9 +824,6 @@ int lbl_gas_close(lbl_gas* g)
         if (g->ev_out_ready[i]) cudaEventDestroy(g->ev_out_ready[i]);
         if (g->ev_out_free[i]) cudaEventDestroy(g->ev_out_free[i]);
     }
-    if (g->s_compute) cudaStreamDestroy(g->s_compute);
-    if (g->s_side) cudaStreamDestroy(g->s_side);
-    if (g->s_copy) cudaStreamDestroy(g->s_copy);
     delete g;
     return 0;
 }
@@ -903,16 +944,11 @@ static int submit_call(lbl_gas* g, bool blocking, int n_layers, const double* pr
          (ped_chain ? sizeof(double) * ped_wpad : 0) + (fp32 ? sizeof(Far32) : 0));
     const size_t out_per_layer = sizeof(double) * (size_t)grid.n;
     // Memory budget of one layer group (records + pedestal terms, and one output slab): a
-    // quarter of what is free on the device now, between 6 and 48 GB.  Fewer, larger groups
-    // matter with the pedestal on: the chain takes as long for 10 layers as for 60.
-    size_t budget = (size_t)6 << 30;
-    {
-        size_t free_bytes = 0, total_bytes = 0;
-        if (cudaMemGetInfo(&free_bytes, &total_bytes) == cudaSuccess)
-        {
-            budget = std::min<size_t>(std::max<size_t>(free_bytes / 4, budget), (size_t)48 << 30);
-        }
-    }
+    // quarter of what was free on the device when the handle was opened, between 6 and 48 GB.
+    // Fewer, larger groups matter with the pedestal on: the chain takes as long for 10 layers
+    // as for 60.  (Not queried per call: cudaMemGetInfo stalls the submitting thread for tens
+    // of milliseconds while the GPU is busy.)
+    const size_t budget = g->group_budget;
     long long chunk = std::min<long long>(n_layers,
                                           std::max<long long>(1, (long long)(budget / rec_per_layer)));
     chunk = std::min<long long>(chunk, std::max<long long>(1, (long long)(budget / out_per_layer)));
@@ -1022,9 +1058,11 @@ static int submit_call(lbl_gas* g, bool blocking, int n_layers, const double* pr
         g->last_layers[l] = ly;
     }
 
-    cudaStream_t sc = g->s_compute;
-    cudaStream_t sm = nullptr;
-    if (main_stream(g->device, &sm)) return 1;
+    cudaStream_t sc = g->s_compute;               // early: uploads and scaling kernels
+    cudaStream_t sm = g->s_main;                  // summation kernels
+    cudaStream_t sl = g->s_late;                  // apply, statistics
+    cudaStream_t ss = next_side_stream(g->streams);   // pedestal terms + chain of this call
+    cudaEvent_t previous_applied = nullptr;
     LBL_CUDA(cudaEventRecord(g->ev_call_begin, sc));
     LBL_CUDA(cudaMemcpyAsync(g->layers_dev.p, g->layers_host, sizeof(LayerIn) * n_layers,
                              cudaMemcpyHostToDevice, sc));
@@ -1060,12 +1098,18 @@ static int submit_call(lbl_gas* g, bool blocking, int n_layers, const double* pr
         ev.k1_end = next_event(g);
         ev.ped_begin = next_event(g);
         ev.ped_end = next_event(g);
+        ev.applied = next_event(g);
 
         if (g->out_busy[slot])
         {
             // The previous copy out of this buffer must have drained.
-            LBL_CUDA(cudaStreamWaitEvent(sc, g->ev_out_free[slot], 0));
+            LBL_CUDA(cudaStreamWaitEvent(sm, g->ev_out_free[slot], 0));
             g->out_busy[slot] = false;
+        }
+        if (previous_applied)
+        {
+            // The records, terms and corrections of the previous layer group are rewritten.
+            LBL_CUDA(cudaStreamWaitEvent(sc, previous_applied, 0));
         }
 
         // K1 (+ K1f in FP32 mode)
@@ -1087,8 +1131,8 @@ static int submit_call(lbl_gas* g, bool blocking, int n_layers, const double* pr
         // K3 + K4a on the side stream, concurrent with K2.
         if (remove_pedestal)
         {
-            LBL_CUDA(cudaStreamWaitEvent(g->s_side, ev.k1_end, 0));
-            LBL_CUDA(cudaEventRecord(ev.ped_begin, g->s_side));
+            LBL_CUDA(cudaStreamWaitEvent(ss, ev.k1_end, 0));
+            LBL_CUDA(cudaEventRecord(ev.ped_begin, ss));
             PedArgs pa;
             pa.lines = lines;
             pa.rec = rec;
@@ -1100,22 +1144,22 @@ static int submit_call(lbl_gas* g, bool blocking, int n_layers, const double* pr
                 cudaError_t ce = cudaSuccess;
                 switch (ped_k)
                 {
-                    case 1: ce = launch_chain<1>(pa, g->pedterms.as<double>(), scratch, nl, ped_smem, g->s_side); break;
-                    case 2: ce = launch_chain<2>(pa, g->pedterms.as<double>(), scratch, nl, ped_smem, g->s_side); break;
-                    default: ce = launch_chain<4>(pa, g->pedterms.as<double>(), scratch, nl, ped_smem, g->s_side); break;
+                    case 1: ce = launch_chain<1>(pa, g->pedterms.as<double>(), scratch, nl, ped_smem, ss); break;
+                    case 2: ce = launch_chain<2>(pa, g->pedterms.as<double>(), scratch, nl, ped_smem, ss); break;
+                    default: ce = launch_chain<4>(pa, g->pedterms.as<double>(), scratch, nl, ped_smem, ss); break;
                 }
                 LBL_CUDA(ce);
                 st.total_launches++;
             }
             else
             {
-                pedestal_kernel<<<nl, 32, ped_smem, g->s_side>>>(pa, scratch);
+                pedestal_kernel<<<nl, 32, ped_smem, ss>>>(pa, scratch);
             }
             const int cells = nl * grid.ncell;
-            pedestal_cells_kernel<<<(cells + 127) / 128, 128, 0, g->s_side>>>(
+            pedestal_cells_kernel<<<(cells + 127) / 128, 128, 0, ss>>>(
                 g->pedbin.as<double>(), grid, nl, g->pedcorr.as<double>());
             st.total_launches += 2;
-            LBL_CUDA(cudaEventRecord(ev.ped_end, g->s_side));
+            LBL_CUDA(cudaEventRecord(ev.ped_end, ss));
         }
 
         // K2
@@ -1158,7 +1202,7 @@ static int submit_call(lbl_gas* g, bool blocking, int n_layers, const double* pr
             n_groups = (blocking && nl >= 16) ? 2 : 1;
             if (const char* env = getenv("PYLBL_B200_COPY_GROUPS")) n_groups = std::max(1, std::min(atoi(env), nl));
         }
-        LBL_CUDA(cudaStreamWaitEvent(sm, ev.k1_end, 0));   // also orders sm after out_free[slot]
+        LBL_CUDA(cudaStreamWaitEvent(sm, ev.k1_end, 0));
         for (int q = 0; q < n_groups; ++q)
         {
             const int q0 = (int)((long long)nl * q / n_groups);
@@ -1209,16 +1253,16 @@ static int submit_call(lbl_gas* g, bool blocking, int n_layers, const double* pr
             st.sum_launches++;
             st.total_launches += 2;
             g->sum_events.push_back(se);
-            // Back on the handle's stream (the next chunk's scaling kernel rewrites the records
-            // the summation kernels are reading).
-            LBL_CUDA(cudaStreamWaitEvent(sc, se.k2b_end, 0));
+            // The late stream takes over: apply the pedestal corrections, hand the group to the
+            // copy stream.
+            LBL_CUDA(cudaStreamWaitEvent(sl, se.k2b_end, 0));
 
             if (remove_pedestal)
             {
-                if (q == 0) LBL_CUDA(cudaStreamWaitEvent(sc, ev.ped_end, 0));
+                if (q == 0) LBL_CUDA(cudaStreamWaitEvent(sl, ev.ped_end, 0));
                 const size_t total = (size_t)(q1 - q0) * grid.n;
                 const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
-                pedestal_apply_kernel<<<blocks, 256, 0, sc>>>(
+                pedestal_apply_kernel<<<blocks, 256, 0, sl>>>(
                     g->out[slot].as<double>() + (size_t)q0 * grid.n,
                     g->pedcorr.as<double>() + 2 * (size_t)q0 * grid.ncell, grid, q1 - q0);
                 st.total_launches++;
@@ -1227,7 +1271,7 @@ static int submit_call(lbl_gas* g, bool blocking, int n_layers, const double* pr
 
             if (k_host)
             {
-                LBL_CUDA(cudaEventRecord(g->ev_out_ready[slot], sc));
+                LBL_CUDA(cudaEventRecord(g->ev_out_ready[slot], sl));
                 LBL_CUDA(cudaStreamWaitEvent(g->s_copy, g->ev_out_ready[slot], 0));
                 LBL_CUDA(cudaMemcpyAsync(k_host + (size_t)(first + q0) * grid.n,
                                          g->out[slot].as<double>() + (size_t)q0 * grid.n,
@@ -1235,6 +1279,8 @@ static int submit_call(lbl_gas* g, bool blocking, int n_layers, const double* pr
                 st.d2h_bytes += (long long)(out_per_layer * (q1 - q0));
             }
         }
+        LBL_CUDA(cudaEventRecord(ev.applied, sl));
+        previous_applied = ev.applied;
         g->chunk_events.push_back(ev);
         if (k_host)
         {
@@ -1246,23 +1292,23 @@ static int submit_call(lbl_gas* g, bool blocking, int n_layers, const double* pr
         g->last_slot = slot;
     }
     LBL_CUDA(cudaMemcpyAsync(g->evals_host, g->evals_dev.p, sizeof(unsigned long long) * n_layers,
-                             cudaMemcpyDeviceToHost, sc));
+                             cudaMemcpyDeviceToHost, sl));
     if (farfield)
     {
         LBL_CUDA(cudaMemcpyAsync(g->executed_host, g->executed_dev.p, sizeof(unsigned long long),
-                                 cudaMemcpyDeviceToHost, sc));
+                                 cudaMemcpyDeviceToHost, sl));
     }
     if (k_host)
     {
         // The call ends when the last copy has landed: the end mark goes on the copy stream,
         // after the kernels' end mark.
-        LBL_CUDA(cudaEventRecord(g->ev_compute_end, sc));
+        LBL_CUDA(cudaEventRecord(g->ev_compute_end, sl));
         LBL_CUDA(cudaStreamWaitEvent(g->s_copy, g->ev_compute_end, 0));
         LBL_CUDA(cudaEventRecord(g->ev_call_end, g->s_copy));
     }
     else
     {
-        LBL_CUDA(cudaEventRecord(g->ev_call_end, sc));
+        LBL_CUDA(cudaEventRecord(g->ev_call_end, sl));
     }
     g->pending = true;
     return 0;
@@ -1301,6 +1347,20 @@ int lbl_gas_wait(lbl_gas* g)
     }
     LBL_CUDA(cudaEventElapsedTime(&ms, g->ev_call_begin, g->ev_call_end));
     st.total_ms = ms;
+    if (getenv("PYLBL_B200_TIMELINE"))
+    {
+        // debugging aid: when this call's kernels and copies ended, relative to lbl_timer_start
+        DeviceTimer* t = nullptr;
+        if (get_timer(g->device, &t) == 0 && !g->sum_events.empty())
+        {
+            float a = 0.f, b = 0.f, c = 0.f;
+            cudaEventElapsedTime(&a, t->begin, g->ev_call_begin);
+            cudaEventElapsedTime(&b, t->begin, g->sum_events.back().k2b_end);
+            cudaEventElapsedTime(&c, t->begin, g->ev_call_end);
+            fprintf(stderr, "timeline %-4s begin %7.2f  sum+k2b end %7.2f  call end %7.2f ms\n",
+                    g->formula.c_str(), a, b, c);
+        }
+    }
     return 0;
 }
 
