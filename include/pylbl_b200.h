@@ -112,6 +112,14 @@ LBL_API int lbl_gas_submit(lbl_gas* gas, int n_layers, const double* pressure,
                    int precision, double* k_host);
 LBL_API int lbl_gas_wait(lbl_gas* gas);
 
+/* Layer groups for the copy back to the host (fine grids, k_host != NULL): the layers of a
+ * call are summed, corrected and copied out in `groups` consecutive groups, so that all but
+ * the last group's copy overlaps later kernels.  Every extra group costs a kernel tail; it
+ * pays for a call nothing is queued behind (a blocking call, or the last gas of a column).
+ * 0 = automatic: two groups for lbl_gas_compute, one for lbl_gas_submit.
+ */
+LBL_API int lbl_gas_set_copy_groups(lbl_gas* gas, int groups);
+
 /* Results of the last call. */
 LBL_API int lbl_gas_stats(lbl_gas* gas, lbl_stats* out);
 /* Device pointer to the spectra of the last chunk of layers ([layers][n] doubles). */

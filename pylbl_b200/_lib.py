@@ -48,7 +48,7 @@ EXPORTS = (
     "lbl_set_chunk_layers", "lbl_last_error", "lbl_version", "lbl_timer_start",
     "lbl_timer_join", "lbl_timer_stop", "lbl_measure_fp64_peak", "lbl_mix_open", "lbl_mix_reset",
     "lbl_mix_add", "lbl_mix_download", "lbl_mix_close", "lbl_pack_database", "lbl_pack_info",
-    "lbl_gas_open_pack",
+    "lbl_gas_open_pack", "lbl_gas_set_copy_groups",
 )
 
 _library = None
@@ -94,6 +94,7 @@ def library():
     lib.lbl_gas_compute.argtypes = batched
     lib.lbl_gas_submit.argtypes = batched
     lib.lbl_gas_wait.argtypes = [c_void_p]
+    lib.lbl_gas_set_copy_groups.argtypes = [c_void_p, c_int]
     lib.lbl_gas_stats.argtypes = [c_void_p, POINTER(Stats)]
     lib.lbl_gas_device_result.argtypes = [c_void_p, POINTER(c_void_p), POINTER(c_longlong)]
     lib.lbl_gas_windows.argtypes = [c_void_p, c_int, i32, i32, c_int]

@@ -146,6 +146,7 @@ struct lbl_gas
     cudaStream_t s_compute = nullptr, s_late = nullptr, s_copy = nullptr, s_main = nullptr;
     DeviceStreams* streams = nullptr;
     size_t group_budget = (size_t)6 << 30;   // bytes per layer group, see lbl_gas_submit
+    int copy_groups = 0;                     // lbl_gas_set_copy_groups (0 = automatic)
     DevBuf rec_ab, rec_cc, rec_chk, rec_gen, layers_dev, evals_dev, pedbin, pedcorr, pednodes,
         pedterms, rec_f32, amp_max, cheb_nodes, cheb_weights, cheb_nodes16, cheb_weights16, cheb_nodes8, cheb_weights8,
         executed_dev;
@@ -1200,6 +1201,7 @@ static int submit_call(lbl_gas* g, bool blocking, int n_layers, const double* pr
             // call (nothing else would hide the copy); with several calls in flight the copy of
             // one gas hides behind the kernels of the next and one group is best.
             n_groups = (blocking && nl >= 16) ? 2 : 1;
+            if (g->copy_groups > 0) n_groups = std::min(g->copy_groups, nl);
             if (const char* env = getenv("PYLBL_B200_COPY_GROUPS")) n_groups = std::max(1, std::min(atoi(env), nl));
         }
         LBL_CUDA(cudaStreamWaitEvent(sm, ev.k1_end, 0));
@@ -1382,6 +1384,14 @@ int lbl_gas_compute(lbl_gas* g, int n_layers, const double* pressure, const doub
         return 1;
     }
     return lbl_gas_wait(g);
+}
+
+int lbl_gas_set_copy_groups(lbl_gas* g, int groups)
+{
+    if (!g) return fail("Error: null handle.");
+    if (groups < 0) return fail("Error: negative group count.");
+    g->copy_groups = groups;
+    return 0;
 }
 
 int lbl_gas_stats(lbl_gas* g, lbl_stats* out)
