@@ -986,7 +986,7 @@ struct __align__(16) PedRow
 // the rows -- and parked in shared memory; the row loop then reads it by broadcast and every
 // lane evaluates the Lorentz form at its K slots.
 template <int K>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 6)
 pedestal_terms_kernel(const PedArgs a, double* __restrict__ terms)
 {
     __shared__ PedRow tile_rows[4][kPedTileRows];
