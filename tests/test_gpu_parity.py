@@ -397,3 +397,24 @@ def test_spectroscopy_adapter_matches_the_reference_driver_loop(small_db, atmosp
     for j in np.ndindex(shape):
         assert scaled_error(total[j], want["H2O"][j] + want["CO2"][j], 100) <= FP64_TOL
     s.close()
+
+
+@pytest.mark.parametrize("farfield,nearblock", [("1", "0"), ("0", "1"), ("0", "0")])
+def test_fallback_kernels_on_a_fine_grid(small_db, atmosphere, monkeypatch, farfield, nearblock):
+    """The kernels a fine grid does not normally use -- the direct summation kernel K2 and the
+    point-major near-zone kernel -- selected through the library's environment knobs, against
+    the oracle and against the default path."""
+    bounds = (1, 301, 100)
+    gas = Gas(Db(small_db), "H2O")
+    x = atmosphere.vmr["H2O"]
+    default = gas.absorption_coefficients(atmosphere.t, atmosphere.p, x, bounds=bounds,
+                                          remove_pedestal=True)
+    monkeypatch.setenv("PYLBL_B200_FARFIELD", farfield)
+    monkeypatch.setenv("PYLBL_B200_NEARBLOCK", nearblock)
+    k = gas.absorption_coefficients(atmosphere.t, atmosphere.p, x, bounds=bounds, remove_pedestal=True)
+    ref = OracleGas(small_db, "H2O")
+    for layer in range(atmosphere.t.size):
+        want = ref.absorption(atmosphere.t[layer], atmosphere.p[layer], x[layer], *bounds, True)
+        assert scaled_error(k[layer], want, bounds[2]) <= FP64_TOL
+        assert scaled_error(k[layer], default[layer], bounds[2]) <= 1e-10
+    gas.close()
