@@ -1,11 +1,17 @@
 // lbl_kernels.cuh -- sm_100a kernels of the line-by-line path.
 //
-//   K1 scale_kernel          per-(layer, line) scaling      replaces spectra.c:17-45
-//   K2 sum_kernel<P>         gather Voigt summation         replaces spectra.c:48-65 + voigt.c
-//   K3 pedestal_kernel       pedestal recurrence            replaces spectra.c:66-78
-//   K4 pedestal_cells/apply  pedestal correction per point
+//   K1  scale_kernel                per-(layer, line) scaling           replaces spectra.c:17-45
+//   K2  sum_kernel<P>               direct far-wing sum (coarse grids)  replaces spectra.c:48-65 + voigt.c:79-83
+//   K2c sum_cell_kernel<G>          cell-tiled sum with the Chebyshev far field (fine grids), same rows
+//   K2b near_block_kernel           near zone (Humlicek regions 1-3, CPF12) and node terms, line-major
+//       fixup_kernel<T>             the same, point-major (coarse grids, tiny cut-offs)   voigt.c:84-187
+//   K3a pedestal_terms_kernel<K>    line values at the tracked points   spectra.c:66-78
+//   K3b pedestal_chain_kernel<K>    the accumulated-pedestal recurrence (pedestal_kernel: generic fallback)
+//   K4  pedestal_cells/apply        pedestal correction per point
 //
-// None of these uses atomics on the spectrum: every output point is owned by one thread.
+// None of these uses atomics on the spectrum: every output point has one owner, and where
+// several warps contribute to a point (near_block_kernel) they do so through private stripes
+// that are added in a fixed order.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -73,10 +79,10 @@ sum_kernel(const SumArgs a)
 // block = 128 threads = 4 independent warps; warp = G consecutive cells of layer blockIdx.y.
 //
 // Phase 1  lane = node: the far lines at this lane's node of each cell (cell_far_lane).
-// Phase 2  lane = kCellP consecutive points: the direct lines in Lorentz form, near-zone
-//          points masked (cell_direct_lane); spectra stored.
+// Phase 2  lane = kCellP consecutive points: the direct lines in Lorentz form at every point
+//          (cell_direct_lane); spectra stored.
 // Phase 3  lane = points lane, lane+32, ...: + interpolated far field (cell_field_lane).
-// The near zone and the node terms are added afterwards by K2b (fixup_kernel).
+// The near zone (profile - Lorentz) and the node terms are added afterwards by K2b.
 // ---- TMA bulk copy + mbarrier (PTX; SASS: UBLKCP / SYNCS) ------------------------------------
 __device__ __forceinline__ unsigned smem_addr(const void* p)
 {
