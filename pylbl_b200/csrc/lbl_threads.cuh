@@ -520,31 +520,35 @@ LBL_HD void sum32_thread(const SumArgs& a, int layer_group, int tile, int lane)
 //
 // A warp owns a group of G consecutive integer-wavenumber cells of one layer.  All points
 // (r > 0) of a cell share the line window [cell-cut, cell+cut], so there are no window
-// edges inside a cell.  Lines are split by the distance of their centre from the group:
-//   direct   within kFarMin = 0.4 cm-1 of the group's cells.  Evaluated at every grid point
-//            (kCellP consecutive points per thread).  Unlike K2, this kernel adds the
-//            Lorentz form at a line's near-zone points too -- a smooth function that the
-//            interpolation handles like any other -- and K2b adds (profile - Lorentz) there.
-//   mid      up to kVeryFar = 2 cm-1 beyond the cells.  Each pole sits >= 1.8 half-widths a
-//            from a cell centre, i.e. outside the Bernstein ellipse rho = 3.3 of the cell
-//            interval: the Chebyshev interpolant of the lines' sum through kNodes = 32 nodes
-//            is exact to ~rho^-32 ~ 1e-16 of a line's size on the cell.  Lane k evaluates the
-//            mid lines at node k of each cell.
-//   very far the rest of the window (~90 % of the lines): poles >= 5a away, rho = 9.9, and
-//            kNodes16 = 16 nodes do (rho^-16 ~ 1e-16).  A half-warp takes a cell's 16 nodes
-//            (G = 2), or the two half-warps split the lines of the one cell (G = 1): one
-//            evaluation per lane per line.
-// Every point of a cell then receives the two interpolants, evaluated from their Chebyshev
-// coefficients (a 32x32 and a 16x16 transform of the node sums, lbl_cheb.h) by Clenshaw's
-// recurrence.
+// edges inside a cell.  Lines are split by the distance d of their centre beyond the cells'
+// edges.  With h the half-length of the cell interval (~0.5 cm-1), a line at distance d has its
+// poles outside the Bernstein ellipse rho = c + sqrt(c^2 - 1), c = (d + h)/h, of that interval,
+// and the Chebyshev interpolant of the lines' sum through n nodes is exact to ~rho^-n of a
+// line's size on the cell:
+//   direct   d < kFarMin = 0.25.  Evaluated at every grid point (kCellP consecutive points per
+//            thread).  Unlike K2, this kernel adds the Lorentz form at a line's near-zone
+//            points too -- a smooth function that the interpolation handles like any other --
+//            and K2b adds (profile - Lorentz) there.
+//   mid      kFarMin <= d < kVeryFar = 1.0: kNodes = 32 nodes (rho >= 2.6, rho^-32 = 4e-14).
+//            Lane k evaluates the mid lines at node k of each cell.
+//   very far kVeryFar <= d < kFar8 = 6.0: kNodes16 = 16 nodes (rho >= 5.9, rho^-16 = 5e-13).  A
+//            half-warp takes a cell's 16 nodes (G = 2), or the two half-warps split the lines
+//            of the one cell (G = 1): one evaluation per lane per line.
+//   far-8    d >= kFar8, three quarters of the window: kNodes8 = 8 nodes (rho >= 26,
+//            rho^-8 = 5e-12), the lanes of a cell splitting the lines 2 or 4 ways.
+// The boundaries are set so that the far field as a whole stays within 1e-11 of the direct sum
+// (tests/test_emulated_kernels.py::test_far_field_kernel_against_direct_kernel), a hundredth
+// of the parity budget.  The three node sums are turned into Chebyshev coefficients (32x32,
+// 16x16 and 8x8 transforms, lbl_cheb.h), the coefficients are added -- the series live on the
+// same interval -- and every point of the cell receives the sum by Clenshaw's recurrence.
 // ---------------------------------------------------------------------------------------
 constexpr int kNodes = 32;
 constexpr int kNodes16 = 16;
 constexpr int kNodes8 = 8;
 constexpr int kCellP = 4;         // points per thread in the direct part
-constexpr double kFarMin = 0.4;   // cm-1 beyond the cell edges where the 32-node field starts
-constexpr double kVeryFar = 2.0;  // cm-1 beyond the cell edges where the 16-node field starts
-constexpr double kFar8 = 8.0;     // cm-1 beyond the cell edges where the 8-node field starts
+constexpr double kFarMin = 0.25;  // cm-1 beyond the cell edges where the 32-node field starts
+constexpr double kVeryFar = 1.0;  // cm-1 beyond the cell edges where the 16-node field starts
+constexpr double kFar8 = 6.0;     // cm-1 beyond the cell edges where the 8-node field starts
 
 struct CellArgs
 {
