@@ -439,10 +439,10 @@ def run_ours(args, rank, local_rank, world, dist):
     # The summation kernel on fine grids interpolates the far field: it PERFORMS `executed`
     # Lorentz evaluations to deliver `evals` reference-equivalent ones.  The roofline counts
     # the work performed; `value` counts the work delivered.
-    # K2c also evaluates the three interpolants at every point: Clenshaw, one FMA + one add per
-    # (point, coefficient), 32 + 16 + 8 coefficients; and 2*(32^2 + 16^2 + 8^2) flop per cell
-    # for the node-sum -> coefficient transforms.
-    interp_flops = ((3.0 * 56 * n + 2.0 * (32 * 32 + 16 * 16 + 8 * 8) * (vn - v0))
+    # K2c also evaluates the interpolant at every point: Clenshaw over the summed series, one
+    # FMA + one add per (point, coefficient), 32 coefficients; and 2*(32^2 + 16^2 + 8^2) flop
+    # per cell for the node-sum -> coefficient transforms.
+    interp_flops = ((3.0 * 32 * n + 2.0 * (32 * 32 + 16 * 16 + 8 * 8) * (vn - v0))
                     * N_LAYERS * len(GASES) * args.steps) if cells else 0.0
     flops = FLOP_PER_EVAL * executed + interp_flops     # this rank, timed region
     achieved = flops / (sum_ms * 1e-3) / 1e12 if sum_ms > 0 else 0.0
