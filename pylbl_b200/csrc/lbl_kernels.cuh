@@ -1256,32 +1256,27 @@ pedestal_chain_kernel(const PedArgs a, const double* __restrict__ terms, double*
             }
             else
             {
-                // Lane m takes line m of the run: d before it = d0 + sum_{j<m} (fs_j - fe_j).
+                // Lane m takes line m of the run: d before it = d0 + sum_{j<m} (fs_j - fe_j),
+                // and K3a's rows already hold those sums: row j, slot t = sum over the run's
+                // lines 0..j of f[t].  No scan is needed.
                 const bool mine = lane < run;
                 const double fs = mine ? row0[(size_t)lane * wpad + spare] : 0.;
                 const double fe = mine ? row0[(size_t)lane * wpad + spare + 1] : 0.;
-                const double diff = fs - fe;
-                double scan = diff;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1)
-                {
-                    const double up = shfl_up_f64(scan, o);
-                    if (lane >= o) scan += up;
-                }
-                const double d_prev = (st.ks - st.ke) + (scan - diff);
+                const bool later = mine && lane > 0;
+                const double ps = later ? row0[(size_t)(lane - 1) * wpad + st.w.s_slot] : 0.;
+                const double pe = later ? row0[(size_t)(lane - 1) * wpad + st.w.e_slot] : 0.;
+                const double d_prev = (st.ks - st.ke) + (ps - pe);
                 const double ks_prev = (lane == 0) ? st.ks : fmax(d_prev, 0.);
                 const double ke_prev = (lane == 0) ? st.ke : fmax(-d_prev, 0.);
                 double ks_new, ke_new;
-                double ped = ped_line_value(ks_prev, ke_prev, fs, fe, ks_new, ke_new);
-                if (!mine) ped = 0.;
-                pedsum = ped;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1)
-                {
-                    pedsum += __shfl_xor_sync(0xffffffffu, pedsum, o);
-                }
+                (void)ped_line_value(ks_prev, ke_prev, fs, fe, ks_new, ke_new);
+                // The pedestals telescope: ped_l = ks_prev_l + fs_l - ks_new_l and
+                // ks_prev_(l+1) = ks_new_l, so their sum over the run is
+                // sum(fs) + ks_before - ks_after, and sum(fs) is the last row's slot s.
+                const double ks_before = st.ks;
                 st.ks = __shfl_sync(0xffffffffu, ks_new, run - 1);
                 st.ke = __shfl_sync(0xffffffffu, ke_new, run - 1);
+                pedsum = (row0[(size_t)(run - 1) * wpad + st.w.s_slot] + ks_before) - st.ks;
             }
             ped_lane_slots(st, row0 + (size_t)(run - 1) * wpad, pedsum);
             l += run;
