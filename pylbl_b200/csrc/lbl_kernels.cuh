@@ -1163,6 +1163,7 @@ __global__ void __launch_bounds__(32)
 pedestal_chain_kernel(const PedArgs a, const double* __restrict__ terms, double* scratch)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ alignas(8) unsigned long long full[kPedStages];
     const GridSpec& g = a.grid;
     constexpr int wpad = 32 * K;
     const int layer = blockIdx.x;
@@ -1192,9 +1193,13 @@ pedestal_chain_kernel(const PedArgs a, const double* __restrict__ terms, double*
             const char* gsrc = reinterpret_cast<const char*>(src + (size_t)first * wpad);
             char* sdst = reinterpret_cast<char*>(ring + (size_t)stage * kPedTile * wpad);
             const int bytes = cnt * wpad * 8;
-            for (int o = lane * 16; o < bytes; o += 32 * 16)
+            if (lane == 0)
             {
-                cp_async16(sdst + o, gsrc + o);
+                // one TMA bulk copy per tile (16 KB of terms) instead of 32 cp.async per lane:
+                // this warp is a serial chain, every instruction it issues is on the clock
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect_tx(&full[stage], (unsigned)bytes);
+                bulk_copy_g2s(sdst, gsrc, (unsigned)bytes, &full[stage]);
             }
             if (lane < cnt)
             {
@@ -1205,6 +1210,11 @@ pedestal_chain_kernel(const PedArgs a, const double* __restrict__ terms, double*
         }
         cp_async_commit();
     };
+    if (lane == 0)
+    {
+        for (int st = 0; st < kPedStages; ++st) mbar_init(&full[st], 1);
+    }
+    __syncwarp();
     for (int t = 0; t < kPedStages - 1; ++t) issue(t);
 
     PedLane<K> st;
@@ -1213,8 +1223,9 @@ pedestal_chain_kernel(const PedArgs a, const double* __restrict__ terms, double*
     {
         issue(t + kPedStages - 1);
         cp_async_wait<kPedStages - 1>();
-        __syncwarp();
         const int stage = t % kPedStages;
+        mbar_wait(&full[stage], (unsigned)((t / kPedStages) & 1));
+        __syncwarp();
         const int first = t * kPedTile;
         const int cnt = (n - first < kPedTile) ? n - first : kPedTile;
         const double* rows = ring + (size_t)stage * kPedTile * wpad;
