@@ -1,0 +1,50 @@
+"""Host-side logic of the Spectroscopy adapter that needs no GPU (the numbers are checked on
+the GPU in tests/test_gpu_parity.py::test_spectroscopy_adapter_matches_the_reference_driver_loop)."""
+import numpy as np
+import pytest
+
+from pylbl_b200 import Spectroscopy, number_density
+from pylbl_b200.spectroscopy import MECHANISMS
+
+
+class Member(object):
+    def __init__(self, data):
+        self.data = data
+
+
+def atmosphere(shape=(2, 3)):
+    t = np.full(shape, 250.)
+    p = np.full(shape, 5.0e4)
+    return {"temperature": t, "pressure": p, "gases": {"H2O": np.full(shape, 1e-3)}}
+
+
+def test_accepts_dicts_and_data_members():
+    grid = np.arange(1., 11., 0.01)
+    a = atmosphere()
+    s1 = Spectroscopy(a, grid, "no-such.db")
+    wrapped = type("A", (), {})()
+    wrapped.temperature = Member(a["temperature"])
+    wrapped.pressure = Member(a["pressure"])
+    wrapped.gases = {"H2O": Member(a["gases"]["H2O"])}
+    s2 = Spectroscopy(wrapped, grid, type("Db", (), {"path": "no-such.db"})())
+    assert s1.database == s2.database == "no-such.db"
+    assert np.array_equal(s1.temperature, s2.temperature) and s1.temperature.dtype == np.float64
+    assert list(s1.gases) == ["H2O"] and s2.gases["H2O"].shape == (2, 3)
+
+
+def test_rejects_mismatched_shapes_and_formats():
+    grid = np.arange(1., 11., 0.01)
+    a = atmosphere()
+    a["gases"]["CO2"] = np.full((3, 2), 4e-4)
+    with pytest.raises(ValueError):
+        Spectroscopy(a, grid, "no-such.db")
+    s = Spectroscopy(atmosphere(), grid, "no-such.db")
+    with pytest.raises(ValueError):
+        s.compute_absorption(output_format="everything")
+
+
+def test_mechanism_axis_and_number_density_follow_the_reference():
+    # pyLBL/spectroscopy.py:126 and :18-29 (n = p*x/(kB*T), kB = 1.38064852e-23)
+    assert MECHANISMS == ["lines", "continuum", "cross_section"]
+    n = number_density(288.99, 98388., 6.637074e-3)
+    assert n == pytest.approx(98388. * 6.637074e-3 / (1.38064852e-23 * 288.99), rel=1e-15)
