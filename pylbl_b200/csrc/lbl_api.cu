@@ -890,8 +890,16 @@ static int submit_call(lbl_gas* g, bool blocking, int n_layers, const double* pr
     st.n_active = plan.n_active;
     // Fine grids use the cell-tiled kernel with the polynomial far field (K2c); coarse grids
     // (a cell holds fewer points than the 32 interpolation nodes would cost) use K2.
-    bool farfield = n_per_v >= 64;
-    if (const char* env = getenv("PYLBL_B200_FARFIELD")) farfield = farfield && atoi(env) != 0;
+    // K2c pays ~2.3 ns of set-up per (cell, layer) whatever the number of lines, K2 ~2 ns per
+    // (line, layer) on a 0.01 cm-1 grid: below ~0.8 lines per cm-1 (measured cross-over on
+    // config 2: CO, O2) the direct kernel is the faster one.  On finer grids K2's cost per line
+    // grows with n_per_v, K2c's set-up only in part, so the cross-over density falls.
+    const double sparse = 0.8 * std::min(1.0, 300.0 / (double)n_per_v);
+    bool farfield = n_per_v >= 64 && (double)plan.n_active >= sparse * (double)grid.ncell;
+    if (const char* env = getenv("PYLBL_B200_FARFIELD"))
+    {
+        farfield = n_per_v >= 64 && atoi(env) != 0 && (atoi(env) == 2 || farfield);   // 2 = always
+    }
     // The FP32 mode is a mode of the direct kernel K2.  Where K2c runs it is already faster
     // in FP64 than K2 is in FP32, so the request is honoured with FP64 arithmetic there.
     const bool fp32 = fp32_requested && !farfield;
