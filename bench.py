@@ -417,6 +417,9 @@ def run_ours(args, rank, local_rank, world, dist):
     e2e_seconds = max_over_ranks(time.perf_counter() - t0)
     barrier()
     e2e_value = sum_over_ranks(float(e2e_evals)) / e2e_seconds
+    h2d = int(sum_over_ranks(float(h2d)))     # whole job, like `value`
+    d2h = int(sum_over_ranks(float(d2h)))
+    launches = int(sum_over_ranks(float(launches)))
     # ---- the summation kernel alone (untimed extra pass) ---------------------------------
     # One more pass with the gases run one at a time and the pedestal off (the summation kernel
     # does not depend on it): nothing else is on the GPU while the kernel runs, which gives
