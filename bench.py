@@ -15,9 +15,15 @@ data path.
 Prints ONE JSON line (rank 0).  Keys beyond the base contract:
   value      line-grid evaluations / s with the packed line lists resident in HBM and the
              spectra left in HBM; device-timed (CUDA events), max over ranks
-  e2e        the same metric through the public ``Gas`` API with HOST buffers: per step the
-             (p, T, vmr) arrays go host->device and every spectrum comes back to pinned host
-             memory inside the timed region
+  e2e        the same metric through the public API with HOST buffers, gas-summed output
+             (``Mixture.total_absorption``, pyLBL's output_format="total"): per step the
+             (p, T, vmr) arrays go host->device, the gases are scaled by their number densities
+             and summed on the device, and ONE array per column comes back to pinned host memory
+             inside the timed region
+  e2e_gas    the same with per-gas output (``Gas.submit``/``Gas.wait``; output_format="gas"):
+             seven arrays per column come back.  Both carry the measured device-to-host copy
+             ceiling for their bytes (all ranks copying at once) and the step's floor
+             max(kernels, copy)
   roofline   FP64-pipe roofline of the summation kernel: algorithmic flops (7.3 per
              evaluation) / CUDA-event duration of its launches,
              against the FP64 FMA peak measured live on this GPU
@@ -165,15 +171,23 @@ class ClockSampler(object):
 # --------------------------------------------------------------------------------------
 # CPU arm: the reference C library on the host cores
 # --------------------------------------------------------------------------------------
+def cpu_sample_layers(threads):
+    """Layers of the 60-layer column that make up the CPU sample: enough (gas, layer) jobs to
+    keep every host thread busy (>= 4 jobs per thread, spread evenly over the column)."""
+    count = min(N_LAYERS, max(4, -(-4 * threads // len(GASES))))
+    return sorted(set(int(round(i)) for i in np.linspace(0, N_LAYERS - 1, count)))
+
+
 def cpu_reference_run(db, column, layers, threads):
     """Runs absorption() for every gas x the given layers on `threads` host threads (ctypes
-    releases the GIL; the library is stateless).  Returns
-    (evals, seconds, kind)."""
+    releases the GIL; the library is stateless); the longest jobs are
+    queued first.  threads == 1 is the reference's own serial gas-outer / layer-inner loop
+    (pyLBL/spectroscopy.py:166-191).  Returns (seconds, kind, jobs)."""
     from oracle import OracleGas, ReferenceGas, have_reference
     v0, vn, npv = synth.config_grid(CONFIG)
     kind = "reference" if have_reference() else "port"
     counters = {f: OracleGas(db, f) for f in GASES} if kind == "port" else None
-    jobs = [(f, l) for l in layers for f in GASES]
+    jobs = [(f, l) for f in sorted(GASES, key=lambda f: -synth.CONFIG2_SHARES[f]) for l in layers]
 
     def one(job):
         f, l = job
@@ -186,8 +200,12 @@ def cpu_reference_run(db, column, layers, threads):
         return 0
 
     t0 = time.perf_counter()
-    with ThreadPoolExecutor(max_workers=threads) as pool:
-        list(pool.map(one, jobs))
+    if threads == 1:
+        for job in jobs:
+            one(job)
+    else:
+        with ThreadPoolExecutor(max_workers=threads) as pool:
+            list(pool.map(one, jobs))
     seconds = time.perf_counter() - t0
     return seconds, kind, len(jobs)
 
@@ -221,7 +239,7 @@ def run_reference_arm(args, rank, world):
     db = database_path(0, lambda: None)
     column = synth.standard_column(N_LAYERS, column=0)
     threads = os.cpu_count() or 1
-    layers = [0, 20, 40, 59]
+    layers = cpu_sample_layers(threads)
     evals = count_evals(db, column, layers)
     times = []
     kind = "port"
@@ -231,8 +249,9 @@ def run_reference_arm(args, rank, world):
             times.append(seconds)
     mean = sum(times) / len(times)
     value = evals / mean
-    sample = (f"{len(GASES)} gases x layers {layers} of the 60-layer column "
-              f"({len(GASES) * len(layers)} absorption() calls, {evals:.3e} evaluations per step)")
+    sample = (f"{len(GASES)} gases x {len(layers)} layers {layers} of the 60-layer column "
+              f"({len(GASES) * len(layers)} absorption() calls incl. their sqlite reads, longest first, "
+              f"on {threads} threads; {evals:.3e} evaluations per step)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": mean * 1e3,
@@ -284,11 +303,62 @@ def rank_column(rank):
 # --------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(local_rank):
+    """Keeps this rank's host threads -- and with them the page-locked buffers it allocates
+    (first touch) -- on the NUMA node its GPU hangs off: a device-to-host copy that crosses the
+    socket interconnect is the first thing that slows down when eight GPUs copy at once.
+    Returns what was done (for the JSON line); any failure leaves the process unbound."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = torch.cuda.get_device_properties(local_rank).pci_domain_id
+        dev = torch.cuda.get_device_properties(local_rank).pci_device_id
+        name = f"{dom:04x}:{bus:02x}:{dev:02x}.0"
+        node = int(Path(f"/sys/bus/pci/devices/{name}/numa_node").read_text())
+        if node < 0:
+            return {"node": None, "why": "no NUMA information for the GPU"}
+        cpus = set()
+        for part in Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return {"node": node, "why": "none of the node's CPUs is available to this process"}
+        os.sched_setaffinity(0, cpus)
+        return {"node": node, "cpus": len(cpus)}
+    except Exception as exc:   # no sysfs, no permission, ...: run unbound
+        return {"node": None, "why": f"{type(exc).__name__}: {exc}"}
+
+
+def copy_ceiling(local_rank, nbytes, barrier, max_over_ranks, repeats=5):
+    """Plain device-to-host copy of `nbytes` into page-locked memory on every rank at once:
+    the ceiling of any end-to-end number that returns that many bytes.  GB/s of this rank's
+    copy, slowest rank."""
+    import torch
+    dev = torch.empty(nbytes // 8, dtype=torch.float64, device=f"cuda:{local_rank}")
+    host = torch.empty(nbytes // 8, dtype=torch.float64, pin_memory=True)
+    host.copy_(dev, non_blocking=True)
+    torch.cuda.synchronize()
+    best = 0.0
+    for _ in range(repeats):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        host.copy_(dev, non_blocking=True)
+        e1.record()
+        e1.synchronize()
+        seconds = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
+        best = max(best, nbytes / seconds / 1e9)
+    del dev, host
+    return best
+
+
 def run_ours(args, rank, local_rank, world, dist):
     import torch
-    from pylbl_b200 import Gas, _lib
+    from pylbl_b200 import Gas, Mixture, _lib
 
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if os.environ.get("BENCH_NUMA", "1") != "0" else None
     lib = _lib.library()
     ranks = Ranks(dist, f"cuda:{local_rank}")
     barrier, max_over_ranks, sum_over_ranks = ranks.barrier, ranks.max, ranks.sum
@@ -299,39 +369,40 @@ def run_ours(args, rank, local_rank, world, dist):
     n = (vn - v0) * npv
     column = rank_column(rank)
     gases = {f: Gas(db, f, devices=[local_rank]) for f in GASES}
+    mixture = Mixture.from_gases({f: gases[f] for f in SUBMIT_ORDER}, local_rank)
 
     peak = ctypes.c_double(0.)
     lib.lbl_measure_fp64_peak(local_rank, ctypes.byref(peak))
 
     def submit_all(destinations):
-        """Submits every gas of the column (each handle has its own CUDA streams, the
-        summation kernels share the device's main stream in submission order), then waits."""
-        handles = []
+        """Submits every gas of the column through the public non-blocking `Gas.submit` (the
+        gases overlap on the device: scaling kernels and pedestal chains side by side, summation
+        kernels gas after gas, copies under the next gas's kernels), then waits for all."""
         for f in SUBMIT_ORDER:
-            h = gases[f]._handle(local_rank)
-            t = np.ascontiguousarray(column.t)
-            p = np.ascontiguousarray(column.p)
-            x = np.ascontiguousarray(column.vmr[f])
-            dst = destinations[f].array.ctypes.data_as(ctypes.c_void_p) if destinations else None
-            lib.lbl_gas_submit(h.ptr, N_LAYERS, p, t, x, v0, vn, npv, CUT_OFF,
-                               1 if REMOVE_PEDESTAL else 0, 0, dst)
-            handles.append(h)
-        stats = []
-        for h in handles:
-            lib.lbl_gas_wait(h.ptr)
-            stats.append(h.stats())
-        return stats
+            gases[f].submit(column.t, column.p, column.vmr[f], bounds=bounds,
+                            remove_pedestal=REMOVE_PEDESTAL, cut_off=CUT_OFF,
+                            out=destinations[f].array if destinations else None)
+        return [gases[f].wait() for f in SUBMIT_ORDER]
 
     def step_resident():
         """All gases, spectra left on the device."""
         return submit_all(None)
 
     pinned = {f: _lib.PinnedArray((N_LAYERS, n)) for f in GASES}
+    pinned_total = _lib.PinnedArray((N_LAYERS, n))
 
-    def step_e2e():
-        """Public API with host buffers: inputs go up and every spectrum comes back to pinned
-        host memory."""
+    def step_e2e_gas():
+        """Per-gas output (pyLBL's output_format="gas"/"all": one array per gas): inputs go up
+        and all seven spectra arrays come back to pinned host memory."""
         return submit_all(pinned)
+
+    def step_e2e_total():
+        """Gas-summed output (pyLBL's output_format="total", spectroscopy.py:225-234): the
+        number densities are applied and the gases summed on the device; one array comes back."""
+        mixture.total_absorption(column.t, column.p, column.vmr, bounds=bounds,
+                                 remove_pedestal=REMOVE_PEDESTAL, cut_off=CUT_OFF,
+                                 out=pinned_total.array)
+        return [gases[f].last_stats[0] for f in SUBMIT_ORDER]
 
     # ---- device-resident throughput ("value") ------------------------------------------
     # Settle first: on a fresh box the first steps run slow (allocations, clocks and power
@@ -395,31 +466,55 @@ def run_ours(args, rank, local_rank, world, dist):
     value = total_evals / seconds
 
     # ---- end to end through the public API with host buffers ---------------------------
-    for _ in range(args.warmup):
-        step_e2e()
-    torch.cuda.synchronize()
-    barrier()
-    t0 = time.perf_counter()
-    e2e_evals = 0
-    h2d = d2h = 0
-    for _ in range(args.steps):
-        _t0 = time.perf_counter()
-        if os.environ.get("BENCH_DEBUG"):
-            lib.lbl_timer_start(local_rank)   # origin of PYLBL_B200_TIMELINE's printout
-        _st = step_e2e()
-        if os.environ.get("BENCH_DEBUG"):
-            print(f"e2e step: {(time.perf_counter() - _t0) * 1e3:.2f} ms wall", file=sys.stderr)
-        for s in _st:
-            e2e_evals += s["evals"]
-            h2d += s["h2d_bytes"]
-            d2h += s["d2h_bytes"]
-    torch.cuda.synchronize()
-    e2e_seconds = max_over_ranks(time.perf_counter() - t0)
-    barrier()
-    e2e_value = sum_over_ranks(float(e2e_evals)) / e2e_seconds
-    h2d = int(sum_over_ranks(float(h2d)))     # whole job, like `value`
-    d2h = int(sum_over_ranks(float(d2h)))
+    def time_e2e(step):
+        for _ in range(args.warmup):
+            step()
+        torch.cuda.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        n_evals = 0
+        up = down = 0
+        for _ in range(args.steps):
+            _t0 = time.perf_counter()
+            if os.environ.get("BENCH_DEBUG"):
+                lib.lbl_timer_start(local_rank)   # origin of PYLBL_B200_TIMELINE's printout
+            _st = step()
+            if os.environ.get("BENCH_DEBUG"):
+                print(f"e2e step: {(time.perf_counter() - _t0) * 1e3:.2f} ms wall", file=sys.stderr)
+            for s in _st:
+                n_evals += s["evals"]
+                up += s["h2d_bytes"]
+                down += s["d2h_bytes"]
+        torch.cuda.synchronize()
+        e2e_seconds = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        return {"value": sum_over_ranks(float(n_evals)) / e2e_seconds, "unit": UNIT,
+                "h2d_bytes_per_step": int(sum_over_ranks(float(up))) // args.steps,      # whole job,
+                "d2h_bytes_per_step": int(sum_over_ranks(float(down))) // args.steps,    # like `value`
+                "ms_per_step": e2e_seconds * 1e3 / args.steps,
+                "layer_spectra_per_s": world * N_LAYERS * args.steps / e2e_seconds}
+
+    e2e_total = time_e2e(step_e2e_total)
+    e2e_total["output"] = ("total: sum over gases of n_gas*k_gas formed on the device, one "
+                           "(60, 500000) f64 array per column back to pinned host memory "
+                           "(pyLBL output_format='total'); public API Mixture.total_absorption")
+    e2e_gas = time_e2e(step_e2e_gas)
+    e2e_gas["output"] = ("gas: seven (60, 500000) f64 arrays per column back to pinned host memory "
+                         "(pyLBL output_format='gas'/'all'); public API Gas.submit / Gas.wait")
     launches = int(sum_over_ranks(float(launches)))
+
+    # ---- the copy ceiling: the same bytes per rank, copy alone, all ranks at once ----------
+    ceiling_gas = copy_ceiling(local_rank, 8 * N_LAYERS * n * len(GASES), barrier, max_over_ranks)
+    ceiling_total = copy_ceiling(local_rank, 8 * N_LAYERS * n, barrier, max_over_ranks)
+    for block, gbs, nbytes in ((e2e_gas, ceiling_gas, 8 * N_LAYERS * n * len(GASES)),
+                               (e2e_total, ceiling_total, 8 * N_LAYERS * n)):
+        copy_ms = nbytes / (gbs * 1e9) * 1e3
+        block["d2h_ceiling_gbs_per_gpu"] = gbs
+        block["d2h_alone_ms_per_step"] = copy_ms
+        # a step cannot be shorter than its kernels nor than its copy
+        block["floor_ms_per_step"] = max(copy_ms, seconds * 1e3 / args.steps)
+        block["frac_of_floor"] = block["floor_ms_per_step"] / block["ms_per_step"]
+
     # ---- the summation kernel alone (untimed extra pass) ---------------------------------
     # One more pass with the gases run one at a time and the pedestal off (the summation kernel
     # does not depend on it): nothing else is on the GPU while the kernel runs, which gives
@@ -435,15 +530,31 @@ def run_ours(args, rank, local_rank, world, dist):
             isolated_ms += st["sum_ms"]
             isolated_launches += st["sum_launches"]
 
-    # parity spot check of what came back (one spectrum, against the oracle)
+    # parity spot check of what came back, against the oracle: a gas the far-field kernel
+    # summed (CO2, the longest line list), one layer; with the pedestal as benchmarked in the
+    # window-scaled metric, and without it pointwise
     check = None
     if rank == 0 and not args.no_check:
         from oracle import OracleGas
-        ref = OracleGas(db, "CO")
+        sys.path.insert(0, str(ROOT / "tests"))
+        from helpers import relative_error, scaled_error
+        ref = OracleGas(db, "CO2")
         layer = 37
-        k_ref = ref.absorption(column.t[layer], column.p[layer], column.vmr["CO"][layer], v0, vn,
-                               npv, REMOVE_PEDESTAL, CUT_OFF)
-        check = float(np.max(np.abs(pinned["CO"].array[layer] - k_ref)) / np.max(np.abs(k_ref)))
+        state = (column.t[layer], column.p[layer], column.vmr["CO2"][layer])
+        k_ref = ref.absorption(*state, v0, vn, npv, REMOVE_PEDESTAL, CUT_OFF)
+        check = {"gas": "CO2", "layer": layer,
+                 "scaled_error_as_benchmarked": scaled_error(pinned["CO2"].array[layer], k_ref, npv, CUT_OFF)}
+        k_plain = gases["CO2"].absorption_coefficients([state[0]], [state[1]], [state[2]], bounds=bounds,
+                                                       remove_pedestal=False, cut_off=CUT_OFF)[0]
+        check["cells_per_warp"] = gases["CO2"].last_stats[0]["cells_per_warp"]
+        check["pointwise_relative_error_no_pedestal"] = relative_error(
+            k_plain, ref.absorption(*state, v0, vn, npv, False, CUT_OFF))
+        # the device-side sum against the per-gas arrays that came back
+        from pylbl_b200 import number_density
+        want = np.zeros(n)
+        for f in GASES:
+            want += number_density(*state[:2], column.vmr[f][layer]) * pinned[f].array[layer]
+        check["total_vs_sum_of_gases_scaled_error"] = scaled_error(pinned_total.array[layer], want, npv, CUT_OFF)
 
     # ---- roofline of the summation kernel ----------------------------------------------
     # The summation kernel on fine grids interpolates the far field: it PERFORMS `executed`
@@ -458,11 +569,13 @@ def run_ours(args, rank, local_rank, world, dist):
     achieved = flops / (sum_ms * 1e-3) / 1e12 if sum_ms > 0 else 0.0
     kernel = f"lbl::sum_cell_kernel<{cells}>" if cells else f"lbl::sum_kernel<{points}>"
     # DRAM bytes per launch of that kernel from the committed `ncu --set full` capture
-    # (profiles/r1_sum_cell_dram.json, written by tools/ncu_dram.py), or null.
+    # (written by tools/ncu_dram.py), or null.
     traffic = None
-    dram_file = ROOT / "profiles" / "r1_sum_cell_dram.json"
-    if cells and dram_file.exists():
-        traffic = json.loads(dram_file.read_text()).get("dram_bytes_per_launch")
+    for name in ("r2_sum_cell_dram.json", "r1_sum_cell_dram.json"):
+        dram_file = ROOT / "profiles" / name
+        if cells and dram_file.exists():
+            traffic = json.loads(dram_file.read_text()).get("dram_bytes_per_launch")
+            break
     roofline = {
         "bound": "fp64", "kernel": kernel, "achieved": achieved,
         "peak": peak.value, "unit": "TFLOP/s",
@@ -493,17 +606,31 @@ def run_ours(args, rank, local_rank, world, dist):
     }
 
     # ---- CPU baseline on rank 0 at N=1 ---------------------------------------------------
-    cpu = None
+    cpu = cpu_serial = cpu_config1 = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        os.sched_setaffinity(0, range(os.cpu_count() or 1)) if numa and numa.get("cpus") else None
         threads = os.cpu_count() or 1
-        layers = [0, 20, 40, 59]
+        layers = cpu_sample_layers(threads)
         base_column = synth.standard_column(N_LAYERS, column=0)
         cpu_evals = count_evals(db, base_column, layers)
         cpu_seconds, kind, jobs = cpu_reference_run(db, base_column, layers, threads)
         cpu = {"value": cpu_evals / cpu_seconds, "unit": UNIT, "cores": threads, "kind": kind,
-               "sample": f"{len(GASES)} gases x layers {layers} of the 60-layer column "
-                         f"({jobs} absorption() calls incl. their sqlite reads, "
+               "mode": "(ii) all host cores: thread pool over (gas, layer) calls",
+               "layer_spectra_per_s": len(layers) / cpu_seconds,
+               "sample": f"{len(GASES)} gases x {len(layers)} layers of the 60-layer column "
+                         f"({jobs} absorption() calls incl. their sqlite reads, longest first, "
                          f"{cpu_evals:.3e} evaluations, {cpu_seconds:.1f} s)"}
+        # mode (i), "as shipped": one thread, the reference driver's serial gas-outer /
+        # layer-inner loop (pyLBL/spectroscopy.py:166-191), sqlite re-read on every call
+        serial_layers = [0, N_LAYERS - 1]
+        serial_evals = count_evals(db, base_column, serial_layers)
+        serial_seconds, kind, jobs = cpu_reference_run(db, base_column, serial_layers, 1)
+        cpu_serial = {"value": serial_evals / serial_seconds, "unit": UNIT, "cores": 1, "kind": kind,
+                      "mode": "(i) as shipped: one thread, serial gas x layer loop",
+                      "layer_spectra_per_s": len(serial_layers) / serial_seconds,
+                      "sample": f"{len(GASES)} gases x layers {serial_layers} ({jobs} calls, "
+                                f"{serial_evals:.3e} evaluations, {serial_seconds:.1f} s)"}
+        cpu_config1 = cpu_config1_point(local_rank)
 
     if rank == 0:
         line = {
@@ -513,18 +640,63 @@ def run_ours(args, rank, local_rank, world, dist):
             "data": "synthetic", "config": workload_config(world),
             "layer_spectra_per_s": world * N_LAYERS * args.steps / seconds,
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT,
-                    "h2d_bytes_per_step": h2d // args.steps, "d2h_bytes_per_step": d2h // args.steps,
-                    "ms_per_step": e2e_seconds * 1e3 / args.steps,
-                    "layer_spectra_per_s": world * N_LAYERS * args.steps / e2e_seconds,
-                    "parity_spot_check_max_rel_to_peak": check},
+            "e2e": e2e_total,
+            "e2e_gas": e2e_gas,
+            "parity_spot_check": check,
             "gpu_launches": launches,
             "roofline": roofline,
             "cpu_baseline": cpu,
+            "cpu_baseline_serial": cpu_serial,
+            "cpu_config1": cpu_config1,
+            "numa": numa,
         }
         print(json.dumps(line), flush=True)
+    mixture.close()
     for g in gases.values():
         g.close()
+
+
+def cpu_config1_point(device):
+    """BASELINE configs[0], the reference's own CPU-runnable case: one layer (98388 Pa, 289 K),
+    H2O+CO2+O3, ~50k lines, 1-5000 cm-1 @0.1: the reference on one host thread and this
+    library (direct kernel K2) on the same database, pedestal as benchmarked."""
+    from oracle import ReferenceGas, OracleGas, have_reference
+    from pylbl_b200 import Gas
+    cache = Path(tempfile.gettempdir()) / "pylbl_b200_bench"
+    path = cache / "config1.db"
+    if not path.exists():
+        synth.write_database(str(path), synth.config_line_lists(1))
+    atm = synth.fixture_atmosphere()
+    layer = 3
+    bounds = synth.config_grid(1)
+    cls = ReferenceGas if have_reference() else OracleGas
+    counter = {f: OracleGas(str(path), f) for f in ("H2O", "CO2", "O3")}
+    evals = 0
+    for f, ref in counter.items():
+        ref.absorption(atm.t[layer], atm.p[layer], atm.vmr[f][layer], *bounds, REMOVE_PEDESTAL, CUT_OFF)
+        evals += ref.last_evals
+    best = float("inf")
+    for _ in range(5):
+        t0 = time.perf_counter()
+        for f in counter:
+            cls(str(path), f).absorption(atm.t[layer], atm.p[layer], atm.vmr[f][layer], *bounds,
+                                         REMOVE_PEDESTAL, CUT_OFF)
+        best = min(best, time.perf_counter() - t0)
+    gases = {f: Gas(str(path), f, devices=[device]) for f in counter}
+    gpu_best = float("inf")
+    for _ in range(10):
+        t0 = time.perf_counter()
+        for f, g in gases.items():
+            g.absorption_coefficient(atm.t[layer], atm.p[layer], atm.vmr[f][layer],
+                                     synth.grid_from_bounds(*bounds), remove_pedestal=REMOVE_PEDESTAL,
+                                     cut_off=CUT_OFF)
+        gpu_best = min(gpu_best, time.perf_counter() - t0)
+    for g in gases.values():
+        g.close()
+    return {"workload": "BASELINE configs[0]: one layer, H2O+CO2+O3 (~50k lines), 1-5000 cm-1 @0.1",
+            "evals": evals, "cpu_value": evals / best, "cpu_seconds": best, "cpu_cores": 1,
+            "cpu_kind": "reference" if have_reference() else "port",
+            "gpu_value_scalar_plugin_calls": evals / gpu_best, "gpu_seconds": gpu_best, "unit": UNIT}
 
 
 def main():

@@ -45,11 +45,13 @@ typedef struct lbl_stats
     int n_lines;            /* transition rows of the molecule */
     int n_active;           /* rows before the reference's early break (absorption.c:80-83) */
     int n_layers;
-    int n_points;           /* (vn - v0)*n_per_v */
+    int n_points;           /* output points per layer: (vn - v0)*n_per_v, or the band's share */
     int points_per_thread;
     int cells_per_warp;     /* > 0: the cell-tiled summation kernel with the far-field interpolation ran */
     int sum_launches;       /* launches of the summation kernel */
     int total_launches;     /* all kernel launches */
+    int fp32_used;          /* 1: the far wings were summed in FP32 (LBL_PRECISION_FP32 on the direct
+                               kernel); 0: in FP64 (always on the far-field kernel) */
     float scale_ms;         /* K1, CUDA events on the launching stream */
     float sum_ms;           /* K2 (dominant kernel), summed over launches */
     float fixup_ms;         /* K2b (near-zone and node terms) */
@@ -112,6 +114,29 @@ LBL_API int lbl_gas_submit(lbl_gas* gas, int n_layers, const double* pressure,
                    int precision, double* k_host);
 LBL_API int lbl_gas_wait(lbl_gas* gas);
 
+/* Spectral band of a grid (band sharding of one spectrum over several GPUs).
+ * Computes the output cells [band_lo, band_hi) -- integer wavenumbers v0+band_lo .. v0+band_hi --
+ * of the grid (v0, vn, n_per_v): k_host[L*m .. L*m+m), m = (band_hi-band_lo)*n_per_v, receives
+ * points [band_lo*n_per_v, band_hi*n_per_v) of what lbl_gas_submit would write for layer L, bit
+ * for bit.  The line windows (spectra.c:48-62), the active-line prefix before the reference's
+ * early break (absorption.c:80-83) and the accumulated pedestal (spectra.c:66-78) are those of
+ * the WHOLE grid: a separate reference call on the band's own (v0, vn) would see a different
+ * prefix (typically none) and different pedestals.  Bands of one grid are
+ * independent: one handle per device, no communication.  lbl_stats.evals counts the band's
+ * share of every line window. */
+LBL_API int lbl_gas_submit_band(lbl_gas* gas, int n_layers, const double* pressure,
+                   const double* temperature, const double* volume_mixing_ratio,
+                   int v0, int vn, int n_per_v, int cut_off, int remove_pedestal,
+                   int precision, int band_lo, int band_hi, double* k_host,
+                   long long k_pitch);
+/* k_pitch: doubles between the starts of consecutive host rows (0 = dense, m); with
+ * k_pitch = (vn-v0)*n_per_v and k_host pointing at column band_lo*n_per_v of a whole-grid array,
+ * the bands of several devices land side by side in one array.
+ * lbl_gas_band_edges proposes n_bands contiguous bands of about equal work for this molecule:
+ * edges[0..n_bands] are cell indices, band b = [edges[b], edges[b+1]).  Needs no GPU work. */
+LBL_API int lbl_gas_band_edges(lbl_gas* gas, int v0, int vn, int n_per_v, int cut_off, int n_bands,
+                   int* edges);
+
 /* Layer groups for the copy back to the host (fine grids, k_host != NULL): the layers of a
  * call are summed, corrected and copied out in `groups` consecutive groups, so that all but
  * the last group's copy overlaps later kernels.  Every extra group costs a kernel tail; it
@@ -136,16 +161,33 @@ LBL_API int lbl_gas_scaled(lbl_gas* gas, int layer, double* out, int capacity);
  * pyLBL/spectroscopy.py:181-191,225-234 (output_format="total", lines mechanism): the
  * spectra of several gases stay on the device, are scaled per layer and summed there, and
  * one array comes back instead of one per gas.
- *   lbl_mix_open   allocates a zeroed accumulator of n_layers*n doubles on `device`
- *   lbl_mix_add    acc[L][i] += scale[L] * k_gas[L][i] with the spectra of the gas's last
- *                  call, which must still be resident on the device (k_host == NULL, one
- *                  layer group); scale = number density p*x/(kB*T) for beta in m-1
- *   lbl_mix_download  copies the accumulator to host memory (blocking) */
+ *   lbl_mix_open    allocates a zeroed accumulator of n_layers*n_points doubles on `device`
+ *   lbl_mix_reset   zeroes it again (asynchronous)
+ *   lbl_gas_submit_mix  like lbl_gas_submit with k_host == NULL, and then, on the device,
+ *                   acc[row0+L][i] += scale[L] * k[L][i]   (scale = number density p*x/(kB*T)
+ *                   gives beta in m-1, spectroscopy.py:18-29); nothing waits on the host, so the
+ *                   gases of a column are all in flight together; the additions of successive
+ *                   calls run in submission order (no atomics).  total_host != NULL marks the
+ *                   LAST gas of the sum: each layer group of the accumulator is copied to
+ *                   total_host[(row0+L)*n_points ..] as soon as this gas has been added to it,
+ *                   while later groups still compute
+ *   lbl_mix_wait    blocks until every addition and copy enqueued so far has finished
+ *   lbl_mix_add     adds the spectra a gas's last call left resident on the device (k_host ==
+ *                   NULL, one layer group); blocking
+ *   lbl_mix_download  copies the whole accumulator to host memory (blocking)
+ *   lbl_mix_device_result  device pointer to the accumulator */
 typedef struct lbl_mix lbl_mix;
 LBL_API int lbl_mix_open(int device, int n_layers, int n_points, lbl_mix** out);
 LBL_API int lbl_mix_reset(lbl_mix* mix);
+LBL_API int lbl_gas_submit_mix(lbl_gas* gas, int n_layers, const double* pressure,
+                   const double* temperature, const double* volume_mixing_ratio,
+                   int v0, int vn, int n_per_v, int cut_off, int remove_pedestal,
+                   int precision, lbl_mix* mix, int row0, const double* scale,
+                   double* total_host);
+LBL_API int lbl_mix_wait(lbl_mix* mix);
 LBL_API int lbl_mix_add(lbl_mix* mix, lbl_gas* gas, const double* scale);
 LBL_API int lbl_mix_download(lbl_mix* mix, double* host);
+LBL_API int lbl_mix_device_result(lbl_mix* mix, double** device_ptr, long long* count);
 LBL_API int lbl_mix_close(lbl_mix* mix);
 
 /* Pinned host memory for k_host (lets the device->host copy run asynchronously). */

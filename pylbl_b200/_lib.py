@@ -31,7 +31,7 @@ class Stats(Structure):
         ("d2h_bytes", c_longlong),
         ("n_lines", c_int), ("n_active", c_int), ("n_layers", c_int), ("n_points", c_int),
         ("points_per_thread", c_int), ("cells_per_warp", c_int), ("sum_launches", c_int),
-        ("total_launches", c_int),
+        ("total_launches", c_int), ("fp32_used", c_int),
         ("scale_ms", c_float), ("sum_ms", c_float), ("fixup_ms", c_float),
         ("pedestal_ms", c_float),
         ("total_ms", c_float),
@@ -48,7 +48,8 @@ EXPORTS = (
     "lbl_set_chunk_layers", "lbl_last_error", "lbl_version", "lbl_timer_start",
     "lbl_timer_join", "lbl_timer_stop", "lbl_measure_fp64_peak", "lbl_mix_open", "lbl_mix_reset",
     "lbl_mix_add", "lbl_mix_download", "lbl_mix_close", "lbl_pack_database", "lbl_pack_info",
-    "lbl_gas_open_pack", "lbl_gas_set_copy_groups",
+    "lbl_gas_open_pack", "lbl_gas_set_copy_groups", "lbl_gas_submit_band", "lbl_gas_submit_mix",
+    "lbl_mix_wait", "lbl_mix_device_result", "lbl_gas_band_edges",
 )
 
 _library = None
@@ -93,6 +94,13 @@ def library():
     batched = [c_void_p, c_int, f64, f64, f64] + 6 * [c_int] + [c_void_p]
     lib.lbl_gas_compute.argtypes = batched
     lib.lbl_gas_submit.argtypes = batched
+    lib.lbl_gas_submit_band.argtypes = [c_void_p, c_int, f64, f64, f64] + 6 * [c_int] + \
+        [c_int, c_int, c_void_p, c_longlong]
+    lib.lbl_gas_band_edges.argtypes = [c_void_p] + 5 * [c_int] + [i32]
+    lib.lbl_gas_submit_mix.argtypes = [c_void_p, c_int, f64, f64, f64] + 6 * [c_int] + \
+        [c_void_p, c_int, f64, c_void_p]
+    lib.lbl_mix_wait.argtypes = [c_void_p]
+    lib.lbl_mix_device_result.argtypes = [c_void_p, POINTER(c_void_p), POINTER(c_longlong)]
     lib.lbl_gas_wait.argtypes = [c_void_p]
     lib.lbl_gas_set_copy_groups.argtypes = [c_void_p, c_int]
     lib.lbl_gas_stats.argtypes = [c_void_p, POINTER(Stats)]

@@ -152,7 +152,9 @@ struct lbl_gas
         executed_dev;
     int cheb_npv = 0;
     unsigned long long* executed_host = nullptr;  // pinned
-    DevBuf out[2];
+    DevBuf out[2], mix_scale_dev;
+    double* mix_scale_host = nullptr;  // pinned
+    size_t mix_scale_host_cap = 0;
     LayerIn* layers_host = nullptr;  // pinned
     size_t layers_host_cap = 0;
     unsigned long long* evals_host = nullptr;  // pinned
@@ -268,6 +270,18 @@ int make_plan(lbl_gas* g, int v0, int vn, int cut_off)
     p.vn = vn;
     p.cut_off = cut_off;
     p.n_active = active_prefix(g->mol, v0, vn, cut_off);
+    if (g->mol.has_tips)
+    {
+        // Only rows the reference would touch are held to this (it indexes the TIPS block
+        // local_iso_id-1 without a check, spectra.c:41-42).
+        for (int r = 0; r < p.n_active; ++r)
+        {
+            if (g->mol.iso[r] > g->mol.num_iso)
+            {
+                return fail("Error: line refers to an isotopologue without TIPS data.");
+            }
+        }
+    }
     p.sorted_to_db.clear();
     if (!g->mol.sorted && p.n_active > 0)
     {
@@ -340,9 +354,12 @@ int pick_threads_per_layer(int n_per_v, int P, int n_layers)
 }
 
 template <int P>
-void launch_sum(const SumArgs& a, int n_layers, bool fp32, cudaStream_t s)
+void launch_sum(SumArgs a, int n_layers, bool fp32, cudaStream_t s)
 {
-    const int tiles = (a.grid.n + a.tpw * P - 1) / (a.tpw * P);   // one warp each
+    // one warp per tile of tpw*P points; a band launches the tiles (of the whole grid) it meets
+    const int tile_points = a.tpw * P;
+    a.tile0 = band_first_point(a.grid) / tile_points;
+    const int tiles = (band_end_point(a.grid) + tile_points - 1) / tile_points - a.tile0;
     const int lp = 32 / a.tpw;
     dim3 grid((tiles + kSumBlock / 32 - 1) / (kSumBlock / 32), (n_layers + lp - 1) / lp);
     if (fp32)
@@ -395,17 +412,19 @@ bool near_block_applies(const SumArgs& a, const std::vector<LayerIn>& layers, in
     return true;
 }
 
-void launch_near_block(const SumArgs& a, int n_layers, cudaStream_t s)
+void launch_near_block(SumArgs a, int n_layers, cudaStream_t s)
 {
     cudaFuncSetAttribute(near_block_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                          cudaSharedmemCarveoutMaxShared);   // 8 blocks x 28 KB per SM
-    dim3 grid((a.grid.n + kNbSpan - 1) / kNbSpan, n_layers);
+    a.tile0 = band_first_point(a.grid) / kNbSpan;
+    dim3 grid((band_end_point(a.grid) + kNbSpan - 1) / kNbSpan - a.tile0, n_layers);
     near_block_kernel<<<grid, 128, 0, s>>>(a);
 }
 
-void launch_fixup_dispatch(int T, const SumArgs& a, int n_layers, cudaStream_t s)
+void launch_fixup_dispatch(int T, SumArgs a, int n_layers, cudaStream_t s)
 {
-    const int tiles = (a.grid.n + T - 1) / T;
+    a.tile0 = band_first_point(a.grid) / T;
+    const int tiles = (band_end_point(a.grid) + T - 1) / T - a.tile0;
     const int lp = 32 / T;
     dim3 grid((tiles + 3) / 4, (n_layers + lp - 1) / lp);
     switch (T)
@@ -427,7 +446,7 @@ cudaError_t launch_chain(const PedArgs& pa, double* terms, double* scratch, int 
 {
     cudaError_t e = cudaSuccess;
     {
-        const int tiles = (pa.lines.n + kPedTileRows - 1) / kPedTileRows;
+        const int tiles = (pa.n_rows + kPedTileRows - 1) / kPedTileRows;
         dim3 tg((tiles + 3) / 4, n_layers);
         pedestal_terms_kernel<K><<<tg, 128, 0, s>>>(pa, terms);
     }
@@ -538,7 +557,7 @@ const char* lbl_last_error(void)
 
 int lbl_version(void)
 {
-    return 100;
+    return 200;
 }
 
 int lbl_set_chunk_layers(int layers)
@@ -814,6 +833,8 @@ int lbl_gas_close(lbl_gas* g)
         b->release();
     }
     if (g->layers_host) cudaFreeHost(g->layers_host);
+    if (g->mix_scale_host) cudaFreeHost(g->mix_scale_host);
+    g->mix_scale_dev.release();
     if (g->evals_host) cudaFreeHost(g->evals_host);
     if (g->executed_host) cudaFreeHost(g->executed_host);
     for (cudaEvent_t e : g->ev_pool) cudaEventDestroy(e);
@@ -829,12 +850,71 @@ int lbl_gas_close(lbl_gas* g)
     return 0;
 }
 
-static int submit_call(lbl_gas* g, bool blocking, int n_layers, const double* pressure,
-                       const double* temperature, const double* vmr, int v0, int vn, int n_per_v,
-                       int cut_off, int remove_pedestal, int precision, double* k_host)
+}  // extern "C"
+
+// Accumulator of the device-side gas sum.  All additions run on the device's `late` stream, in
+// submission order: no atomics, and the sum does not depend on timing.
+struct lbl_mix
 {
+    int device = 0;
+    int n_layers = 0, n = 0;
+    DeviceStreams* streams = nullptr;
+    cudaEvent_t ev_added = nullptr;    // after the last enqueued addition (late stream)
+    cudaEvent_t ev_copied = nullptr;   // after the last enqueued copy to the host (copy stream)
+    bool copies_pending = false;
+    DevBuf acc;
+};
+
+namespace
+{
+// Everything one call may ask for (the extern "C" entry points fill this in).
+struct CallSpec
+{
+    bool blocking = false;
+    int n_layers = 0;
+    const double* pressure = nullptr;
+    const double* temperature = nullptr;
+    const double* vmr = nullptr;
+    int v0 = 0, vn = 0, n_per_v = 0, cut_off = 0, remove_pedestal = 0, precision = 0;
+    int band_lo = 0, band_hi = 0;      // cells [band_lo, band_hi) of the grid; 0, 0 = all of it
+    double* k_host = nullptr;          // [n_layers][band points], or NULL
+    long long k_pitch = 0;             // doubles between the starts of host rows (0 = dense)
+    lbl_mix* mix = nullptr;            // accumulate scale[L]*k[L][:] into rows mix_row0 + L
+    int mix_row0 = 0;
+    const double* mix_scale = nullptr; // [n_layers], host
+    double* mix_host = nullptr;        // non-NULL: copy each finished layer group of the
+                                       // accumulator to mix_host (this is the sum's last gas)
+};
+
+// The accumulator rows [row0, row0 + rows) go to the host once the additions enqueued so far
+// have run.
+int mix_rows_to_host(lbl_mix* m, int row0, int rows, double* host)
+{
+    LBL_CUDA(cudaEventRecord(m->ev_added, m->streams->late));
+    LBL_CUDA(cudaStreamWaitEvent(m->streams->copy, m->ev_added, 0));
+    LBL_CUDA(cudaMemcpyAsync(host + (size_t)row0 * m->n, m->acc.as<double>() + (size_t)row0 * m->n,
+                             sizeof(double) * (size_t)rows * m->n, cudaMemcpyDeviceToHost,
+                             m->streams->copy));
+    LBL_CUDA(cudaEventRecord(m->ev_copied, m->streams->copy));
+    m->copies_pending = true;
+    return 0;
+}
+}  // namespace
+
+static int submit_call(lbl_gas* g, const CallSpec& call)
+{
+    const bool blocking = call.blocking;
+    const int n_layers = call.n_layers;
+    const double* pressure = call.pressure;
+    const double* temperature = call.temperature;
+    const double* vmr = call.vmr;
+    const int v0 = call.v0, vn = call.vn, n_per_v = call.n_per_v, cut_off = call.cut_off;
+    const int remove_pedestal = call.remove_pedestal, precision = call.precision;
+    double* k_host = call.k_host;
+    lbl_mix* mix = call.mix;
     if (!g) return fail("Error: null handle.");
     if (g->pending && lbl_gas_wait(g)) return 1;
+    if (mix && k_host) return fail("Error: a call feeds either the host array or the accumulator.");
     if (precision != LBL_PRECISION_FP64 && precision != LBL_PRECISION_FP32)
     {
         return fail("Error: unsupported precision mode.");
@@ -859,12 +939,35 @@ static int submit_call(lbl_gas* g, bool blocking, int n_layers, const double* pr
     grid.n = (int)n_ll;
     grid.ncell = vn - v0;
     grid.dv = 1. / n_per_v;  // absorption.c:33
+    grid.cell_lo = 0;
+    grid.cell_hi = grid.ncell;
+    if (call.band_lo != 0 || call.band_hi != 0)
+    {
+        if (call.band_lo < 0 || call.band_hi > grid.ncell || call.band_lo >= call.band_hi)
+        {
+            return fail("Error: band is not a non-empty cell range of the grid.");
+        }
+        grid.cell_lo = call.band_lo;
+        grid.cell_hi = call.band_hi;
+    }
+    const bool whole_grid = grid.cell_lo == 0 && grid.cell_hi == grid.ncell;
+    const int band_n = (grid.cell_hi - grid.cell_lo) * n_per_v;   // output points per layer
+    const int band_p0 = grid.cell_lo * n_per_v;
+    if (mix)
+    {
+        if (mix->device != g->device) return fail("Error: gas and accumulator live on different devices.");
+        if (mix->n != band_n || call.mix_row0 < 0 || call.mix_row0 + n_layers > mix->n_layers)
+        {
+            return fail("Error: accumulator shape does not fit this call.");
+        }
+        if (!call.mix_scale) return fail("Error: null scale array.");
+    }
 
     lbl_stats& st = g->stats;
     st = lbl_stats{};
     st.n_lines = (int)g->mol.nu.size();
     st.n_layers = n_layers;
-    st.n_points = grid.n;
+    st.n_points = band_n;
     g->chunk_events.clear();
     g->sum_events.clear();
     g->ev_used = 0;
@@ -878,9 +981,16 @@ static int submit_call(lbl_gas* g, bool blocking, int n_layers, const double* pr
     if (n_layers == 0) return 0;
 
     // No TIPS rows: "lines can't be calculated", absorption.c:53-59 -> zeros, success.
+    if (call.k_pitch != 0 && call.k_pitch < band_n) return fail("Error: host row pitch shorter than a row.");
+    auto zero_host = [&]() {
+        if (!k_host) return;
+        const size_t pitch = call.k_pitch > 0 ? (size_t)call.k_pitch : (size_t)band_n;
+        for (int l = 0; l < n_layers; ++l) std::memset(k_host + (size_t)l * pitch, 0, sizeof(double) * band_n);
+    };
     if (!g->mol.has_tips)
     {
-        if (k_host) std::memset(k_host, 0, sizeof(double) * (size_t)n_layers * grid.n);
+        zero_host();
+        if (mix && call.mix_host) return mix_rows_to_host(mix, call.mix_row0, n_layers, call.mix_host);
         return 0;
     }
     const size_t h2d_before = g->open_h2d;
@@ -903,17 +1013,24 @@ static int submit_call(lbl_gas* g, bool blocking, int n_layers, const double* pr
     // The FP32 mode is a mode of the direct kernel K2.  Where K2c runs it is already faster
     // in FP64 than K2 is in FP32, so the request is honoured with FP64 arithmetic there.
     const bool fp32 = fp32_requested && !farfield;
+    st.fp32_used = fp32 ? 1 : 0;
     const int P = farfield ? kCellP : pick_points_per_thread(n_per_v);
     st.points_per_thread = P;
 
     // The reference indexes the TIPS table without a bounds check
     // (spectral_database.c:102-103); outside the table that is undefined behaviour, so it
     // is an error here.
-    const double t0 = g->mol.tips_t[0];
+    // Checked per isotopologue block, each against its own first temperature, as the kernel
+    // (and the reference) index it.
     auto tips_ok = [&](double t) {
         if (!(t == t)) return false;
-        const long long i = (long long)std::floor(t) - (long long)(int)t0;
-        return i >= 0 && i + 1 < g->mol.num_t;
+        for (int iso = 0; iso < g->mol.num_iso; ++iso)
+        {
+            const double t0 = g->mol.tips_t[(size_t)iso * g->mol.num_t];
+            const long long i = (long long)std::floor(t) - (long long)(int)t0;
+            if (!(i >= 0 && i + 1 < g->mol.num_t)) return false;
+        }
+        return true;
     };
     if (!tips_ok(296.)) return fail("Error: TIPS table does not cover 296 K.");
     for (int l = 0; l < n_layers; ++l)
@@ -927,7 +1044,8 @@ static int submit_call(lbl_gas* g, bool blocking, int n_layers, const double* pr
     if (plan.n_active == 0)
     {
         // Every row is past the early break: the reference returns the zeroed k.
-        if (k_host) std::memset(k_host, 0, sizeof(double) * (size_t)n_layers * grid.n);
+        zero_host();
+        if (mix && call.mix_host) return mix_rows_to_host(mix, call.mix_row0, n_layers, call.mix_host);
         return 0;
     }
     const DeviceLines& dl = g->mol.sorted ? g->base : plan.own;
@@ -961,6 +1079,7 @@ static int submit_call(lbl_gas* g, bool blocking, int n_layers, const double* pr
     long long chunk = std::min<long long>(n_layers,
                                           std::max<long long>(1, (long long)(budget / rec_per_layer)));
     chunk = std::min<long long>(chunk, std::max<long long>(1, (long long)(budget / out_per_layer)));
+    chunk = std::min<long long>(chunk, 65535);   // layers are gridDim.y of the kernels
     int chunk_override = g_chunk_layers;
     if (const char* env = getenv("PYLBL_B200_CHUNK_LAYERS")) chunk_override = atoi(env);
     if (chunk_override > 0)
@@ -1067,6 +1186,34 @@ static int submit_call(lbl_gas* g, bool blocking, int n_layers, const double* pr
         g->last_layers[l] = ly;
     }
 
+    // Rows the pedestal recurrence must walk.  It runs in database order over the whole grid's
+    // active lines; for a band of a nu-sorted database the rows past the band's last window
+    // (window cell > cell_hi-1+cut, i.e. nu > v0+cell_hi+cut+slack) come later in the order
+    // and cannot reach the band's bins.
+    int ped_rows = plan.n_active;
+    if (remove_pedestal && !whole_grid && g->mol.sorted)
+    {
+        double slack_max = 0.;
+        for (int l = 0; l < n_layers; ++l) slack_max = std::max(slack_max, g->layers_host[l].slack);
+        const double limit = (double)v0 + (double)grid.cell_hi + (double)cut_off + slack_max;
+        ped_rows = (int)(std::upper_bound(g->mol.nu.begin(), g->mol.nu.begin() + plan.n_active, limit) -
+                         g->mol.nu.begin());
+    }
+    if (mix)
+    {
+        // the scales ride behind the layer states in the same pinned buffer / device buffer
+        LBL_CUDA(g->mix_scale_dev.reserve(sizeof(double) * (size_t)n_layers));
+        if (g->mix_scale_host_cap < (size_t)n_layers)
+        {
+            if (g->mix_scale_host) cudaFreeHost(g->mix_scale_host);
+            g->mix_scale_host = nullptr;
+            LBL_CUDA(cudaHostAlloc((void**)&g->mix_scale_host, sizeof(double) * n_layers,
+                                   cudaHostAllocDefault));
+            g->mix_scale_host_cap = n_layers;
+        }
+        std::memcpy(g->mix_scale_host, call.mix_scale, sizeof(double) * (size_t)n_layers);
+    }
+
     cudaStream_t sc = g->s_compute;               // early: uploads and scaling kernels
     cudaStream_t sm = g->s_main;                  // summation kernels
     cudaStream_t sl = g->s_late;                  // apply, statistics
@@ -1076,6 +1223,12 @@ static int submit_call(lbl_gas* g, bool blocking, int n_layers, const double* pr
     LBL_CUDA(cudaMemcpyAsync(g->layers_dev.p, g->layers_host, sizeof(LayerIn) * n_layers,
                              cudaMemcpyHostToDevice, sc));
     LBL_CUDA(cudaMemsetAsync(g->evals_dev.p, 0, sizeof(unsigned long long) * n_layers, sc));
+    if (mix)
+    {
+        LBL_CUDA(cudaMemcpyAsync(g->mix_scale_dev.p, g->mix_scale_host, sizeof(double) * n_layers,
+                                 cudaMemcpyHostToDevice, sc));
+        st.h2d_bytes += (long long)(sizeof(double) * n_layers);
+    }
     if (farfield)
     {
         LBL_CUDA(cudaMemsetAsync(g->executed_dev.p, 0, sizeof(unsigned long long), sc));
@@ -1147,6 +1300,7 @@ static int submit_call(lbl_gas* g, bool blocking, int n_layers, const double* pr
             pa.rec = rec;
             pa.grid = grid;
             pa.pedbin = g->pedbin.as<double>();
+            pa.n_rows = ped_rows;
             double* scratch = ped_nodes_in_smem ? nullptr : g->pednodes.as<double>();
             if (ped_chain)
             {
@@ -1203,12 +1357,14 @@ static int submit_call(lbl_gas* g, bool blocking, int n_layers, const double* pr
         // records and the pedestal chain are per chunk (the chain takes as long for 15 layers
         // as for 60).
         int n_groups = 1;
-        if (farfield && k_host)
+        if (farfield && (k_host || (mix && call.mix_host)))
         {
             // Splitting costs a kernel tail per group.  It pays when the caller blocks on this
             // call (nothing else would hide the copy); with several calls in flight the copy of
             // one gas hides behind the kernels of the next and one group is best.
             n_groups = (blocking && nl >= 16) ? 2 : 1;
+            // the last gas of a device-side sum: only its last group's rows are copied exposed
+            if (mix && call.mix_host && nl >= 16) n_groups = 4;
             if (g->copy_groups > 0) n_groups = std::min(g->copy_groups, nl);
             if (const char* env = getenv("PYLBL_B200_COPY_GROUPS")) n_groups = std::max(1, std::min(atoi(env), nl));
         }
@@ -1227,7 +1383,7 @@ static int submit_call(lbl_gas* g, bool blocking, int n_layers, const double* pr
             if (farfield)
             {
                 ca.sum = sa;
-                const int groups = (grid.ncell + cells_per_warp - 1) / cells_per_warp;
+                const int groups = (grid.cell_hi - grid.cell_lo + cells_per_warp - 1) / cells_per_warp;
                 dim3 gridc((groups + kSumBlock / 32 - 1) / (kSumBlock / 32), q1 - q0);
                 // 23 KB of static shared memory per block: ask for the large carve-out so that
                 // shared memory does not cap the resident blocks below the register limit.
@@ -1267,14 +1423,23 @@ static int submit_call(lbl_gas* g, bool blocking, int n_layers, const double* pr
             // copy stream.
             LBL_CUDA(cudaStreamWaitEvent(sl, se.k2b_end, 0));
 
-            if (remove_pedestal)
+            if (remove_pedestal && q == 0) LBL_CUDA(cudaStreamWaitEvent(sl, ev.ped_end, 0));
+            if (remove_pedestal || mix)
             {
-                if (q == 0) LBL_CUDA(cudaStreamWaitEvent(sl, ev.ped_end, 0));
-                const size_t total = (size_t)(q1 - q0) * grid.n;
+                const size_t total = (size_t)(q1 - q0) * band_n;
                 const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
-                pedestal_apply_kernel<<<blocks, 256, 0, sl>>>(
-                    g->out[slot].as<double>() + (size_t)q0 * grid.n,
-                    g->pedcorr.as<double>() + 2 * (size_t)q0 * grid.ncell, grid, q1 - q0);
+                double* out_q = g->out[slot].as<double>() + (size_t)q0 * grid.n;
+                const double* corr_q = remove_pedestal
+                    ? g->pedcorr.as<double>() + 2 * (size_t)q0 * grid.ncell : nullptr;
+                double* acc_q = mix ? mix->acc.as<double>() +
+                                          (size_t)(call.mix_row0 + first + q0) * band_n : nullptr;
+                const double* scale_q = mix ? g->mix_scale_dev.as<double>() + first + q0 : nullptr;
+                if (mix && remove_pedestal)
+                    apply_kernel<true, true><<<blocks, 256, 0, sl>>>(out_q, corr_q, grid, q1 - q0, acc_q, scale_q);
+                else if (mix)
+                    apply_kernel<false, true><<<blocks, 256, 0, sl>>>(out_q, corr_q, grid, q1 - q0, acc_q, scale_q);
+                else
+                    apply_kernel<true, false><<<blocks, 256, 0, sl>>>(out_q, corr_q, grid, q1 - q0, acc_q, scale_q);
                 st.total_launches++;
             }
             LBL_CUDA(cudaGetLastError());
@@ -1283,10 +1448,29 @@ static int submit_call(lbl_gas* g, bool blocking, int n_layers, const double* pr
             {
                 LBL_CUDA(cudaEventRecord(g->ev_out_ready[slot], sl));
                 LBL_CUDA(cudaStreamWaitEvent(g->s_copy, g->ev_out_ready[slot], 0));
-                LBL_CUDA(cudaMemcpyAsync(k_host + (size_t)(first + q0) * grid.n,
-                                         g->out[slot].as<double>() + (size_t)q0 * grid.n,
-                                         out_per_layer * (q1 - q0), cudaMemcpyDeviceToHost, g->s_copy));
-                st.d2h_bytes += (long long)(out_per_layer * (q1 - q0));
+                const size_t pitch = call.k_pitch > 0 ? (size_t)call.k_pitch : (size_t)band_n;
+                if (whole_grid && pitch == (size_t)grid.n)
+                {
+                    LBL_CUDA(cudaMemcpyAsync(k_host + (size_t)(first + q0) * grid.n,
+                                             g->out[slot].as<double>() + (size_t)q0 * grid.n,
+                                             out_per_layer * (q1 - q0), cudaMemcpyDeviceToHost, g->s_copy));
+                }
+                else
+                {
+                    // the band's columns of the whole-grid rows
+                    LBL_CUDA(cudaMemcpy2DAsync(k_host + (size_t)(first + q0) * pitch,
+                                               sizeof(double) * pitch,
+                                               g->out[slot].as<double>() + (size_t)q0 * grid.n + band_p0,
+                                               sizeof(double) * grid.n, sizeof(double) * band_n,
+                                               q1 - q0, cudaMemcpyDeviceToHost, g->s_copy));
+                }
+                st.d2h_bytes += (long long)(sizeof(double) * (size_t)band_n * (q1 - q0));
+            }
+            if (mix && call.mix_host)
+            {
+                // last gas of the sum: these rows of the accumulator are final
+                if (mix_rows_to_host(mix, call.mix_row0 + first + q0, q1 - q0, call.mix_host)) return 1;
+                st.d2h_bytes += (long long)(sizeof(double) * (size_t)band_n * (q1 - q0));
             }
         }
         LBL_CUDA(cudaEventRecord(ev.applied, sl));
@@ -1308,7 +1492,11 @@ static int submit_call(lbl_gas* g, bool blocking, int n_layers, const double* pr
         LBL_CUDA(cudaMemcpyAsync(g->executed_host, g->executed_dev.p, sizeof(unsigned long long),
                                  cudaMemcpyDeviceToHost, sl));
     }
-    if (k_host)
+    if (mix)
+    {
+        LBL_CUDA(cudaEventRecord(mix->ev_added, sl));
+    }
+    if (k_host || (mix && call.mix_host))
     {
         // The call ends when the last copy has landed: the end mark goes on the copy stream,
         // after the kernels' end mark.
@@ -1321,8 +1509,11 @@ static int submit_call(lbl_gas* g, bool blocking, int n_layers, const double* pr
         LBL_CUDA(cudaEventRecord(g->ev_call_end, sl));
     }
     g->pending = true;
+    if (mix) g->last_chunk_layers = 0;   // the spectra went into the accumulator, uncorrected here
     return 0;
 }
+
+extern "C" {
 
 int lbl_gas_wait(lbl_gas* g)
 {
@@ -1374,24 +1565,107 @@ int lbl_gas_wait(lbl_gas* g)
     return 0;
 }
 
+static CallSpec basic_call(bool blocking, int n_layers, const double* pressure,
+                           const double* temperature, const double* vmr, int v0, int vn, int n_per_v,
+                           int cut_off, int remove_pedestal, int precision, double* k_host)
+{
+    CallSpec c;
+    c.blocking = blocking;
+    c.n_layers = n_layers;
+    c.pressure = pressure;
+    c.temperature = temperature;
+    c.vmr = vmr;
+    c.v0 = v0;
+    c.vn = vn;
+    c.n_per_v = n_per_v;
+    c.cut_off = cut_off;
+    c.remove_pedestal = remove_pedestal;
+    c.precision = precision;
+    c.k_host = k_host;
+    return c;
+}
+
 int lbl_gas_submit(lbl_gas* g, int n_layers, const double* pressure, const double* temperature,
                    const double* vmr, int v0, int vn, int n_per_v, int cut_off,
                    int remove_pedestal, int precision, double* k_host)
 {
-    return submit_call(g, false, n_layers, pressure, temperature, vmr, v0, vn, n_per_v, cut_off,
-                       remove_pedestal, precision, k_host);
+    return submit_call(g, basic_call(false, n_layers, pressure, temperature, vmr, v0, vn, n_per_v,
+                                     cut_off, remove_pedestal, precision, k_host));
 }
 
 int lbl_gas_compute(lbl_gas* g, int n_layers, const double* pressure, const double* temperature,
                     const double* vmr, int v0, int vn, int n_per_v, int cut_off,
                     int remove_pedestal, int precision, double* k_host)
 {
-    if (submit_call(g, true, n_layers, pressure, temperature, vmr, v0, vn, n_per_v, cut_off,
-                    remove_pedestal, precision, k_host))
+    if (submit_call(g, basic_call(true, n_layers, pressure, temperature, vmr, v0, vn, n_per_v,
+                                  cut_off, remove_pedestal, precision, k_host)))
     {
         return 1;
     }
     return lbl_gas_wait(g);
+}
+
+int lbl_gas_submit_band(lbl_gas* g, int n_layers, const double* pressure, const double* temperature,
+                        const double* vmr, int v0, int vn, int n_per_v, int cut_off,
+                        int remove_pedestal, int precision, int band_lo, int band_hi, double* k_host,
+                        long long k_pitch)
+{
+    CallSpec c = basic_call(false, n_layers, pressure, temperature, vmr, v0, vn, n_per_v, cut_off,
+                            remove_pedestal, precision, k_host);
+    if (band_lo == 0 && band_hi == 0) return fail("Error: empty band.");
+    c.band_lo = band_lo;
+    c.band_hi = band_hi;
+    c.k_pitch = k_pitch;
+    return submit_call(g, c);
+}
+
+int lbl_gas_submit_mix(lbl_gas* g, int n_layers, const double* pressure, const double* temperature,
+                       const double* vmr, int v0, int vn, int n_per_v, int cut_off,
+                       int remove_pedestal, int precision, lbl_mix* mix, int row0,
+                       const double* scale, double* total_host)
+{
+    if (!mix) return fail("Error: null accumulator.");
+    CallSpec c = basic_call(false, n_layers, pressure, temperature, vmr, v0, vn, n_per_v, cut_off,
+                            remove_pedestal, precision, nullptr);
+    c.mix = mix;
+    c.mix_row0 = row0;
+    c.mix_scale = scale;
+    c.mix_host = total_host;
+    return submit_call(g, c);
+}
+
+int lbl_gas_band_edges(lbl_gas* g, int v0, int vn, int n_per_v, int cut_off, int n_bands, int* edges)
+{
+    if (!g || !edges) return fail("Error: null argument.");
+    const int ncell = vn - v0;
+    if (ncell <= 0 || n_bands < 1 || n_per_v < 1 || cut_off < 0) return fail("Error: invalid grid or band count.");
+    // Cost model of one cell (all layers alike): the lines of its window (far field: a few node
+    // evaluations each), the lines next to it (evaluated at every one of its n_per_v points),
+    // and a fixed part (searches, transforms, interpolation).
+    const int na = active_prefix(g->mol, v0, vn, cut_off);
+    std::vector<double> nu(g->mol.nu.begin(), g->mol.nu.begin() + na);
+    if (!g->mol.sorted) std::sort(nu.begin(), nu.end());
+    auto count = [&](double lo, double hi) {
+        return (double)(std::lower_bound(nu.begin(), nu.end(), hi) - std::lower_bound(nu.begin(), nu.end(), lo));
+    };
+    std::vector<double> cum((size_t)ncell + 1, 0.);
+    for (int c = 0; c < ncell; ++c)
+    {
+        const double w = (double)v0 + c;
+        const double cost = 400. + 0.3 * n_per_v + count(w - cut_off, w + cut_off + 1.) +
+                            0.125 * n_per_v * count(w - 0.5, w + 1.5);
+        cum[c + 1] = cum[c] + cost;
+    }
+    edges[0] = 0;
+    for (int b = 1; b < n_bands; ++b)
+    {
+        const double target = cum[ncell] * b / n_bands;
+        int e = (int)(std::lower_bound(cum.begin(), cum.end(), target) - cum.begin());
+        e = std::max(e, edges[b - 1]);
+        edges[b] = std::min(e, ncell);
+    }
+    edges[n_bands] = ncell;
+    return 0;
 }
 
 int lbl_gas_set_copy_groups(lbl_gas* g, int groups)
@@ -1490,18 +1764,6 @@ int lbl_gas_scaled(lbl_gas* g, int layer, double* out, int capacity)
 }
 
 // ---- gas-summed absorption on the device ----------------------------------------------------
-}  // extern "C"
-
-struct lbl_mix
-{
-    int device = 0;
-    int n_layers = 0, n = 0;
-    cudaStream_t stream = nullptr;
-    DevBuf acc, scale;
-};
-
-extern "C" {
-
 int lbl_mix_open(int device, int n_layers, int n_points, lbl_mix** out)
 {
     *out = nullptr;
@@ -1514,29 +1776,38 @@ int lbl_mix_open(int device, int n_layers, int n_points, lbl_mix** out)
     m->n_layers = n_layers;
     m->n = n_points;
     LBL_CUDA(cudaSetDevice(device));
-    LBL_CUDA(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+    if (device_streams(device, &m->streams)) return 1;
+    LBL_CUDA(cudaEventCreateWithFlags(&m->ev_added, cudaEventDisableTiming));
+    LBL_CUDA(cudaEventCreateWithFlags(&m->ev_copied, cudaEventDisableTiming));
     LBL_CUDA(m->acc.reserve(sizeof(double) * (size_t)n_layers * n_points));
-    LBL_CUDA(m->scale.reserve(sizeof(double) * (size_t)n_layers));
-    LBL_CUDA(cudaMemsetAsync(m->acc.p, 0, sizeof(double) * (size_t)n_layers * n_points, m->stream));
-    LBL_CUDA(cudaStreamSynchronize(m->stream));
-    *out = m.release();
-    return 0;
+    lbl_mix* raw = m.release();
+    *out = raw;
+    return lbl_mix_reset(raw);
 }
 
 int lbl_mix_reset(lbl_mix* m)
 {
     if (!m) return fail("Error: null handle.");
     LBL_CUDA(cudaSetDevice(m->device));
-    LBL_CUDA(cudaMemsetAsync(m->acc.p, 0, sizeof(double) * (size_t)m->n_layers * m->n, m->stream));
+    // on the late stream, where the additions run: ordered with them, and behind any copy to
+    // the host still reading the previous sum
+    if (m->copies_pending)
+    {
+        LBL_CUDA(cudaStreamWaitEvent(m->streams->late, m->ev_copied, 0));
+    }
+    LBL_CUDA(cudaMemsetAsync(m->acc.p, 0, sizeof(double) * (size_t)m->n_layers * m->n,
+                             m->streams->late));
+    LBL_CUDA(cudaEventRecord(m->ev_added, m->streams->late));
     return 0;
 }
 
 int lbl_mix_add(lbl_mix* m, lbl_gas* g, const double* scale)
 {
-    if (!m || !g) return fail("Error: null handle.");
+    if (!m || !g || !scale) return fail("Error: null argument.");
     if (g->device != m->device) return fail("Error: gas and accumulator live on different devices.");
     LBL_CUDA(cudaSetDevice(m->device));
-    if (g->stats.n_layers != m->n_layers || g->last_grid.n != m->n)
+    if (g->pending && lbl_gas_wait(g)) return 1;
+    if (g->stats.n_layers != m->n_layers || g->stats.n_points != m->n)
     {
         return fail("Error: accumulator shape differs from the gas's last call.");
     }
@@ -1547,25 +1818,35 @@ int lbl_mix_add(lbl_mix* m, lbl_gas* g, const double* scale)
     if (g->last_chunk_first != 0 || g->last_chunk_layers != m->n_layers)
     {
         return fail("Error: the gas's spectra are not resident on the device "
-                    "(compute with k_host == NULL and a single layer group).");
+                    "(compute with k_host == NULL and a single layer group, or use lbl_gas_submit_mix).");
     }
-    // The accumulator's stream waits for the gas's kernels; accumulations of different gases
-    // are ordered on that one stream, so the sum needs no atomics.
-    if (g->pending)
-    {
-        LBL_CUDA(cudaStreamWaitEvent(m->stream, g->ev_call_end, 0));
-    }
-    // scale[] is consumed asynchronously: stage it through the stream in order
-    LBL_CUDA(cudaMemcpyAsync(m->scale.p, scale, sizeof(double) * m->n_layers, cudaMemcpyHostToDevice,
-                             m->stream));
+    DevBuf scale_dev;
+    LBL_CUDA(scale_dev.reserve(sizeof(double) * (size_t)m->n_layers));
+    cudaStream_t sl = m->streams->late;
+    LBL_CUDA(cudaMemcpyAsync(scale_dev.p, scale, sizeof(double) * m->n_layers, cudaMemcpyHostToDevice, sl));
     const size_t total = (size_t)m->n_layers * m->n;
     const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
-    mix_add_kernel<<<blocks, 256, 0, m->stream>>>(m->acc.as<double>(),
-                                                  g->out[g->last_slot].as<double>(),
-                                                  m->scale.as<double>(), m->n, m->n_layers);
+    apply_kernel<false, true><<<blocks, 256, 0, sl>>>(g->out[g->last_slot].as<double>(), nullptr,
+                                                      g->last_grid, m->n_layers, m->acc.as<double>(),
+                                                      scale_dev.as<double>());
     LBL_CUDA(cudaGetLastError());
-    // the gas must not start a new call before its spectra have been consumed
-    LBL_CUDA(cudaStreamSynchronize(m->stream));
+    LBL_CUDA(cudaEventRecord(m->ev_added, sl));
+    // the gas's spectra and the staged scales are consumed before anything reuses them
+    LBL_CUDA(cudaStreamSynchronize(sl));
+    scale_dev.release();
+    return 0;
+}
+
+int lbl_mix_wait(lbl_mix* m)
+{
+    if (!m) return fail("Error: null handle.");
+    LBL_CUDA(cudaSetDevice(m->device));
+    LBL_CUDA(cudaEventSynchronize(m->ev_added));
+    if (m->copies_pending)
+    {
+        LBL_CUDA(cudaEventSynchronize(m->ev_copied));
+        m->copies_pending = false;
+    }
     return 0;
 }
 
@@ -1573,9 +1854,20 @@ int lbl_mix_download(lbl_mix* m, double* host)
 {
     if (!m || !host) return fail("Error: null argument.");
     LBL_CUDA(cudaSetDevice(m->device));
+    LBL_CUDA(cudaStreamWaitEvent(m->streams->copy, m->ev_added, 0));
     LBL_CUDA(cudaMemcpyAsync(host, m->acc.p, sizeof(double) * (size_t)m->n_layers * m->n,
-                             cudaMemcpyDeviceToHost, m->stream));
-    LBL_CUDA(cudaStreamSynchronize(m->stream));
+                             cudaMemcpyDeviceToHost, m->streams->copy));
+    LBL_CUDA(cudaEventRecord(m->ev_copied, m->streams->copy));
+    LBL_CUDA(cudaEventSynchronize(m->ev_copied));
+    m->copies_pending = false;
+    return 0;
+}
+
+int lbl_mix_device_result(lbl_mix* m, double** device_ptr, long long* count)
+{
+    if (!m || !device_ptr || !count) return fail("Error: null argument.");
+    *device_ptr = m->acc.as<double>();
+    *count = (long long)m->n_layers * m->n;
     return 0;
 }
 
@@ -1583,9 +1875,10 @@ int lbl_mix_close(lbl_mix* m)
 {
     if (!m) return 0;
     cudaSetDevice(m->device);
+    lbl_mix_wait(m);
     m->acc.release();
-    m->scale.release();
-    if (m->stream) cudaStreamDestroy(m->stream);
+    if (m->ev_added) cudaEventDestroy(m->ev_added);
+    if (m->ev_copied) cudaEventDestroy(m->ev_copied);
     delete m;
     return 0;
 }

@@ -203,6 +203,11 @@ int read_molecule(const char* path, const char* formula, MoleculeData& out, std:
             }
             out.iso_mass[i - 1] = s.column_double(st.st, 1);
         }
+        if (failed)
+        {
+            err = std::string("Error: ") + s.errmsg(con.db);
+            return 1;
+        }
     }
 
     // Line parameters, absorption.c:67-79 + spectral_database.c:163-180.
@@ -226,11 +231,8 @@ int read_molecule(const char* path, const char* formula, MoleculeData& out, std:
                 err = "Error: local_iso_id outside 1..32.";
                 return 1;
             }
-            if (out.has_tips && iso > out.num_iso)
-            {
-                err = "Error: line refers to an isotopologue without TIPS data.";
-                return 1;
-            }
+            // (iso <= num_iso is checked per grid, for the rows the reference would touch:
+            // make_plan in lbl_api.cu)
             const double delta = s.column_double(st.st, 6);
             const double m = out.iso_mass[iso - 1];
             out.nu.push_back(nu);

@@ -217,8 +217,8 @@ sum_cell_kernel(const CellArgs a)
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int layer = blockIdx.y + a.sum.layer0;
-    const int cell0 = (blockIdx.x * kWarps + warp) * G;
-    const bool active = cell0 < g.ncell;      // idle warps of the last block still join the barriers
+    const int cell0 = g.cell_lo + (blockIdx.x * kWarps + warp) * G;
+    const bool active = cell0 < g.cell_hi;    // idle warps of the last block still join the barriers
     const LayerIn ly = a.sum.layers[layer];
     // ten searches, one per lane, shared by shuffle
     int mine = 0;
@@ -233,7 +233,7 @@ sum_cell_kernel(const CellArgs a)
         found[which] = __shfl_sync(0xffffffffu, mine, which);
     }
     const CellSegments seg = cell_segments_from(found);
-    int cells = active ? g.ncell - cell0 : 0;
+    int cells = active ? g.cell_hi - cell0 : 0;
     if (cells > G) cells = G;
 
     // ---- phase 1: far fields at the nodes ------------------------------------------------
@@ -442,7 +442,8 @@ __device__ __forceinline__ void fixup_warp(const SumArgs& a, int tile, int layer
     constexpr int LP = 32 / T;
     int layer = layer_group * LP + lane / T;
     int i = tile * T + lane % T;
-    const bool valid = (layer < a.n_layers) && (i < g.n);
+    const bool valid = (layer < a.n_layers) && (i < g.n) && i >= band_first_point(g) &&
+                       i < band_end_point(g);
     if (layer >= a.n_layers) layer = a.n_layers - 1;
     if (i >= g.n) i = g.n - 1;
     const int t_first = tile * T;
@@ -573,7 +574,7 @@ __device__ __forceinline__ void fixup_warp_staged(const SumArgs& a, int tile, in
 {
     const GridSpec& g = a.grid;
     int i = tile * 32 + lane;
-    const bool valid = i < g.n;
+    const bool valid = i < g.n && i >= band_first_point(g) && i < band_end_point(g);
     if (i >= g.n) i = g.n - 1;
     const int t_first = tile * 32;
     int t_last = t_first + 31;
@@ -787,7 +788,7 @@ near_block_kernel(const SumArgs a)
     __shared__ int batch_count[2];
     const GridSpec& g = a.grid;
     const int layer = blockIdx.y + a.layer0;
-    const int p0 = blockIdx.x * kNbSpan;
+    const int p0 = (a.tile0 + blockIdx.x) * kNbSpan;   // spans of the whole grid, also for a band
     const int p1 = min(p0 + kNbSpan, g.n) - 1;
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -924,7 +925,7 @@ near_block_kernel(const SumArgs a)
     for (int k = threadIdx.x; p0 + k <= p1; k += 128)
     {
         const double total = (acc[0][k] + acc[1][k]) + (acc[2][k] + acc[3][k]);
-        if (total != 0.)
+        if (total != 0. && p0 + k >= band_first_point(g) && p0 + k < band_end_point(g))
         {
             a.out[(size_t)layer * g.n + p0 + k] += total;
         }
@@ -936,7 +937,7 @@ __global__ void __launch_bounds__(128, 10)
 fixup_kernel(const SumArgs a)
 {
     __shared__ int queues[4][kFixQueue];
-    const int tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int tile = a.tile0 + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (T == 32)
     {
         __shared__ __align__(16) NearLine slots[4][32];
@@ -1000,7 +1001,7 @@ pedestal_terms_kernel(const PedArgs a, double* __restrict__ terms)
     const int layer = blockIdx.y;
     const int tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (tile * kPedTileRows >= a.lines.n)
+    if (tile * kPedTileRows >= a.n_rows)
     {
         return;
     }
@@ -1010,7 +1011,7 @@ pedestal_terms_kernel(const PedArgs a, double* __restrict__ terms)
     const int spare = 2 * g.cut_off + 3;
     const int tail_slot = 2 * g.cut_off + 2;
     const int first = tile * kPedTileRows;
-    const int cnt = min(a.lines.n - first, kPedTileRows);
+    const int cnt = min(a.n_rows - first, kPedTileRows);
 
     if (lane < cnt)
     {
@@ -1168,7 +1169,8 @@ pedestal_chain_kernel(const PedArgs a, const double* __restrict__ terms, double*
     constexpr int wpad = 32 * K;
     const int layer = blockIdx.x;
     const int lane = threadIdx.x;
-    const int n = a.lines.n;
+    const int n = a.n_rows;           // rows walked
+    const int stride = a.lines.n;     // rows per layer in the record and term arrays
     const int nb = g.ncell + 2 * g.cut_off + 2;
     double* ring = reinterpret_cast<double*>(smem_raw);
     int4* hdr = reinterpret_cast<int4*>(ring + kPedStages * kPedTile * wpad);
@@ -1180,8 +1182,8 @@ pedestal_chain_kernel(const PedArgs a, const double* __restrict__ terms, double*
     for (int b = lane; b < nb; b += 32) bins[b] = 0.;
     __syncwarp();
 
-    const double* src = terms + (size_t)layer * n * wpad;
-    const LineChk* chk = a.rec.chk + (size_t)layer * n;
+    const double* src = terms + (size_t)layer * stride * wpad;
+    const LineChk* chk = a.rec.chk + (size_t)layer * stride;
     const int ntiles = (n + kPedTile - 1) / kPedTile;
 
     auto issue = [&](int t) {
@@ -1317,19 +1319,38 @@ __global__ void pedestal_cells_kernel(const double* __restrict__ pedbin, GridSpe
     pedestal_cell(pedbin + (size_t)layer * nb, cell, g.cut_off, corr + 2 * (size_t)idx);
 }
 
-// K4b.  k[layer][i] -= pedestal(cell(i), i is the cell's first point).
-__global__ void pedestal_apply_kernel(double* __restrict__ out, const double* __restrict__ corr,
-                                      GridSpec g, int n_layers)
+// K4b.  k[layer][i] -= pedestal(cell(i), i is the cell's first point), over the band's points.
+// With an accumulator (the device-side gas sum, spectroscopy.py:181-191,225-234) the corrected
+// value is not stored but added, scaled, into acc[layer][i - band start]:
+//   acc += scale[layer] * (k - pedestal).
+template <bool kPedestal, bool kMix>
+__global__ void apply_kernel(double* __restrict__ out, const double* __restrict__ corr, GridSpec g,
+                             int n_layers, double* __restrict__ acc, const double* __restrict__ scale)
 {
-    const size_t total = (size_t)n_layers * g.n;
+    const int p_lo = band_first_point(g);
+    const int width = band_end_point(g) - p_lo;
+    const size_t total = (size_t)n_layers * width;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (size_t)gridDim.x * blockDim.x)
     {
-        const int layer = (int)(idx / g.n);
-        const int i = (int)(idx - (size_t)layer * g.n);
-        const int cell = i / g.n_per_v;
-        const int r = i - cell * g.n_per_v;
-        out[idx] -= corr[2 * ((size_t)layer * g.ncell + cell) + (r == 0 ? 1 : 0)];
+        const int layer = (int)(idx / width);
+        const int i = p_lo + (int)(idx - (size_t)layer * width);
+        const size_t o = (size_t)layer * g.n + i;
+        double k = out[o];
+        if (kPedestal)
+        {
+            const int cell = i / g.n_per_v;
+            const int r = i - cell * g.n_per_v;
+            k -= corr[2 * ((size_t)layer * g.ncell + cell) + (r == 0 ? 1 : 0)];
+        }
+        if (kMix)
+        {
+            acc[idx] = fma(scale[layer], k, acc[idx]);
+        }
+        else
+        {
+            out[o] = k;
+        }
     }
 }
 

@@ -10,13 +10,14 @@
 //   f64 tips_t[num_iso*num_t], tips_q[num_iso*num_t]
 //   f64 nu[n], sw[n], gamma_air[n], gamma_self[n], n_air[n], elower[n], delta_air[n], mass[n]
 //   i32 iso[n]  (+ 4 bytes of padding when n is odd)
-//   u64 FNV-1a of everything between header and checksum
+//   u64 FNV-1a of everything before it, header included
 // Rows keep DATABASE ROW ORDER: the reference's early break (absorption.c:80-83) and its
 // accumulated pedestal (spectra.c:66-78) depend on it.
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <unistd.h>
 #include <vector>
 
 #include "lbl_db.h"
@@ -27,7 +28,7 @@ namespace
 {
 
 constexpr char kMagic[8] = {'L', 'B', 'L', 'P', 'A', 'C', 'K', '1'};
-constexpr uint32_t kPackVersion = 1;
+constexpr uint32_t kPackVersion = 2;   // 2: the checksum covers the header too
 
 struct PackHeader
 {
@@ -85,7 +86,9 @@ struct Reader
 int write_pack(const char* path, const char* formula, const MoleculeData& m, long long source_size,
                long long source_mtime, std::string& err)
 {
-    const std::string tmp = std::string(path) + ".tmp";
+    // A name of its own per writer: several ranks may build the same pack at the same time.
+    const std::string tmp = std::string(path) + ".tmp." + std::to_string((long long)getpid()) + "." +
+                            std::to_string((unsigned long long)(uintptr_t)&err);
     FILE* f = fopen(tmp.c_str(), "wb");
     if (!f)
     {
@@ -107,8 +110,9 @@ int write_pack(const char* path, const char* formula, const MoleculeData& m, lon
     strncpy(h.formula, formula, sizeof(h.formula) - 1);
     h.source_size = source_size;
     h.source_mtime = source_mtime;
-    bool ok = fwrite(&h, 1, sizeof(h), f) == sizeof(h);
+    bool ok = true;
     Writer w{f};
+    w.put(&h, sizeof(h));
     w.put(m.tips_t.data(), sizeof(double) * m.tips_t.size());
     w.put(m.tips_q.data(), sizeof(double) * m.tips_q.size());
     const std::vector<double>* cols[8] = {&m.nu, &m.sw, &m.gamma_air, &m.gamma_self,
@@ -122,11 +126,23 @@ int write_pack(const char* path, const char* formula, const MoleculeData& m, lon
     }
     ok = ok && w.ok && fwrite(&w.hash, 1, sizeof(w.hash), f) == sizeof(w.hash);
     ok = (fclose(f) == 0) && ok;
-    if (!ok || rename(tmp.c_str(), path) != 0)   // atomic: readers never see a partial pack
+    if (!ok)
     {
         remove(tmp.c_str());
         err = std::string("Error: writing ") + path + " failed.";
         return 1;
+    }
+    if (rename(tmp.c_str(), path) != 0)   // atomic: readers never see a partial pack
+    {
+        remove(tmp.c_str());
+        // another writer's complete pack already being there is as good as ours
+        FILE* there = fopen(path, "rb");
+        if (!there)
+        {
+            err = std::string("Error: writing ") + path + " failed.";
+            return 1;
+        }
+        fclose(there);
     }
     return 0;
 }
@@ -146,8 +162,10 @@ int read_pack(const char* path, MoleculeData& out, PackInfo& info, bool header_o
         err = std::string("Error: ") + path + " is not a line-list pack.";
         return 1;
     }
+    const bool tips_flag = (h.flags & 1u) != 0;
     if (h.version != kPackVersion || h.n_lines < 0 || h.n_lines > 0x7fffffff || h.num_iso < 0 ||
-        h.num_iso > 32 || h.num_t < 0 || (int64_t)h.num_iso * h.num_t > (1 << 28))
+        h.num_iso > 32 || h.num_t < 0 || (int64_t)h.num_iso * h.num_t > (1 << 28) ||
+        (tips_flag && (h.num_t < 2 || h.num_iso < 1)) || (!tips_flag && (h.num_t != 0 || h.num_iso != 0)))
     {
         fclose(f);
         err = std::string("Error: ") + path + ": unsupported pack version or corrupt header.";
@@ -162,11 +180,6 @@ int read_pack(const char* path, MoleculeData& out, PackInfo& info, bool header_o
     info.has_tips = (h.flags & 1u) != 0;
     info.source_size = h.source_size;
     info.source_mtime = h.source_mtime;
-    if (header_only)
-    {
-        fclose(f);
-        return 0;
-    }
     const size_t n = (size_t)h.n_lines;
     const size_t nt = (size_t)h.num_iso * (size_t)h.num_t;
     out = MoleculeData();
@@ -179,6 +192,7 @@ int read_pack(const char* path, MoleculeData& out, PackInfo& info, bool header_o
     out.min_mass = h.min_mass;
     memcpy(out.iso_mass, h.iso_mass, sizeof(out.iso_mass));
     Reader r{f};
+    r.hash = fnv1a(&h, sizeof(h), r.hash);
     out.tips_t.resize(nt);
     out.tips_q.resize(nt);
     r.get(out.tips_t.data(), sizeof(double) * nt);
@@ -205,6 +219,15 @@ int read_pack(const char* path, MoleculeData& out, PackInfo& info, bool header_o
         err = std::string("Error: ") + path + ": truncated pack or checksum mismatch.";
         return 1;
     }
+    for (size_t i = 0; i < n; ++i)
+    {
+        if (out.iso[i] < 1 || out.iso[i] > 32)
+        {
+            err = std::string("Error: ") + path + ": local_iso_id outside 1..32.";
+            return 1;
+        }
+    }
+    (void)header_only;   // the whole file is always read: the checksum is what vouches for it
     return 0;
 }
 

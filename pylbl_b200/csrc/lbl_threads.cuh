@@ -92,7 +92,15 @@ struct GridSpec
     int n;      // (vn - v0)*n_per_v output points per layer
     int ncell;  // vn - v0
     double dv;  // 1./n_per_v
+    // Spectral band of this call: only the cells [cell_lo, cell_hi) of the grid are computed
+    // (0, ncell = the whole grid).  Windows, the active-line prefix and the pedestal
+    // recurrence are always those of the WHOLE grid (spectra.c:48-62, absorption.c:80-83), so
+    // the bands of a grid, computed separately, are the slices of the whole computation.
+    int cell_lo, cell_hi;
 };
+
+LBL_HD int band_first_point(const GridSpec& g) { return g.cell_lo * g.n_per_v; }
+LBL_HD int band_end_point(const GridSpec& g) { return g.cell_hi * g.n_per_v; }   // exclusive
 
 // Lorentz amplitude A = sw'*gamma/pi of a record (0 for a dropped line).
 LBL_HD double record_amplitude(const FarAB& ab)
@@ -151,6 +159,9 @@ LBL_HD long long scale_thread(const LinesView& ln, const TipsView& tips, const L
     {
         e = g.n - 1;
     }
+    // the band's share of the window
+    if (s < (long long)band_first_point(g)) s = band_first_point(g);
+    if (e > (long long)band_end_point(g) - 1) e = (long long)band_end_point(g) - 1;
     return (e >= s) ? (e - s + 1) : 0;
 }
 
@@ -219,6 +230,8 @@ struct SumArgs
                   // tpw*P consecutive points of 32/tpw consecutive layers
     int near_masked;  // 1: the summation kernel left near-zone points out (K2); 0: it added the
                       // Lorentz form there too (K2c) and K2b must add (profile - Lorentz)
+    int tile0 = 0;    // K2, K2b: first tile / span of this launch (band calls; tiles are always
+                      // those of the whole grid, so that a band reproduces its slice bit for bit)
     int layer0 = 0;   // K2c and K2b<32>: first layer of this launch (grid.y counts from here;
                       // n_layers stays the end bound), so that a group of layers can be summed,
                       // corrected and copied out while the next group computes
@@ -323,7 +336,7 @@ LBL_HD SumLane sum_lane(const SumArgs& a, int layer_group, int tile, int lane)
     s.layer = layer_group * lp + lane / a.tpw;
     const bool layer_ok = s.layer < a.n_layers;
     if (!layer_ok) s.layer = a.n_layers - 1;
-    s.group_first = tile * a.tpw * P;
+    s.group_first = (tile + a.tile0) * a.tpw * P;
     s.any = s.group_first < g.n;
     s.group_last = s.group_first + a.tpw * P - 1;
     if (s.group_last > g.n - 1) s.group_last = g.n - 1;
@@ -1046,8 +1059,10 @@ LBL_HD void fixup_thread(const SumArgs& a, int tile, int layer_group, int lane)
     const GridSpec& g = a.grid;
     constexpr int LP = 32 / T;
     int layer = layer_group * LP + lane / T;
+    tile += a.tile0;
     int i = tile * T + lane % T;
-    const bool valid = (layer < a.n_layers) && (i < g.n);
+    const bool valid = (layer < a.n_layers) && (i < g.n) && i >= band_first_point(g) &&
+                       i < band_end_point(g);
     if (layer >= a.n_layers) layer = a.n_layers - 1;
     if (i >= g.n) i = g.n - 1;
     const int t_first = tile * T;
@@ -1134,6 +1149,8 @@ struct PedArgs
     Records rec;
     GridSpec grid;
     double* pedbin;  // [layer][ncell + 2*cut + 2]
+    int n_rows = 0;  // database rows the recurrence walks (<= lines.n; fewer for a band call on
+                     // a nu-sorted database: rows past the band's last window cannot reach it)
 };
 
 struct PedWindow
@@ -1215,7 +1232,7 @@ LBL_HD void pedestal_terms_tile(const PedArgs& a, int layer, int tile, int lane,
     constexpr int wpad = 32 * K;
     const int spare = 2 * g.cut_off + 3;
     const int first = tile * kPedTileRows;
-    const int cnt = (a.lines.n - first < kPedTileRows) ? a.lines.n - first : kPedTileRows;
+    const int cnt = (a.n_rows - first < kPedTileRows) ? a.n_rows - first : kPedTileRows;
     double run_sum[K];
     int prev_cb = 0;
 #if defined(__CUDA_ARCH__)
@@ -1455,7 +1472,7 @@ LBL_HD void pedestal_layer(const PedArgs& a, int layer, int lane, int nlanes, do
         bins[b] = 0.;
     }
     sync();
-    for (int r = 0; r < a.lines.n; ++r)
+    for (int r = 0; r < a.n_rows; ++r)
     {
         const int j = a.lines.db_to_sorted ? a.lines.db_to_sorted[r] : r;
         const int cb = a.rec.chk[(size_t)layer * a.lines.n + j].cb;

@@ -115,11 +115,14 @@ class Gas(object):
     Attributes:
         database: String path to the spectral sqlite3 database.
         formula: String chemical formula.
-        devices: CUDA device indices this object spreads layers over.
+        devices: CUDA device indices this object spreads a call over.
+        shard: "layer" (contiguous layer shards, one per device) or "band" (contiguous spectral
+               bands of about equal work, one per device; every device computes all layers).
         precision: "fp64" (default) or "fp32".
     """
 
-    def __init__(self, lines_database, formula, devices=None, precision="fp64", cache_dir=None):
+    def __init__(self, lines_database, formula, devices=None, precision="fp64", cache_dir=None,
+                 shard="layer"):
         """Initializes the object.
 
         Args:
@@ -127,6 +130,8 @@ class Gas(object):
                             pyLBL/c_lib/gas_optics.py:43) or a path string.
             formula: String chemical formula.
             devices: int, list of ints, or None (see default_device()).
+            shard: how a call is split over several devices, "layer" or "band" (SURVEY.md 8(e):
+                   layers/columns for many states, spectral bands for one huge spectrum).
             precision: "fp64" or "fp32".
             cache_dir: directory for the packed line-list cache (default: the environment
                        variable PYLBL_B200_CACHE, else no cache).  With a cache the sqlite file
@@ -139,19 +144,43 @@ class Gas(object):
         elif isinstance(devices, int):
             devices = [devices]
         self.devices = list(devices)
+        if shard not in ("layer", "band"):
+            raise ValueError("shard must be 'layer' or 'band'")
+        self.shard = shard
         self.precision = {"fp64": _lib.PRECISION_FP64, "fp32": _lib.PRECISION_FP32}[precision]
         self._handles = {}
         self._cache = {}
         self.last_stats = []
         if cache_dir is None:
             cache_dir = os.environ.get("PYLBL_B200_CACHE") or None
+        self.cache_dir = cache_dir
         self.pack = cached_pack(self.database, formula, cache_dir) if cache_dir else None
 
     # -- handles -----------------------------------------------------------------------
     def _handle(self, device):
         if device not in self._handles:
-            self._handles[device] = _Handle(self.database, self.formula, device, pack=self.pack)
+            try:
+                self._handles[device] = _Handle(self.database, self.formula, device, pack=self.pack)
+            except ValueError:
+                if self.pack is None or not os.path.exists(self.database):
+                    raise
+                # A pack that passed the header check but does not open (truncated or corrupt
+                # payload): read the sqlite file instead and write the pack anew.
+                self._handles[device] = _Handle(self.database, self.formula, device, pack=None)
+                try:
+                    pack_database(self.database, self.formula, self.pack)
+                except ValueError:
+                    self.pack = None
         return self._handles[device]
+
+    def band_edges(self, bounds, n_bands, cut_off=25):
+        """Cell indices edges[0..n_bands] of ``n_bands`` contiguous spectral bands of about equal
+        work on the grid ``bounds = (v0, vn, n_per_v)``; band b is cells [edges[b], edges[b+1])."""
+        v0, vn, n_per_v = bounds
+        edges = np.zeros(n_bands + 1, dtype=np.int32)
+        _lib.library().lbl_gas_band_edges(self._handle(self.devices[0]).ptr, v0, vn, n_per_v,
+                                          int(cut_off), int(n_bands), edges)
+        return edges
 
     def close(self):
         for h in self._handles.values():
@@ -197,8 +226,10 @@ class Gas(object):
             out: optional C-contiguous float64 array (n_layers, n) to fill (e.g. pinned).
             to_host: False leaves the spectra on the device (benchmarks) and returns None.
 
-        Layers are split into contiguous shards, one per device in ``self.devices``; shards
-        are independent, so there is no inter-device communication.
+        With several devices the call is split into contiguous layer shards
+        (``shard="layer"``) or into spectral bands of the grid (``shard="band"``, see
+        ``absorption_band``), one per device; the pieces are independent, so there is no
+        inter-device communication.
         """
         v0, vn, n_per_v = bounds if bounds is not None else grid_to_ints(grid)
         t = np.ascontiguousarray(temperature, dtype=np.float64).ravel()
@@ -213,6 +244,8 @@ class Gas(object):
             raise ValueError("out must be a C-contiguous float64 array of shape (n_layers, n)")
         lib = _lib.library()
         ped = 1 if remove_pedestal else 0
+        if self.shard == "band" and len(self.devices) > 1 and to_host:
+            return self._band_sharded(t, p, x, (v0, vn, n_per_v), ped, int(cut_off), out)
         ndev = max(1, min(len(self.devices), n_layers))
         edges = np.linspace(0, n_layers, ndev + 1).astype(int)
         submitted = []
@@ -249,6 +282,95 @@ class Gas(object):
             lib.lbl_gas_wait(h.ptr)
         self.last_stats = [h.stats() for h in submitted]
         return out if to_host else None
+
+    def submit(self, temperature, pressure, volume_mixing_ratio, grid=None, remove_pedestal=False,
+               cut_off=25, bounds=None, out=None, device_index=0):
+        """Non-blocking ``absorption_coefficients`` on one device: the work is enqueued and the
+        call returns; ``wait()`` completes it.  Several gases submitted back to back overlap on
+        the device (scaling kernels and pedestal chains side by side, summation kernels gas after
+        gas, each gas's copy to the host under the next gas's kernels).  ``out``: C-contiguous
+        float64 (n_layers, n) -- page-locked (``_lib.PinnedArray``) for the copy to be
+        asynchronous -- or None to leave the spectra on the device."""
+        v0, vn, n_per_v = bounds if bounds is not None else grid_to_ints(grid)
+        t = np.ascontiguousarray(temperature, dtype=np.float64).ravel()
+        p = np.ascontiguousarray(pressure, dtype=np.float64).ravel()
+        x = np.ascontiguousarray(volume_mixing_ratio, dtype=np.float64).ravel()
+        n = (vn - v0) * n_per_v
+        if out is not None and (out.shape != (t.size, n) or out.dtype != np.float64
+                                or not out.flags["C_CONTIGUOUS"]):
+            raise ValueError("out must be a C-contiguous float64 array of shape (n_layers, n)")
+        h = self._handle(self.devices[device_index])
+        _lib.library().lbl_gas_submit(h.ptr, t.size, p, t, x, v0, vn, n_per_v, int(cut_off),
+                                      1 if remove_pedestal else 0, self.precision,
+                                      out.ctypes.data_as(c_void_p) if out is not None else None)
+        self._submitted = h
+        return out
+
+    def wait(self):
+        """Completes the last ``submit``; returns its statistics."""
+        h = getattr(self, "_submitted", None)
+        if h is None:
+            return None
+        _lib.library().lbl_gas_wait(h.ptr)
+        self._submitted = None
+        self.last_stats = [h.stats()]
+        return self.last_stats[0]
+
+    def absorption_band(self, temperature, pressure, volume_mixing_ratio, bounds, band,
+                        remove_pedestal=False, cut_off=25, out=None, device_index=0, wait=True):
+        """Cells ``band = (lo, hi)`` of the grid ``bounds``: columns [lo*n_per_v, hi*n_per_v) of
+        what ``absorption_coefficients`` returns for the whole grid, bit for bit (the line
+        windows, the active-line prefix and the pedestal are those of the whole grid).  ``out``
+        may be a column slice of a whole-grid array (rows C-contiguous)."""
+        v0, vn, n_per_v = bounds
+        lo, hi = int(band[0]), int(band[1])
+        t = np.ascontiguousarray(temperature, dtype=np.float64).ravel()
+        p = np.ascontiguousarray(pressure, dtype=np.float64).ravel()
+        x = np.ascontiguousarray(volume_mixing_ratio, dtype=np.float64).ravel()
+        m = (hi - lo) * n_per_v
+        if out is None:
+            out = np.empty((t.size, m))
+        if out.shape != (t.size, m) or out.dtype != np.float64 or out.strides[1] != 8 \
+                or out.strides[0] % 8 or out.strides[0] < 8 * m:
+            raise ValueError("out must be float64 of shape (n_layers, band points), rows contiguous")
+        h = self._handle(self.devices[device_index])
+        _lib.library().lbl_gas_submit_band(h.ptr, t.size, p, t, x, v0, vn, n_per_v, int(cut_off),
+                                           1 if remove_pedestal else 0, self.precision, lo, hi,
+                                           out.ctypes.data_as(c_void_p), out.strides[0] // 8)
+        if wait:
+            _lib.library().lbl_gas_wait(h.ptr)
+            self.last_stats = [h.stats()]
+        return out
+
+    def _band_sharded(self, t, p, x, bounds, ped, cut_off, out):
+        """One band per device (``shard="band"``), every band written into its columns of ``out``."""
+        n_per_v = bounds[2]
+        ndev = len(self.devices)
+        edges = self.band_edges(bounds, ndev, cut_off)
+        errors, handles = [], []
+
+        def work(d):
+            lo, hi = int(edges[d]), int(edges[d + 1])
+            if hi <= lo:
+                return
+            try:
+                self.absorption_band(t, p, x, bounds, (lo, hi), remove_pedestal=bool(ped),
+                                     cut_off=cut_off, out=out[:, lo * n_per_v:hi * n_per_v],
+                                     device_index=d, wait=False)
+                h = self._handle(self.devices[d])
+                _lib.library().lbl_gas_wait(h.ptr)
+                handles.append((d, h))
+            except Exception as exc:  # re-raised below
+                errors.append(exc)
+        threads = [threading.Thread(target=work, args=(d,)) for d in range(ndev)]
+        for th in threads:
+            th.start()
+        for th in threads:
+            th.join()
+        if errors:
+            raise errors[0]
+        self.last_stats = [h.stats() for _, h in sorted(handles, key=lambda e: e[0])]
+        return out
 
     def prefetch(self, temperature, pressure, volume_mixing_ratio, grid, remove_pedestal=False,
                  cut_off=25):

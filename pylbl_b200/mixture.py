@@ -4,7 +4,8 @@ pyLBL's driver turns each gas's cross-sections into absorption coefficients on t
 ``beta = n * k[:grid.size]`` with ``n = p*x/(kB*T)`` (pyLBL/spectroscopy.py:18-29,181-191),
 and sums the gases when ``output_format="total"`` (:225-234).  With every spectrum coming
 back over PCIe that sum costs seven device-to-host copies per column.  ``Mixture`` keeps the
-per-gas spectra on the GPU, applies the number densities there and returns one array.
+per-gas spectra on the GPU, applies the number densities there and returns one array
+(``lbl_gas_submit_mix``: nothing waits on the host between the gases).
 """
 from __future__ import annotations
 
@@ -34,12 +35,28 @@ class Mixture(object):
         self._mix = None
         self._shape = None
 
+        self._owns_gases = True
+
+    @classmethod
+    def from_gases(cls, gases, device=None):
+        """A mixture over existing ``Gas`` objects ({formula: Gas}, all holding ``device``); they
+        stay open when the mixture is closed."""
+        self = cls.__new__(cls)
+        self.device = default_device() if device is None else int(device)
+        self.gases = dict(gases)
+        self._mix = None
+        self._shape = None
+        self._owns_gases = False
+        return self
+
     def close(self):
         if self._mix is not None:
             _lib.library().lbl_mix_close(self._mix)
             self._mix = None
-        for g in self.gases.values():
-            g.close()
+        if self._owns_gases:
+            for g in self.gases.values():
+                g.close()
+        self.gases = {}
 
     def __del__(self):
         try:
@@ -69,14 +86,29 @@ class Mixture(object):
             self._shape = (n_layers, n)
         else:
             lib.lbl_mix_reset(self._mix)
-        for formula, gas in self.gases.items():
-            x = np.ascontiguousarray(volume_mixing_ratio[formula], dtype=np.float64).ravel()
-            gas.absorption_coefficients(t, p, x, bounds=(v0, vn, n_per_v),
-                                        remove_pedestal=remove_pedestal, cut_off=cut_off,
-                                        to_host=False)
-            scale = np.ascontiguousarray(number_density(t, p, x))
-            lib.lbl_mix_add(self._mix, gas._handle(self.device).ptr, scale)
         if out is None:
             out = np.empty((n_layers, n))
-        lib.lbl_mix_download(self._mix, out.ctypes.data_as(c_void_p))
+        if out.shape != (n_layers, n) or out.dtype != np.float64 or not out.flags["C_CONTIGUOUS"]:
+            raise ValueError("out must be a C-contiguous float64 array of shape (n_layers, n)")
+        # Every gas is submitted without waiting for the one before: their scaling kernels and
+        # pedestal chains overlap, the summation kernels run gas after gas, and each gas is
+        # added into the accumulator on the device as soon as it is done.  The gas with the most
+        # lines goes last; its layer groups are copied to the host while the next ones compute.
+        order = sorted(self.gases.items(), key=lambda item: item[1]._handle(self.device).stats()["n_lines"])
+        handles = []
+        for i, (formula, gas) in enumerate(order):
+            x = np.ascontiguousarray(volume_mixing_ratio[formula], dtype=np.float64).ravel()
+            scale = np.ascontiguousarray(number_density(t, p, x))
+            h = gas._handle(self.device)
+            last = i == len(order) - 1
+            lib.lbl_gas_submit_mix(h.ptr, n_layers, p, t, x, v0, vn, n_per_v, int(cut_off),
+                                   1 if remove_pedestal else 0, gas.precision, self._mix, 0, scale,
+                                   out.ctypes.data_as(c_void_p) if last else None)
+            handles.append((gas, h))
+        lib.lbl_mix_wait(self._mix)
+        for gas, h in handles:
+            lib.lbl_gas_wait(h.ptr)
+            gas.last_stats = [h.stats()]
+        if not handles:
+            out[:] = 0.
         return out

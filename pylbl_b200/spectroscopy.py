@@ -59,25 +59,48 @@ class Spectroscopy(object):
         self.precision = precision
         self.cache_dir = cache_dir
         self.cache = {}          # formula -> Gas, or None when the database has no such molecule
+        self._pinned = {}        # formula -> PinnedArray (staging of the per-gas formats)
+
+    PINNED_LIMIT = 2 << 30
 
     def _gas(self, name):
-        """The reference tolerates molecules without line data (``gas = None``,
-        pyLBL/spectroscopy.py:53-57)."""
+        """The reference tolerates molecules the database has no line data for (``gas = None``
+        on AliasNotFoundError / IsotopologuesNotFoundError / TipsDataNotFoundError /
+        TransitionsNotFoundError, pyLBL/spectroscopy.py:53-57) -- and nothing else: a missing
+        database file, a CUDA failure or a corrupt cache still raise.  (A molecule without TIPS
+        rows or without transitions opens and yields zeros, pyLBL/c_lib/absorption.c:53-59.)"""
         if name not in self.cache:
             try:
                 gas = Gas(self.database, name, devices=[self.device], precision=self.precision,
                           cache_dir=self.cache_dir)
                 gas._handle(self.device)
             except ValueError:
+                if "not found in database" not in _lib.last_error():
+                    raise
                 gas = None
             self.cache[name] = gas
         return self.cache[name]
+
+    def _staging(self, name, shape):
+        """Page-locked destination of one gas's spectra, kept across calls (device-to-host
+        copies into pageable memory are synchronous: the gases would run one after the other).
+        Beyond PINNED_LIMIT bytes per gas an ordinary array is used."""
+        count = int(np.prod(shape))
+        if count * 8 > self.PINNED_LIMIT:
+            return np.empty(shape)
+        held = self._pinned.get(name)
+        if held is None or held.array.size < count:
+            self._pinned.pop(name, None)
+            held = _lib.PinnedArray((count,))
+            self._pinned[name] = held
+        return held.array[:count].reshape(shape)
 
     def close(self):
         for gas in self.cache.values():
             if gas is not None:
                 gas.close()
         self.cache = {}
+        self._pinned = {}
 
     def compute_absorption(self, output_format="all", remove_pedestal=None, cut_off=25):
         """Absorption coefficients [m-1], pyLBL/spectroscopy.py:144-206.
@@ -109,16 +132,12 @@ class Spectroscopy(object):
             total = np.zeros((t.size, size))
             names = [name for name, gas in present.items() if gas is not None]
             if names:
-                mix = Mixture.__new__(Mixture)      # share this object's handles
-                mix.device, mix.gases, mix._mix, mix._shape = \
-                    self.device, {n: present[n] for n in names}, None, None
+                mix = Mixture.from_gases({n: present[n] for n in names}, self.device)
                 k = mix.total_absorption(t, p, {n: self.gases[n].ravel() for n in names},
                                          bounds=(v0, vn, n_per_v), remove_pedestal=remove_pedestal,
                                          cut_off=cut_off)
                 total = k[:, :size]
-                _lib.library().lbl_mix_close(mix._mix)
-                mix._mix = None
-                mix.gases = {}
+                mix.close()
             out["absorption"] = total.reshape(shape + (size,))
             return out
 
@@ -131,7 +150,7 @@ class Spectroscopy(object):
             if gas is None:
                 continue
             x = np.ascontiguousarray(self.gases[name].ravel())
-            k = np.empty((t.size, n_k))
+            k = self._staging(name, (t.size, n_k))
             h = gas._handle(self.device)
             lib.lbl_gas_submit(h.ptr, t.size, p, t, x, v0, vn, n_per_v, int(cut_off), ped,
                                gas.precision, k.ctypes.data_as(c_void_p))

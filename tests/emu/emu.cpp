@@ -201,6 +201,8 @@ extern "C" int emu_absorption(int n_layers, const double* pressure, const double
     g.cut_off = cut_off;
     g.n = (vn - v0) * n_per_v;
     g.ncell = vn - v0;
+    g.cell_lo = 0;
+    g.cell_hi = vn - v0;
     g.dv = 1. / n_per_v;
     std::memset(k, 0, sizeof(double) * (size_t)n_layers * g.n);
     *n_evals = 0;
@@ -354,6 +356,7 @@ extern "C" int emu_absorption(int n_layers, const double* pressure, const double
         pa.rec = rec;
         pa.grid = g;
         pa.pedbin = pedbin.data();
+        pa.n_rows = ln.n;
         for (int l = 0; l < n_layers; ++l)
         {
             switch ((2 * cut_off + 5 + 31) / 32)

@@ -1,7 +1,7 @@
 """BASELINE.json configurations at full size on the GPU.
 
-Where the oracle finishes in seconds it is the judge (configs 1, 3, the small gases of 2, one
-band of 4).  Where it does not, size-independent properties are: superposition (the spectrum
+Where the oracle finishes in seconds it is the judge (config 1; every gas of config 2 on three
+layers; two layers of config 3; two bands of 4).  Beyond that, size-independent properties are: superposition (the spectrum
 of a line list is the sum of the spectra of a partition of it), band decomposition (a band
 computed from a database pre-filtered to [v0-26, vn+26] equals the same slice of the wide
 computation), and the evaluation count (sum of window lengths), which is known in closed
@@ -43,22 +43,51 @@ def test_config1_full_size(db_dir):
             assert gas.last_stats[0]["evals"] == ref.last_evals
 
 
-def test_config2_small_gases_and_superposition(db_dir):
-    """configs[1]: 60-layer column, 7 gases, 1-5000 @0.01 (500 000 points per spectrum)."""
+CONFIG2_DENSE = ("H2O", "CO2", "O3", "N2O", "CH4")     # 6-18 lines per cm-1: the far-field kernel K2c
+CONFIG2_SPARSE = ("CO", "O2")                          # < 0.8 lines per cm-1: the direct kernel K2
+
+
+@pytest.fixture(scope="module")
+def config2(db_dir):
     lists = synth.config_line_lists(2)
     path = str(db_dir / "c2.db")
     synth.write_database(path, lists)
+    return path, lists
+
+
+@pytest.mark.parametrize("formula", CONFIG2_DENSE + CONFIG2_SPARSE)
+def test_config2_every_gas_against_the_oracle(config2, formula):
+    """configs[1], the benchmark's workload: 60-layer column, 1-5000 @0.01 (500 000 points per
+    spectrum).  Every gas against the oracle on three layers (surface, tropopause, top), without
+    the pedestal pointwise and with it in the window-scaled metric, and the kernel that
+    `bench.py` times must be the one that ran: the far-field kernel for the five dense gases."""
+    path, _ = config2
     col = synth.standard_column(60)
     bounds = synth.config_grid(2)
-    # direct parity for the two short line lists, a few layers, pedestal on
-    for formula in ("CO", "O2"):
-        gas, ref = Gas(path, formula), OracleGas(path, formula)
+    layers = [0, 31, 59]
+    gas, ref = Gas(path, formula), OracleGas(path, formula)
+    for ped in (False, True):
         k = gas.absorption_coefficients(col.t, col.p, col.vmr[formula], bounds=bounds,
-                                        remove_pedestal=True)
-        for layer in (0, 31, 59):
-            k_ref = ref.absorption(col.t[layer], col.p[layer], col.vmr[formula][layer], *bounds, True)
+                                        remove_pedestal=ped)
+        stats = gas.last_stats[0]
+        if formula in CONFIG2_DENSE:
+            assert stats["cells_per_warp"] > 0, "the selector routed a dense gas around K2c"
+        else:
+            assert stats["cells_per_warp"] == 0
+        for layer in layers:
+            k_ref = ref.absorption(col.t[layer], col.p[layer], col.vmr[formula][layer], *bounds, ped)
+            assert np.any(k_ref)
             assert scaled_error(k[layer], k_ref, bounds[2]) <= FP64_TOL
-    # superposition at full size: H2O = odd lines + even lines (no pedestal: it is not linear)
+            if not ped:
+                assert relative_error(k[layer], k_ref) <= FP64_TOL
+    gas.close()
+
+
+def test_config2_superposition(config2, db_dir):
+    """Superposition at full size: H2O = odd lines + even lines (no pedestal: it is not linear)."""
+    path, lists = config2
+    col = synth.standard_column(60)
+    bounds = synth.config_grid(2)
     h2o = lists["H2O"]
     halves = []
     for parity in (0, 1):
@@ -76,20 +105,59 @@ def test_config2_small_gases_and_superposition(db_dir):
     assert relative_error(parts, whole) <= 1e-10
 
 
+@pytest.mark.parametrize("config", [2, 3, 4])
+def test_far_field_kernel_against_the_direct_kernel(db_dir, config, monkeypatch):
+    """K2c (forced, PYLBL_B200_FARFIELD=2) against the direct kernel K2 (=0) on the fine
+    BASELINE grids, pedestal off, pointwise: the interpolated far field must stay within
+    1e-11 of the sum it replaces (a hundredth of the parity budget)."""
+    formula = {2: "N2O", 3: "CO2", 4: "XX"}[config]
+    path = str(db_dir / f"ff{config}.db")
+    if config == 4:
+        # one band of the million-line list (the direct kernel on the whole of it is slow)
+        lines = synth.config_line_lists(4)["XX"]
+        keep = (lines["nu"] >= 2000 - 26) & (lines["nu"] <= 2040 + 26)
+        synth.write_database(path, {"XX": {key: val[keep] for key, val in lines.items()}})
+        bounds = (2000, 2040, 1000)
+    else:
+        synth.write_database(path, {formula: synth.config_line_lists(config)[formula]})
+        bounds = synth.config_grid(config)
+    col = synth.standard_column(60)
+    layers = [0, 59] if config != 3 else [0, 30, 59]
+    t, p, x = col.t[layers], col.p[layers], col.vmr[formula][layers]
+    gas = Gas(path, formula)
+    monkeypatch.setenv("PYLBL_B200_FARFIELD", "2")
+    far = gas.absorption_coefficients(t, p, x, bounds=bounds)
+    assert gas.last_stats[0]["cells_per_warp"] > 0
+    monkeypatch.setenv("PYLBL_B200_FARFIELD", "0")
+    direct = gas.absorption_coefficients(t, p, x, bounds=bounds)
+    assert gas.last_stats[0]["cells_per_warp"] == 0
+    assert np.all(direct > 0)
+    assert relative_error(far, direct) <= 1e-11
+    gas.close()
+
+
 def test_config3_dense_band(db_dir):
-    """configs[2]: CO2 15-um band 500-850 cm-1 @0.0005 (702 000 points), ~60k lines."""
+    """configs[2]: CO2 15-um band 500-850 cm-1 @0.0005 (702 000 points), ~60k lines.  Two layers:
+    mid-troposphere (y ~ 1) and the top of the column (10 Pa: y << 1, where the near zone is
+    CPF12 territory); without the pedestal pointwise, with it in the window-scaled metric."""
     path = str(db_dir / "c3.db")
     synth.write_database(path, synth.config_line_lists(3))
     col = synth.standard_column(60)
     bounds = synth.config_grid(3)
     gas, ref = Gas(path, "CO2"), OracleGas(path, "CO2")
-    layer = 25
-    k = gas.absorption_coefficients(col.t[layer:layer + 1], col.p[layer:layer + 1],
-                                    col.vmr["CO2"][layer:layer + 1], bounds=bounds,
-                                    remove_pedestal=True)[0]
-    k_ref = ref.absorption(col.t[layer], col.p[layer], col.vmr["CO2"][layer], *bounds, True)
-    assert scaled_error(k, k_ref, bounds[2]) <= FP64_TOL
-    assert gas.last_stats[0]["evals"] == ref.last_evals
+    layers = [25, 59]
+    for ped in (False, True):
+        k = gas.absorption_coefficients(col.t[layers], col.p[layers], col.vmr["CO2"][layers],
+                                        bounds=bounds, remove_pedestal=ped)
+        assert gas.last_stats[0]["cells_per_warp"] > 0
+        total = 0
+        for row, layer in enumerate(layers):
+            k_ref = ref.absorption(col.t[layer], col.p[layer], col.vmr["CO2"][layer], *bounds, ped)
+            total += ref.last_evals
+            assert scaled_error(k[row], k_ref, bounds[2]) <= FP64_TOL
+            if not ped:
+                assert relative_error(k[row], k_ref) <= FP64_TOL
+        assert gas.last_stats[0]["evals"] == total
 
 
 def test_config4_million_lines_bands(db_dir):

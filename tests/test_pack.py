@@ -57,6 +57,46 @@ def test_cached_pack_refreshes_when_database_changes(small_db, tmp_path):
     assert pack_info(first)["source_mtime"] == int(os.stat(db).st_mtime)
 
 
+def test_corrupt_pack_is_detected_without_a_gpu_and_rebuilt(small_db, tmp_path):
+    """The checksum covers header and payload, and `pack_info` verifies it: a pack whose stamps
+    still match the database but whose bytes are damaged is rewritten by `cached_pack`."""
+    db, _ = small_db
+    cache = str(tmp_path / "cache")
+    pack = cached_pack(db, "CO2", cache)
+    good = open(pack, "rb").read()
+    for where in (40, len(good) // 2, len(good) - 3):       # header field, payload, checksum
+        bad = bytearray(good)
+        bad[where] ^= 0x01
+        open(pack, "wb").write(bytes(bad))
+        with pytest.raises(ValueError):
+            pack_info(pack)
+        assert cached_pack(db, "CO2", cache) == pack
+        assert open(pack, "rb").read() == good
+
+
+def test_concurrent_writers_leave_one_good_pack(small_db, tmp_path):
+    """Several ranks sharing PYLBL_B200_CACHE write the same pack at the same time."""
+    import threading
+    db, _ = small_db
+    target = str(tmp_path / "shared.lblpack")
+    errors = []
+
+    def work():
+        try:
+            for _ in range(5):
+                pack_database(db, "O3", target)
+        except Exception as exc:
+            errors.append(exc)
+    threads = [threading.Thread(target=work) for _ in range(6)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors
+    assert pack_info(target)["formula"] == "O3"
+    assert [f for f in os.listdir(tmp_path) if ".tmp." in f] == []
+
+
 @pytest.mark.gpu
 def test_pack_handle_is_bit_identical(small_db, tmp_path):
     db, _ = small_db

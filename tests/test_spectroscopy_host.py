@@ -48,3 +48,33 @@ def test_mechanism_axis_and_number_density_follow_the_reference():
     assert MECHANISMS == ["lines", "continuum", "cross_section"]
     n = number_density(288.99, 98388., 6.637074e-3)
     assert n == pytest.approx(98388. * 6.637074e-3 / (1.38064852e-23 * 288.99), rel=1e-15)
+
+
+def test_only_a_missing_molecule_is_tolerated(small_db):
+    """pyLBL/spectroscopy.py:53-57 sets gas = None for molecules the database has no data for
+    -- and for nothing else.  A database that cannot be opened must raise, not come back as an
+    all-zero spectrum."""
+    grid = np.arange(1., 11., 0.01)
+    a = atmosphere()
+    a["gases"]["XeF6"] = np.full((2, 3), 1e-9)
+    s = Spectroscopy(a, grid, small_db)
+    assert s._gas("XeF6") is None                      # alias not in the database
+    bad = Spectroscopy(atmosphere(), grid, "/nonexistent/dir/file.db")
+    with pytest.raises(ValueError):
+        bad._gas("H2O")
+    for fmt in ("gas", "total"):
+        with pytest.raises(ValueError):
+            bad.compute_absorption(fmt)
+
+
+def test_band_edges_partition_the_grid(small_db):
+    """Band sharding: contiguous cell ranges that cover the grid once, balanced
+    by a cost model of the lines in and next to each cell.  Needs no GPU work -- but a handle,
+    so it is skipped where none can be opened."""
+    from pylbl_b200 import Gas, _lib
+    if _lib.device_count() == 0:
+        pytest.skip("a handle needs a CUDA device")
+    gas = Gas(small_db, "CO2")
+    for n_bands in (1, 2, 3, 8):
+        edges = gas.band_edges((1, 2001, 100), n_bands)
+        assert edges[0] == 0 and edges[-1] == 2000 and np.all(np.diff(edges) >= 0)
