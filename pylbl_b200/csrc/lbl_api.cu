@@ -148,7 +148,7 @@ struct lbl_gas
     size_t group_budget = (size_t)6 << 30;   // bytes per layer group, see lbl_gas_submit
     int copy_groups = 0;                     // lbl_gas_set_copy_groups (0 = automatic)
     DevBuf rec_ab, rec_cc, rec_chk, rec_gen, layers_dev, evals_dev, pedbin, pedcorr, pednodes,
-        pedterms, rec_f32, amp_max, cheb_nodes, cheb_weights, cheb_nodes16, cheb_weights16, cheb_nodes8, cheb_weights8,
+        pedterms, rec_f32, amp_max, cell_keys, cheb_nodes, cheb_weights, cheb_nodes16, cheb_weights16, cheb_nodes8, cheb_weights8,
         executed_dev;
     int cheb_npv = 0;
     unsigned long long* executed_host = nullptr;  // pinned
@@ -825,7 +825,7 @@ int lbl_gas_close(lbl_gas* g)
     g->plan.cell_first.release();
     for (DevBuf* b : {&g->tips_t, &g->tips_q, &g->rec_ab, &g->rec_cc, &g->rec_chk, &g->rec_gen,
                       &g->layers_dev, &g->evals_dev, &g->pedbin, &g->pedcorr, &g->pednodes,
-                      &g->pedterms, &g->rec_f32, &g->amp_max, &g->cheb_nodes, &g->cheb_weights,
+                      &g->pedterms, &g->rec_f32, &g->amp_max, &g->cell_keys, &g->cheb_nodes, &g->cheb_weights,
                       &g->cheb_nodes16, &g->cheb_weights16, &g->cheb_nodes8, &g->cheb_weights8,
                       &g->executed_dev,
                       &g->out[0], &g->out[1]})
@@ -1014,6 +1014,18 @@ static int submit_call(lbl_gas* g, const CallSpec& call)
     // in FP64 than K2 is in FP32, so the request is honoured with FP64 arithmetic there.
     const bool fp32 = fp32_requested && !farfield;
     st.fp32_used = fp32 ? 1 : 0;
+    // cells per warp of K2c: two cells share the loads of the 32-node lines, but one cell per
+    // warp needs fewer registers (8 resident blocks per SM) and has no per-cell window edges
+    // inside the group; measured faster on every BASELINE grid
+    int cells_per_warp = 0;
+    if (farfield)
+    {
+        cells_per_warp = 1;
+        if (const char* env = getenv("PYLBL_B200_CELLS")) cells_per_warp = atoi(env) == 2 ? 2 : 1;
+    }
+    const int cell_groups = farfield ? (grid.cell_hi - grid.cell_lo + cells_per_warp - 1) / cells_per_warp : 0;
+    bool hoisted_keys = farfield;
+    if (const char* env = getenv("PYLBL_B200_KEYS")) hoisted_keys = farfield && atoi(env) != 0;
     const int P = farfield ? kCellP : pick_points_per_thread(n_per_v);
     st.points_per_thread = P;
 
@@ -1097,6 +1109,10 @@ static int submit_call(lbl_gas* g, const CallSpec& call)
     {
         LBL_CUDA(g->rec_f32.reserve(sizeof(Far32) * (size_t)plan.n_active * chunk));
         LBL_CUDA(g->amp_max.reserve(sizeof(unsigned long long) * (size_t)n_layers));
+    }
+    if (hoisted_keys)
+    {
+        LBL_CUDA(g->cell_keys.reserve(sizeof(int) * kKeyStride * (size_t)cell_groups * chunk));
     }
     LBL_CUDA(g->layers_dev.reserve(sizeof(LayerIn) * (size_t)n_layers));
     LBL_CUDA(g->evals_dev.reserve(sizeof(unsigned long long) * (size_t)n_layers));
@@ -1287,6 +1303,13 @@ static int submit_call(lbl_gas* g, const CallSpec& call)
                 far32_kernel<<<grid1, kScaleBlock, 0, sc>>>(rec, plan.n_active);
                 st.total_launches++;
             }
+            if (hoisted_keys)
+            {
+                dim3 gridk((cell_groups * kKeyStride + 255) / 256, nl);
+                cell_keys_kernel<<<gridk, 256, 0, sc>>>(lines, grid, layers_c, cells_per_warp, cell_groups,
+                                                        g->cell_keys.as<int>());
+                st.total_launches++;
+            }
         }
         LBL_CUDA(cudaEventRecord(ev.k1_end, sc));
 
@@ -1335,7 +1358,6 @@ static int submit_call(lbl_gas* g, const CallSpec& call)
         sa.tpw = pick_threads_per_layer(n_per_v, P, nl);
         sa.near_masked = farfield ? 0 : 1;
         CellArgs ca;
-        int cells_per_warp = 0;
         if (farfield)
         {
             ca.node_offset = g->cheb_nodes.as<double>();
@@ -1345,11 +1367,8 @@ static int submit_call(lbl_gas* g, const CallSpec& call)
             ca.node_offset8 = g->cheb_nodes8.as<double>();
             ca.transform8 = g->cheb_weights8.as<double>();
             ca.executed = g->executed_dev.as<unsigned long long>();
-            // cells per warp: two cells share the loads of the 32-node lines, but one cell per
-            // warp needs fewer registers (8 resident blocks per SM) and has no per-cell window
-            // edges inside the group; measured faster on every BASELINE grid
-            cells_per_warp = 1;
-            if (const char* env = getenv("PYLBL_B200_CELLS")) cells_per_warp = atoi(env) == 2 ? 2 : 1;
+            ca.keys = hoisted_keys ? g->cell_keys.as<int>() : nullptr;
+            ca.key_groups = cell_groups;
             st.cells_per_warp = cells_per_warp;
         }
         // Layer groups of this chunk: each is summed (main stream), corrected and copied out
@@ -1383,7 +1402,8 @@ static int submit_call(lbl_gas* g, const CallSpec& call)
             if (farfield)
             {
                 ca.sum = sa;
-                const int groups = (grid.cell_hi - grid.cell_lo + cells_per_warp - 1) / cells_per_warp;
+                ca.key_layer0 = q0;
+                const int groups = cell_groups;
                 dim3 gridc((groups + kSumBlock / 32 - 1) / (kSumBlock / 32), q1 - q0);
                 // 23 KB of static shared memory per block: ask for the large carve-out so that
                 // shared memory does not cap the resident blocks below the register limit.

@@ -176,6 +176,20 @@ LBL_HD double far_term(double v, double a, double b, double c, double acc)
     return fma_(r0, e2, acc);
 }
 
+// The same term with the seed's low word borrowed from d, as far_terms() forms it: the near-zone
+// kernels take the Lorentz form back with THIS function at points where the summation kernel
+// added it through far_terms(), so that both sides hold the same bits.  (Close to a line centre
+// at low pressure the Lorentz form is 1/(sqrt(pi)*y) times the true profile, 1e4 and more: a
+// difference of 1e-12 between two ways of forming it would be 1e-8 of the result.)
+LBL_HD double far_term_lo(double v, double a, double b, double c, double acc)
+{
+    double d = fma_(v, a, b);
+    double q = fma_(d, d, c);
+    double r0 = rcp_seed_lo(q, d);
+    double e2 = fma_(-q, r0, 2.0);
+    return fma_(r0, e2, acc);
+}
+
 // The same arithmetic for P points at once, written stage by stage so that the P
 // independent dependency chains are interleaved in the instruction stream (the in-order
 // warp scheduler cannot do that by itself): all d, then all q, all seeds, all corrections.

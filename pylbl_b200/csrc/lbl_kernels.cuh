@@ -201,6 +201,27 @@ __device__ __forceinline__ double node16_plain_staged(const double2* __restrict_
     return (acc[0] + acc[1]) + (acc[2] + acc[3]);
 }
 
+// K2c prologue, hoisted out of the summation kernel: the ten range searches of every
+// (layer, cell group) -- 4-7 dependent loads each -- are done here, one search per thread, so
+// that a warp of the summation kernel starts from one coalesced 40-byte load instead of a chain
+// of dependent ones.  grid = (ceil(groups*16/256), layers of the chunk).
+__global__ void __launch_bounds__(256)
+cell_keys_kernel(LinesView lines, GridSpec g, const LayerIn* __restrict__ layers, int cells_per_group,
+                 int groups, int* __restrict__ keys)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int group = idx / kKeyStride;
+    const int which = idx - group * kKeyStride;
+    if (group >= groups || which >= kCellKeys)
+    {
+        return;
+    }
+    const int layer = blockIdx.y;
+    const int cell0 = g.cell_lo + group * cells_per_group;
+    keys[((size_t)layer * groups + group) * kKeyStride + which] =
+        first_line_at(lines, cell_search_key(g, layers[layer], cell0, cells_per_group, which));
+}
+
 template <int G>
 __global__ void __launch_bounds__(kSumBlock, 8)
 sum_cell_kernel(const CellArgs a)
@@ -219,12 +240,19 @@ sum_cell_kernel(const CellArgs a)
     const int layer = blockIdx.y + a.sum.layer0;
     const int cell0 = g.cell_lo + (blockIdx.x * kWarps + warp) * G;
     const bool active = cell0 < g.cell_hi;    // idle warps of the last block still join the barriers
-    const LayerIn ly = a.sum.layers[layer];
-    // ten searches, one per lane, shared by shuffle
+    // the ten range boundaries, one per lane, shared by shuffle
     int mine = 0;
     if (active && lane < kCellKeys)
     {
-        mine = first_line_at(a.sum.lines, cell_search_key(g, ly, cell0, G, lane));
+        if (a.keys)
+        {
+            const size_t row = (size_t)(blockIdx.y + a.key_layer0) * a.key_groups + (blockIdx.x * kWarps + warp);
+            mine = __ldg(a.keys + row * kKeyStride + lane);
+        }
+        else
+        {
+            mine = first_line_at(a.sum.lines, cell_search_key(g, a.sum.layers[layer], cell0, G, lane));
+        }
     }
     int found[kCellKeys];
 #pragma unroll
@@ -494,7 +522,7 @@ __device__ __forceinline__ void fixup_warp(const SumArgs& a, int tile, int layer
                     {
                         // the summation kernel added the Lorentz form here: take it back
                         const double2 l = __ldg(reinterpret_cast<const double2*>(a.rec.ab + off + j));
-                        acc -= far_term(v, l.x, l.y, __ldg(a.rec.cc + off + j), 0.);
+                        acc -= far_term_lo(v, l.x, l.y, __ldg(a.rec.cc + off + j), 0.);
                     }
                     if (abx >= voigt_outer_limit(g1.x, g2.x, g2.y))
                     {
@@ -740,22 +768,36 @@ __device__ __forceinline__ void fixup_warp_staged(const SumArgs& a, int tile, in
 // ---------------------------------------------------------------------------------------
 constexpr int kNbSpan = 512;
 constexpr int kNbBatch = 64;
+constexpr int kNbQueue = 64;   // entries per queue: at most 31 left over + 32 new
 
-__device__ __forceinline__ void near_block_drain(const SumArgs& a, const int* q, int cnt, int lane,
-                                                 int layer, int p0, double* mine)
+// Drains `cnt` (<= 32) queued (slot, point) pairs with the lanes packed: lane e evaluates entry
+// e -- region 2 of W4 (kInner == false) or region 3 / CPF12 (kInner == true), plus the Lorentz
+// form taken back where the summation kernel added it -- and adds it to its point.
+template <bool kInner>
+__device__ __forceinline__ void near_block_drain(const GridSpec& g, const NearLine* slots, const int* q,
+                                                 int cnt, int lane, int p0, double* mine)
 {
-    const GridSpec& g = a.grid;
-    const int e = lane < cnt ? lane : 0;
-    const int jj = q[2 * e];
-    const int i = q[2 * e + 1];
+    const int entry = q[lane < cnt ? lane : 0];
+    const int k = entry & 0xffff;          // point, relative to the span
     double val = 0.;
     bool pending = lane < cnt;
     if (pending)
     {
-        const LineGen* gp = a.rec.gen + (size_t)layer * a.lines.n + jj;
-        const double2 g0 = __ldg(reinterpret_cast<const double2*>(gp));
-        const double2 g1 = __ldg(reinterpret_cast<const double2*>(gp) + 1);
-        val = g1.y * voigt_inner((grid_point(g.v0, g.dv, i) - g0.x) * g0.y, g1.x);
+        const NearLine& nl = slots[entry >> 16];
+        const double v = grid_point(g.v0, g.dv, p0 + k);
+        const double xi = (v - nl.nu) * nl.repwid;
+        if (kInner)
+        {
+            val = nl.cof * voigt_inner(xi, nl.y);
+        }
+        else
+        {
+            val = nl.cof * voigt_region2(xi * xi, nl.y);
+        }
+        if ((nl.tag & 1) == 0)
+        {
+            val -= far_term_lo(v, nl.a, nl.b, nl.c, 0.);   // the bits the summation kernel added
+        }
     }
     // Two entries may name the same point (two lines' cores overlapping): the lowest lane of
     // each group of equal points goes first, the others in later rounds.
@@ -768,13 +810,43 @@ __device__ __forceinline__ void near_block_drain(const SumArgs& a, const int* q,
         }
         if (pending)
         {
-            const unsigned peers = __match_any_sync(todo, i);
+            const unsigned peers = __match_any_sync(todo, k);
             if (lane == __ffs(peers) - 1)
             {
-                mine[i - p0] += val;
+                mine[k] += val;
                 pending = false;
             }
         }
+        __syncwarp();
+    }
+}
+
+// Appends the lanes flagged `push` to a queue (lane-compacted) and drains a full warp's worth.
+template <bool kInner>
+__device__ __forceinline__ void near_block_push(const GridSpec& g, const NearLine* slots, int* q, int& qn,
+                                                bool push, int entry, int lane, unsigned below, int p0,
+                                                double* mine)
+{
+    const unsigned m = __ballot_sync(0xffffffffu, push);
+    if (m == 0)
+    {
+        return;
+    }
+    if (push)
+    {
+        q[qn + __popc(m & below)] = entry;
+    }
+    qn += __popc(m);
+    __syncwarp();
+    if (qn >= 32)
+    {
+        near_block_drain<kInner>(g, slots, q, 32, lane, p0, mine);
+        __syncwarp();
+        const int keep = qn - 32;
+        const int moved = (lane < keep) ? q[32 + lane] : 0;
+        __syncwarp();
+        if (lane < keep) q[lane] = moved;
+        qn = keep;
         __syncwarp();
     }
 }
@@ -784,7 +856,7 @@ near_block_kernel(const SumArgs a)
 {
     __shared__ double acc[4][kNbSpan];
     __shared__ __align__(16) NearLine slots[kNbBatch];
-    __shared__ int queues[4][2 * kFixQueue];
+    __shared__ int queues[4][2][kNbQueue];
     __shared__ int batch_count[2];
     const GridSpec& g = a.grid;
     const int layer = blockIdx.y + a.layer0;
@@ -801,8 +873,9 @@ near_block_kernel(const SumArgs a)
     const LineChk* chk = a.rec.chk + off;
     const LineGen* gen = a.rec.gen + off;
     double* mine = acc[warp];
-    int* q = queues[warp];
-    int qn = 0;
+    int* q_r2 = queues[warp][0];      // W4 region 2: a short rational
+    int* q_in = queues[warp][1];      // W4 region 3 / CPF12: long
+    int n_r2 = 0, n_in = 0;
 
     int jlo, jhi;
     near_candidates(a.lines, g, ly, p0, p1, jlo, jhi);
@@ -839,46 +912,53 @@ near_block_kernel(const SumArgs a)
         const int n_listed = batch_count[0] + batch_count[1];
         for (int s = warp; s < n_listed; s += 4)
         {
+            // The line's constants live in registers for the walk over its zone; the stores to
+            // the accumulator stripe would otherwise force a reload from shared memory per point.
             const NearLine& nl = slots[s];
-            const int zhi = nl.nhi;
-            for (int i0 = nl.nlo; i0 <= zhi; i0 += 32)
+            const int zlo = nl.nlo, zhi = nl.nhi;
+            const bool lorentz_added = (nl.tag & 1) == 0;
+            const double nu = nl.nu, repwid = nl.repwid, lim_outer = nl.lim_outer, lim_r2 = nl.lim_r2;
+            const double xlim0 = nl.xlim0, ax = nl.ax, d0 = nl.d0, d2 = nl.d2, n0 = nl.n0, yq = nl.yq;
+            for (int i0 = zlo; i0 <= zhi; i0 += 32)
             {
                 const int i = i0 + lane;
-                bool core = false;
-                if (i <= zhi)
+                const bool inside = i <= zhi;
+                const double v = grid_point(g.v0, g.dv, i);
+                const double abx = fabs((v - nu) * repwid);
+                const double xq = abx * abx;
+                const bool outer = inside && abx >= lim_outer;
+                if (outer)
                 {
-                    mine[i - p0] += near_point(nl, grid_point(g.v0, g.dv, i), core);
-                }
-                const unsigned mc = __ballot_sync(0xffffffffu, core);
-                if (mc)
-                {
-                    if (core)
+                    // W4 regions 0 and 1 (voigt.c:79-97): where the Lorentz form is already in the
+                    // spectrum, region 0 adds nothing and region 1 the closed-form difference
+                    // (near_point); otherwise the regions themselves
+                    if (lorentz_added)
                     {
-                        const int e = qn + __popc(mc & below);
-                        q[2 * e] = nl.tag >> 1;
-                        q[2 * e + 1] = i;
+                        if (abx < xlim0)
+                        {
+                            const double den = fma_(xq, d2 + xq, d0) * (xq + yq);
+                            mine[i - p0] += (ax * fma_(1.5, xq, n0)) * rcp_newton2(den);
+                        }
                     }
-                    qn += __popc(mc);
-                    __syncwarp();
-                    if (qn >= 32)
+                    else
                     {
-                        near_block_drain(a, q, 32, lane, layer, p0, mine);
-                        __syncwarp();
-                        const int keep = qn - 32;
-                        int m0 = 0, m1 = 0;
-                        if (lane < keep) { m0 = q[64 + 2 * lane]; m1 = q[64 + 2 * lane + 1]; }
-                        __syncwarp();
-                        if (lane < keep) { q[2 * lane] = m0; q[2 * lane + 1] = m1; }
-                        qn = keep;
-                        __syncwarp();
+                        mine[i - p0] += nl.cof * voigt_outer(abx, xq, nl.y, xlim0);
                     }
                 }
+                // the few points per line inside |x| < xlim1 are queued, by kind, and evaluated
+                // 32 at a time: no branch of the profile runs with two or three lanes active
+                const bool core = inside && !outer;
+                const bool r2 = core && abx >= lim_r2;
+                const int entry = (s << 16) | (i - p0);
+                near_block_push<false>(g, slots, q_r2, n_r2, r2, entry, lane, below, p0, mine);
+                near_block_push<true>(g, slots, q_in, n_in, core && !r2, entry, lane, below, p0, mine);
             }
         }
-    }
-    if (qn > 0)
-    {
-        near_block_drain(a, q, qn, lane, layer, p0, mine);
+        // the queues name slots of this batch: empty them before the slots are rewritten
+        if (n_r2 > 0) near_block_drain<false>(g, slots, q_r2, n_r2, lane, p0, mine);
+        if (n_in > 0) near_block_drain<true>(g, slots, q_in, n_in, lane, p0, mine);
+        n_r2 = n_in = 0;
+        __syncwarp();
     }
 
     // node terms: lines with cb == cell-cut-1 reach exactly the cell's first point.  Warp w

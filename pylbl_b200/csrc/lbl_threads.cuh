@@ -259,6 +259,18 @@ LBL_HD void plain_range(const FarAB* __restrict__ ab, const double* __restrict__
     }
 }
 
+// Lines [jb, je) one at a time (far_terms: one reciprocal each).
+template <int P>
+LBL_HD void single_range(const FarAB* __restrict__ ab, const double* __restrict__ cc, int jb, int je,
+                         const double (&v)[P], double (&acc)[P])
+{
+    for (int j = jb; j < je; ++j)
+    {
+        const double2 l = LBL_LDG(reinterpret_cast<const double2*>(ab + j));
+        far_terms<P>(v, l.x, l.y, LBL_LDG(cc + j), acc);
+    }
+}
+
 template <int P>
 LBL_HD void masked_range(const FarAB* __restrict__ ab, const double* __restrict__ cc,
                          const LineChk* __restrict__ chk, int jb, int je, int i_first, int cell,
@@ -573,7 +585,13 @@ struct CellArgs
     const double* node_offset8;    // [kNodes8]
     const double* transform8;      // [kNodes8][kNodes8]
     unsigned long long* executed;  // statistics: evaluations actually performed (or nullptr)
+    // The range searches of every (layer, cell group), done ahead by cell_keys_kernel:
+    // keys[(layer_in_launch_chunk * key_groups + group) * kKeyStride + which] (nullptr: search here)
+    const int* keys = nullptr;
+    int key_groups = 0;
+    int key_layer0 = 0;   // chunk-local layer index of the launch's first layer
 };
+constexpr int kKeyStride = 16;   // ints per (layer, cell group): ten keys, padded to 64 bytes
 
 // Line ranges of a cell group, as indices into the nu-sorted line list, from below:
 //   [j0,j1) window edge, tested per cell (16 nodes) | [j1,j2) 8-node | [j2,j3) 16-node |
@@ -864,7 +882,10 @@ LBL_HD void cell_direct_lane(const CellArgs& a, int layer, int cell, int chunk, 
     {
         // Direct lines lie within kFarMin of the (at most 2-cell) group: their window cell is
         // within 2 of this cell, inside any window with cut_off >= 4 -- no per-line test.
-        plain_range<P>(a.sum.rec.ab + off, a.sum.rec.cc + off, seg.j[4], seg.j[5], v, acc);
+        // One reciprocal per line here, not one per pair: K2b takes these terms back at the
+        // points next to the line centre and must be able to form the very same bits
+        // (far_term_lo); a pair's combined reciprocal cannot be reproduced line by line.
+        single_range<P>(a.sum.rec.ab + off, a.sum.rec.cc + off, seg.j[4], seg.j[5], v, acc);
     }
     else
     {
@@ -1044,7 +1065,7 @@ LBL_HD double near_point(const NearLine& nl, double v, bool& core)
         }
         return nl.cof * voigt_outer(abx, xq, nl.y, nl.xlim0);
     }
-    const double back = lorentz_added ? -far_term(v, nl.a, nl.b, nl.c, 0.) : 0.;
+    const double back = lorentz_added ? -far_term_lo(v, nl.a, nl.b, nl.c, 0.) : 0.;
     if (abx >= nl.lim_r2)
     {
         return back + nl.cof * voigt_region2(xq, nl.y);   // short rational: on the spot

@@ -539,3 +539,22 @@ def test_total_absorption_in_several_layer_groups(small_db):
     assert np.array_equal(parts, whole)
     assert np.all(whole > 0) or True
     mix.close()
+
+
+@pytest.mark.parametrize("farfield", ["2", "0"])
+def test_line_cores_at_very_low_pressure(dense_db, farfield, monkeypatch):
+    """Mesospheric layers (1 Pa and 0.1 Pa): y = sqrt(ln2)*gamma/alpha falls to 1e-5..1e-7, the
+    Lorentz form at a line centre is 1e4..1e6 times the profile, and whatever the far-field
+    kernel adds there must be taken back bit for bit (far_term_lo); y <= 1e-6 also switches the
+    W4 regions 1 and 2 off (voigt.c:48-53).  Pointwise, without the pedestal."""
+    monkeypatch.setenv("PYLBL_B200_FARFIELD", farfield)
+    bounds = (600, 720, 200)
+    t = np.array([190.0, 210.0, 250.0])
+    p = np.array([0.1, 1.0, 10.0])
+    x = np.array([3.6e-4, 3.6e-4, 3.6e-4])
+    gas, ref = Gas(dense_db, "CO2"), OracleGas(dense_db, "CO2")
+    k = gas.absorption_coefficients(t, p, x, bounds=bounds)
+    assert (gas.last_stats[0]["cells_per_warp"] > 0) == (farfield == "2")
+    for layer in range(3):
+        k_ref = ref.absorption(t[layer], p[layer], x[layer], *bounds)
+        assert relative_error(k[layer], k_ref) <= FP64_TOL
