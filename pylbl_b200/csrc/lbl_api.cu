@@ -148,7 +148,7 @@ struct lbl_gas
     size_t group_budget = (size_t)6 << 30;   // bytes per layer group, see lbl_gas_submit
     int copy_groups = 0;                     // lbl_gas_set_copy_groups (0 = automatic)
     DevBuf rec_ab, rec_cc, rec_chk, rec_gen, layers_dev, evals_dev, pedbin, pedcorr, pednodes,
-        pedterms, rec_f32, amp_max, cell_keys, cheb_nodes, cheb_weights, cheb_nodes16, cheb_weights16, cheb_nodes8, cheb_weights8,
+        pedterms, ped_tiles, ped_run_row, ped_n_runs, ped_run_cb, ped_run_sums, rec_f32, amp_max, cell_keys, cheb_nodes, cheb_weights, cheb_nodes16, cheb_weights16, cheb_nodes8, cheb_weights8,
         executed_dev;
     int cheb_npv = 0;
     unsigned long long* executed_host = nullptr;  // pinned
@@ -825,7 +825,8 @@ int lbl_gas_close(lbl_gas* g)
     g->plan.cell_first.release();
     for (DevBuf* b : {&g->tips_t, &g->tips_q, &g->rec_ab, &g->rec_cc, &g->rec_chk, &g->rec_gen,
                       &g->layers_dev, &g->evals_dev, &g->pedbin, &g->pedcorr, &g->pednodes,
-                      &g->pedterms, &g->rec_f32, &g->amp_max, &g->cell_keys, &g->cheb_nodes, &g->cheb_weights,
+                      &g->pedterms, &g->ped_tiles, &g->ped_run_row, &g->ped_n_runs, &g->ped_run_cb,
+                      &g->ped_run_sums, &g->rec_f32, &g->amp_max, &g->cell_keys, &g->cheb_nodes, &g->cheb_weights,
                       &g->cheb_nodes16, &g->cheb_weights16, &g->cheb_nodes8, &g->cheb_weights8,
                       &g->executed_dev,
                       &g->out[0], &g->out[1]})
@@ -1076,11 +1077,16 @@ static int submit_call(lbl_gas* g, const CallSpec& call)
     // (+2 spare slots per row for the bare f[s], f[e] of each line.)
     int ped_k = (2 * cut_off + 5 + 31) / 32;
     if (ped_k == 3) ped_k = 4;   // the node ring is indexed with a power-of-two mask
-    const bool ped_chain = remove_pedestal && ped_k <= 4;
+    // nu-sorted databases (HITRAN order): the run-based recurrence (PedRunArgs); otherwise the
+    // slot-ring kernels, which make no assumption on the row order.
+    bool ped_runs = remove_pedestal && g->mol.sorted;
+    if (const char* env = getenv("PYLBL_B200_PEDRUNS")) ped_runs = ped_runs && atoi(env) != 0;
+    const bool ped_chain = remove_pedestal && !ped_runs && ped_k <= 4;
     const int ped_wpad = 32 * ped_k;
     const size_t rec_per_layer = (size_t)plan.n_active *
         (sizeof(FarAB) + sizeof(double) + sizeof(LineChk) + sizeof(LineGen) +
-         (ped_chain ? sizeof(double) * ped_wpad : 0) + (fp32 ? sizeof(Far32) : 0));
+         (ped_chain ? sizeof(double) * ped_wpad : 0) + (ped_runs ? 4 * sizeof(double) + 2 * sizeof(int) : 0) +
+         (fp32 ? sizeof(Far32) : 0));
     const size_t out_per_layer = sizeof(double) * (size_t)grid.n;
     // Memory budget of one layer group (records + pedestal terms, and one output slab): a
     // quarter of what was free on the device when the handle was opened, between 6 and 48 GB.
@@ -1144,7 +1150,24 @@ static int submit_call(lbl_gas* g, const CallSpec& call)
             ped_smem = ring_bytes;
             ped_nodes_in_smem = false;
         }
-        if (ped_chain)
+        if (ped_runs)
+        {
+            // sized for the worst case (every row its own run); only the runs' share is touched
+            const size_t rows = (size_t)plan.n_active;
+            const size_t tiles = (rows + kRunTile - 1) / kRunTile;
+            LBL_CUDA(g->ped_tiles.reserve(sizeof(int) * tiles * chunk));
+            LBL_CUDA(g->ped_run_row.reserve(sizeof(int) * (rows + 1) * chunk));
+            LBL_CUDA(g->ped_n_runs.reserve(sizeof(int) * (size_t)chunk));
+            LBL_CUDA(g->ped_run_cb.reserve(sizeof(int) * rows * chunk));
+            LBL_CUDA(g->ped_run_sums.reserve(sizeof(double) * 4 * rows * chunk));
+            ped_smem = sizeof(double) * (size_t)nb <= 100 * 1024 ? sizeof(double) * (size_t)nb : 0;
+            if (ped_smem > 48 * 1024)
+            {
+                LBL_CUDA(cudaFuncSetAttribute(ped_chain_runs_kernel,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ped_smem));
+            }
+        }
+        else if (ped_chain)
         {
             LBL_CUDA(g->pedterms.reserve(sizeof(double) * ped_wpad * (size_t)plan.n_active * chunk));
         }
@@ -1325,7 +1348,40 @@ static int submit_call(lbl_gas* g, const CallSpec& call)
             pa.pedbin = g->pedbin.as<double>();
             pa.n_rows = ped_rows;
             double* scratch = ped_nodes_in_smem ? nullptr : g->pednodes.as<double>();
-            if (ped_chain)
+            if (ped_runs)
+            {
+                PedRunArgs ra;
+                ra.lines = lines;
+                ra.rec = rec;
+                ra.grid = grid;
+                ra.layers = layers_c;
+                ra.n_rows = ped_rows;
+                ra.run_row = g->ped_run_row.as<int>();
+                ra.n_runs = g->ped_n_runs.as<int>();
+                ra.run_cb = g->ped_run_cb.as<int>();
+                ra.run_sums = g->ped_run_sums.as<double>();
+                ra.pedbin = g->pedbin.as<double>();
+                const int tiles = (ped_rows + kRunTile - 1) / kRunTile;
+                if (tiles > 0)
+                {
+                    dim3 gt(tiles, nl);
+                    ped_run_count_kernel<<<gt, kRunTile, 0, ss>>>(rec.chk, lines.n, ped_rows,
+                                                                 g->ped_tiles.as<int>());
+                    ped_run_scatter_kernel<<<gt, kRunTile, 0, ss>>>(rec.chk, lines.n, ped_rows,
+                                                                   g->ped_tiles.as<int>(), ra.run_row, ra.n_runs);
+                    // about one run per occupied cell: enough warps to take them in a few rounds
+                    const int runs_guess = std::min(ped_rows, grid.ncell + 2 * cut_off + 8);
+                    dim3 gn(std::max(1, std::min(64, (runs_guess + 31) / 32)), nl);
+                    ped_nodes_kernel<<<gn, 256, 0, ss>>>(ra);
+                }
+                else
+                {
+                    LBL_CUDA(cudaMemsetAsync(ra.n_runs, 0, sizeof(int) * nl, ss));
+                }
+                ped_chain_runs_kernel<<<nl, 32, ped_smem, ss>>>(ra, ped_smem > 0 ? 1 : 0);
+                st.total_launches += 4;
+            }
+            else if (ped_chain)
             {
                 cudaError_t ce = cudaSuccess;
                 switch (ped_k)
@@ -1407,20 +1463,19 @@ static int submit_call(lbl_gas* g, const CallSpec& call)
                 dim3 gridc((groups + kSumBlock / 32 - 1) / (kSumBlock / 32), q1 - q0);
                 // 23 KB of static shared memory per block: ask for the large carve-out so that
                 // shared memory does not cap the resident blocks below the register limit.
-                if (cells_per_warp == 1)
-                {
-                    LBL_CUDA(cudaFuncSetAttribute(sum_cell_kernel<1>,
-                                                  cudaFuncAttributePreferredSharedMemoryCarveout,
-                                                  cudaSharedmemCarveoutMaxShared));
-                    sum_cell_kernel<1><<<gridc, kSumBlock, 0, sm>>>(ca);
-                }
-                else
-                {
-                    LBL_CUDA(cudaFuncSetAttribute(sum_cell_kernel<2>,
-                                                  cudaFuncAttributePreferredSharedMemoryCarveout,
-                                                  cudaSharedmemCarveoutMaxShared));
-                    sum_cell_kernel<2><<<gridc, kSumBlock, 0, sm>>>(ca);
-                }
+                int far_mode = 1;
+                if (const char* env = getenv("PYLBL_B200_FARLOOP")) far_mode = atoi(env);
+                auto launch = [&](auto kernel) -> cudaError_t {
+                    cudaError_t ce = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                                          cudaSharedmemCarveoutMaxShared);
+                    if (ce != cudaSuccess) return ce;
+                    kernel<<<gridc, kSumBlock, 0, sm>>>(ca);
+                    return cudaSuccess;
+                };
+                if (cells_per_warp == 2) LBL_CUDA(launch(sum_cell_kernel<2, 0>));
+                else if (far_mode == 2) LBL_CUDA(launch(sum_cell_kernel<1, 2>));
+                else if (far_mode == 0) LBL_CUDA(launch(sum_cell_kernel<1, 0>));
+                else LBL_CUDA(launch(sum_cell_kernel<1, 1>));
             }
             else
             {

@@ -222,7 +222,9 @@ cell_keys_kernel(LinesView lines, GridSpec g, const LayerIn* __restrict__ layers
         first_line_at(lines, cell_search_key(g, layers[layer], cell0, cells_per_group, which));
 }
 
-template <int G>
+// M: how the far-range loops are instantiated (2: one generic copy, 1: one copy per node count
+// with literal strides, 0: one per range).
+template <int G, int M>
 __global__ void __launch_bounds__(kSumBlock, 8)
 sum_cell_kernel(const CellArgs a)
 {
@@ -234,6 +236,7 @@ sum_cell_kernel(const CellArgs a)
     __shared__ alignas(16) double s_cc[kStages][kStageLines];
     __shared__ alignas(8) unsigned long long full[kStages];
     __shared__ int s_range[kWarps][2];
+    __shared__ int s_seg[kWarps][kCellKeys];
     const GridSpec& g = a.sum.grid;
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -321,10 +324,24 @@ sum_cell_kernel(const CellArgs a)
         v[q] = ((double)g.v0 + (double)(cell0 + q)) + a.node_offset[lane];
         f[q] = 0.;
     }
+    // One copy of each loop for all the ranges that use it (`unroll 1`; the range bounds are read
+    // from shared memory by index): with every range's loop inlined separately the kernel was 60 KB
+    // of code and its warps -- each in a different range -- stalled on instruction fetch more
+    // than on anything else.
+    if (lane == 0)
+    {
+#pragma unroll
+        for (int q = 0; q < kCellKeys; ++q) s_seg[warp][q] = seg.j[q];
+    }
+    __syncwarp();
     if (active)
     {
-        f16 += node16_tested(ab, cc, chk, seg.j[0], seg.j[1], m16.first, m16.stride, my_cell, g.cut_off, v16);
-        f16 += node16_tested(ab, cc, chk, seg.j[8], seg.j[9], m16.first, m16.stride, my_cell, g.cut_off, v16);
+#pragma unroll 1
+        for (int side = 0; side < 2; ++side)
+        {
+            f16 += node16_tested(ab, cc, chk, s_seg[warp][8 * side], s_seg[warp][8 * side + 1], m16.first,
+                                 m16.stride, my_cell, g.cut_off, v16);
+        }
     }
     for (int t = 0; t < n_chunks; ++t)
     {
@@ -334,18 +351,66 @@ sum_cell_kernel(const CellArgs a)
         const int last = min(first + kStageLines, hi_all);
         if (active)
         {
-            int b = max(first, seg.j[1]), e = min(last, seg.j[2]);
-            if (b < e) f8 += node16_plain_staged(s_ab[stage], s_cc[stage], first, b, e, m8.first, m8.stride, v8);
-            b = max(first, seg.j[2]); e = min(last, seg.j[3]);
-            if (b < e) f16 += node16_plain_staged(s_ab[stage], s_cc[stage], first, b, e, m16.first, m16.stride, v16);
-            b = max(first, seg.j[3]); e = min(last, seg.j[4]);
-            if (b < e) node_plain_staged<G>(s_ab[stage], s_cc[stage], first, b, e, v, f);
-            b = max(first, seg.j[5]); e = min(last, seg.j[6]);
-            if (b < e) node_plain_staged<G>(s_ab[stage], s_cc[stage], first, b, e, v, f);
-            b = max(first, seg.j[6]); e = min(last, seg.j[7]);
-            if (b < e) f16 += node16_plain_staged(s_ab[stage], s_cc[stage], first, b, e, m16.first, m16.stride, v16);
-            b = max(first, seg.j[7]); e = min(last, seg.j[8]);
-            if (b < e) f8 += node16_plain_staged(s_ab[stage], s_cc[stage], first, b, e, m8.first, m8.stride, v8);
+            if (G == 1 && M == 2)
+            {
+                // ranges j1..j4 and j5..j8: 8-, 16-, 32-node | 32-, 16-, 8-node lines; every kind
+                // is "pairs of lines at one point per lane", shared among 4, 2 or 1 groups of lanes
+#pragma unroll 1
+                for (int k = 0; k < 6; ++k)
+                {
+                    const int q = (k < 3) ? k + 1 : k + 2;
+                    const int b = max(first, s_seg[warp][q]);
+                    const int e = min(last, s_seg[warp][q + 1]);
+                    if (b < e)
+                    {
+                        const int kind = (k < 3) ? k : 5 - k;     // 0: 8 nodes, 1: 16 nodes, 2: 32 nodes
+                        const double vk = (kind == 0) ? v8 : ((kind == 1) ? v16 : v[0]);
+                        const int first_k = (kind == 0) ? m8.first : ((kind == 1) ? m16.first : 0);
+                        const int stride_k = (kind == 0) ? m8.stride : ((kind == 1) ? m16.stride : 1);
+                        const double r = node16_plain_staged(s_ab[stage], s_cc[stage], first, b, e, first_k,
+                                                             stride_k, vk);
+                        f8 += (kind == 0) ? r : 0.;
+                        f16 += (kind == 1) ? r : 0.;
+                        f[0] += (kind == 2) ? r : 0.;
+                    }
+                }
+            }
+            else if (G == 1 && M == 1)
+            {
+#pragma unroll 1
+                for (int k = 0; k < 6; ++k)
+                {
+                    const int q = (k < 3) ? k + 1 : k + 2;
+                    const int b = max(first, s_seg[warp][q]);
+                    const int e = min(last, s_seg[warp][q + 1]);
+                    if (b < e)
+                    {
+                        // (the stride is a literal in each call: three copies of the loop, not six)
+                        const int kind = (k < 3) ? k : 5 - k;     // 0: 8 nodes, 1: 16 nodes, 2: 32 nodes
+                        if (kind == 0)
+                            f8 += node16_plain_staged(s_ab[stage], s_cc[stage], first, b, e, m8.first, 4, v8);
+                        else if (kind == 1)
+                            f16 += node16_plain_staged(s_ab[stage], s_cc[stage], first, b, e, m16.first, 2, v16);
+                        else
+                            f[0] += node16_plain_staged(s_ab[stage], s_cc[stage], first, b, e, 0, 1, v[0]);
+                    }
+                }
+            }
+            else
+            {
+                int b = max(first, seg.j[1]), e = min(last, seg.j[2]);
+                if (b < e) f8 += node16_plain_staged(s_ab[stage], s_cc[stage], first, b, e, m8.first, m8.stride, v8);
+                b = max(first, seg.j[2]); e = min(last, seg.j[3]);
+                if (b < e) f16 += node16_plain_staged(s_ab[stage], s_cc[stage], first, b, e, m16.first, m16.stride, v16);
+                b = max(first, seg.j[3]); e = min(last, seg.j[4]);
+                if (b < e) node_plain_staged<G>(s_ab[stage], s_cc[stage], first, b, e, v, f);
+                b = max(first, seg.j[5]); e = min(last, seg.j[6]);
+                if (b < e) node_plain_staged<G>(s_ab[stage], s_cc[stage], first, b, e, v, f);
+                b = max(first, seg.j[6]); e = min(last, seg.j[7]);
+                if (b < e) f16 += node16_plain_staged(s_ab[stage], s_cc[stage], first, b, e, m16.first, m16.stride, v16);
+                b = max(first, seg.j[7]); e = min(last, seg.j[8]);
+                if (b < e) f8 += node16_plain_staged(s_ab[stage], s_cc[stage], first, b, e, m8.first, m8.stride, v8);
+            }
         }
         __syncthreads();   // every warp is done with this stage
         if (threadIdx.x == 0 && t + kStages < n_chunks) issue(t + kStages);
@@ -771,8 +836,9 @@ constexpr int kNbBatch = 64;
 constexpr int kNbQueue = 64;   // entries per queue: at most 31 left over + 32 new
 
 // Drains `cnt` (<= 32) queued (slot, point) pairs with the lanes packed: lane e evaluates entry
-// e -- region 2 of W4 (kInner == false) or region 3 / CPF12 (kInner == true), plus the Lorentz
-// form taken back where the summation kernel added it -- and adds it to its point.
+// e and adds it to its point.  kInner == false: points around |x| = xlim1 -- W4 region 2, or
+// region 0/1 for the boundary points the index range took along; kInner == true: W4 region 3 /
+// CPF12.  Inside xlim1 the Lorentz form is taken back where the summation kernel added it.
 template <bool kInner>
 __device__ __forceinline__ void near_block_drain(const GridSpec& g, const NearLine* slots, const int* q,
                                                  int cnt, int lane, int p0, double* mine)
@@ -786,17 +852,16 @@ __device__ __forceinline__ void near_block_drain(const GridSpec& g, const NearLi
         const NearLine& nl = slots[entry >> 16];
         const double v = grid_point(g.v0, g.dv, p0 + k);
         const double xi = (v - nl.nu) * nl.repwid;
+        const bool lorentz_added = (nl.tag & 1) == 0;
         if (kInner)
         {
             val = nl.cof * voigt_inner(xi, nl.y);
+            if (lorentz_added) val -= far_term_lo(v, nl.a, nl.b, nl.c, 0.);   // the bits K2c added
         }
         else
         {
-            val = nl.cof * voigt_region2(xi * xi, nl.y);
-        }
-        if ((nl.tag & 1) == 0)
-        {
-            val -= far_term_lo(v, nl.a, nl.b, nl.c, 0.);   // the bits the summation kernel added
+            bool core;
+            val = near_point(nl, v, core);   // regions 0, 1, 2 (never `core`: sorted at the push)
         }
     }
     // Two entries may name the same point (two lines' cores overlapping): the lowest lane of
@@ -851,6 +916,19 @@ __device__ __forceinline__ void near_block_push(const GridSpec& g, const NearLin
     }
 }
 
+// Core index range of a staged line inside the span [p0, p1]: the points with |x| < lim_outer
+// (W4 regions 2, 3 and CPF12, voigt.c:98-186) lie in [c_lo, c_hi].  One index of margin either
+// side (the bounds are exact to ~1e-10 of an index): the range may hold a few region-0/1
+// points, which the queue evaluates as such, but no core point is ever outside it.
+__device__ __forceinline__ void near_core_range(const NearLine& nl, const GridSpec& g, int& c_lo, int& c_hi)
+{
+    const double half = nl.lim_outer / nl.repwid;
+    const double lo = ceil((nl.nu - half - (double)g.v0) * (double)g.n_per_v) - 1.;
+    const double hi = floor((nl.nu + half - (double)g.v0) * (double)g.n_per_v) + 1.;
+    c_lo = (int)fmin(fmax(lo, (double)nl.nlo), (double)nl.nhi + 1.);
+    c_hi = (int)fmax(fmin(hi, (double)nl.nhi), (double)c_lo - 1.);
+}
+
 __global__ void __launch_bounds__(128, 8)
 near_block_kernel(const SumArgs a)
 {
@@ -873,9 +951,9 @@ near_block_kernel(const SumArgs a)
     const LineChk* chk = a.rec.chk + off;
     const LineGen* gen = a.rec.gen + off;
     double* mine = acc[warp];
-    int* q_r2 = queues[warp][0];      // W4 region 2: a short rational
+    int* q_mid = queues[warp][0];     // around |x| = xlim1: W4 region 2 and boundary points
     int* q_in = queues[warp][1];      // W4 region 3 / CPF12: long
-    int n_r2 = 0, n_in = 0;
+    int n_mid = 0, n_in = 0;
 
     int jlo, jhi;
     near_candidates(a.lines, g, ly, p0, p1, jlo, jhi);
@@ -906,58 +984,63 @@ near_block_kernel(const SumArgs a)
             NearLine nl = near_line(ck, j, gn, ab, __ldg(a.rec.cc + off + j), a.near_masked != 0);
             nl.nlo = max(ck.y, p0);   // the zone, clipped to the span
             nl.nhi = min(ck.z, p1);
+            near_core_range(nl, g, nl.c_lo, nl.c_hi);
             slots[__popc(listed & below) + (warp == 1 ? batch_count[0] : 0)] = nl;
         }
         __syncthreads();
         const int n_listed = batch_count[0] + batch_count[1];
         for (int s = warp; s < n_listed; s += 4)
         {
-            // The line's constants live in registers for the walk over its zone; the stores to
-            // the accumulator stripe would otherwise force a reload from shared memory per point.
             const NearLine& nl = slots[s];
             const int zlo = nl.nlo, zhi = nl.nhi;
-            const bool lorentz_added = (nl.tag & 1) == 0;
-            const double nu = nl.nu, repwid = nl.repwid, lim_outer = nl.lim_outer, lim_r2 = nl.lim_r2;
-            const double xlim0 = nl.xlim0, ax = nl.ax, d0 = nl.d0, d2 = nl.d2, n0 = nl.n0, yq = nl.yq;
-            for (int i0 = zlo; i0 <= zhi; i0 += 32)
+            const int c_lo = nl.c_lo, c_hi = nl.c_hi;
+            // ---- the few points inside |x| < xlim1 (and its boundary): sorted by kind into the
+            // two queues, evaluated 32 at a time -- no branch of the profile ever runs with two
+            // or three lanes active
+            for (int i0 = c_lo; i0 <= c_hi; i0 += 32)
             {
                 const int i = i0 + lane;
-                const bool inside = i <= zhi;
+                const bool inside = i <= c_hi;
+                const double v = grid_point(g.v0, g.dv, i);
+                const double abx = fabs((v - nl.nu) * nl.repwid);
+                const bool inner = inside && abx < nl.lim_r2;
+                const int entry = (s << 16) | (i - p0);
+                near_block_push<false>(g, slots, q_mid, n_mid, inside && !inner, entry, lane, below, p0, mine);
+                near_block_push<true>(g, slots, q_in, n_in, inner, entry, lane, below, p0, mine);
+            }
+            // ---- the zone outside it, W4 regions 0 and 1 (voigt.c:79-97), left part then right
+            // part, lanes packed across the gap.  Where the Lorentz form is already in the spectrum
+            // region 0 adds nothing and region 1 the closed-form difference (near_point).
+            const int n_left = c_lo - zlo;
+            const int n_out = n_left + (zhi - c_hi);
+            const bool lorentz_added = (nl.tag & 1) == 0;
+            const double nu = nl.nu, repwid = nl.repwid, xlim0 = nl.xlim0;
+            const double ax = nl.ax, d0 = nl.d0, d2 = nl.d2, n0 = nl.n0, yq = nl.yq;
+            for (int t0 = 0; t0 < n_out; t0 += 32)
+            {
+                const int t = t0 + lane;
+                const bool inside = t < n_out;
+                const int i = (t < n_left) ? zlo + t : c_hi + 1 + (t - n_left);
                 const double v = grid_point(g.v0, g.dv, i);
                 const double abx = fabs((v - nu) * repwid);
                 const double xq = abx * abx;
-                const bool outer = inside && abx >= lim_outer;
-                if (outer)
+                double add = 0.;
+                if (lorentz_added)
                 {
-                    // W4 regions 0 and 1 (voigt.c:79-97): where the Lorentz form is already in the
-                    // spectrum, region 0 adds nothing and region 1 the closed-form difference
-                    // (near_point); otherwise the regions themselves
-                    if (lorentz_added)
-                    {
-                        if (abx < xlim0)
-                        {
-                            const double den = fma_(xq, d2 + xq, d0) * (xq + yq);
-                            mine[i - p0] += (ax * fma_(1.5, xq, n0)) * rcp_newton2(den);
-                        }
-                    }
-                    else
-                    {
-                        mine[i - p0] += nl.cof * voigt_outer(abx, xq, nl.y, xlim0);
-                    }
+                    const double den = fma_(xq, d2 + xq, d0) * (xq + yq);
+                    add = (abx < xlim0) ? (ax * fma_(1.5, xq, n0)) * rcp_newton2(den) : 0.;
                 }
-                // the few points per line inside |x| < xlim1 are queued, by kind, and evaluated
-                // 32 at a time: no branch of the profile runs with two or three lanes active
-                const bool core = inside && !outer;
-                const bool r2 = core && abx >= lim_r2;
-                const int entry = (s << 16) | (i - p0);
-                near_block_push<false>(g, slots, q_r2, n_r2, r2, entry, lane, below, p0, mine);
-                near_block_push<true>(g, slots, q_in, n_in, core && !r2, entry, lane, below, p0, mine);
+                else
+                {
+                    add = nl.cof * voigt_outer(abx, xq, nl.y, xlim0);
+                }
+                if (inside) mine[i - p0] += add;
             }
         }
         // the queues name slots of this batch: empty them before the slots are rewritten
-        if (n_r2 > 0) near_block_drain<false>(g, slots, q_r2, n_r2, lane, p0, mine);
+        if (n_mid > 0) near_block_drain<false>(g, slots, q_mid, n_mid, lane, p0, mine);
         if (n_in > 0) near_block_drain<true>(g, slots, q_in, n_in, lane, p0, mine);
-        n_r2 = n_in = 0;
+        n_mid = n_in = 0;
         __syncwarp();
     }
 
@@ -1379,6 +1462,166 @@ pedestal_chain_kernel(const PedArgs a, const double* __restrict__ terms, double*
     ped_lane_finish(st, g, lane, bins);
     __syncwarp();
     if (!scratch)
+    {
+        for (int b = lane; b < nb; b += 32) out_bins[b] = bins[b];
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// K3 for nu-sorted databases (see PedRunArgs in lbl_threads.cuh): runs -> node sums -> chain.
+// ---------------------------------------------------------------------------------------
+constexpr int kRunTile = 256;
+
+// K3r-1.  Run starts per tile of kRunTile rows.  grid = (tiles, layers).
+__global__ void __launch_bounds__(kRunTile)
+ped_run_count_kernel(const LineChk* __restrict__ chk, int stride, int n_rows, int* __restrict__ tile_count)
+{
+    const int j = blockIdx.x * kRunTile + threadIdx.x;
+    const LineChk* c = chk + (size_t)blockIdx.y * stride;
+    const bool start = j < n_rows && (j == 0 || c[j].cb != c[j - 1].cb);
+    const int count = __syncthreads_count(start);
+    if (threadIdx.x == 0) tile_count[(size_t)blockIdx.y * gridDim.x + blockIdx.x] = count;
+}
+
+// K3r-2.  Compacts the run starts: run_row[layer][r] = first row of run r (ascending), then the
+// sentinel n_rows; n_runs[layer].  grid = (tiles, layers).
+__global__ void __launch_bounds__(kRunTile)
+ped_run_scatter_kernel(const LineChk* __restrict__ chk, int stride, int n_rows,
+                       const int* __restrict__ tile_count, int* __restrict__ run_row,
+                       int* __restrict__ n_runs)
+{
+    __shared__ int warp_count[kRunTile / 32];
+    __shared__ int base_s;
+    const int layer = blockIdx.y;
+    const int tiles = gridDim.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int j = blockIdx.x * kRunTile + threadIdx.x;
+    const LineChk* c = chk + (size_t)layer * stride;
+    const bool start = j < n_rows && (j == 0 || c[j].cb != c[j - 1].cb);
+    const unsigned m = __ballot_sync(0xffffffffu, start);
+    if (lane == 0) warp_count[warp] = __popc(m);
+    if (warp == 0)
+    {
+        // runs in the tiles before this one
+        int before = 0;
+        for (int t = lane; t < (int)blockIdx.x; t += 32) before += tile_count[(size_t)layer * tiles + t];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
+        if (lane == 0) base_s = before;
+    }
+    __syncthreads();
+    int rank = base_s + __popc(m & ((1u << lane) - 1u));
+    for (int w = 0; w < warp; ++w) rank += warp_count[w];
+    int* rows = run_row + (size_t)layer * (n_rows + 1);
+    if (start) rows[rank] = j;
+    if (blockIdx.x == tiles - 1 && threadIdx.x == 0)
+    {
+        int total = base_s;
+        for (int w = 0; w < kRunTile / 32; ++w) total += warp_count[w];
+        n_runs[layer] = total;
+        rows[total] = n_rows;
+    }
+}
+
+// K3n.  The four gathered sums of every run (ped_run_sums): a warp per run, lanes over the rows.
+// grid = (blocks, layers), the warps of a layer striding over its runs.
+__global__ void __launch_bounds__(256)
+ped_nodes_kernel(const PedRunArgs a)
+{
+    const int layer = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    const int n_runs = a.n_runs[layer];
+    const int* rows = a.run_row + (size_t)layer * (a.n_rows + 1);
+    for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_runs; r += warps)
+    {
+        const int row_lo = rows[r], row_hi = rows[r + 1];
+        double sums[4];
+        ped_run_sums(a, layer, row_lo, row_hi, lane, 32, sums);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+        {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sums[q] += __shfl_xor_sync(0xffffffffu, sums[q], o);
+        }
+        if (lane == 0)
+        {
+            const size_t o = (size_t)layer * a.n_rows + r;
+            a.run_cb[o] = a.rec.chk[(size_t)layer * a.lines.n + row_lo].cb;
+            double2* dst = reinterpret_cast<double2*>(a.run_sums + 4 * o);
+            dst[0] = make_double2(sums[0], sums[1]);
+            dst[1] = make_double2(sums[2], sums[3]);
+        }
+    }
+}
+
+// K3c.  The chain over the runs of one layer (ped_chain_run): one warp per layer; the pedestal
+// bins live in shared memory (or, for very wide grids, in the global pedbin array itself).
+// grid = layers, block = 32, dynamic shared memory = nb doubles (0: bins in global memory).
+__global__ void __launch_bounds__(32)
+ped_chain_runs_kernel(const PedRunArgs a, int bins_in_smem)
+{
+    extern __shared__ double smem_bins[];
+    const GridSpec& g = a.grid;
+    const int layer = blockIdx.x;
+    const int lane = threadIdx.x;
+    const int nb = g.ncell + 2 * g.cut_off + 2;
+    double* out_bins = a.pedbin + (size_t)layer * nb;
+    double* bins = bins_in_smem ? smem_bins : out_bins;
+    for (int b = lane; b < nb; b += 32) bins[b] = 0.;
+    __syncwarp();
+    const int n_runs = a.n_runs[layer];
+    const int* cbs = a.run_cb + (size_t)layer * a.n_rows;
+    const double2* sums = reinterpret_cast<const double2*>(a.run_sums + 4 * (size_t)layer * a.n_rows);
+    // this lane's run of the next tile of 32, fetched one tile ahead
+    int my_cb = 0;
+    double2 my_f = make_double2(0., 0.), my_k = make_double2(0., 0.);
+    if (lane < n_runs)
+    {
+        my_cb = cbs[lane];
+        my_f = sums[2 * lane];
+        my_k = sums[2 * lane + 1];
+    }
+    for (int r0 = 0; r0 < n_runs; r0 += 32)
+    {
+        const int cb_t = my_cb;
+        const double2 f_t = my_f, k_t = my_k;
+        const int nxt = r0 + 32 + lane;
+        if (nxt < n_runs)
+        {
+            my_cb = cbs[nxt];
+            my_f = sums[2 * nxt];
+            my_k = sums[2 * nxt + 1];
+        }
+        const int cnt = min(32, n_runs - r0);
+        for (int m = 0; m < cnt; ++m)
+        {
+            const int cb = __shfl_sync(0xffffffffu, cb_t, m);
+            double s4[4];
+            s4[0] = __shfl_sync(0xffffffffu, f_t.x, m);
+            s4[1] = __shfl_sync(0xffffffffu, f_t.y, m);
+            s4[2] = __shfl_sync(0xffffffffu, k_t.x, m);
+            s4[3] = __shfl_sync(0xffffffffu, k_t.y, m);
+            const PedPoints pp = ped_points(cb, g);
+            if (pp.skip)
+            {
+                continue;
+            }
+            double ps = 0., pe = 0.;
+            for (int k = lane; k < pp.ns; k += 32) ps += bins[pp.bs + k];
+            for (int k = lane; k < pp.ne; k += 32) pe += bins[pp.be + k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+            {
+                ps += __shfl_xor_sync(0xffffffffu, ps, o);
+                pe += __shfl_xor_sync(0xffffffffu, pe, o);
+            }
+            const double pedestal = ped_chain_run(s4, ps, pe);
+            if (lane == 0) bins[cb + g.cut_off + 1] += pedestal;
+            __syncwarp();
+        }
+    }
+    if (bins_in_smem)
     {
         for (int b = lane; b < nb; b += 32) out_bins[b] = bins[b];
     }

@@ -1004,8 +1004,10 @@ struct NearLine
     double ax, d0, d2, n0;
     double yq, lim_r2, y, cof;
     double a, b, c;               // the summation kernel's operands (far_term)
-    double pad;                   // 144 B: a multiple of 16, and as a shared-memory stride free of
-                                  // bank conflicts for the 16-byte stores of 8 lanes (128 B is not)
+    int c_lo, c_hi;               // near_block_kernel: grid indices that hold the points with
+                                  // |x| < lim_outer (regions 2, 3, CPF12), clipped to the span
+                                  // (144 B: a multiple of 16, and as a shared-memory stride free of
+                                  // bank conflicts for the 16-byte stores of 8 lanes; 128 B is not)
 };
 
 LBL_HD NearLine near_line(const int4& ck, int j, const LineGen& gen, const FarAB& ab, double cc,
@@ -1033,7 +1035,8 @@ LBL_HD NearLine near_line(const int4& ck, int j, const LineGen& gen, const FarAB
     nl.a = ab.a;
     nl.b = ab.b;
     nl.c = cc;
-    nl.pad = 0.;
+    nl.c_lo = 0;
+    nl.c_hi = -1;
     return nl;
 }
 
@@ -1523,6 +1526,135 @@ LBL_HD void pedestal_layer(const PedArgs& a, int layer, int lane, int nlanes, do
         }
         sync();
     }
+}
+
+// ---------------------------------------------------------------------------------------
+// K3 for nu-sorted databases: the recurrence in closed form per RUN, without node state.
+//
+// A run is a maximal stretch of consecutive database rows with the same window cell cb (all
+// lines of one integer-wavenumber bin, or a fragment of it where pressure shifts put two
+// neighbouring lines' cells out of order).  All lines of a run share the window [s, e].
+// With k[] the reference's running spectrum, d = k[s] - k[e]: every line adds (f[s], f[e]) and
+// then removes min(k[s], k[e]) from both, so after it k[s] = max(d, 0), k[e] = max(-d, 0) and
+// d moves by f[s] - f[e] -- the clamping never feeds back into d.  Over a whole run:
+//     d_end = (k[s] - k[e])_before + sum(f[s]) - sum(f[e])
+//     sum of the run's pedestals = sum(f[s]) + k[s]_before - max(d_end, 0)       (telescoping)
+// and the values before the run are sums over the EARLIER rows whose windows cover the point,
+//     k[x]_before = sum_l f_l(x)  -  sum_l pedestal_l ,
+// the first a plain gather (ped_run_sums: every run of every layer in parallel, like the
+// summation kernel but at one point per run), the second a sum over the <= 2*cut+2 pedestal
+// bins (index cb + cut + 1) of the cells whose windows cover x -- the only sequential part
+// (ped_chain_run: a handful of dependent operations per run).  "Earlier" is by database row,
+// and the coverage test is on each line's own cell, so out-of-order cells are reproduced.
+// Rows of a sorted database that precede a run are the rows before its first row; unsorted
+// databases keep the slot-ring kernels above.
+// ---------------------------------------------------------------------------------------
+struct PedRunArgs
+{
+    LinesView lines;
+    Records rec;
+    GridSpec grid;
+    const LayerIn* layers;
+    int n_rows;          // rows the recurrence walks (<= lines.n)
+    int* run_row;        // [layer][n_rows + 1] first row of each run, then the sentinel n_rows
+    int* n_runs;         // [layer]
+    int* run_cb;         // [layer][n_rows] window cell of each run
+    double* run_sums;    // [layer][n_rows][4] per run: sum f[s], sum f[e] over its lines;
+                         //   sum over earlier covering rows of f(s-point), of f(e-point)
+    double* pedbin;      // [layer][ncell + 2*cut + 2]
+};
+
+// The two grid points that decide a run's pedestals, and for each the range of pedestal bins
+// (index cb' + cut + 1) of the cells whose windows cover it:  a node c*n_per_v is covered by
+// cb' in [c-cut-1, c+cut]; the last grid point n-1 (when it is not a node) by
+// cb' in [ncell-cut-1, ncell-1+cut]  (spectra.c:48-62).
+struct PedPoints
+{
+    bool skip;
+    int i_s, i_e;      // grid indices of k[s], k[e]
+    int bs, ns;        // bins [bs, bs+ns) cover k[s]
+    int be, ne;        // bins [be, be+ne) cover k[e]
+};
+
+LBL_HD PedPoints ped_points(int cb, const GridSpec& g)
+{
+    const PedWindow w = ped_window(cb, g);
+    PedPoints p;
+    p.skip = w.skip;
+    p.i_s = w.s_node * g.n_per_v;
+    p.i_e = w.tail ? g.n - 1 : w.e_node * g.n_per_v;
+    p.bs = w.s_node;
+    p.ns = 2 * g.cut_off + 2;
+    p.be = w.tail ? g.ncell : w.e_node;
+    p.ne = w.tail ? 2 * g.cut_off + 1 : 2 * g.cut_off + 2;
+    return p;
+}
+
+// One line at one grid point, by the path the summation kernels take there.
+LBL_HD double ped_line_at(const PedRunArgs& a, size_t o, const int4& ck, double v, int i)
+{
+    if (i >= ck.y && i <= ck.z)
+    {
+        const LineGen gen = a.rec.gen[o];
+        return voigt_general(v, gen.nu, gen.repwid, gen.y, gen.cof, gen.xlim0, gen.xlim1);
+    }
+    const double2 l = LBL_LDG(reinterpret_cast<const double2*>(a.rec.ab + o));
+    return far_term(v, l.x, l.y, LBL_LDG(a.rec.cc + o), 0.);
+}
+
+// This lane's share (rows lane, lane + nlanes, ...) of the four sums of the run [row_lo, row_hi).
+LBL_HD void ped_run_sums(const PedRunArgs& a, int layer, int row_lo, int row_hi, int lane, int nlanes,
+                         double (&out)[4])
+{
+    const GridSpec& g = a.grid;
+    const size_t off = (size_t)layer * a.lines.n;
+    out[0] = out[1] = out[2] = out[3] = 0.;
+    const int cb = LBL_LDG(reinterpret_cast<const int4*>(a.rec.chk + off + row_lo)).x;
+    const PedPoints pp = ped_points(cb, g);
+    if (pp.skip)
+    {
+        return;
+    }
+    const double v_s = grid_point(g.v0, g.dv, pp.i_s);
+    const double v_e = grid_point(g.v0, g.dv, pp.i_e);
+    for (int j = row_lo + lane; j < row_hi; j += nlanes)
+    {
+        const int4 ck = LBL_LDG(reinterpret_cast<const int4*>(a.rec.chk + off + j));
+        out[0] += ped_line_at(a, off + j, ck, v_s, pp.i_s);
+        out[1] += ped_line_at(a, off + j, ck, v_e, pp.i_e);
+    }
+    // Earlier rows that can cover a point: cell >= first covering cell, i.e. shifted centre
+    // >= v0 + that cell, i.e. unshifted centre within `slack` of it.
+    const double slack = a.layers[layer].slack;
+    const int j_s = first_line_at(a.lines, (double)g.v0 + (double)(pp.bs - g.cut_off - 1) - slack);
+    for (int j = j_s + lane; j < row_lo; j += nlanes)
+    {
+        const int4 ck = LBL_LDG(reinterpret_cast<const int4*>(a.rec.chk + off + j));
+        if ((unsigned)(ck.x + g.cut_off + 1 - pp.bs) < (unsigned)pp.ns)
+        {
+            out[2] += ped_line_at(a, off + j, ck, v_s, pp.i_s);
+        }
+    }
+    const int j_e = first_line_at(a.lines, (double)g.v0 + (double)(pp.be - g.cut_off - 1) - slack);
+    for (int j = j_e + lane; j < row_lo; j += nlanes)
+    {
+        const int4 ck = LBL_LDG(reinterpret_cast<const int4*>(a.rec.chk + off + j));
+        if ((unsigned)(ck.x + g.cut_off + 1 - pp.be) < (unsigned)pp.ne)
+        {
+            out[3] += ped_line_at(a, off + j, ck, v_e, pp.i_e);
+        }
+    }
+}
+
+// The sequential step: the run's pedestal sum from its four gathered sums and the pedestals
+// already binned (sum_ps, sum_pe: over the bins that cover k[s], k[e]).
+LBL_HD double ped_chain_run(const double (&sums)[4], double sum_ps, double sum_pe)
+{
+    const double ks0 = sums[2] - sum_ps;
+    const double ke0 = sums[3] - sum_pe;
+    const double d_end = (ks0 - ke0) + (sums[0] - sums[1]);
+    const double ks_end = d_end > 0. ? d_end : 0.;
+    return (sums[0] + ks0) - ks_end;
 }
 
 // K4a: pedestal seen by the points of one cell: corr[0] for r > 0, corr[1] for r == 0.

@@ -184,6 +184,35 @@ static void run_chain(const PedArgs& pa, int layer, double* nodes)
     for (int lane = 0; lane < 32; ++lane) ped_lane_finish(lanes[lane], g, lane, bins);
 }
 
+// The run-based recurrence for nu-sorted rows (PedRunArgs): what ped_run_count/scatter,
+// ped_nodes_kernel and ped_chain_runs_kernel do, one emulated lane.
+static void run_chain_sorted(const PedRunArgs& ra, int layer, const LayerIn* layers)
+{
+    const GridSpec& g = ra.grid;
+    const int nb = g.ncell + 2 * g.cut_off + 2;
+    double* bins = ra.pedbin + (size_t)layer * nb;
+    for (int b = 0; b < nb; ++b) bins[b] = 0.;
+    const size_t off = (size_t)layer * ra.lines.n;
+    std::vector<int> starts;
+    for (int j = 0; j < ra.n_rows; ++j)
+    {
+        if (j == 0 || ra.rec.chk[off + j].cb != ra.rec.chk[off + j - 1].cb) starts.push_back(j);
+    }
+    starts.push_back(ra.n_rows);
+    for (size_t r = 0; r + 1 < starts.size(); ++r)
+    {
+        double sums[4];
+        ped_run_sums(ra, layer, starts[r], starts[r + 1], 0, 1, sums);
+        const int cb = ra.rec.chk[off + starts[r]].cb;
+        const PedPoints pp = ped_points(cb, g);
+        if (pp.skip) continue;
+        double ps = 0., pe = 0.;
+        for (int k = 0; k < pp.ns; ++k) ps += bins[pp.bs + k];
+        for (int k = 0; k < pp.ne; ++k) pe += bins[pp.be + k];
+        bins[cb + g.cut_off + 1] += ped_chain_run(sums, ps, pe);
+    }
+}
+
 extern "C" int emu_absorption(int n_layers, const double* pressure, const double* temperature,
                               const double* vmr, int v0, int vn, int n_per_v, double* k,
                               int n_lines, const double* nu, const double* sw,
@@ -357,8 +386,26 @@ extern "C" int emu_absorption(int n_layers, const double* pressure, const double
         pa.grid = g;
         pa.pedbin = pedbin.data();
         pa.n_rows = ln.n;
+        PedRunArgs ra;
+        ra.lines = ln;
+        ra.rec = rec;
+        ra.grid = g;
+        ra.layers = layers.data();
+        ra.n_rows = ln.n;
+        ra.run_row = nullptr;
+        ra.n_runs = nullptr;
+        ra.run_cb = nullptr;
+        ra.run_sums = nullptr;
+        ra.pedbin = pedbin.data();
+        // nu-sorted rows: the run-based recurrence; otherwise (or on request) the slot ring
+        const bool runs_path = ln.db_to_sorted == nullptr && getenv("EMU_PED_SLOTS") == nullptr;
         for (int l = 0; l < n_layers; ++l)
         {
+            if (runs_path)
+            {
+                run_chain_sorted(ra, l, layers.data());
+            }
+            else
             switch ((2 * cut_off + 5 + 31) / 32)
             {
                 case 1: run_chain<1>(pa, l, nodes.data()); break;

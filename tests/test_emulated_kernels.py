@@ -179,3 +179,31 @@ def test_far_field_kernel_against_direct_kernel(emu, small_db, atmosphere):
             for layer in range(4):
                 if np.any(direct[layer]):
                     assert scaled_error(fast[layer], direct[layer], bounds[2]) <= 1e-11
+
+
+@pytest.mark.parametrize("bounds,cut", [((1, 801, 10), 25), ((1, 301, 100), 25), ((5, 161, 20), 5),
+                                        ((1, 500, 4), 40), ((20, 140, 64), 1)])
+def test_run_based_pedestal_against_the_slot_ring(emu, tmp_path, monkeypatch, bounds, cut):
+    """The two formulations of the accumulated pedestal (spectra.c:66-78) -- explicit node state
+    walked line by line (slot ring; any row order) and the closed form per run of equal window
+    cell (nu-sorted rows) -- on lines that sit on integer wavenumbers with shifts of both signs
+    (window cells out of order between neighbouring rows), clamped windows at both ends of the
+    grid, and against the oracle."""
+    lines = synth.make_line_list("O2", 300, 0.5, 170.0, seed=9)
+    lines["nu"] = np.sort(np.round(lines["nu"]) + np.tile([0.0, 1e-6, -1e-6, 0.5, 0.999], 60))
+    lines["delta_air"] = np.tile([-0.02, 0.02, 0.0199, -0.0003, 0.015], 60)
+    path = str(tmp_path / "shift.db")
+    synth.write_database(path, {"O2": lines})
+    gas = OracleGas(path, "O2")
+    t = np.array([250.0, 296.0]); p = np.array([101325.0, 5.0e4]); x = np.array([0.209, 0.209])
+    monkeypatch.delenv("EMU_PED_SLOTS", raising=False)
+    runs, _ = run(emu, gas, t, p, x, bounds, 1, cut=cut)
+    monkeypatch.setenv("EMU_PED_SLOTS", "1")
+    slots, _ = run(emu, gas, t, p, x, bounds, 1, cut=cut)
+    for layer in range(2):
+        k_ref = gas.absorption(t[layer], p[layer], x[layer], *bounds, 1, cut)
+        if not np.any(k_ref):
+            assert not np.any(runs[layer])
+            continue
+        assert scaled_error(runs[layer], k_ref, bounds[2], max(cut, 1)) <= FP64_TOL
+        assert scaled_error(runs[layer], slots[layer], bounds[2], max(cut, 1)) <= 1e-12
