@@ -1538,7 +1538,8 @@ LBL_HD void pedestal_layer(const PedArgs& a, int layer, int lane, int nlanes, do
 // then removes min(k[s], k[e]) from both, so after it k[s] = max(d, 0), k[e] = max(-d, 0) and
 // d moves by f[s] - f[e] -- the clamping never feeds back into d.  Over a whole run:
 //     d_end = (k[s] - k[e])_before + sum(f[s]) - sum(f[e])
-//     sum of the run's pedestals = sum(f[s]) + k[s]_before - max(d_end, 0)       (telescoping)
+//     sum of the run's pedestals = sum(f[e]) + k[e]_before   if d_end > 0   (k[e] ends at zero)
+//                                = sum(f[s]) + k[s]_before   otherwise      (telescoping)
 // and the values before the run are sums over the EARLIER rows whose windows cover the point,
 //     k[x]_before = sum_l f_l(x)  -  sum_l pedestal_l ,
 // the first a plain gather (ped_run_sums: every run of every layer in parallel, like the
@@ -1653,8 +1654,12 @@ LBL_HD double ped_chain_run(const double (&sums)[4], double sum_ps, double sum_p
     const double ks0 = sums[2] - sum_ps;
     const double ke0 = sums[3] - sum_pe;
     const double d_end = (ks0 - ke0) + (sums[0] - sums[1]);
-    const double ks_end = d_end > 0. ? d_end : 0.;
-    return (sums[0] + ks0) - ks_end;
+    // The pedestals telescope on either side: sum = sum f[s] + k[s]_before - k[s]_after
+    //                                             = sum f[e] + k[e]_before - k[e]_after,
+    // and one of k[s]_after = max(d_end, 0), k[e]_after = max(-d_end, 0) is exactly zero: taking
+    // that side keeps the sum free of cancellation (k[s] next to a strong line's core can be
+    // 1e10 times k[e]; the reference's min() returns the small one exactly).
+    return d_end > 0. ? sums[1] + ke0 : sums[0] + ks0;
 }
 
 // K4a: pedestal seen by the points of one cell: corr[0] for r > 0, corr[1] for r == 0.

@@ -274,7 +274,9 @@ extern "C" int emu_absorption(int n_layers, const double* pressure, const double
     ln.nu = c_nu.data(); ln.sw = c_sw.data(); ln.gamma_air = c_ga.data();
     ln.gamma_self = c_gs.data(); ln.n_air = c_na.data(); ln.elower = c_el.data();
     ln.delta_air = c_da.data(); ln.mass = c_m.data(); ln.iso = c_iso.data();
-    ln.db_to_sorted = inv.data();
+    bool identity = true;
+    for (int j = 0; j < na; ++j) identity = identity && order[j] == j;
+    ln.db_to_sorted = identity ? nullptr : inv.data();   // as the library: no permutation for sorted rows
     // per-wavenumber index, as make_plan builds it
     std::vector<int> cell_first((size_t)((vn - v0) + 2 * cut_off + 7));
     ln.cell_w0 = v0 - cut_off - 3;
