@@ -190,6 +190,34 @@ LBL_API int lbl_mix_download(lbl_mix* mix, double* host);
 LBL_API int lbl_mix_device_result(lbl_mix* mix, double** device_ptr, long long* count);
 LBL_API int lbl_mix_close(lbl_mix* mix);
 
+/* ---- MT-CKD continua on the device (the other mechanism the driver adds per gas) -------------
+ * Replaces the host-side plugin pyLBL/mt_ckd, i.e. what spectroscopy.py:194-198 calls per
+ * (gas, layer): BandedContinuum.spectra(T, p, vmr, grid) (mt_ckd/utils.py:157-174) -- every
+ * band's formula (mt_ckd/carbon_dioxide.py, water_vapor.py, nitrogen.py, oxygen.py, ozone.py) on
+ * the band's own coarse grid, numpy.interp onto the caller's grid (zero outside the band), times
+ * 100 -- for all layers at once, on the grid (v0, vn, n_per_v) of the lines calls.
+ *   lbl_continuum_create / _set_spectrum / _finalize: the coefficient table, variable by
+ *       variable as the reference's file names them (bfco2, bs296, ..., with the wavenumber_*
+ *       attributes of each), then the band tables are built on the device.  No file format of
+ *       its own: the host side reads pylbl_b200/data/mt_ckd.npz (tools/convert_mt_ckd.py).
+ *   lbl_continuum_compute: continuum `name` ("CO2", "H2OForeign", "H2OSelf", "N2", "O2", "O3")
+ *       in m-1 for n_layers states; vmr6[L*6 ..] = mole fractions of H2O, CO2, O3, N2, O2 and
+ *       the sum over ALL gases of the atmosphere (utils.py:18-30); pressure in Pa.  Either
+ *       k_host[L*n ..] receives it, or (mix != NULL) it is added to rows row0+L of the
+ *       device-side accumulator.  Blocking. */
+typedef struct lbl_continuum lbl_continuum;
+LBL_API int lbl_continuum_create(int device, lbl_continuum** out);
+LBL_API int lbl_continuum_set_spectrum(lbl_continuum* c, const char* name, double lower_bound,
+                   double upper_bound, double resolution, int count, const double* data);
+LBL_API int lbl_continuum_finalize(lbl_continuum* c);
+LBL_API int lbl_continuum_compute(lbl_continuum* c, const char* name, int n_layers,
+                   const double* temperature, const double* pressure, const double* vmr6,
+                   int v0, int vn, int n_per_v, lbl_mix* mix, int row0, double* k_host);
+/* CUDA-event durations of the last call's two kernels: the band formulas (K5a) and the
+ * interpolate-and-add pass over the output (K5b, HBM-bound). */
+LBL_API int lbl_continuum_last_ms(lbl_continuum* c, float* bands_ms, float* apply_ms);
+LBL_API int lbl_continuum_close(lbl_continuum* c);
+
 /* Pinned host memory for k_host (lets the device->host copy run asynchronously). */
 LBL_API int lbl_host_alloc(size_t bytes, void** ptr);
 LBL_API int lbl_host_free(void* ptr);

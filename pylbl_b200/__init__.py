@@ -9,6 +9,7 @@ runs the line-by-line calculation on the GPU with everything else unchanged
 (pyLBL/plugins.py:9-15, pyLBL/spectroscopy.py:117-118).
 """
 from .gas_optics import Gas, grid_to_ints, pack_database, pack_info  # noqa: F401
+from .continuum import Continuum, continua_of  # noqa: F401
 from .mixture import Mixture, number_density  # noqa: F401
 from .spectroscopy import Spectroscopy  # noqa: F401
 

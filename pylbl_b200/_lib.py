@@ -49,7 +49,9 @@ EXPORTS = (
     "lbl_timer_join", "lbl_timer_stop", "lbl_measure_fp64_peak", "lbl_mix_open", "lbl_mix_reset",
     "lbl_mix_add", "lbl_mix_download", "lbl_mix_close", "lbl_pack_database", "lbl_pack_info",
     "lbl_gas_open_pack", "lbl_gas_set_copy_groups", "lbl_gas_submit_band", "lbl_gas_submit_mix",
-    "lbl_mix_wait", "lbl_mix_device_result", "lbl_gas_band_edges",
+    "lbl_mix_wait", "lbl_mix_device_result", "lbl_gas_band_edges", "lbl_continuum_create",
+    "lbl_continuum_set_spectrum", "lbl_continuum_finalize", "lbl_continuum_compute",
+    "lbl_continuum_close", "lbl_continuum_last_ms",
 )
 
 _library = None
@@ -99,6 +101,13 @@ def library():
     lib.lbl_gas_band_edges.argtypes = [c_void_p] + 5 * [c_int] + [i32]
     lib.lbl_gas_submit_mix.argtypes = [c_void_p, c_int, f64, f64, f64] + 6 * [c_int] + \
         [c_void_p, c_int, f64, c_void_p]
+    lib.lbl_continuum_create.argtypes = [c_int, POINTER(c_void_p)]
+    lib.lbl_continuum_set_spectrum.argtypes = [c_void_p, c_char_p, c_double, c_double, c_double, c_int, f64]
+    lib.lbl_continuum_finalize.argtypes = [c_void_p]
+    lib.lbl_continuum_compute.argtypes = [c_void_p, c_char_p, c_int, f64, f64, f64, c_int, c_int, c_int,
+                                          c_void_p, c_int, c_void_p]
+    lib.lbl_continuum_close.argtypes = [c_void_p]
+    lib.lbl_continuum_last_ms.argtypes = [c_void_p, POINTER(c_float), POINTER(c_float)]
     lib.lbl_mix_wait.argtypes = [c_void_p]
     lib.lbl_mix_device_result.argtypes = [c_void_p, POINTER(c_void_p), POINTER(c_longlong)]
     lib.lbl_gas_wait.argtypes = [c_void_p]

@@ -1958,6 +1958,339 @@ int lbl_mix_close(lbl_mix* m)
     return 0;
 }
 
+// ---- MT-CKD continua on the device ----------------------------------------------------------
+}  // extern "C"
+
+#include "lbl_continuum.cuh"
+
+struct lbl_continuum
+{
+    int device = 0;
+    DeviceStreams* streams = nullptr;
+    struct Spectrum
+    {
+        double lower = 0., upper = 0., resolution = 0.;
+        std::vector<double> data;
+    };
+    std::map<std::string, Spectrum> table;
+    std::vector<std::unique_ptr<DevBuf>> arrays;   // coefficient arrays on the device
+    std::map<std::string, ContinuumView> continua;
+    DevBuf layers_dev, values_dev, out_dev;
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};   // before K5a, between, after K5b
+    bool timed = false;
+    bool finalized = false;
+};
+
+namespace
+{
+// wavenumbers of a table variable, as utils.py:138-144 forms them
+std::vector<double> wavenumbers(const lbl_continuum::Spectrum& s)
+{
+    std::vector<double> w(s.data.size());
+    for (size_t i = 0; i < w.size(); ++i) w[i] = s.lower + (double)i * s.resolution;
+    return w;
+}
+
+// `sub` laid over the grid of `host` (utils.py:64-81): first and last host index it covers.
+int subgrid_bounds(const lbl_continuum::Spectrum& host, const lbl_continuum::Spectrum& sub, int* lower,
+                   int* upper)
+{
+    if (host.resolution != sub.resolution) return fail("Error: grid and subgrid have different resolutions.");
+    if (host.lower > sub.lower || host.upper < sub.upper) return fail("Error: subgrid not contained in grid.");
+    *lower = (int)((sub.lower - host.lower) / host.resolution);
+    *upper = (int)((sub.upper - host.lower) / host.resolution);
+    if (*upper - *lower + 1 != (int)sub.data.size() || *upper >= (int)host.data.size())
+    {
+        return fail("Error: subgrid does not fit its grid.");
+    }
+    return 0;
+}
+
+int continuum_upload(lbl_continuum* c, const std::vector<double>& v, const double** out)
+{
+    c->arrays.emplace_back(new DevBuf);
+    DevBuf& b = *c->arrays.back();
+    LBL_CUDA(b.reserve(sizeof(double) * std::max<size_t>(v.size(), 1)));
+    LBL_CUDA(cudaMemcpy(b.p, v.data(), sizeof(double) * v.size(), cudaMemcpyHostToDevice));
+    *out = b.as<double>();
+    return 0;
+}
+
+int continuum_band(lbl_continuum* c, ContinuumView& cv, int kind, double lower, double resolution,
+                   std::initializer_list<const std::vector<double>*> coefficients)
+{
+    if (cv.n_bands >= kMaxBands) return fail("Error: too many bands.");
+    BandView& b = cv.band[cv.n_bands++];
+    b.kind = kind;
+    b.n = (int)(*coefficients.begin())->size();
+    b.lower = lower;
+    b.resolution = resolution;
+    b.value_offset = cv.row;
+    cv.row += b.n;
+    int k = 0;
+    for (int q = 0; q < 4; ++q) b.c[q] = nullptr;
+    for (const std::vector<double>* v : coefficients)
+    {
+        if ((int)v->size() != b.n) return fail("Error: coefficient arrays of a band differ in length.");
+        if (continuum_upload(c, *v, &b.c[k++])) return 1;
+    }
+    return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int lbl_continuum_create(int device, lbl_continuum** out)
+{
+    *out = nullptr;
+    int ndev = 0;
+    if (lbl_device_count(&ndev)) return 1;
+    if (ndev == 0) return fail("Error: no CUDA device (" + g_last_error + "); this library has no CPU path.");
+    if (device < 0 || device >= ndev) return fail("Error: CUDA device index out of range.");
+    std::unique_ptr<lbl_continuum> c(new lbl_continuum);
+    c->device = device;
+    LBL_CUDA(cudaSetDevice(device));
+    if (device_streams(device, &c->streams)) return 1;
+    for (cudaEvent_t& e : c->ev) LBL_CUDA(cudaEventCreate(&e));
+    *out = c.release();
+    return 0;
+}
+
+int lbl_continuum_last_ms(lbl_continuum* c, float* bands_ms, float* apply_ms)
+{
+    if (!c || !bands_ms || !apply_ms) return fail("Error: null argument.");
+    if (!c->timed) return fail("Error: no continuum call to report.");
+    LBL_CUDA(cudaSetDevice(c->device));
+    LBL_CUDA(cudaEventSynchronize(c->ev[2]));
+    LBL_CUDA(cudaEventElapsedTime(bands_ms, c->ev[0], c->ev[1]));
+    LBL_CUDA(cudaEventElapsedTime(apply_ms, c->ev[1], c->ev[2]));
+    return 0;
+}
+
+int lbl_continuum_set_spectrum(lbl_continuum* c, const char* name, double lower, double upper,
+                               double resolution, int count, const double* data)
+{
+    if (!c || !name || !data || count < 1) return fail("Error: invalid continuum spectrum.");
+    if (c->finalized) return fail("Error: continuum table already finalized.");
+    lbl_continuum::Spectrum& s = c->table[name];
+    s.lower = lower;
+    s.upper = upper;
+    s.resolution = resolution;
+    s.data.assign(data, data + count);
+    return 0;
+}
+
+int lbl_continuum_finalize(lbl_continuum* c)
+{
+    if (!c) return fail("Error: null handle.");
+    if (c->finalized) return 0;
+    LBL_CUDA(cudaSetDevice(c->device));
+    auto need = [&](const char* name, const lbl_continuum::Spectrum** out) {
+        auto it = c->table.find(name);
+        if (it == c->table.end()) return fail(std::string("Error: continuum table lacks ") + name + ".");
+        *out = &it->second;
+        return 0;
+    };
+    auto simple = [&](ContinuumView& cv, int kind, std::initializer_list<const char*> names) {
+        std::vector<const lbl_continuum::Spectrum*> sp;
+        for (const char* n : names)
+        {
+            const lbl_continuum::Spectrum* s = nullptr;
+            if (need(n, &s)) return 1;
+            sp.push_back(s);
+        }
+        std::vector<const std::vector<double>*> co;
+        for (const lbl_continuum::Spectrum* s : sp) co.push_back(&s->data);
+        if (cv.n_bands >= kMaxBands) return fail("Error: too many bands.");
+        // initializer_list cannot be built at run time: add the band by hand
+        BandView& b = cv.band[cv.n_bands++];
+        b.kind = kind;
+        b.n = (int)sp[0]->data.size();
+        b.lower = sp[0]->lower;
+        b.resolution = sp[0]->resolution;
+        b.value_offset = cv.row;
+        cv.row += b.n;
+        for (int q = 0; q < 4; ++q) b.c[q] = nullptr;
+        for (size_t k = 0; k < co.size(); ++k)
+        {
+            if ((int)co[k]->size() != b.n) return fail("Error: coefficient arrays of a band differ in length.");
+            if (continuum_upload(c, *co[k], &b.c[k])) return 1;
+        }
+        return 0;
+    };
+    const lbl_continuum::Spectrum* s = nullptr;
+    const lbl_continuum::Spectrum* x = nullptr;
+
+    {   // CO2, carbon_dioxide.py:9-45
+        ContinuumView cv{};
+        if (need("bfco2", &s)) return 1;
+        std::vector<double> tcorr(s->data.size(), 1.), xfac(s->data.size(), 1.);
+        int lo = 0, hi = 0;
+        if (need("tdep_bandhead", &x) || subgrid_bounds(*s, *x, &lo, &hi)) return 1;
+        std::copy(x->data.begin(), x->data.end(), tcorr.begin() + lo);
+        if (need("x_factor_co2", &x) || subgrid_bounds(*s, *x, &lo, &hi)) return 1;
+        std::copy(x->data.begin(), x->data.end(), xfac.begin() + lo);
+        if (continuum_band(c, cv, kCo2Hartmann, s->lower, s->resolution, {&s->data, &xfac, &tcorr})) return 1;
+        c->continua["CO2"] = cv;
+    }
+    {   // H2O self, water_vapor.py:7-35
+        ContinuumView cv{};
+        if (simple(cv, kH2oSelf, {"bs296", "bs260"})) return 1;
+        c->continua["H2OSelf"] = cv;
+    }
+    {   // H2O foreign, water_vapor.py:38-79
+        ContinuumView cv{};
+        if (need("bfh2o", &s) || need("xfac_rhu", &x)) return 1;
+        int lo = 0, hi = 0;
+        if (subgrid_bounds(*s, *x, &lo, &hi)) return 1;
+        std::vector<double> scale(s->data.size(), 0.);
+        for (int i = 1; i < (int)x->data.size(); ++i) scale[lo + i] = x->data[i];
+        scale[lo] = scale[lo + 1];
+        const std::vector<double> w = wavenumbers(*s);
+        for (size_t i = (size_t)hi + 1; i < scale.size(); ++i)
+        {
+            const double vdelsq1 = (w[i] - 255.67) * (w[i] - 255.67);
+            const double vf1 = std::pow((w[i] - 255.67) / 57.83, 8);
+            const double vdelmsq1 = (w[i] + 255.67) * (w[i] + 255.67);
+            const double vmf1 = std::pow((w[i] + 255.67) / 57.83, 8);
+            const double vf2 = std::pow(w[i] / 630., 8);
+            scale[i] = 1. + (0.06 - 0.42 * ((57600. / (vdelsq1 + 57600. + vf1)) +
+                                            (57600. / (vdelmsq1 + 57600. + vmf1)))) / (1. + 0.3 * vf2);
+        }
+        if (continuum_band(c, cv, kH2oForeign, s->lower, s->resolution, {&s->data, &scale})) return 1;
+        c->continua["H2OForeign"] = cv;
+    }
+    {   // N2, nitrogen.py:7-79
+        ContinuumView cv{};
+        if (simple(cv, kN2Rotation, {"ct_296", "ct_220", "sf_296", "sf_220"})) return 1;
+        if (simple(cv, kN2Fundamental, {"xn2_272", "xn2_228", "a_h2o"})) return 1;
+        if (simple(cv, kN2Overtone, {"xn2"})) return 1;
+        c->continua["N2"] = cv;
+    }
+    {   // O2, oxygen.py:7-148
+        ContinuumView cv{};
+        if (simple(cv, kO2Fundamental, {"o2_f", "o2_t"})) return 1;
+        if (simple(cv, kO2Nir, {"o2_inf1"})) return 1;
+        {   // oxygen.py:57-71: analytic, on arange(9100., 11002., 2.)
+            std::vector<double> data;
+            const double hw1 = 58.96, hw2 = 45.04;
+            for (int i = 0; 9100. + 2. * i < 11002.; ++i)
+            {
+                const double g = 9100. + 2. * i;
+                const double dv1 = g - 9375., dv2 = g - 9439.;
+                const double damp1 = dv1 < 0. ? std::exp(dv1 / 176.1) : 1.;
+                const double damp2 = dv2 < 0. ? std::exp(dv2 / 176.1) : 1.;
+                const double o2inf = 0.31831 * (((1.166e-04 * damp1 / hw1) / (1. + (dv1 / hw1) * (dv1 / hw1))) +
+                                                ((3.086e-05 * damp2 / hw2) / (1. + (dv2 / hw2) * (dv2 / hw2)))) * 1.054;
+                data.push_back(o2inf / g);
+            }
+            if (continuum_band(c, cv, kO2Nir2, 9100., 2., {&data})) return 1;
+        }
+        if (simple(cv, kO2Nir3, {"o2_inf3"})) return 1;
+        if (simple(cv, kO2Visible, {"o2_invis"})) return 1;
+        {   // oxygen.py:114-126: analytic, on arange(36000., 100010., 10.)
+            std::vector<double> data;
+            for (int i = 0; 36000. + 10. * i < 100010.; ++i)
+            {
+                const double g = 36000. + 10. * i;
+                if (g <= 36000.)
+                {
+                    data.push_back(0.);
+                    continue;
+                }
+                const double corr = g <= 40000. ? ((40000. - g) / 4000.) * 7.917e-7 : 0.;
+                const double yratio = g / 48811.0;
+                data.push_back(6.884e-4 * yratio * std::exp(-69.738 * std::pow(std::log(yratio), 2)) - corr);
+            }
+            if (continuum_band(c, cv, kO2Herzberg, 36000., 10., {&data})) return 1;
+        }
+        if (simple(cv, kO2Uv, {"o2_infuv"})) return 1;
+        c->continua["O2"] = cv;
+    }
+    {   // O3, ozone.py:5-70
+        ContinuumView cv{};
+        if (simple(cv, kO3ChappuisWulf, {"x_o3", "y_o3", "z_o3"})) return 1;
+        if (simple(cv, kO3HartleyHuggins, {"o3_hh0", "o3_hh1", "o3_hh2"})) return 1;
+        if (simple(cv, kO3Uv, {"o3_huv"})) return 1;
+        c->continua["O3"] = cv;
+    }
+    c->finalized = true;
+    return 0;
+}
+
+int lbl_continuum_compute(lbl_continuum* c, const char* name, int n_layers, const double* temperature,
+                          const double* pressure, const double* vmr6, int v0, int vn, int n_per_v,
+                          lbl_mix* mix, int row0, double* k_host)
+{
+    if (!c || !name || !temperature || !pressure || !vmr6) return fail("Error: null argument.");
+    if (!c->finalized) return fail("Error: continuum table not finalized.");
+    auto it = c->continua.find(name);
+    if (it == c->continua.end()) return fail(std::string("Error: no continuum named ") + name + ".");
+    if (n_layers < 1 || n_per_v < 1 || vn <= v0) return fail("Error: invalid grid or layer count.");
+    const long long n_ll = (long long)(vn - v0) * n_per_v;
+    if (n_ll > (1ll << 30)) return fail("Error: spectral grid too large for 32-bit indices.");
+    const int n = (int)n_ll;
+    if (mix && k_host) return fail("Error: a call feeds either the host array or the accumulator.");
+    if (!mix && !k_host) return fail("Error: nowhere to put the continuum.");
+    if (mix && (mix->device != c->device || mix->n != n || row0 < 0 || row0 + n_layers > mix->n_layers))
+    {
+        return fail("Error: accumulator shape does not fit this call.");
+    }
+    LBL_CUDA(cudaSetDevice(c->device));
+    const ContinuumView& cv = it->second;
+    std::vector<ContinuumLayer> layers((size_t)n_layers);
+    for (int l = 0; l < n_layers; ++l)
+    {
+        const double* x = vmr6 + 6 * (size_t)l;
+        layers[l] = ContinuumLayer{temperature[l], pressure[l], x[0], x[1], x[2], x[3], x[4], x[5]};
+    }
+    cudaStream_t sl = c->streams->late;    // where the accumulator's additions are ordered
+    LBL_CUDA(cudaStreamSynchronize(sl));   // the previous call's buffers are free
+    LBL_CUDA(c->layers_dev.reserve(sizeof(ContinuumLayer) * (size_t)n_layers));
+    LBL_CUDA(c->values_dev.reserve(sizeof(double) * (size_t)cv.row * n_layers));
+    LBL_CUDA(cudaMemcpyAsync(c->layers_dev.p, layers.data(), sizeof(ContinuumLayer) * n_layers,
+                             cudaMemcpyHostToDevice, sl));
+    dim3 gb((cv.row + 127) / 128, n_layers);
+    LBL_CUDA(cudaEventRecord(c->ev[0], sl));
+    continuum_bands_kernel<<<gb, 128, 0, sl>>>(cv, c->layers_dev.as<ContinuumLayer>(), c->values_dev.as<double>());
+    LBL_CUDA(cudaEventRecord(c->ev[1], sl));
+    c->timed = true;
+    const size_t total = (size_t)n_layers * n;
+    const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
+    if (mix)
+    {
+        continuum_apply_kernel<true><<<blocks, 256, 0, sl>>>(
+            cv, c->values_dev.as<double>(), v0, 1. / n_per_v, 0, n, n_layers,
+            mix->acc.as<double>() + (size_t)row0 * n);
+        LBL_CUDA(cudaGetLastError());
+        LBL_CUDA(cudaEventRecord(c->ev[2], sl));
+        LBL_CUDA(cudaEventRecord(mix->ev_added, sl));
+        LBL_CUDA(cudaStreamSynchronize(sl));   // `layers` goes out of scope
+        return 0;
+    }
+    LBL_CUDA(c->out_dev.reserve(sizeof(double) * total));
+    continuum_apply_kernel<false><<<blocks, 256, 0, sl>>>(cv, c->values_dev.as<double>(), v0, 1. / n_per_v, 0,
+                                                          n, n_layers, c->out_dev.as<double>());
+    LBL_CUDA(cudaGetLastError());
+    LBL_CUDA(cudaEventRecord(c->ev[2], sl));
+    LBL_CUDA(cudaMemcpyAsync(k_host, c->out_dev.p, sizeof(double) * total, cudaMemcpyDeviceToHost, sl));
+    LBL_CUDA(cudaStreamSynchronize(sl));
+    return 0;
+}
+
+int lbl_continuum_close(lbl_continuum* c)
+{
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    for (auto& b : c->arrays) b->release();
+    c->layers_dev.release();
+    c->values_dev.release();
+    c->out_dev.release();
+    for (cudaEvent_t e : c->ev) if (e) cudaEventDestroy(e);
+    delete c;
+    return 0;
+}
+
 // ---- the reference's own entry point (absorption.c:19-30) ---------------------------------
 int absorption(double pressure, double temperature, double volume_mixing_ratio, int v0, int vn,
                int n_per_v, double* k, char* database, char* formula, int cut_off,

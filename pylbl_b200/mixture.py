@@ -65,13 +65,17 @@ class Mixture(object):
             pass
 
     def total_absorption(self, temperature, pressure, volume_mixing_ratio, grid=None,
-                         remove_pedestal=True, cut_off=25, bounds=None, out=None):
+                         remove_pedestal=True, cut_off=25, bounds=None, out=None, continuum=None):
         """sum over gases of n_gas * k_gas [m-1], shape (n_layers, (vn-v0)*n_per_v).
 
         Args:
-            volume_mixing_ratio: {formula: array over layers}.
+            volume_mixing_ratio: {formula: array over layers}; every gas of the atmosphere when
+                                 ``continuum`` is given (the continua read them all).
             remove_pedestal: True is what ``Spectroscopy.compute_absorption`` passes with the
                              MT-CKD continuum backend (pyLBL/spectroscopy.py:163-164).
+            continuum: a ``Continuum`` on this device: the MT-CKD continua of every gas of
+                       ``volume_mixing_ratio`` are added on the device too
+                       (pyLBL/spectroscopy.py:194-198,225-234).
         """
         v0, vn, n_per_v = bounds if bounds is not None else grid_to_ints(grid)
         t = np.ascontiguousarray(temperature, dtype=np.float64).ravel()
@@ -94,6 +98,12 @@ class Mixture(object):
         # pedestal chains overlap, the summation kernels run gas after gas, and each gas is
         # added into the accumulator on the device as soon as it is done.  The gas with the most
         # lines goes last; its layer groups are copied to the host while the next ones compute.
+        if continuum is not None:
+            from .continuum import continua_of
+            for formula in volume_mixing_ratio:
+                for name in continua_of(formula):
+                    continuum.spectra(name, t, p, volume_mixing_ratio, bounds=(v0, vn, n_per_v),
+                                      mix=self._mix)
         order = sorted(self.gases.items(), key=lambda item: item[1]._handle(self.device).stats()["n_lines"])
         handles = []
         for i, (formula, gas) in enumerate(order):
@@ -110,5 +120,5 @@ class Mixture(object):
             lib.lbl_gas_wait(h.ptr)
             gas.last_stats = [h.stats()]
         if not handles:
-            out[:] = 0.
+            lib.lbl_mix_download(self._mix, out.ctypes.data_as(c_void_p))
         return out

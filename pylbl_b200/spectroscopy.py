@@ -11,9 +11,10 @@ members carry ``.data``, or plain arrays / a dict), and results are numpy arrays
 reference's layout; ``to_dataset`` wraps them into the reference's xarray ``Dataset`` when
 xarray is installed.
 
-Only the "lines" mechanism is computed here (index 0 of the ``mechanism`` axis); continua and
-cross-sections are other plugins of the reference and stay zero, as they do in the reference
-when those engines have no data for a gas (pyLBL/spectroscopy.py:59-70).
+Mechanism 0 ("lines") and mechanism 1 ("continuum", the MT-CKD continua on the device,
+``continua_backend="mt_ckd"`` as in the reference; ``None`` switches them off) are computed
+here; cross-sections (arts-crossfit) are another plugin of the reference and stay zero, as they
+do in the reference when that engine has no data for a gas (pyLBL/spectroscopy.py:66-70).
 """
 from __future__ import annotations
 
@@ -23,6 +24,7 @@ from ctypes import c_void_p
 import numpy as np
 
 from . import _lib
+from .continuum import Continuum, continua_of
 from .gas_optics import Gas, default_device, grid_to_ints
 from .mixture import Mixture, number_density
 
@@ -46,7 +48,8 @@ class Spectroscopy(object):
         grid: wavenumber grid [cm-1] (integer first point, step 1/integer: README.rst:229-230).
     """
 
-    def __init__(self, atmosphere, grid, database, device=None, precision="fp64", cache_dir=None):
+    def __init__(self, atmosphere, grid, database, device=None, precision="fp64", cache_dir=None,
+                 continua_backend="mt_ckd"):
         self.temperature = _values(_member(atmosphere, "temperature"))
         self.pressure = _values(_member(atmosphere, "pressure"))
         self.gases = {name: _values(x) for name, x in dict(_member(atmosphere, "gases")).items()}
@@ -60,6 +63,17 @@ class Spectroscopy(object):
         self.cache_dir = cache_dir
         self.cache = {}          # formula -> Gas, or None when the database has no such molecule
         self._pinned = {}        # formula -> PinnedArray (staging of the per-gas formats)
+        if continua_backend not in ("mt_ckd", None):
+            raise ValueError("continua_backend must be 'mt_ckd' or None")
+        self.continua_backend = continua_backend     # pyLBL/spectroscopy.py:89,119
+        self._continuum = None
+
+    def _continua(self):
+        if self.continua_backend is None:
+            return None
+        if self._continuum is None:
+            self._continuum = Continuum(self.device)
+        return self._continuum
 
     PINNED_LIMIT = 2 << 30
 
@@ -101,6 +115,9 @@ class Spectroscopy(object):
                 gas.close()
         self.cache = {}
         self._pinned = {}
+        if self._continuum is not None:
+            self._continuum.close()
+            self._continuum = None
 
     def compute_absorption(self, output_format="all", remove_pedestal=None, cut_off=25):
         """Absorption coefficients [m-1], pyLBL/spectroscopy.py:144-206.
@@ -110,15 +127,15 @@ class Spectroscopy(object):
                                    as in the reference (only "lines" is filled);
                            "gas"   {"<gas>_absorption": (*shape, grid.size)};
                            "total" {"absorption": (*shape, grid.size)}, summed on the device.
-            remove_pedestal: None = True, what the reference passes with its default MT-CKD
-                             continuum backend (pyLBL/spectroscopy.py:163-164).
+            remove_pedestal: None = whether the continuum backend is MT-CKD, as in the reference
+                             (pyLBL/spectroscopy.py:163-164).
         Returns:
             dict of numpy arrays, plus "wavenumber" (and "mechanism" for "all").
         """
         if output_format not in ("all", "gas", "total"):
             raise ValueError("output_format must be 'all', 'gas' or 'total'")
         if remove_pedestal is None:
-            remove_pedestal = True
+            remove_pedestal = self.continua_backend == "mt_ckd"
         shape = self.temperature.shape
         t = np.ascontiguousarray(self.temperature.ravel())
         p = np.ascontiguousarray(self.pressure.ravel())
@@ -128,14 +145,16 @@ class Spectroscopy(object):
         out = {"wavenumber": self.grid}
         present = {name: self._gas(name) for name in self.gases}
 
+        continuum = self._continua()
+        flat = {name: np.ascontiguousarray(x.ravel()) for name, x in self.gases.items()}
         if output_format == "total":
             total = np.zeros((t.size, size))
             names = [name for name, gas in present.items() if gas is not None]
-            if names:
+            if names or continuum is not None:
                 mix = Mixture.from_gases({n: present[n] for n in names}, self.device)
-                k = mix.total_absorption(t, p, {n: self.gases[n].ravel() for n in names},
+                k = mix.total_absorption(t, p, flat if continuum is not None else {n: flat[n] for n in names},
                                          bounds=(v0, vn, n_per_v), remove_pedestal=remove_pedestal,
-                                         cut_off=cut_off)
+                                         cut_off=cut_off, continuum=continuum)
                 total = k[:, :size]
                 mix.close()
             out["absorption"] = total.reshape(shape + (size,))
@@ -161,13 +180,22 @@ class Spectroscopy(object):
             lines[name] = number_density(t, p, x)[:, None] * k[:, :size]   # n*k[:grid.size]
         for name in self.gases:
             beta = lines.get(name)
+            cont = None
+            if continuum is not None:
+                for cname in continua_of(name):                   # spectroscopy.py:194-198
+                    k = continuum.spectra(cname, t, p, flat, bounds=(v0, vn, n_per_v))[:, :size]
+                    cont = k if cont is None else cont + k
             if output_format == "gas":
                 arr = np.zeros((t.size, size)) if beta is None else beta
+                if cont is not None:
+                    arr = arr + cont
                 out[f"{name}_absorption"] = arr.reshape(shape + (size,))
             else:
                 arr = np.zeros((t.size, len(MECHANISMS), size))
                 if beta is not None:
                     arr[:, 0, :] = beta
+                if cont is not None:
+                    arr[:, 1, :] = cont
                 out[f"{name}_absorption"] = arr.reshape(shape + (len(MECHANISMS), size))
         if output_format == "all":
             out["mechanism"] = list(MECHANISMS)

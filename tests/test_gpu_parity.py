@@ -421,6 +421,20 @@ def test_spectroscopy_adapter_matches_the_reference_driver_loop(small_db, atmosp
             beta[j] = number_density(t, p, x) * k[:grid.size]
         want[n] = beta
 
+    # continua the reference attaches per gas (spectroscopy.py:58-65,194-198), from the oracle
+    from oracle import mt_ckd
+    cont = {}
+    for n in names:
+        c = np.zeros(shape + (grid.size,))
+        for cname in mt_ckd.continua_of(n):
+            oracle = mt_ckd.OracleContinuum(cname)
+            for i in range(4):
+                j = np.unravel_index(i, shape)
+                vmr = {m: float(atm.gases[m].data.flat[i]) for m in names}
+                c[j] += oracle.spectra(atmosphere.t[i], atmosphere.p[i], vmr, grid)
+        cont[n] = c
+    assert cont["H2O"].any() and cont["CO2"].any() and not cont["XeF6"].any()
+
     allv = s.compute_absorption(output_format="all")
     assert allv["mechanism"] == ["lines", "continuum", "cross_section"]
     gasv = s.compute_absorption(output_format="gas")
@@ -429,14 +443,22 @@ def test_spectroscopy_adapter_matches_the_reference_driver_loop(small_db, atmosp
     for n in names[:2]:
         a = allv[f"{n}_absorption"]
         assert a.shape == shape + (3, grid.size)
-        assert not a[..., 1:, :].any()
-        assert np.array_equal(a[..., 0, :], gasv[f"{n}_absorption"])
+        assert not a[..., 2, :].any()
         for j in np.ndindex(shape):
             assert scaled_error(a[j][0], want[n][j], 100) <= FP64_TOL
+            assert np.abs(a[j][1] - cont[n][j]).max() <= 1e-12 * np.abs(cont[n][j]).max()
+            assert scaled_error(gasv[f"{n}_absorption"][j], want[n][j] + cont[n][j], 100) <= FP64_TOL
     assert not allv["XeF6_absorption"].any() and not gasv["XeF6_absorption"].any()
     for j in np.ndindex(shape):
-        assert scaled_error(total[j], want["H2O"][j] + want["CO2"][j], 100) <= FP64_TOL
+        everything = want["H2O"][j] + want["CO2"][j] + cont["H2O"][j] + cont["CO2"][j]
+        assert scaled_error(total[j], everything, 100) <= FP64_TOL
     s.close()
+    # and with the continua switched off: the lines alone, pedestal kept (spectroscopy.py:163-164)
+    plain = Spectroscopy(atm, grid, Db(small_db), continua_backend=None)
+    allp = plain.compute_absorption(output_format="all", remove_pedestal=True)
+    assert not allp["H2O_absorption"][..., 1:, :].any()
+    assert np.array_equal(allp["H2O_absorption"][..., 0, :], allv["H2O_absorption"][..., 0, :])
+    plain.close()
 
 
 @pytest.mark.parametrize("farfield,nearblock", [("2", "0"), ("2", "1"), ("0", "1"), ("0", "0")])
@@ -558,3 +580,63 @@ def test_line_cores_at_very_low_pressure(dense_db, farfield, monkeypatch):
     for layer in range(3):
         k_ref = ref.absorption(t[layer], p[layer], x[layer], *bounds)
         assert relative_error(k[layer], k_ref) <= FP64_TOL
+
+
+@pytest.mark.parametrize("bounds", [(1, 5001, 1), (2380, 2441, 50), (7000, 60000, 1), (1, 3251, 10)])
+def test_continuum_against_the_oracle(atmosphere, bounds):
+    """MT-CKD continua on the device (every band formula + numpy.interp semantics, zero outside a
+    band) against the numpy restatement that tests/test_oracle_mt_ckd.py pins to the reference's
+    own modules: the reference's fixture atmosphere (all eight gases), every continuum, grids
+    over the infrared, across the CO2 band head sub-grids, and up to the ultra-violet bands."""
+    from oracle import mt_ckd
+    from pylbl_b200 import Continuum
+    gases = ["H2O", "CO2", "O3", "N2O", "CH4", "CO", "O2"]
+    vmr = {g: atmosphere.vmr[g] for g in gases}
+    vmr["N2"] = np.full(4, 0.78)                       # tests/conftest.py:76 of the reference
+    cont = Continuum()
+    grid = synth.grid_from_bounds(*bounds)
+    n = (bounds[1] - bounds[0]) * bounds[2]
+    v = bounds[0] + np.arange(n) * (1. / bounds[2])     # the grid as absorption.c:33-39 forms it
+    seen = 0
+    for name in ("CO2", "H2OForeign", "H2OSelf", "N2", "O2", "O3"):
+        k = cont.spectra(name, atmosphere.t, atmosphere.p, vmr, bounds=bounds)
+        assert k.shape == (4, n)
+        oracle = mt_ckd.OracleContinuum(name)
+        for layer in range(4):
+            want = oracle.spectra(atmosphere.t[layer], atmosphere.p[layer],
+                                  {g: float(x[layer]) for g, x in vmr.items()}, v)
+            scale = np.abs(want).max()
+            if scale == 0.:
+                assert not k[layer].any()
+                continue
+            seen += 1
+            assert np.abs(k[layer] - want).max() <= 1e-12 * scale
+            assert np.array_equal(k[layer] == 0., want == 0.)      # the same points outside every band
+    assert seen >= 8
+    # a gas the formulas need but the atmosphere lacks: the reference's dictionary lookup fails
+    with pytest.raises(KeyError):
+        cont.spectra("N2", atmosphere.t, atmosphere.p, {g: atmosphere.vmr[g] for g in gases}, bounds=bounds)
+    cont.close()
+
+
+def test_continuum_into_the_gas_sum(small_db, atmosphere):
+    """`Mixture.total_absorption(continuum=...)`: lines of every gas plus the continua of every
+    gas of the atmosphere, summed on the device, against the pieces computed separately."""
+    from pylbl_b200 import Continuum, Mixture, continua_of
+    bounds = (1, 801, 100)
+    gases = ["H2O", "CO2", "O3"]
+    vmr = {g: atmosphere.vmr[g] for g in gases + ["O2"]}
+    vmr["N2"] = np.full(4, 0.78)
+    mix = Mixture(small_db, gases)
+    cont = Continuum()
+    lines = mix.total_absorption(atmosphere.t, atmosphere.p, vmr, bounds=bounds).copy()
+    both = mix.total_absorption(atmosphere.t, atmosphere.p, vmr, bounds=bounds, continuum=cont)
+    extra = np.zeros_like(lines)
+    for formula in vmr:
+        for name in continua_of(formula):
+            extra += cont.spectra(name, atmosphere.t, atmosphere.p, vmr, bounds=bounds)
+    assert extra.any()
+    for layer in range(4):
+        assert scaled_error(both[layer], lines[layer] + extra[layer], bounds[2]) <= 1e-13
+    mix.close()
+    cont.close()
