@@ -699,6 +699,173 @@ def cpu_config1_point(device):
             "gpu_value_scalar_plugin_calls": evals / gpu_best, "gpu_seconds": gpu_best, "unit": UNIT}
 
 
+# --------------------------------------------------------------------------------------
+# the other BASELINE configurations (run by hand; the driver runs the default, configs[1])
+# --------------------------------------------------------------------------------------
+def aux_database(config, local_rank, barrier):
+    cache = Path(tempfile.gettempdir()) / "pylbl_b200_bench"
+    cache.mkdir(exist_ok=True)
+    path = cache / f"config{config}.db"
+    done = cache / f"config{config}.done"
+    if local_rank == 0 and not done.exists():
+        synth.write_database(str(path), synth.config_line_lists(config))
+        done.write_text("ok")
+    barrier()
+    while not done.exists():
+        time.sleep(0.2)
+    return str(path)
+
+
+def timed_steps(args, step, barrier, max_over_ranks):
+    """W warm-up steps, K timed ones; wall clock bracketed by synchronise + barrier, max over ranks."""
+    import torch
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    torch.cuda.synchronize()
+    seconds = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    return seconds
+
+
+def run_config4(args, rank, local_rank, world, dist):
+    """BASELINE configs[3]: ~1M-line list x 60 layers, 10-3500 cm-1 @0.001, one spectral band per
+    GPU (strong scaling: the bands of the N ranks tile the one grid; no collective)."""
+    import torch
+    from pylbl_b200 import Gas, _lib
+    torch.cuda.set_device(local_rank)
+    ranks = Ranks(dist, f"cuda:{local_rank}")
+    db = aux_database(4, local_rank, ranks.barrier)
+    bounds = synth.config_grid(4)
+    v0, vn, npv = bounds
+    column = synth.standard_column(N_LAYERS, column=0)
+    gas = Gas(db, "XX", devices=[local_rank])
+    edges = gas.band_edges(bounds, world, CUT_OFF)
+    lo, hi = int(edges[rank]), int(edges[rank + 1])
+    width = (hi - lo) * npv
+    pinned = _lib.PinnedArray((N_LAYERS, width))
+    lib = _lib.library()
+    h = gas._handle(local_rank)
+
+    def submit(dst):
+        lib.lbl_gas_submit_band(h.ptr, N_LAYERS, np.ascontiguousarray(column.p), np.ascontiguousarray(column.t),
+                                np.ascontiguousarray(column.vmr["XX"]), v0, vn, npv, CUT_OFF,
+                                1 if REMOVE_PEDESTAL else 0, 0, lo, hi, dst, 0)
+        lib.lbl_gas_wait(h.ptr)
+        return h.stats()
+
+    resident_seconds = timed_steps(args, lambda: submit(None), ranks.barrier, ranks.max)
+    stats = h.stats()
+    e2e_seconds = timed_steps(args, lambda: submit(pinned.array.ctypes.data_as(ctypes.c_void_p)),
+                              ranks.barrier, ranks.max)
+    evals = ranks.sum(float(stats["evals"]))
+    points = ranks.sum(float(width))
+    slowest_kernels = ranks.max(stats["sum_ms"] + stats["fixup_ms"])
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": evals * args.steps / resident_seconds, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": resident_seconds * 1e3 / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": "BASELINE configs[3]: synthetic ~1M-line list x 60 layers, grid 10-3500 cm-1 "
+                                   "@0.001 cm-1, one spectral band per GPU",
+                       "v0": v0, "vn": vn, "n_per_v": npv, "n_points": int(points), "n_layers": N_LAYERS,
+                       "n_lines": 1000000, "remove_pedestal": REMOVE_PEDESTAL, "cut_off": CUT_OFF,
+                       "band_edges_cells": [int(x) for x in edges],
+                       "sharding": f"{world} contiguous bands of about equal work (lbl_gas_band_edges), "
+                                   "windows/prefix/pedestal of the whole grid, no collective"},
+            "layer_spectra_per_s": N_LAYERS * args.steps / resident_seconds,
+            "e2e": {"value": evals * args.steps / e2e_seconds, "unit": UNIT,
+                    "h2d_bytes_per_step": int(ranks.sum(float(stats["h2d_bytes"]))),
+                    "d2h_bytes_per_step": int(8 * N_LAYERS * points), "ms_per_step": e2e_seconds * 1e3 / args.steps},
+            "slowest_rank_sum_plus_near_ms": slowest_kernels, "gpu_launches": int(ranks.sum(float(stats["total_launches"]))) * args.steps,
+        }), flush=True)
+    else:
+        pass
+    gas.close()
+
+
+def run_config5(args, rank, local_rank, world, dist):
+    """BASELINE configs[4]: 256 columns x 60 layers, 7 gases + MT-CKD continuum on the grid
+    1-5000 cm-1 @0.1, columns dealt round-robin to the GPUs, everything summed on
+    the device: one (layers, 50000) array of total absorption per rank comes back."""
+    import torch
+    from pylbl_b200 import Continuum, Gas, Mixture, _lib
+    torch.cuda.set_device(local_rank)
+    ranks = Ranks(dist, f"cuda:{local_rank}")
+    db = database_path(local_rank, ranks.barrier)          # the line lists of configs[1]
+    bounds = synth.config_grid(5)
+    v0, vn, npv = bounds
+    n = (vn - v0) * npv
+    n_columns = int(os.environ.get("BENCH_COLUMNS", "256"))
+    mine = [c for c in range(n_columns) if c % world == rank]
+    cols = [synth.standard_column(N_LAYERS, column=c) for c in mine]
+    t = np.concatenate([c.t for c in cols])
+    p = np.concatenate([c.p for c in cols])
+    vmr = {f: np.concatenate([c.vmr[f] for c in cols]) for f in GASES}
+    vmr["N2"] = np.full(t.size, 0.78)      # no lines in the database; the O2 and N2 continua read it
+    gases = {f: Gas(db, f, devices=[local_rank]) for f in GASES}
+    mixture = Mixture.from_gases(gases, local_rank)
+    continuum = Continuum(local_rank)
+    pinned = _lib.PinnedArray((t.size, n))
+
+    def step():
+        mixture.total_absorption(t, p, vmr, bounds=bounds, remove_pedestal=REMOVE_PEDESTAL, cut_off=CUT_OFF,
+                                 out=pinned.array, continuum=continuum)
+
+    seconds = timed_steps(args, step, ranks.barrier, ranks.max)
+    stats = [gases[f].last_stats[0] for f in GASES]
+    evals = ranks.sum(float(sum(s["evals"] for s in stats)))
+    kernels = ranks.max(sum(s["sum_ms"] + s["fixup_ms"] for s in stats))
+    check = None
+    if rank == 0 and not args.no_check:
+        from oracle import OracleGas, mt_ckd
+        from pylbl_b200 import continua_of, number_density
+        sys.path.insert(0, str(ROOT / "tests"))
+        from helpers import scaled_error
+        row = 61 if t.size > 61 else 0                     # a layer of this rank's second column
+        state = {f: float(vmr[f][row]) for f in vmr}
+        grid = v0 + np.arange(n) * (1. / npv)
+        want = np.zeros(n)
+        for f in GASES:
+            k = OracleGas(db, f).absorption(t[row], p[row], state[f], v0, vn, npv, REMOVE_PEDESTAL, CUT_OFF)
+            want += number_density(t[row], p[row], state[f]) * k
+        for f in vmr:
+            for name in continua_of(f):
+                want += mt_ckd.OracleContinuum(name).spectra(t[row], p[row], state, grid)
+        check = {"row": row, "scaled_error_vs_oracle_lines_plus_continuum": scaled_error(pinned.array[row], want, npv, CUT_OFF)}
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": evals * args.steps / seconds, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": seconds * 1e3 / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": f"BASELINE configs[4]: {n_columns} columns x 60 layers, 7 gases + MT-CKD continuum, "
+                                   "grid 1-5000 cm-1 @0.1 cm-1, columns round-robin over the GPUs",
+                       "v0": v0, "vn": vn, "n_per_v": npv, "n_points": n, "n_layers": N_LAYERS,
+                       "n_columns": n_columns, "gases": GASES + ["N2 (continuum only)"],
+                       "remove_pedestal": REMOVE_PEDESTAL, "cut_off": CUT_OFF,
+                       "output": "total absorption summed on the device, one array per rank to pinned host memory",
+                       "timing": "end to end (host inputs, host output) -- the only number of this mode"},
+            "layer_spectra_per_s": n_columns * N_LAYERS * args.steps / seconds,
+            "e2e": {"value": evals * args.steps / seconds, "unit": UNIT,
+                    "h2d_bytes_per_step": int(ranks.sum(float(sum(s["h2d_bytes"] for s in stats)))),
+                    "d2h_bytes_per_step": int(8 * n_columns * N_LAYERS * n), "ms_per_step": seconds * 1e3 / args.steps},
+            "slowest_rank_sum_plus_near_ms_per_step": kernels,
+            "direct_kernel": "lbl::sum_kernel<5>",
+            "parity_spot_check": check,
+            "gpu_launches": int(ranks.sum(float(sum(s["total_launches"] for s in stats)))) * args.steps,
+        }), flush=True)
+    mixture.close()
+    continuum.close()
+    for g in gases.values():
+        g.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -707,6 +874,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-check", action="store_true")
+    ap.add_argument("--config", type=int, default=2, choices=[2, 4, 5],
+                    help="BASELINE configuration: 2 (the benchmark of record, default), "
+                         "4 (1M lines, band-sharded: configs[3]), 5 (256 columns + continuum: configs[4])")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -725,7 +895,12 @@ def main():
         dist_mod.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
         dist = dist_mod
     try:
-        run_ours(args, rank, local_rank, world, dist)
+        if args.config == 4:
+            run_config4(args, rank, local_rank, world, dist)
+        elif args.config == 5:
+            run_config5(args, rank, local_rank, world, dist)
+        else:
+            run_ours(args, rank, local_rank, world, dist)
     finally:
         if dist is not None:
             dist.destroy_process_group()
