@@ -97,14 +97,16 @@ class Continuum(object):
         state = np.ascontiguousarray(self.state(volume_mixing_ratio, t.size))
         n = (vn - v0) * n_per_v
         lib = _lib.library()
-        if mix is not None:
-            lib.lbl_continuum_compute(self.ptr, name.encode(), t.size, t, p, state, v0, vn, n_per_v,
-                                      mix, int(row0), None)
-            return None
-        if out is None:
-            out = np.empty((t.size, n))
-        if out.shape != (t.size, n) or out.dtype != np.float64 or not out.flags["C_CONTIGUOUS"]:
-            raise ValueError("out must be a C-contiguous float64 array of shape (n_layers, n)")
-        lib.lbl_continuum_compute(self.ptr, name.encode(), t.size, t, p, state, v0, vn, n_per_v,
-                                  None, 0, out.ctypes.data_as(c_void_p))
-        return out
+        if mix is None:
+            if out is None:
+                out = np.empty((t.size, n))
+            if out.shape != (t.size, n) or out.dtype != np.float64 or not out.flags["C_CONTIGUOUS"]:
+                raise ValueError("out must be a C-contiguous float64 array of shape (n_layers, n)")
+        for lo in range(0, t.size, self.MAX_LAYERS):       # layers are a grid dimension of the kernels
+            hi = min(lo + self.MAX_LAYERS, t.size)
+            lib.lbl_continuum_compute(self.ptr, name.encode(), hi - lo, t[lo:hi], p[lo:hi], state[lo:hi],
+                                      v0, vn, n_per_v, mix, int(row0) + lo if mix is not None else 0,
+                                      None if mix is not None else out[lo:hi].ctypes.data_as(c_void_p))
+        return out if mix is None else None
+
+    MAX_LAYERS = 32768

@@ -145,7 +145,7 @@ struct lbl_gas
     // the device's shared streams (DeviceStreams); s_compute = early
     cudaStream_t s_compute = nullptr, s_late = nullptr, s_copy = nullptr, s_main = nullptr;
     DeviceStreams* streams = nullptr;
-    size_t group_budget = (size_t)6 << 30;   // bytes per layer group, see lbl_gas_submit
+    size_t group_budget = (size_t)4 << 30;   // bytes per layer group, see lbl_gas_submit
     int copy_groups = 0;                     // lbl_gas_set_copy_groups (0 = automatic)
     DevBuf rec_ab, rec_cc, rec_chk, rec_gen, layers_dev, evals_dev, pedbin, pedcorr, pednodes,
         pedterms, ped_tiles, ped_run_row, ped_n_runs, ped_run_cb, ped_run_sums, rec_f32, amp_max, cell_keys, cheb_nodes, cheb_weights, cheb_nodes16, cheb_weights16, cheb_nodes8, cheb_weights8,
@@ -779,8 +779,11 @@ static int open_handle(std::unique_ptr<lbl_gas>& g, int device, lbl_gas** out)
         size_t free_bytes = 0, total_bytes = 0;
         if (cudaMemGetInfo(&free_bytes, &total_bytes) == cudaSuccess)
         {
-            g->group_budget = std::min<size_t>(std::max<size_t>(free_bytes / 4, g->group_budget),
-                                               (size_t)48 << 30);
+            // A share of what is free now: a column's gases each hold a handle on the device (and
+            // each handle up to three such groups: records and two output slabs), and every handle
+            // keeps what it has grown to.
+            g->group_budget = std::min<size_t>(std::max<size_t>(free_bytes / 20, (size_t)2 << 30),
+                                               (size_t)8 << 30);
         }
     }
     if (device_streams(device, &g->streams)) return 1;
@@ -1088,8 +1091,8 @@ static int submit_call(lbl_gas* g, const CallSpec& call)
          (ped_chain ? sizeof(double) * ped_wpad : 0) + (ped_runs ? 4 * sizeof(double) + 2 * sizeof(int) : 0) +
          (fp32 ? sizeof(Far32) : 0));
     const size_t out_per_layer = sizeof(double) * (size_t)grid.n;
-    // Memory budget of one layer group (records + pedestal terms, and one output slab): a
-    // quarter of what was free on the device when the handle was opened, between 6 and 48 GB.
+    // Memory budget of one layer group (records + pedestal buffers, and one output slab): a
+    // twentieth of what was free on the device when the handle was opened, between 2 and 8 GB.
     // Fewer, larger groups matter with the pedestal on: the chain takes as long for 10 layers
     // as for 60.  (Not queried per call: cudaMemGetInfo stalls the submitting thread for tens
     // of milliseconds while the GPU is busy.)
@@ -2025,6 +2028,7 @@ int continuum_band(lbl_continuum* c, ContinuumView& cv, int kind, double lower, 
     b.n = (int)(*coefficients.begin())->size();
     b.lower = lower;
     b.resolution = resolution;
+    b.inv_resolution = 1. / resolution;
     b.value_offset = cv.row;
     cv.row += b.n;
     int k = 0;
@@ -2108,6 +2112,7 @@ int lbl_continuum_finalize(lbl_continuum* c)
         b.n = (int)sp[0]->data.size();
         b.lower = sp[0]->lower;
         b.resolution = sp[0]->resolution;
+        b.inv_resolution = 1. / b.resolution;
         b.value_offset = cv.row;
         cv.row += b.n;
         for (int q = 0; q < 4; ++q) b.c[q] = nullptr;
@@ -2247,20 +2252,22 @@ int lbl_continuum_compute(lbl_continuum* c, const char* name, int n_layers, cons
     cudaStream_t sl = c->streams->late;    // where the accumulator's additions are ordered
     LBL_CUDA(cudaStreamSynchronize(sl));   // the previous call's buffers are free
     LBL_CUDA(c->layers_dev.reserve(sizeof(ContinuumLayer) * (size_t)n_layers));
-    LBL_CUDA(c->values_dev.reserve(sizeof(double) * (size_t)cv.row * n_layers));
+    LBL_CUDA(c->values_dev.reserve(sizeof(double) * 2 * (size_t)cv.row * n_layers));
     LBL_CUDA(cudaMemcpyAsync(c->layers_dev.p, layers.data(), sizeof(ContinuumLayer) * n_layers,
                              cudaMemcpyHostToDevice, sl));
     dim3 gb((cv.row + 127) / 128, n_layers);
     LBL_CUDA(cudaEventRecord(c->ev[0], sl));
     continuum_bands_kernel<<<gb, 128, 0, sl>>>(cv, c->layers_dev.as<ContinuumLayer>(), c->values_dev.as<double>());
+    continuum_slopes_kernel<<<gb, 128, 0, sl>>>(cv, c->values_dev.as<double>());
     LBL_CUDA(cudaEventRecord(c->ev[1], sl));
     c->timed = true;
     const size_t total = (size_t)n_layers * n;
-    const int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
+    if (n_layers > 65535) return fail("Error: more than 65535 layers in one continuum call.");
+    const dim3 ga((n + 511) / 512, n_layers);    // two points per thread
     if (mix)
     {
-        continuum_apply_kernel<true><<<blocks, 256, 0, sl>>>(
-            cv, c->values_dev.as<double>(), v0, 1. / n_per_v, 0, n, n_layers,
+        continuum_apply_kernel<true><<<ga, 256, 0, sl>>>(
+            cv, c->values_dev.as<double>(), v0, 1. / n_per_v, 0, n,
             mix->acc.as<double>() + (size_t)row0 * n);
         LBL_CUDA(cudaGetLastError());
         LBL_CUDA(cudaEventRecord(c->ev[2], sl));
@@ -2269,8 +2276,8 @@ int lbl_continuum_compute(lbl_continuum* c, const char* name, int n_layers, cons
         return 0;
     }
     LBL_CUDA(c->out_dev.reserve(sizeof(double) * total));
-    continuum_apply_kernel<false><<<blocks, 256, 0, sl>>>(cv, c->values_dev.as<double>(), v0, 1. / n_per_v, 0,
-                                                          n, n_layers, c->out_dev.as<double>());
+    continuum_apply_kernel<false><<<ga, 256, 0, sl>>>(cv, c->values_dev.as<double>(), v0, 1. / n_per_v, 0, n,
+                                                      c->out_dev.as<double>());
     LBL_CUDA(cudaGetLastError());
     LBL_CUDA(cudaEventRecord(c->ev[2], sl));
     LBL_CUDA(cudaMemcpyAsync(k_host, c->out_dev.p, sizeof(double) * total, cudaMemcpyDeviceToHost, sl));

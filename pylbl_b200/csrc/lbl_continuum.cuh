@@ -32,6 +32,7 @@ struct BandView
 {
     int kind, n;
     double lower, resolution;     // band grid w_j = lower + j*resolution (utils.py:138-144)
+    double inv_resolution;
     const double* c[4];           // coefficient arrays on the band grid
     int value_offset;             // of this band in the per-layer value row
 };
@@ -167,7 +168,8 @@ __device__ double band_value(const BandView& b, const ContinuumLayer& ly, int j)
     }
 }
 
-// K5a.  values[layer][band offset + j].  grid = (ceil(row/128), layers).
+// K5a.  values[layer][band offset + j] (2*row doubles per layer: values, then slopes).
+// grid = (ceil(row/128), layers).
 __global__ void __launch_bounds__(128)
 continuum_bands_kernel(const ContinuumView cv, const ContinuumLayer* __restrict__ layers,
                        double* __restrict__ values)
@@ -180,55 +182,78 @@ continuum_bands_kernel(const ContinuumView cv, const ContinuumLayer* __restrict_
     int b = 0;
     while (b + 1 < cv.n_bands && idx >= cv.band[b + 1].value_offset) ++b;
     const int j = idx - cv.band[b].value_offset;
-    values[(size_t)blockIdx.y * cv.row + idx] = band_value(cv.band[b], layers[blockIdx.y], j);
+    values[(size_t)blockIdx.y * 2 * cv.row + idx] = band_value(cv.band[b], layers[blockIdx.y], j);
 }
 
-// numpy.interp(x, xp, fp, left=0, right=0) for xp[j] = lower + j*res.
-__device__ __forceinline__ double band_interp(const BandView& b, const double* __restrict__ fp, double x)
+// K5a'.  slopes[layer][band offset + j] = (f[j+1] - f[j]) / (x[j+1] - x[j]), the slope numpy.interp
+// uses on [x_j, x_j+1) (numpy precomputes them the same way); stored behind the values of the
+// layer.  grid = (ceil(row/128), layers).
+__global__ void __launch_bounds__(128)
+continuum_slopes_kernel(const ContinuumView cv, double* __restrict__ values)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= cv.row)
+    {
+        return;
+    }
+    int b = 0;
+    while (b + 1 < cv.n_bands && idx >= cv.band[b + 1].value_offset) ++b;
+    const BandView& band = cv.band[b];
+    const int j = idx - band.value_offset;
+    double* f = values + (size_t)blockIdx.y * 2 * cv.row;
+    double slope = 0.;
+    if (j + 1 < band.n)
+    {
+        const double xj = band.lower + (double)j * band.resolution;
+        const double xn = band.lower + (double)(j + 1) * band.resolution;
+        slope = __ddiv_rn(__dsub_rn(f[idx + 1], f[idx]), __dsub_rn(xn, xj));
+    }
+    f[cv.row + idx] = slope;
+}
+
+// numpy.interp(x, xp, fp, left=0, right=0) for xp[j] = lower + j*res; fp and the slopes of this
+// layer's band at `f` and `f + row`.
+__device__ __forceinline__ double band_interp(const BandView& b, const double* __restrict__ f, int row,
+                                              double x)
 {
     const int last = b.n - 1;
-    const double x_first = b.lower;
     const double x_last = b.lower + (double)last * b.resolution;
-    if (!(x >= x_first) || !(x <= x_last))
+    if (!(x >= b.lower) || !(x <= x_last))
     {
         return 0.;
     }
-    int j = (int)floor((x - b.lower) / b.resolution);
+    int j = (int)((x - b.lower) * b.inv_resolution);
     j = j < 0 ? 0 : (j > last ? last : j);
-    // largest j with xp[j] <= x (the division above can be one off at a grid point)
+    // largest j with xp[j] <= x (the guess above can be one off next to a grid point)
     while (j < last && b.lower + (double)(j + 1) * b.resolution <= x) ++j;
     while (j > 0 && b.lower + (double)j * b.resolution > x) --j;
     const double xj = b.lower + (double)j * b.resolution;
     if (j == last || xj == x)
     {
-        return fp[j];
+        return f[j];
     }
-    const double xn = b.lower + (double)(j + 1) * b.resolution;
-    const double slope = __ddiv_rn(__dsub_rn(fp[j + 1], fp[j]), __dsub_rn(xn, xj));
-    return __dadd_rn(__dmul_rn(slope, __dsub_rn(x, xj)), fp[j]);
+    return __dadd_rn(__dmul_rn(f[row + j], __dsub_rn(x, xj)), f[j]);
 }
 
-// K5b.  dst[layer][i] (+)= 100 * sum over the bands of interp(v_i) (utils.py:168-174), over the
-// grid points [p_lo, p_lo + width) of every layer.  kAdd: into the gas-sum accumulator.
+// K5b.  dst[layer][k] (+)= 100 * sum over the bands of interp(v) (utils.py:168-174) for the grid
+// points p_lo + k, k < width, of layer blockIdx.y.  kAdd: into the gas-sum accumulator.
+// HBM-bound: 8 bytes written per point, and 8 read when adding.
 template <bool kAdd>
-__global__ void continuum_apply_kernel(const ContinuumView cv, const double* __restrict__ values,
-                                       int v0, double dv, int p_lo, int width, int n_layers,
-                                       double* __restrict__ dst)
+__global__ void __launch_bounds__(256)
+continuum_apply_kernel(const ContinuumView cv, const double* __restrict__ values, int v0, double dv,
+                       int p_lo, int width, double* __restrict__ dst)
 {
-    const size_t total = (size_t)n_layers * width;
-    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-         idx += (size_t)gridDim.x * blockDim.x)
+    const double* f = values + (size_t)blockIdx.y * 2 * cv.row;
+    double* out = dst + (size_t)blockIdx.y * width;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < width; k += gridDim.x * blockDim.x)
     {
-        const int layer = (int)(idx / width);
-        const int i = p_lo + (int)(idx - (size_t)layer * width);
-        const double v = grid_point(v0, dv, i);
-        const double* row = values + (size_t)layer * cv.row;
+        const double v = grid_point(v0, dv, p_lo + k);
         double s = 0.;
         for (int b = 0; b < cv.n_bands; ++b)
         {
-            s += band_interp(cv.band[b], row + cv.band[b].value_offset, v) * 100.;
+            s += band_interp(cv.band[b], f + cv.band[b].value_offset, cv.row, v) * 100.;
         }
-        dst[idx] = kAdd ? dst[idx] + s : s;
+        out[k] = kAdd ? out[k] + s : s;
     }
 }
 

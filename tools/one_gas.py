@@ -9,7 +9,7 @@ f = sys.argv[1] if len(sys.argv) > 1 else "H2O"
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 ped = "--no-pedestal" not in sys.argv
 db = bench.database_path(0, lambda: None)
-bounds = synth.config_grid(2)
+bounds = synth.config_grid(5 if "--config5" in sys.argv else 2)
 col = synth.standard_column(60)
 g = Gas(db, f, devices=[0])
 for rep in range(reps):

@@ -8,7 +8,8 @@ from pylbl_b200 import Gas, synth, _lib
 
 ped = "--no-pedestal" not in sys.argv
 db = bench.database_path(0, lambda: None)
-bounds = synth.config_grid(2)
+config = 5 if "--config5" in sys.argv else 2       # same line lists; 5: the 0.1 cm-1 grid
+bounds = synth.config_grid(config)
 col = synth.standard_column(60)
 rows = []
 for f in bench.GASES:
