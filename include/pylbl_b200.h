@@ -200,7 +200,8 @@ LBL_API int lbl_mix_close(lbl_mix* mix);
  *       variable as the reference's file names them (bfco2, bs296, ..., with the wavenumber_*
  *       attributes of each), then the band tables are built on the device.  No file format of
  *       its own: the host side reads pylbl_b200/data/mt_ckd.npz (tools/convert_mt_ckd.py).
- *   lbl_continuum_compute: continuum `name` ("CO2", "H2OForeign", "H2OSelf", "N2", "O2", "O3")
+ *   lbl_continuum_compute: continuum `name` ("CO2", "H2OForeign", "H2OSelf", "N2", "O2", "O3";
+ *       or several, comma-separated: their sum, in one pass over the output)
  *       in m-1 for n_layers states; vmr6[L*6 ..] = mole fractions of H2O, CO2, O3, N2, O2 and
  *       the sum over ALL gases of the atmosphere (utils.py:18-30); pressure in Pa.  Either
  *       k_host[L*n ..] receives it, or (mix != NULL) it is added to rows row0+L of the

@@ -81,7 +81,8 @@ class Continuum(object):
 
     def spectra(self, name, temperature, pressure, volume_mixing_ratio, grid=None, bounds=None,
                 out=None, mix=None, row0=0):
-        """Continuum extinction [m-1] of continuum ``name`` for every layer, shape
+        """Continuum extinction [m-1] of continuum ``name`` (or the sum of several: a list of names,
+        one pass over the output) for every layer, shape
         (n_layers, (vn-v0)*n_per_v): row L is ``BandedContinuum.spectra(T[L], p[L], vmr[L], grid)``
         (pyLBL/mt_ckd/utils.py:157-174).  ``volume_mixing_ratio``: {formula: array over layers}
         of ALL gases of the atmosphere.  ``mix``: an lbl_mix accumulator to add into instead."""
@@ -90,10 +91,12 @@ class Continuum(object):
         p = np.ascontiguousarray(pressure, dtype=np.float64).ravel()
         if "H2O" not in volume_mixing_ratio:
             raise KeyError("H2O")      # dry_air_number_density, mt_ckd/utils.py:44
-        needs = {"CO2": ["CO2"], "O3": ["O3"], "N2": ["N2", "O2"], "O2": ["O2", "N2"]}.get(name, [])
-        for gas in needs:
-            if gas not in volume_mixing_ratio:
-                raise KeyError(gas)
+        names = [name] if isinstance(name, str) else list(name)
+        for one in names:
+            for gas in {"CO2": ["CO2"], "O3": ["O3"], "N2": ["N2", "O2"], "O2": ["O2", "N2"]}.get(one, []):
+                if gas not in volume_mixing_ratio:
+                    raise KeyError(gas)
+        name = ",".join(names)
         state = np.ascontiguousarray(self.state(volume_mixing_ratio, t.size))
         n = (vn - v0) * n_per_v
         lib = _lib.library()

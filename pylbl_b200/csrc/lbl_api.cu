@@ -348,6 +348,16 @@ int pick_points_per_thread(int n_per_v)
 int pick_threads_per_layer(int n_per_v, int P, int n_layers)
 {
     int tpw = 32;
+    if (const char* env = getenv("PYLBL_B200_TPW"))   // tuning experiments: 1, 2, 4, 8, 16 or 32
+    {
+        const int t = atoi(env);
+        if (t >= 1 && t <= 32 && (t & (t - 1)) == 0)
+        {
+            tpw = t;
+            while (tpw < 32 && (32 / tpw) > n_layers) tpw <<= 1;
+            return tpw;
+        }
+    }
     while (tpw > 1 && tpw * P > 2 * n_per_v) tpw >>= 1;
     while (tpw < 32 && (32 / tpw) > n_layers) tpw <<= 1;
     return tpw;
@@ -1088,7 +1098,7 @@ static int submit_call(lbl_gas* g, const CallSpec& call)
     const int ped_wpad = 32 * ped_k;
     const size_t rec_per_layer = (size_t)plan.n_active *
         (sizeof(FarAB) + sizeof(double) + sizeof(LineChk) + sizeof(LineGen) +
-         (ped_chain ? sizeof(double) * ped_wpad : 0) + (ped_runs ? 4 * sizeof(double) + 2 * sizeof(int) : 0) +
+         (ped_chain ? sizeof(double) * ped_wpad : 0) + (ped_runs ? 4 * sizeof(double) + 5 * sizeof(int) : 0) +
          (fp32 ? sizeof(Far32) : 0));
     const size_t out_per_layer = sizeof(double) * (size_t)grid.n;
     // Memory budget of one layer group (records + pedestal buffers, and one output slab): a
@@ -1161,7 +1171,7 @@ static int submit_call(lbl_gas* g, const CallSpec& call)
             LBL_CUDA(g->ped_tiles.reserve(sizeof(int) * tiles * chunk));
             LBL_CUDA(g->ped_run_row.reserve(sizeof(int) * (rows + 1) * chunk));
             LBL_CUDA(g->ped_n_runs.reserve(sizeof(int) * (size_t)chunk));
-            LBL_CUDA(g->ped_run_cb.reserve(sizeof(int) * rows * chunk));
+            LBL_CUDA(g->ped_run_cb.reserve(sizeof(int) * 4 * rows * chunk));
             LBL_CUDA(g->ped_run_sums.reserve(sizeof(double) * 4 * rows * chunk));
             ped_smem = sizeof(double) * (size_t)nb <= 100 * 1024 ? sizeof(double) * (size_t)nb : 0;
             if (ped_smem > 48 * 1024)
@@ -1373,8 +1383,10 @@ static int submit_call(lbl_gas* g, const CallSpec& call)
                     ped_run_scatter_kernel<<<gt, kRunTile, 0, ss>>>(rec.chk, lines.n, ped_rows,
                                                                    g->ped_tiles.as<int>(), ra.run_row, ra.n_runs);
                     // about one run per occupied cell: enough warps to take them in a few rounds
+                    // (with few layers -- the scalar plugin call -- more warps per layer)
                     const int runs_guess = std::min(ped_rows, grid.ncell + 2 * cut_off + 8);
-                    dim3 gn(std::max(1, std::min(64, (runs_guess + 31) / 32)), nl);
+                    const int per_layer = std::max(64, 1184 / nl);
+                    dim3 gn(std::max(1, std::min(per_layer, (runs_guess + 7) / 8)), nl);
                     ped_nodes_kernel<<<gn, 256, 0, ss>>>(ra);
                 }
                 else
@@ -2229,8 +2241,28 @@ int lbl_continuum_compute(lbl_continuum* c, const char* name, int n_layers, cons
 {
     if (!c || !name || !temperature || !pressure || !vmr6) return fail("Error: null argument.");
     if (!c->finalized) return fail("Error: continuum table not finalized.");
-    auto it = c->continua.find(name);
-    if (it == c->continua.end()) return fail(std::string("Error: no continuum named ") + name + ".");
+    // one name, or several separated by commas: their bands are summed in one pass over the output
+    ContinuumView merged{};
+    {
+        std::string list(name);
+        size_t pos = 0;
+        while (pos <= list.size())
+        {
+            const size_t comma = std::min(list.find(',', pos), list.size());
+            const std::string one = list.substr(pos, comma - pos);
+            auto it = c->continua.find(one);
+            if (it == c->continua.end()) return fail("Error: no continuum named " + one + ".");
+            for (int b = 0; b < it->second.n_bands; ++b)
+            {
+                if (merged.n_bands >= kMaxBands) return fail("Error: too many bands in one continuum call.");
+                BandView band = it->second.band[b];
+                band.value_offset = merged.row;
+                merged.row += band.n;
+                merged.band[merged.n_bands++] = band;
+            }
+            pos = comma + 1;
+        }
+    }
     if (n_layers < 1 || n_per_v < 1 || vn <= v0) return fail("Error: invalid grid or layer count.");
     const long long n_ll = (long long)(vn - v0) * n_per_v;
     if (n_ll > (1ll << 30)) return fail("Error: spectral grid too large for 32-bit indices.");
@@ -2242,7 +2274,7 @@ int lbl_continuum_compute(lbl_continuum* c, const char* name, int n_layers, cons
         return fail("Error: accumulator shape does not fit this call.");
     }
     LBL_CUDA(cudaSetDevice(c->device));
-    const ContinuumView& cv = it->second;
+    const ContinuumView& cv = merged;
     std::vector<ContinuumLayer> layers((size_t)n_layers);
     for (int l = 0; l < n_layers; ++l)
     {

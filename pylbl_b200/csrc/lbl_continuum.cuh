@@ -19,7 +19,7 @@ constexpr double kLoschmidt = 2.6867775e19;   // utils.py:7
 constexpr double kP0 = 1013.25;               // utils.py:8  [mb]
 constexpr double kT0 = 296.;                  // utils.py:10
 constexpr double kT273 = 273.15;              // utils.py:11
-constexpr int kMaxBands = 8;
+constexpr int kMaxBands = 20;   // all six continua together: 1 + 1 + 1 + 3 + 7 + 3 = 16
 
 enum BandKind
 {

@@ -1546,8 +1546,17 @@ ped_nodes_kernel(const PedRunArgs a)
         }
         if (lane == 0)
         {
+            // with the sums, what the chain needs of the run's window (ped_points): its own bin
+            // and the first bin of the two ranges that cover k[s] and k[e], packed into one int4
             const size_t o = (size_t)layer * a.n_rows + r;
-            a.run_cb[o] = a.rec.chk[(size_t)layer * a.lines.n + row_lo].cb;
+            const int cb = a.rec.chk[(size_t)layer * a.lines.n + row_lo].cb;
+            const PedPoints pp = ped_points(cb, a.grid);
+            int4 w;
+            w.x = pp.skip ? -1 : cb + a.grid.cut_off + 1;      // own bin (-1: not processed)
+            w.y = pp.bs;
+            w.z = pp.be;
+            w.w = pp.ne;
+            reinterpret_cast<int4*>(a.run_cb)[o] = w;
             double2* dst = reinterpret_cast<double2*>(a.run_sums + 4 * o);
             dst[0] = make_double2(sums[0], sums[1]);
             dst[1] = make_double2(sums[2], sums[3]);
@@ -1571,53 +1580,62 @@ ped_chain_runs_kernel(const PedRunArgs a, int bins_in_smem)
     for (int b = lane; b < nb; b += 32) bins[b] = 0.;
     __syncwarp();
     const int n_runs = a.n_runs[layer];
-    const int* cbs = a.run_cb + (size_t)layer * a.n_rows;
+    const int4* wins = reinterpret_cast<const int4*>(a.run_cb) + (size_t)layer * a.n_rows;
     const double2* sums = reinterpret_cast<const double2*>(a.run_sums + 4 * (size_t)layer * a.n_rows);
+    const int ns = 2 * g.cut_off + 2;
     // this lane's run of the next tile of 32, fetched one tile ahead
-    int my_cb = 0;
+    int4 my_w = make_int4(-1, 0, 0, 0);
     double2 my_f = make_double2(0., 0.), my_k = make_double2(0., 0.);
     if (lane < n_runs)
     {
-        my_cb = cbs[lane];
+        my_w = wins[lane];
         my_f = sums[2 * lane];
         my_k = sums[2 * lane + 1];
     }
+    int top = -1;     // highest bin written so far: ranges above it sum to zero
     for (int r0 = 0; r0 < n_runs; r0 += 32)
     {
-        const int cb_t = my_cb;
+        const int4 w_t = my_w;
         const double2 f_t = my_f, k_t = my_k;
         const int nxt = r0 + 32 + lane;
         if (nxt < n_runs)
         {
-            my_cb = cbs[nxt];
+            my_w = wins[nxt];
             my_f = sums[2 * nxt];
             my_k = sums[2 * nxt + 1];
         }
         const int cnt = min(32, n_runs - r0);
         for (int m = 0; m < cnt; ++m)
         {
-            const int cb = __shfl_sync(0xffffffffu, cb_t, m);
+            const int bin = __shfl_sync(0xffffffffu, w_t.x, m);
+            if (bin < 0)
+            {
+                continue;   // the reference does not process these lines on this grid
+            }
+            const int bs = __shfl_sync(0xffffffffu, w_t.y, m);
+            const int be = __shfl_sync(0xffffffffu, w_t.z, m);
+            const int ne = __shfl_sync(0xffffffffu, w_t.w, m);
             double s4[4];
             s4[0] = __shfl_sync(0xffffffffu, f_t.x, m);
             s4[1] = __shfl_sync(0xffffffffu, f_t.y, m);
             s4[2] = __shfl_sync(0xffffffffu, k_t.x, m);
             s4[3] = __shfl_sync(0xffffffffu, k_t.y, m);
-            const PedPoints pp = ped_points(cb, g);
-            if (pp.skip)
-            {
-                continue;
-            }
             double ps = 0., pe = 0.;
-            for (int k = lane; k < pp.ns; k += 32) ps += bins[pp.bs + k];
-            for (int k = lane; k < pp.ne; k += 32) pe += bins[pp.be + k];
+            for (int k = lane; k < ns; k += 32) ps += bins[bs + k];
+            const bool e_side = be <= top;    // else every bin of the range is still zero
+            if (e_side)
+            {
+                for (int k = lane; k < ne; k += 32) pe += bins[be + k];
+            }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1)
             {
                 ps += __shfl_xor_sync(0xffffffffu, ps, o);
-                pe += __shfl_xor_sync(0xffffffffu, pe, o);
+                if (e_side) pe += __shfl_xor_sync(0xffffffffu, pe, o);
             }
             const double pedestal = ped_chain_run(s4, ps, pe);
-            if (lane == 0) bins[cb + g.cut_off + 1] += pedestal;
+            if (lane == 0) bins[bin] += pedestal;
+            top = max(top, bin);
             __syncwarp();
         }
     }

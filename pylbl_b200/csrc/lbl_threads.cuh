@@ -1559,7 +1559,8 @@ struct PedRunArgs
     int n_rows;          // rows the recurrence walks (<= lines.n)
     int* run_row;        // [layer][n_rows + 1] first row of each run, then the sentinel n_rows
     int* n_runs;         // [layer]
-    int* run_cb;         // [layer][n_rows] window cell of each run
+    int* run_cb;         // [layer][n_rows][4] per run: own pedestal bin (-1: skipped), first bins of
+                         //   the ranges covering k[s] and k[e], length of the latter
     double* run_sums;    // [layer][n_rows][4] per run: sum f[s], sum f[e] over its lines;
                          //   sum over earlier covering rows of f(s-point), of f(e-point)
     double* pedbin;      // [layer][ncell + 2*cut + 2]

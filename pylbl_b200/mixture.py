@@ -100,10 +100,10 @@ class Mixture(object):
         # lines goes last; its layer groups are copied to the host while the next ones compute.
         if continuum is not None:
             from .continuum import continua_of
-            for formula in volume_mixing_ratio:
-                for name in continua_of(formula):
-                    continuum.spectra(name, t, p, volume_mixing_ratio, bounds=(v0, vn, n_per_v),
-                                      mix=self._mix)
+            # every continuum of every gas, summed in one pass over the accumulator
+            names = [name for formula in volume_mixing_ratio for name in continua_of(formula)]
+            if names:
+                continuum.spectra(names, t, p, volume_mixing_ratio, bounds=(v0, vn, n_per_v), mix=self._mix)
         order = sorted(self.gases.items(), key=lambda item: item[1]._handle(self.device).stats()["n_lines"])
         handles = []
         for i, (formula, gas) in enumerate(order):
