@@ -2256,6 +2256,14 @@ int lbl_continuum_compute(lbl_continuum* c, const char* name, int n_layers, cons
             {
                 if (merged.n_bands >= kMaxBands) return fail("Error: too many bands in one continuum call.");
                 BandView band = it->second.band[b];
+                // the part of the band's own grid that the call's grid [v0, vn) can reach; a band
+                // wholly outside it contributes zeros and is left out
+                const double first = (double)v0, last = (double)vn;
+                const double j_first = std::floor((first - band.lower) / band.resolution) - 1.;
+                const double j_last = std::ceil((last - band.lower) / band.resolution) + 1.;
+                if (j_last < 0. || j_first > (double)(band.n - 1)) continue;
+                band.j_lo = (int)std::max(j_first, 0.);
+                band.j_hi = (int)std::min(j_last, (double)(band.n - 1));
                 band.value_offset = merged.row;
                 merged.row += band.n;
                 merged.band[merged.n_bands++] = band;
@@ -2284,10 +2292,10 @@ int lbl_continuum_compute(lbl_continuum* c, const char* name, int n_layers, cons
     cudaStream_t sl = c->streams->late;    // where the accumulator's additions are ordered
     LBL_CUDA(cudaStreamSynchronize(sl));   // the previous call's buffers are free
     LBL_CUDA(c->layers_dev.reserve(sizeof(ContinuumLayer) * (size_t)n_layers));
-    LBL_CUDA(c->values_dev.reserve(sizeof(double) * 2 * (size_t)cv.row * n_layers));
+    LBL_CUDA(c->values_dev.reserve(sizeof(double) * 2 * (size_t)std::max(cv.row, 1) * n_layers));
     LBL_CUDA(cudaMemcpyAsync(c->layers_dev.p, layers.data(), sizeof(ContinuumLayer) * n_layers,
                              cudaMemcpyHostToDevice, sl));
-    dim3 gb((cv.row + 127) / 128, n_layers);
+    dim3 gb((std::max(cv.row, 1) + 127) / 128, n_layers);
     LBL_CUDA(cudaEventRecord(c->ev[0], sl));
     continuum_bands_kernel<<<gb, 128, 0, sl>>>(cv, c->layers_dev.as<ContinuumLayer>(), c->values_dev.as<double>());
     continuum_slopes_kernel<<<gb, 128, 0, sl>>>(cv, c->values_dev.as<double>());
@@ -2295,7 +2303,7 @@ int lbl_continuum_compute(lbl_continuum* c, const char* name, int n_layers, cons
     c->timed = true;
     const size_t total = (size_t)n_layers * n;
     if (n_layers > 65535) return fail("Error: more than 65535 layers in one continuum call.");
-    const dim3 ga((n + 511) / 512, n_layers);    // two points per thread
+    const dim3 ga((n + 256 * kContinuumPoints - 1) / (256 * kContinuumPoints), n_layers);
     if (mix)
     {
         continuum_apply_kernel<true><<<ga, 256, 0, sl>>>(

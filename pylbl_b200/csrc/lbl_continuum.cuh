@@ -33,6 +33,7 @@ struct BandView
     int kind, n;
     double lower, resolution;     // band grid w_j = lower + j*resolution (utils.py:138-144)
     double inv_resolution;
+    int j_lo, j_hi;               // part of the band grid the call's wavenumber grid can reach
     const double* c[4];           // coefficient arrays on the band grid
     int value_offset;             // of this band in the per-layer value row
 };
@@ -168,8 +169,8 @@ __device__ double band_value(const BandView& b, const ContinuumLayer& ly, int j)
     }
 }
 
-// K5a.  values[layer][band offset + j] (2*row doubles per layer: values, then slopes).
-// grid = (ceil(row/128), layers).
+// K5a.  values[layer][band offset + j] (2*row doubles per layer: values, then slopes), for the
+// part [j_lo, j_hi] of each band that the call's grid can reach.  grid = (ceil(row/128), layers).
 __global__ void __launch_bounds__(128)
 continuum_bands_kernel(const ContinuumView cv, const ContinuumLayer* __restrict__ layers,
                        double* __restrict__ values)
@@ -182,6 +183,10 @@ continuum_bands_kernel(const ContinuumView cv, const ContinuumLayer* __restrict_
     int b = 0;
     while (b + 1 < cv.n_bands && idx >= cv.band[b + 1].value_offset) ++b;
     const int j = idx - cv.band[b].value_offset;
+    if (j < cv.band[b].j_lo || j > cv.band[b].j_hi)
+    {
+        return;
+    }
     values[(size_t)blockIdx.y * 2 * cv.row + idx] = band_value(cv.band[b], layers[blockIdx.y], j);
 }
 
@@ -200,60 +205,122 @@ continuum_slopes_kernel(const ContinuumView cv, double* __restrict__ values)
     while (b + 1 < cv.n_bands && idx >= cv.band[b + 1].value_offset) ++b;
     const BandView& band = cv.band[b];
     const int j = idx - band.value_offset;
+    if (j < band.j_lo || j >= band.j_hi)
+    {
+        return;
+    }
     double* f = values + (size_t)blockIdx.y * 2 * cv.row;
-    double slope = 0.;
-    if (j + 1 < band.n)
-    {
-        const double xj = band.lower + (double)j * band.resolution;
-        const double xn = band.lower + (double)(j + 1) * band.resolution;
-        slope = __ddiv_rn(__dsub_rn(f[idx + 1], f[idx]), __dsub_rn(xn, xj));
-    }
-    f[cv.row + idx] = slope;
+    const double xj = band.lower + (double)j * band.resolution;
+    const double xn = band.lower + (double)(j + 1) * band.resolution;
+    f[cv.row + idx] = __ddiv_rn(__dsub_rn(f[idx + 1], f[idx]), __dsub_rn(xn, xj));
 }
 
-// numpy.interp(x, xp, fp, left=0, right=0) for xp[j] = lower + j*res; fp and the slopes of this
-// layer's band at `f` and `f + row`.
-__device__ __forceinline__ double band_interp(const BandView& b, const double* __restrict__ f, int row,
-                                              double x)
+// The continuum is piecewise linear in the wavenumber: between two consecutive nodes of the
+// bands' own grids, sum_b 100*interp_b(x) = alpha + beta*(x - origin).  `Segment` holds that line
+// (origin = the wavenumber it was set up at, so that nothing large cancels) and the wavenumber
+// up to which it is valid.
+struct Segment
 {
-    const int last = b.n - 1;
-    const double x_last = b.lower + (double)last * b.resolution;
-    if (!(x >= b.lower) || !(x <= x_last))
+    double alpha, beta, origin, valid_below;
+};
+
+// numpy.interp(x, xp, fp, left=0, right=0) semantics for xp[j] = lower + j*res, accumulated over
+// the bands: exact node hits and the last node return fp[j] (a constant piece), outside a band 0.
+__device__ __forceinline__ Segment continuum_segment(const ContinuumView& cv, const double* __restrict__ f,
+                                                     double x)
+{
+    Segment s;
+    s.alpha = 0.;
+    s.beta = 0.;
+    s.origin = x;
+    s.valid_below = 1.0e300;
+    for (int b = 0; b < cv.n_bands; ++b)
     {
-        return 0.;
+        const BandView& band = cv.band[b];
+        const int last = band.n - 1;
+        const double x_last = band.lower + (double)last * band.resolution;
+        if (!(x >= band.lower))
+        {
+            s.valid_below = fmin(s.valid_below, band.lower);      // the band starts further up
+            continue;
+        }
+        if (!(x <= x_last))
+        {
+            continue;
+        }
+        int j = (int)((x - band.lower) * band.inv_resolution);
+        j = j < 0 ? 0 : (j > last ? last : j);
+        // largest j with xp[j] <= x (the guess above can be one off next to a grid point)
+        while (j < last && band.lower + (double)(j + 1) * band.resolution <= x) ++j;
+        while (j > 0 && band.lower + (double)j * band.resolution > x) --j;
+        const double xj = band.lower + (double)j * band.resolution;
+        const double* fb = f + band.value_offset;
+        if (j == last || xj == x)
+        {
+            // a node: this very point takes fp[j]; the next grid point starts a new segment
+            s.alpha += 100. * fb[j];
+            s.valid_below = x;
+            continue;
+        }
+        const double slope = fb[cv.row + j];
+        s.alpha += 100. * __dadd_rn(__dmul_rn(slope, __dsub_rn(x, xj)), fb[j]);   // numpy's own value at x
+        s.beta += 100. * slope;
+        s.valid_below = fmin(s.valid_below, band.lower + (double)(j + 1) * band.resolution);
     }
-    int j = (int)((x - b.lower) * b.inv_resolution);
-    j = j < 0 ? 0 : (j > last ? last : j);
-    // largest j with xp[j] <= x (the guess above can be one off next to a grid point)
-    while (j < last && b.lower + (double)(j + 1) * b.resolution <= x) ++j;
-    while (j > 0 && b.lower + (double)j * b.resolution > x) --j;
-    const double xj = b.lower + (double)j * b.resolution;
-    if (j == last || xj == x)
-    {
-        return f[j];
-    }
-    return __dadd_rn(__dmul_rn(f[row + j], __dsub_rn(x, xj)), f[j]);
+    return s;
 }
 
-// K5b.  dst[layer][k] (+)= 100 * sum over the bands of interp(v) (utils.py:168-174) for the grid
-// points p_lo + k, k < width, of layer blockIdx.y.  kAdd: into the gas-sum accumulator.
-// HBM-bound: 8 bytes written per point, and 8 read when adding.
+// K5b.  dst[layer][k] (+)= sum over the bands of 100*interp(v) (utils.py:168-174) for the grid
+// points p_lo + k, k < width, of layer blockIdx.y; kPoints consecutive points per thread, which
+// mostly share one segment.  kAdd: into the gas-sum accumulator.  HBM-bound: 8 bytes written per
+// point, and 8 read when adding.
+constexpr int kContinuumPoints = 4;
+
 template <bool kAdd>
 __global__ void __launch_bounds__(256)
 continuum_apply_kernel(const ContinuumView cv, const double* __restrict__ values, int v0, double dv,
                        int p_lo, int width, double* __restrict__ dst)
 {
+    constexpr int P = kContinuumPoints;
     const double* f = values + (size_t)blockIdx.y * 2 * cv.row;
     double* out = dst + (size_t)blockIdx.y * width;
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < width; k += gridDim.x * blockDim.x)
+    const bool vector = (width % 2 == 0) && ((reinterpret_cast<size_t>(out) & 15) == 0);
+    for (int k0 = (blockIdx.x * blockDim.x + threadIdx.x) * P; k0 < width; k0 += gridDim.x * blockDim.x * P)
     {
-        const double v = grid_point(v0, dv, p_lo + k);
-        double s = 0.;
-        for (int b = 0; b < cv.n_bands; ++b)
+        double val[P];
+        Segment seg;
+        seg.valid_below = -1.0e300;
+        seg.alpha = seg.beta = seg.origin = 0.;
+#pragma unroll
+        for (int q = 0; q < P; ++q)
         {
-            s += band_interp(cv.band[b], f + cv.band[b].value_offset, cv.row, v) * 100.;
+            const double v = grid_point(v0, dv, p_lo + min(k0 + q, width - 1));
+            if (!(v < seg.valid_below))
+            {
+                seg = continuum_segment(cv, f, v);
+            }
+            val[q] = fma(seg.beta, v - seg.origin, seg.alpha);
         }
-        out[k] = kAdd ? out[k] + s : s;
+        if (vector && k0 + P <= width)
+        {
+            double2* o2 = reinterpret_cast<double2*>(out + k0);
+#pragma unroll
+            for (int q = 0; q < P; q += 2)
+            {
+                double2 w = kAdd ? o2[q / 2] : make_double2(0., 0.);
+                w.x += val[q];
+                w.y += val[q + 1];
+                o2[q / 2] = w;
+            }
+        }
+        else
+        {
+#pragma unroll
+            for (int q = 0; q < P; ++q)
+            {
+                if (k0 + q < width) out[k0 + q] = kAdd ? out[k0 + q] + val[q] : val[q];
+            }
+        }
     }
 }
 
