@@ -762,9 +762,12 @@ def run_config4(args, rank, local_rank, world, dist):
     stats = h.stats()
     e2e_seconds = timed_steps(args, lambda: submit(pinned.array.ctypes.data_as(ctypes.c_void_p)),
                               ranks.barrier, ranks.max)
+    # every reduction is a collective: all of them happen here, on every rank
     evals = ranks.sum(float(stats["evals"]))
     points = ranks.sum(float(width))
     slowest_kernels = ranks.max(stats["sum_ms"] + stats["fixup_ms"])
+    h2d_total = int(ranks.sum(float(stats["h2d_bytes"])))
+    launches_total = int(ranks.sum(float(stats["total_launches"])))
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": evals * args.steps / resident_seconds, "unit": UNIT, "n_gpus": world,
@@ -780,12 +783,10 @@ def run_config4(args, rank, local_rank, world, dist):
                                    "windows/prefix/pedestal of the whole grid, no collective"},
             "layer_spectra_per_s": N_LAYERS * args.steps / resident_seconds,
             "e2e": {"value": evals * args.steps / e2e_seconds, "unit": UNIT,
-                    "h2d_bytes_per_step": int(ranks.sum(float(stats["h2d_bytes"]))),
+                    "h2d_bytes_per_step": h2d_total,
                     "d2h_bytes_per_step": int(8 * N_LAYERS * points), "ms_per_step": e2e_seconds * 1e3 / args.steps},
-            "slowest_rank_sum_plus_near_ms": slowest_kernels, "gpu_launches": int(ranks.sum(float(stats["total_launches"]))) * args.steps,
+            "slowest_rank_sum_plus_near_ms": slowest_kernels, "gpu_launches": launches_total * args.steps,
         }), flush=True)
-    else:
-        pass
     gas.close()
 
 
@@ -819,8 +820,11 @@ def run_config5(args, rank, local_rank, world, dist):
 
     seconds = timed_steps(args, step, ranks.barrier, ranks.max)
     stats = [gases[f].last_stats[0] for f in GASES]
+    # every reduction is a collective: all of them happen here, on every rank
     evals = ranks.sum(float(sum(s["evals"] for s in stats)))
     kernels = ranks.max(sum(s["sum_ms"] + s["fixup_ms"] for s in stats))
+    h2d_total = int(ranks.sum(float(sum(s["h2d_bytes"] for s in stats))))
+    launches_total = int(ranks.sum(float(sum(s["total_launches"] for s in stats))))
     check = None
     if rank == 0 and not args.no_check:
         from oracle import OracleGas, mt_ckd
@@ -853,12 +857,12 @@ def run_config5(args, rank, local_rank, world, dist):
                        "timing": "end to end (host inputs, host output) -- the only number of this mode"},
             "layer_spectra_per_s": n_columns * N_LAYERS * args.steps / seconds,
             "e2e": {"value": evals * args.steps / seconds, "unit": UNIT,
-                    "h2d_bytes_per_step": int(ranks.sum(float(sum(s["h2d_bytes"] for s in stats)))),
+                    "h2d_bytes_per_step": h2d_total,
                     "d2h_bytes_per_step": int(8 * n_columns * N_LAYERS * n), "ms_per_step": seconds * 1e3 / args.steps},
             "slowest_rank_sum_plus_near_ms_per_step": kernels,
             "direct_kernel": "lbl::sum_kernel<5>",
             "parity_spot_check": check,
-            "gpu_launches": int(ranks.sum(float(sum(s["total_launches"] for s in stats)))) * args.steps,
+            "gpu_launches": launches_total * args.steps,
         }), flush=True)
     mixture.close()
     continuum.close()
@@ -892,7 +896,9 @@ def main():
         import torch.distributed as dist_mod
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.cuda.set_device(local_rank)
-        dist_mod.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+        import datetime
+        dist_mod.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"),
+                                    timeout=datetime.timedelta(seconds=180))
         dist = dist_mod
     try:
         if args.config == 4:

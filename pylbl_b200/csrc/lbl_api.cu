@@ -1454,7 +1454,7 @@ static int submit_call(lbl_gas* g, const CallSpec& call)
             // one gas hides behind the kernels of the next and one group is best.
             n_groups = (blocking && nl >= 16) ? 2 : 1;
             // the last gas of a device-side sum: only its last group's rows are copied exposed
-            if (mix && call.mix_host && nl >= 16) n_groups = 4;
+            if (mix && call.mix_host && nl >= 8) n_groups = std::min(4, nl / 4);
             if (g->copy_groups > 0) n_groups = std::min(g->copy_groups, nl);
             if (const char* env = getenv("PYLBL_B200_COPY_GROUPS")) n_groups = std::max(1, std::min(atoi(env), nl));
         }
@@ -2041,6 +2041,7 @@ int continuum_band(lbl_continuum* c, ContinuumView& cv, int kind, double lower, 
     b.lower = lower;
     b.resolution = resolution;
     b.inv_resolution = 1. / resolution;
+    b.x_last = lower + (double)(b.n - 1) * resolution;
     b.value_offset = cv.row;
     cv.row += b.n;
     int k = 0;
@@ -2125,6 +2126,7 @@ int lbl_continuum_finalize(lbl_continuum* c)
         b.lower = sp[0]->lower;
         b.resolution = sp[0]->resolution;
         b.inv_resolution = 1. / b.resolution;
+        b.x_last = b.lower + (double)(b.n - 1) * b.resolution;
         b.value_offset = cv.row;
         cv.row += b.n;
         for (int q = 0; q < 4; ++q) b.c[q] = nullptr;

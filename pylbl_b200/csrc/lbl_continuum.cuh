@@ -32,7 +32,7 @@ struct BandView
 {
     int kind, n;
     double lower, resolution;     // band grid w_j = lower + j*resolution (utils.py:138-144)
-    double inv_resolution;
+    double inv_resolution, x_last;   // x_last = lower + (n-1)*resolution
     int j_lo, j_hi;               // part of the band grid the call's wavenumber grid can reach
     const double* c[4];           // coefficient arrays on the band grid
     int value_offset;             // of this band in the per-layer value row
@@ -238,13 +238,12 @@ __device__ __forceinline__ Segment continuum_segment(const ContinuumView& cv, co
     {
         const BandView& band = cv.band[b];
         const int last = band.n - 1;
-        const double x_last = band.lower + (double)last * band.resolution;
         if (!(x >= band.lower))
         {
             s.valid_below = fmin(s.valid_below, band.lower);      // the band starts further up
             continue;
         }
-        if (!(x <= x_last))
+        if (!(x <= band.x_last))
         {
             continue;
         }

@@ -385,84 +385,96 @@ LBL_HD double voigt_region2_limit(double y, double xlim0)
     return (y <= 0.000001) ? xlim0 : 6.8 - y;
 }
 
+// W4 region 3 (voigt.c:116-147): |x| < 2.4*y.  Returns K(x,y).
+LBL_HD double voigt_region3(double xq, double y)
+{
+    const double z0 = 272.1014 + y * (1280.829 + y * (2802.870 + y * (3764.966
+                      + y * (3447.629 + y * (2256.981 + y * (1074.409 + y * (369.1989
+                      + y * (88.26741 + y * (13.39880 + y)))))))));
+    const double z2 = 211.678 + y * (902.3066 + y * (1758.336 + y * (2037.310
+                      + y * (1549.675 + y * (793.4273 + y * (266.2987
+                      + y * (53.59518 + y * 5.0)))))));
+    const double z4 = 78.86585 + y * (308.1852 + y * (497.3014 + y * (479.2576
+                      + y * (269.2916 + y * (80.39278 + y * 10.0)))));
+    const double z6 = 22.03523 + y * (55.02933 + y * (92.75679 + y * (53.59518
+                      + y * 10.0)));
+    const double z8 = 1.496460 + y * (13.39880 + y * 5.0);
+    const double p0 = 153.5168 + y * (549.3954 + y * (919.4955 + y * (946.8970
+                      + y * (662.8097 + y * (328.2151 + y * (115.3772 + y * (27.93941
+                      + y * (4.264678 + y * 0.3183291))))))));
+    const double p2 = -34.16955 + y * (-1.322256 + y * (124.5975 + y * (189.7730
+                      + y * (139.4665 + y * (56.81652 + y * (12.79458
+                      + y * 1.2733163))))));
+    const double p4 = 2.584042 + y * (10.46332 + y * (24.01655 + y * (29.81482
+                      + y * (12.79568 + y * 1.9099744))));
+    const double p6 = -0.07272979 + y * (0.9377051 + y * (4.266322 + y * 1.273316));
+    const double p8 = 0.0005480304 + y * 0.3183291;
+    // The reference writes sqrt(pi) as the 8-digit literal here (voigt.c:145).
+    const double d = 1.7724538 * rcp_newton2(z0 + xq * (z2 + xq * (z4 + xq * (z6 + xq * (z8 + xq)))));
+    return d * (p0 + xq * (p2 + xq * (p4 + xq * (p6 + xq * p8))));
+}
+
+// CPF12 (voigt.c:148-186): 2.4*y <= |x| < xlim2; kSubI: |x| <= 18.1*y + 1.65 (sub-region i),
+// else sub-region ii with the exp(-x^2) term.  Returns K(x,y).
+template <bool kSubI>
+LBL_HD double voigt_cpf12(double xi, double y)
+{
+    const double tc[6] = {0.31424038, 0.94778839, 1.5976826, 2.2795071, 3.0206370, 3.8897249};
+    const double cc[6] = {1.0117281, -0.75197147, 0.012557727,
+                          0.010022008, -0.00024206814, 0.00000050084806};
+    const double sc[6] = {1.393237, 0.23115241, -0.15535147,
+                          0.0062183662, 0.000091908299, -0.00000062752596};
+    const double y0 = 1.5;
+    const double ypy0 = y + y0;
+    const double ypy0q = ypy0 * ypy0;
+    const double yf = y + (y0 + y0);
+    const double y0q = y0 * y0;
+    double buf = 0.;
+#pragma unroll
+    for (int j = 0; j < 6; ++j)
+    {
+        const double dm = xi - tc[j];
+        const double mq = dm * dm;
+        const double mf = rcp_newton2(mq + ypy0q);
+        const double xm = mf * dm;
+        const double ym = mf * ypy0;
+        const double dp = xi + tc[j];
+        const double pq = dp * dp;
+        const double pf = rcp_newton2(pq + ypy0q);
+        const double xp = pf * dp;
+        const double yp = pf * ypy0;
+        if (kSubI)
+        {
+            buf += cc[j] * (ym + yp) - sc[j] * (xm - xp);
+        }
+        else
+        {
+            buf += (cc[j] * (mq * mf - y0 * ym) + sc[j] * yf * xm) * rcp_newton2(mq + y0q)
+                 + (cc[j] * (pq * pf - y0 * yp) - sc[j] * yf * xp) * rcp_newton2(pq + y0q);
+        }
+    }
+    if (!kSubI)
+    {
+        buf = y * buf + exp(-(xi * xi));
+    }
+    return buf;
+}
+
+// Which of the three the point takes: 0 region 3, 1 CPF12 sub-region i, 2 sub-region ii.
+LBL_HD int voigt_inner_kind(double abx, double y)
+{
+    if (abx < 2.4 * y) return 0;
+    return (abx <= 18.1 * y + 1.65) ? 1 : 2;
+}
+
 // W4 region 3 and CPF12 (voigt.c:116-186): |x| < xlim2.  Returns K(x,y).
 static LBL_HD_NOINLINE double voigt_inner(double xi, double y)
 {
     const double abx = fabs(xi);
-    const double xq = abx * abx;
-    const double xlim3 = 2.4 * y;
-    const double xlim4 = 18.1 * y + 1.65;
-    double buf;
-    if (abx < xlim3)
-    {
-        const double z0 = 272.1014 + y * (1280.829 + y * (2802.870 + y * (3764.966
-                          + y * (3447.629 + y * (2256.981 + y * (1074.409 + y * (369.1989
-                          + y * (88.26741 + y * (13.39880 + y)))))))));
-        const double z2 = 211.678 + y * (902.3066 + y * (1758.336 + y * (2037.310
-                          + y * (1549.675 + y * (793.4273 + y * (266.2987
-                          + y * (53.59518 + y * 5.0)))))));
-        const double z4 = 78.86585 + y * (308.1852 + y * (497.3014 + y * (479.2576
-                          + y * (269.2916 + y * (80.39278 + y * 10.0)))));
-        const double z6 = 22.03523 + y * (55.02933 + y * (92.75679 + y * (53.59518
-                          + y * 10.0)));
-        const double z8 = 1.496460 + y * (13.39880 + y * 5.0);
-        const double p0 = 153.5168 + y * (549.3954 + y * (919.4955 + y * (946.8970
-                          + y * (662.8097 + y * (328.2151 + y * (115.3772 + y * (27.93941
-                          + y * (4.264678 + y * 0.3183291))))))));
-        const double p2 = -34.16955 + y * (-1.322256 + y * (124.5975 + y * (189.7730
-                          + y * (139.4665 + y * (56.81652 + y * (12.79458
-                          + y * 1.2733163))))));
-        const double p4 = 2.584042 + y * (10.46332 + y * (24.01655 + y * (29.81482
-                          + y * (12.79568 + y * 1.9099744))));
-        const double p6 = -0.07272979 + y * (0.9377051 + y * (4.266322 + y * 1.273316));
-        const double p8 = 0.0005480304 + y * 0.3183291;
-        // The reference writes sqrt(pi) as the 8-digit literal here (voigt.c:145).
-        const double d = 1.7724538 * rcp_newton2(z0 + xq * (z2 + xq * (z4 + xq * (z6 + xq * (z8 + xq)))));
-        buf = d * (p0 + xq * (p2 + xq * (p4 + xq * (p6 + xq * p8))));
-    }
-    else
-    {
-        const double tc[6] = {0.31424038, 0.94778839, 1.5976826, 2.2795071, 3.0206370, 3.8897249};
-        const double cc[6] = {1.0117281, -0.75197147, 0.012557727,
-                              0.010022008, -0.00024206814, 0.00000050084806};
-        const double sc[6] = {1.393237, 0.23115241, -0.15535147,
-                              0.0062183662, 0.000091908299, -0.00000062752596};
-        const double y0 = 1.5;
-        const double ypy0 = y + y0;
-        const double ypy0q = ypy0 * ypy0;
-        const bool inner = abx <= xlim4;
-        const double yf = y + (y0 + y0);
-        const double y0q = y0 * y0;
-        buf = 0.;
-#pragma unroll
-        for (int j = 0; j < 6; ++j)
-        {
-            const double dm = xi - tc[j];
-            const double mq = dm * dm;
-            const double mf = rcp_newton2(mq + ypy0q);
-            const double xm = mf * dm;
-            const double ym = mf * ypy0;
-            const double dp = xi + tc[j];
-            const double pq = dp * dp;
-            const double pf = rcp_newton2(pq + ypy0q);
-            const double xp = pf * dp;
-            const double yp = pf * ypy0;
-            if (inner)
-            {
-                buf += cc[j] * (ym + yp) - sc[j] * (xm - xp);
-            }
-            else
-            {
-                buf += (cc[j] * (mq * mf - y0 * ym) + sc[j] * yf * xm) * rcp_newton2(mq + y0q)
-                     + (cc[j] * (pq * pf - y0 * yp) - sc[j] * yf * xp) * rcp_newton2(pq + y0q);
-            }
-        }
-        if (!inner)
-        {
-            buf = y * buf + exp(-xq);
-        }
-    }
-    return buf;
+    const int kind = voigt_inner_kind(abx, y);
+    if (kind == 0) return voigt_region3(abx * abx, y);
+    if (kind == 1) return voigt_cpf12<true>(xi, y);
+    return voigt_cpf12<false>(xi, y);
 }
 
 // Regions 2, 3 and CPF12 (voigt.c:98-186); requires abx < voigt_outer_limit().  Returns K(x,y).

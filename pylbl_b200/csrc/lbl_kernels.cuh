@@ -835,33 +835,42 @@ constexpr int kNbSpan = 512;
 constexpr int kNbBatch = 64;
 constexpr int kNbQueue = 64;   // entries per queue: at most 31 left over + 32 new
 
-// Drains `cnt` (<= 32) queued (slot, point) pairs with the lanes packed: lane e evaluates entry
-// e and adds it to its point.  kInner == false: points around |x| = xlim1 -- W4 region 2, or
-// region 0/1 for the boundary points the index range took along; kInner == true: W4 region 3 /
-// CPF12.  Inside xlim1 the Lorentz form is taken back where the summation kernel added it.
-template <bool kInner>
-__device__ __forceinline__ void near_block_drain(const GridSpec& g, const NearLine* slots, const int* q,
+// Queues of K2b: (staged slot, point of the span) pairs, 6 + 9 bits, by the branch of the
+// profile the point takes -- every branch is then evaluated with the lanes packed and without
+// divergence.
+//   kMid  around |x| = xlim1: W4 region 2, or region 0/1 for the boundary points the core's
+//         index range took along
+//   kR3   W4 region 3                 (voigt.c:116-147)
+//   kCpfI / kCpfII  CPF12 sub-regions (voigt.c:148-186)
+enum NearQueue { kMid = 0, kR3 = 1, kCpfI = 2, kCpfII = 3, kNearQueues = 4 };
+typedef unsigned short NearEntry;
+
+// Drains `cnt` (<= 32) entries of queue K: lane e evaluates entry e and adds it to its point.
+// Inside xlim1 the Lorentz form is taken back where the summation kernel added it.
+template <int K>
+__device__ __forceinline__ void near_block_drain(const GridSpec& g, const NearLine* slots, const NearEntry* q,
                                                  int cnt, int lane, int p0, double* mine)
 {
     const int entry = q[lane < cnt ? lane : 0];
-    const int k = entry & 0xffff;          // point, relative to the span
+    const int k = entry & 0x1ff;           // point, relative to the span
     double val = 0.;
     bool pending = lane < cnt;
     if (pending)
     {
-        const NearLine& nl = slots[entry >> 16];
+        const NearLine& nl = slots[entry >> 9];
         const double v = grid_point(g.v0, g.dv, p0 + k);
         const double xi = (v - nl.nu) * nl.repwid;
-        const bool lorentz_added = (nl.tag & 1) == 0;
-        if (kInner)
-        {
-            val = nl.cof * voigt_inner(xi, nl.y);
-            if (lorentz_added) val -= far_term_lo(v, nl.a, nl.b, nl.c, 0.);   // the bits K2c added
-        }
-        else
+        if (K == kMid)
         {
             bool core;
             val = near_point(nl, v, core);   // regions 0, 1, 2 (never `core`: sorted at the push)
+        }
+        else
+        {
+            if (K == kR3) val = nl.cof * voigt_region3(xi * xi, nl.y);
+            if (K == kCpfI) val = nl.cof * voigt_cpf12<true>(xi, nl.y);
+            if (K == kCpfII) val = nl.cof * voigt_cpf12<false>(xi, nl.y);
+            if ((nl.tag & 1) == 0) val -= far_term_lo(v, nl.a, nl.b, nl.c, 0.);   // the bits K2c added
         }
     }
     // Two entries may name the same point (two lines' cores overlapping): the lowest lane of
@@ -886,9 +895,9 @@ __device__ __forceinline__ void near_block_drain(const GridSpec& g, const NearLi
     }
 }
 
-// Appends the lanes flagged `push` to a queue (lane-compacted) and drains a full warp's worth.
-template <bool kInner>
-__device__ __forceinline__ void near_block_push(const GridSpec& g, const NearLine* slots, int* q, int& qn,
+// Appends the lanes flagged `push` to queue K (lane-compacted) and drains a full warp's worth.
+template <int K>
+__device__ __forceinline__ void near_block_push(const GridSpec& g, const NearLine* slots, NearEntry* q, int& qn,
                                                 bool push, int entry, int lane, unsigned below, int p0,
                                                 double* mine)
 {
@@ -899,16 +908,16 @@ __device__ __forceinline__ void near_block_push(const GridSpec& g, const NearLin
     }
     if (push)
     {
-        q[qn + __popc(m & below)] = entry;
+        q[qn + __popc(m & below)] = (NearEntry)entry;
     }
     qn += __popc(m);
     __syncwarp();
     if (qn >= 32)
     {
-        near_block_drain<kInner>(g, slots, q, 32, lane, p0, mine);
+        near_block_drain<K>(g, slots, q, 32, lane, p0, mine);
         __syncwarp();
         const int keep = qn - 32;
-        const int moved = (lane < keep) ? q[32 + lane] : 0;
+        const NearEntry moved = (lane < keep) ? q[32 + lane] : (NearEntry)0;
         __syncwarp();
         if (lane < keep) q[lane] = moved;
         qn = keep;
@@ -934,7 +943,7 @@ near_block_kernel(const SumArgs a)
 {
     __shared__ double acc[4][kNbSpan];
     __shared__ __align__(16) NearLine slots[kNbBatch];
-    __shared__ int queues[4][2][kNbQueue];
+    __shared__ NearEntry queues[4][kNearQueues][kNbQueue];
     __shared__ int batch_count[2];
     const GridSpec& g = a.grid;
     const int layer = blockIdx.y + a.layer0;
@@ -951,9 +960,8 @@ near_block_kernel(const SumArgs a)
     const LineChk* chk = a.rec.chk + off;
     const LineGen* gen = a.rec.gen + off;
     double* mine = acc[warp];
-    int* q_mid = queues[warp][0];     // around |x| = xlim1: W4 region 2 and boundary points
-    int* q_in = queues[warp][1];      // W4 region 3 / CPF12: long
-    int n_mid = 0, n_in = 0;
+    NearEntry (*q)[kNbQueue] = queues[warp];
+    int qn[kNearQueues] = {0, 0, 0, 0};
 
     int jlo, jhi;
     near_candidates(a.lines, g, ly, p0, p1, jlo, jhi);
@@ -994,19 +1002,22 @@ near_block_kernel(const SumArgs a)
             const NearLine& nl = slots[s];
             const int zlo = nl.nlo, zhi = nl.nhi;
             const int c_lo = nl.c_lo, c_hi = nl.c_hi;
-            // ---- the few points inside |x| < xlim1 (and its boundary): sorted by kind into the
-            // two queues, evaluated 32 at a time -- no branch of the profile ever runs with two
-            // or three lanes active
+            // ---- the few points inside |x| < xlim1 (and its boundary): sorted by the branch of
+            // the profile they take into four queues, each evaluated 32 at a time -- no branch
+            // ever runs with two or three lanes active, and no drain diverges
             for (int i0 = c_lo; i0 <= c_hi; i0 += 32)
             {
                 const int i = i0 + lane;
                 const bool inside = i <= c_hi;
                 const double v = grid_point(g.v0, g.dv, i);
                 const double abx = fabs((v - nl.nu) * nl.repwid);
-                const bool inner = inside && abx < nl.lim_r2;
-                const int entry = (s << 16) | (i - p0);
-                near_block_push<false>(g, slots, q_mid, n_mid, inside && !inner, entry, lane, below, p0, mine);
-                near_block_push<true>(g, slots, q_in, n_in, inner, entry, lane, below, p0, mine);
+                const int kind = !inside ? -1
+                                 : (abx >= nl.lim_r2 ? (int)kMid : (int)kR3 + voigt_inner_kind(abx, nl.y));
+                const int entry = (s << 9) | (i - p0);
+                near_block_push<kMid>(g, slots, q[kMid], qn[kMid], kind == kMid, entry, lane, below, p0, mine);
+                near_block_push<kR3>(g, slots, q[kR3], qn[kR3], kind == kR3, entry, lane, below, p0, mine);
+                near_block_push<kCpfI>(g, slots, q[kCpfI], qn[kCpfI], kind == kCpfI, entry, lane, below, p0, mine);
+                near_block_push<kCpfII>(g, slots, q[kCpfII], qn[kCpfII], kind == kCpfII, entry, lane, below, p0, mine);
             }
             // ---- the zone outside it, W4 regions 0 and 1 (voigt.c:79-97), left part then right
             // part, lanes packed across the gap.  Where the Lorentz form is already in the spectrum
@@ -1038,9 +1049,11 @@ near_block_kernel(const SumArgs a)
             }
         }
         // the queues name slots of this batch: empty them before the slots are rewritten
-        if (n_mid > 0) near_block_drain<false>(g, slots, q_mid, n_mid, lane, p0, mine);
-        if (n_in > 0) near_block_drain<true>(g, slots, q_in, n_in, lane, p0, mine);
-        n_mid = n_in = 0;
+        if (qn[kMid] > 0) near_block_drain<kMid>(g, slots, q[kMid], qn[kMid], lane, p0, mine);
+        if (qn[kR3] > 0) near_block_drain<kR3>(g, slots, q[kR3], qn[kR3], lane, p0, mine);
+        if (qn[kCpfI] > 0) near_block_drain<kCpfI>(g, slots, q[kCpfI], qn[kCpfI], lane, p0, mine);
+        if (qn[kCpfII] > 0) near_block_drain<kCpfII>(g, slots, q[kCpfII], qn[kCpfII], lane, p0, mine);
+        qn[kMid] = qn[kR3] = qn[kCpfI] = qn[kCpfII] = 0;
         __syncwarp();
     }
 

@@ -64,8 +64,20 @@ class Mixture(object):
         except Exception:
             pass
 
+    @staticmethod
+    def _add_stats(totals, formula, stats):
+        """Statistics of a gas over the layer groups of one call: counters and times add up."""
+        if formula not in totals:
+            totals[formula] = dict(stats)
+            return
+        acc = totals[formula]
+        for key in ("evals", "executed", "h2d_bytes", "d2h_bytes", "n_layers", "sum_launches",
+                    "total_launches", "scale_ms", "sum_ms", "fixup_ms", "pedestal_ms", "total_ms"):
+            acc[key] += stats[key]
+
     def total_absorption(self, temperature, pressure, volume_mixing_ratio, grid=None,
-                         remove_pedestal=True, cut_off=25, bounds=None, out=None, continuum=None):
+                         remove_pedestal=True, cut_off=25, bounds=None, out=None, continuum=None,
+                         layer_groups=None):
         """sum over gases of n_gas * k_gas [m-1], shape (n_layers, (vn-v0)*n_per_v).
 
         Args:
@@ -76,6 +88,12 @@ class Mixture(object):
             continuum: a ``Continuum`` on this device: the MT-CKD continua of every gas of
                        ``volume_mixing_ratio`` are added on the device too
                        (pyLBL/spectroscopy.py:194-198,225-234).
+            layer_groups: the layers are taken in this many consecutive groups, all gases of a
+                          group before the next group, so that a finished group's rows are on
+                          their way to the host while the next group computes (only the last
+                          group's copy is exposed).  None = automatic: groups of at least 12
+                          layers, at most 5.  Worth it when the copy is slow next to the kernels
+                          (several GPUs sharing the host's PCIe and memory bandwidth).
         """
         v0, vn, n_per_v = bounds if bounds is not None else grid_to_ints(grid)
         t = np.ascontiguousarray(temperature, dtype=np.float64).ravel()
@@ -97,28 +115,43 @@ class Mixture(object):
         # Every gas is submitted without waiting for the one before: their scaling kernels and
         # pedestal chains overlap, the summation kernels run gas after gas, and each gas is
         # added into the accumulator on the device as soon as it is done.  The gas with the most
-        # lines goes last; its layer groups are copied to the host while the next ones compute.
-        if continuum is not None:
-            from .continuum import continua_of
-            # every continuum of every gas, summed in one pass over the accumulator
-            names = [name for formula in volume_mixing_ratio for name in continua_of(formula)]
-            if names:
-                continuum.spectra(names, t, p, volume_mixing_ratio, bounds=(v0, vn, n_per_v), mix=self._mix)
+        # lines goes last in every layer group; what it completes is copied to the host while
+        # the next layers compute.
+        if layer_groups is None:
+            layer_groups = max(1, min(5, n_layers // 12))
+        layer_groups = max(1, min(int(layer_groups), n_layers))
+        edges = [n_layers * g // layer_groups for g in range(layer_groups + 1)]
         order = sorted(self.gases.items(), key=lambda item: item[1]._handle(self.device).stats()["n_lines"])
+        states = {formula: np.ascontiguousarray(volume_mixing_ratio[formula], dtype=np.float64).ravel()
+                  for formula, _ in order}
+        scales = {formula: np.ascontiguousarray(number_density(t, p, states[formula])) for formula, _ in order}
         handles = []
-        for i, (formula, gas) in enumerate(order):
-            x = np.ascontiguousarray(volume_mixing_ratio[formula], dtype=np.float64).ravel()
-            scale = np.ascontiguousarray(number_density(t, p, x))
-            h = gas._handle(self.device)
-            last = i == len(order) - 1
-            lib.lbl_gas_submit_mix(h.ptr, n_layers, p, t, x, v0, vn, n_per_v, int(cut_off),
-                                   1 if remove_pedestal else 0, gas.precision, self._mix, 0, scale,
-                                   out.ctypes.data_as(c_void_p) if last else None)
-            handles.append((gas, h))
+        totals = {}
+        for g in range(layer_groups):
+            lo, hi = edges[g], edges[g + 1]
+            for i, (formula, gas) in enumerate(order):
+                h = gas._handle(self.device)
+                last = i == len(order) - 1
+                if g > 0:
+                    # (submitting on a handle waits for its previous call; its statistics are
+                    # collected first)
+                    lib.lbl_gas_wait(h.ptr)
+                    self._add_stats(totals, formula, h.stats())
+                if last:
+                    # the last gas of the last group also hands its layers over in sub-groups
+                    # (automatic); in the other groups that would only cost kernel tails
+                    lib.lbl_gas_set_copy_groups(h.ptr, 0 if g == layer_groups - 1 else 1)
+                lib.lbl_gas_submit_mix(h.ptr, hi - lo, p[lo:hi], t[lo:hi], states[formula][lo:hi],
+                                       v0, vn, n_per_v, int(cut_off), 1 if remove_pedestal else 0,
+                                       gas.precision, self._mix, lo, scales[formula][lo:hi],
+                                       out.ctypes.data_as(c_void_p) if last else None)
+                if g == 0:
+                    handles.append((formula, gas, h))
         lib.lbl_mix_wait(self._mix)
-        for gas, h in handles:
+        for formula, gas, h in handles:
             lib.lbl_gas_wait(h.ptr)
-            gas.last_stats = [h.stats()]
+            self._add_stats(totals, formula, h.stats())
+            gas.last_stats = [totals[formula]]
         if not handles:
             lib.lbl_mix_download(self._mix, out.ctypes.data_as(c_void_p))
         return out
