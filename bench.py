@@ -69,6 +69,9 @@ if os.environ.get("BENCH_GAS_ORDER"):
 N_LAYERS = 60
 REMOVE_PEDESTAL = os.environ.get("BENCH_PEDESTAL", "1") != "0"   # BASELINE: pedestal on (the knob is for experiments)
 CUT_OFF = 25
+# Layer groups of the gas-summed end-to-end path (Mixture.total_absorption): a finished group's
+# rows travel to the host while the next group computes.
+LAYER_GROUPS = int(os.environ["BENCH_LAYER_GROUPS"]) if os.environ.get("BENCH_LAYER_GROUPS") else None
 
 
 def workload_config(n_gpus):
@@ -295,6 +298,16 @@ class Ranks(object):
         return self._reduce(x, None if self.dist is None else self.dist.ReduceOp.SUM)
 
 
+def rank_columns(n_columns, world, rank):
+    """configs[4]: the columns of the batch dealt round-robin to the ranks."""
+    return [c for c in range(n_columns) if c % world == rank]
+
+
+def rank_band(edges, rank):
+    """configs[3]: rank r takes cells [edges[r], edges[r+1]) of the one grid."""
+    return int(edges[rank]), int(edges[rank + 1])
+
+
 def rank_column(rank):
     """Weak scaling: rank r computes its own 60-layer column r."""
     return synth.standard_column(N_LAYERS, column=rank)
@@ -401,7 +414,7 @@ def run_ours(args, rank, local_rank, world, dist):
         number densities are applied and the gases summed on the device; one array comes back."""
         mixture.total_absorption(column.t, column.p, column.vmr, bounds=bounds,
                                  remove_pedestal=REMOVE_PEDESTAL, cut_off=CUT_OFF,
-                                 out=pinned_total.array)
+                                 out=pinned_total.array, layer_groups=LAYER_GROUPS)
         return [gases[f].last_stats[0] for f in SUBMIT_ORDER]
 
     # ---- device-resident throughput ("value") ------------------------------------------
@@ -745,7 +758,7 @@ def run_config4(args, rank, local_rank, world, dist):
     column = synth.standard_column(N_LAYERS, column=0)
     gas = Gas(db, "XX", devices=[local_rank])
     edges = gas.band_edges(bounds, world, CUT_OFF)
-    lo, hi = int(edges[rank]), int(edges[rank + 1])
+    lo, hi = rank_band(edges, rank)
     width = (hi - lo) * npv
     pinned = _lib.PinnedArray((N_LAYERS, width))
     lib = _lib.library()
@@ -803,7 +816,7 @@ def run_config5(args, rank, local_rank, world, dist):
     v0, vn, npv = bounds
     n = (vn - v0) * npv
     n_columns = int(os.environ.get("BENCH_COLUMNS", "256"))
-    mine = [c for c in range(n_columns) if c % world == rank]
+    mine = rank_columns(n_columns, world, rank)
     cols = [synth.standard_column(N_LAYERS, column=c) for c in mine]
     t = np.concatenate([c.t for c in cols])
     p = np.concatenate([c.p for c in cols])

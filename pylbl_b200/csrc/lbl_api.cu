@@ -1393,7 +1393,11 @@ static int submit_call(lbl_gas* g, const CallSpec& call)
                 {
                     LBL_CUDA(cudaMemsetAsync(ra.n_runs, 0, sizeof(int) * nl, ss));
                 }
-                ped_chain_runs_kernel<<<nl, 32, ped_smem, ss>>>(ra, ped_smem > 0 ? 1 : 0);
+                {
+                    int use_scan = 1;
+                    if (const char* env = getenv("PYLBL_B200_PEDSCAN")) use_scan = atoi(env) != 0;
+                    ped_chain_runs_kernel<<<nl, 32, ped_smem, ss>>>(ra, ped_smem > 0 ? 1 : 0, use_scan);
+                }
                 st.total_launches += 4;
             }
             else if (ped_chain)

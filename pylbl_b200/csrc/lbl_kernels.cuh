@@ -835,42 +835,33 @@ constexpr int kNbSpan = 512;
 constexpr int kNbBatch = 64;
 constexpr int kNbQueue = 64;   // entries per queue: at most 31 left over + 32 new
 
-// Queues of K2b: (staged slot, point of the span) pairs, 6 + 9 bits, by the branch of the
-// profile the point takes -- every branch is then evaluated with the lanes packed and without
-// divergence.
-//   kMid  around |x| = xlim1: W4 region 2, or region 0/1 for the boundary points the core's
-//         index range took along
-//   kR3   W4 region 3                 (voigt.c:116-147)
-//   kCpfI / kCpfII  CPF12 sub-regions (voigt.c:148-186)
-enum NearQueue { kMid = 0, kR3 = 1, kCpfI = 2, kCpfII = 3, kNearQueues = 4 };
-typedef unsigned short NearEntry;
-
-// Drains `cnt` (<= 32) entries of queue K: lane e evaluates entry e and adds it to its point.
-// Inside xlim1 the Lorentz form is taken back where the summation kernel added it.
-template <int K>
-__device__ __forceinline__ void near_block_drain(const GridSpec& g, const NearLine* slots, const NearEntry* q,
+// Drains `cnt` (<= 32) queued (slot, point) pairs with the lanes packed: lane e evaluates entry
+// e and adds it to its point.  kInner == false: points around |x| = xlim1 -- W4 region 2, or
+// region 0/1 for the boundary points the index range took along; kInner == true: W4 region 3 /
+// CPF12.  Inside xlim1 the Lorentz form is taken back where the summation kernel added it.
+template <bool kInner>
+__device__ __forceinline__ void near_block_drain(const GridSpec& g, const NearLine* slots, const int* q,
                                                  int cnt, int lane, int p0, double* mine)
 {
     const int entry = q[lane < cnt ? lane : 0];
-    const int k = entry & 0x1ff;           // point, relative to the span
+    const int k = entry & 0xffff;          // point, relative to the span
     double val = 0.;
     bool pending = lane < cnt;
     if (pending)
     {
-        const NearLine& nl = slots[entry >> 9];
+        const NearLine& nl = slots[entry >> 16];
         const double v = grid_point(g.v0, g.dv, p0 + k);
         const double xi = (v - nl.nu) * nl.repwid;
-        if (K == kMid)
+        const bool lorentz_added = (nl.tag & 1) == 0;
+        if (kInner)
         {
-            bool core;
-            val = near_point(nl, v, core);   // regions 0, 1, 2 (never `core`: sorted at the push)
+            val = nl.cof * voigt_inner(xi, nl.y);
+            if (lorentz_added) val -= far_term_lo(v, nl.a, nl.b, nl.c, 0.);   // the bits K2c added
         }
         else
         {
-            if (K == kR3) val = nl.cof * voigt_region3(xi * xi, nl.y);
-            if (K == kCpfI) val = nl.cof * voigt_cpf12<true>(xi, nl.y);
-            if (K == kCpfII) val = nl.cof * voigt_cpf12<false>(xi, nl.y);
-            if ((nl.tag & 1) == 0) val -= far_term_lo(v, nl.a, nl.b, nl.c, 0.);   // the bits K2c added
+            bool core;
+            val = near_point(nl, v, core);   // regions 0, 1, 2 (never `core`: sorted at the push)
         }
     }
     // Two entries may name the same point (two lines' cores overlapping): the lowest lane of
@@ -895,9 +886,9 @@ __device__ __forceinline__ void near_block_drain(const GridSpec& g, const NearLi
     }
 }
 
-// Appends the lanes flagged `push` to queue K (lane-compacted) and drains a full warp's worth.
-template <int K>
-__device__ __forceinline__ void near_block_push(const GridSpec& g, const NearLine* slots, NearEntry* q, int& qn,
+// Appends the lanes flagged `push` to a queue (lane-compacted) and drains a full warp's worth.
+template <bool kInner>
+__device__ __forceinline__ void near_block_push(const GridSpec& g, const NearLine* slots, int* q, int& qn,
                                                 bool push, int entry, int lane, unsigned below, int p0,
                                                 double* mine)
 {
@@ -908,16 +899,16 @@ __device__ __forceinline__ void near_block_push(const GridSpec& g, const NearLin
     }
     if (push)
     {
-        q[qn + __popc(m & below)] = (NearEntry)entry;
+        q[qn + __popc(m & below)] = entry;
     }
     qn += __popc(m);
     __syncwarp();
     if (qn >= 32)
     {
-        near_block_drain<K>(g, slots, q, 32, lane, p0, mine);
+        near_block_drain<kInner>(g, slots, q, 32, lane, p0, mine);
         __syncwarp();
         const int keep = qn - 32;
-        const NearEntry moved = (lane < keep) ? q[32 + lane] : (NearEntry)0;
+        const int moved = (lane < keep) ? q[32 + lane] : 0;
         __syncwarp();
         if (lane < keep) q[lane] = moved;
         qn = keep;
@@ -943,7 +934,7 @@ near_block_kernel(const SumArgs a)
 {
     __shared__ double acc[4][kNbSpan];
     __shared__ __align__(16) NearLine slots[kNbBatch];
-    __shared__ NearEntry queues[4][kNearQueues][kNbQueue];
+    __shared__ int queues[4][2][kNbQueue];
     __shared__ int batch_count[2];
     const GridSpec& g = a.grid;
     const int layer = blockIdx.y + a.layer0;
@@ -960,8 +951,9 @@ near_block_kernel(const SumArgs a)
     const LineChk* chk = a.rec.chk + off;
     const LineGen* gen = a.rec.gen + off;
     double* mine = acc[warp];
-    NearEntry (*q)[kNbQueue] = queues[warp];
-    int qn[kNearQueues] = {0, 0, 0, 0};
+    int* q_mid = queues[warp][0];     // around |x| = xlim1: W4 region 2 and boundary points
+    int* q_in = queues[warp][1];      // W4 region 3 / CPF12: long
+    int n_mid = 0, n_in = 0;
 
     int jlo, jhi;
     near_candidates(a.lines, g, ly, p0, p1, jlo, jhi);
@@ -1002,22 +994,19 @@ near_block_kernel(const SumArgs a)
             const NearLine& nl = slots[s];
             const int zlo = nl.nlo, zhi = nl.nhi;
             const int c_lo = nl.c_lo, c_hi = nl.c_hi;
-            // ---- the few points inside |x| < xlim1 (and its boundary): sorted by the branch of
-            // the profile they take into four queues, each evaluated 32 at a time -- no branch
-            // ever runs with two or three lanes active, and no drain diverges
+            // ---- the few points inside |x| < xlim1 (and its boundary): sorted by kind into the
+            // two queues, evaluated 32 at a time -- no branch of the profile ever runs with two
+            // or three lanes active
             for (int i0 = c_lo; i0 <= c_hi; i0 += 32)
             {
                 const int i = i0 + lane;
                 const bool inside = i <= c_hi;
                 const double v = grid_point(g.v0, g.dv, i);
                 const double abx = fabs((v - nl.nu) * nl.repwid);
-                const int kind = !inside ? -1
-                                 : (abx >= nl.lim_r2 ? (int)kMid : (int)kR3 + voigt_inner_kind(abx, nl.y));
-                const int entry = (s << 9) | (i - p0);
-                near_block_push<kMid>(g, slots, q[kMid], qn[kMid], kind == kMid, entry, lane, below, p0, mine);
-                near_block_push<kR3>(g, slots, q[kR3], qn[kR3], kind == kR3, entry, lane, below, p0, mine);
-                near_block_push<kCpfI>(g, slots, q[kCpfI], qn[kCpfI], kind == kCpfI, entry, lane, below, p0, mine);
-                near_block_push<kCpfII>(g, slots, q[kCpfII], qn[kCpfII], kind == kCpfII, entry, lane, below, p0, mine);
+                const bool inner = inside && abx < nl.lim_r2;
+                const int entry = (s << 16) | (i - p0);
+                near_block_push<false>(g, slots, q_mid, n_mid, inside && !inner, entry, lane, below, p0, mine);
+                near_block_push<true>(g, slots, q_in, n_in, inner, entry, lane, below, p0, mine);
             }
             // ---- the zone outside it, W4 regions 0 and 1 (voigt.c:79-97), left part then right
             // part, lanes packed across the gap.  Where the Lorentz form is already in the spectrum
@@ -1049,11 +1038,9 @@ near_block_kernel(const SumArgs a)
             }
         }
         // the queues name slots of this batch: empty them before the slots are rewritten
-        if (qn[kMid] > 0) near_block_drain<kMid>(g, slots, q[kMid], qn[kMid], lane, p0, mine);
-        if (qn[kR3] > 0) near_block_drain<kR3>(g, slots, q[kR3], qn[kR3], lane, p0, mine);
-        if (qn[kCpfI] > 0) near_block_drain<kCpfI>(g, slots, q[kCpfI], qn[kCpfI], lane, p0, mine);
-        if (qn[kCpfII] > 0) near_block_drain<kCpfII>(g, slots, q[kCpfII], qn[kCpfII], lane, p0, mine);
-        qn[kMid] = qn[kR3] = qn[kCpfI] = qn[kCpfII] = 0;
+        if (n_mid > 0) near_block_drain<false>(g, slots, q_mid, n_mid, lane, p0, mine);
+        if (n_in > 0) near_block_drain<true>(g, slots, q_in, n_in, lane, p0, mine);
+        n_mid = n_in = 0;
         __syncwarp();
     }
 
@@ -1577,11 +1564,15 @@ ped_nodes_kernel(const PedRunArgs a)
     }
 }
 
-// K3c.  The chain over the runs of one layer (ped_chain_run): one warp per layer; the pedestal
-// bins live in shared memory (or, for very wide grids, in the global pedbin array itself).
+// K3c.  The chain over the runs of one layer: one warp per layer; the pedestal bins live in
+// shared memory (or, for very wide grids, in the global pedbin array itself).  Lane i holds run
+// r0 + i; the longest regular prefix of those 32 runs (ped_run_regular; all of them, nearly
+// always) is resolved at once by the (min,+) scan described in lbl_threads.cuh -- a prefix sum
+// and a prefix minimum across the lanes -- and an irregular run by the sequential step
+// (ped_chain_run with explicit sums over the bins).
 // grid = layers, block = 32, dynamic shared memory = nb doubles (0: bins in global memory).
 __global__ void __launch_bounds__(32)
-ped_chain_runs_kernel(const PedRunArgs a, int bins_in_smem)
+ped_chain_runs_kernel(const PedRunArgs a, int bins_in_smem, int use_scan)
 {
     extern __shared__ double smem_bins[];
     const GridSpec& g = a.grid;
@@ -1596,61 +1587,87 @@ ped_chain_runs_kernel(const PedRunArgs a, int bins_in_smem)
     const int4* wins = reinterpret_cast<const int4*>(a.run_cb) + (size_t)layer * a.n_rows;
     const double2* sums = reinterpret_cast<const double2*>(a.run_sums + 4 * (size_t)layer * a.n_rows);
     const int ns = 2 * g.cut_off + 2;
-    // this lane's run of the next tile of 32, fetched one tile ahead
-    int4 my_w = make_int4(-1, 0, 0, 0);
-    double2 my_f = make_double2(0., 0.), my_k = make_double2(0., 0.);
-    if (lane < n_runs)
-    {
-        my_w = wins[lane];
-        my_f = sums[2 * lane];
-        my_k = sums[2 * lane + 1];
-    }
     int top = -1;     // highest bin written so far: ranges above it sum to zero
-    for (int r0 = 0; r0 < n_runs; r0 += 32)
+    int r0 = 0;
+    while (r0 < n_runs)
     {
-        const int4 w_t = my_w;
-        const double2 f_t = my_f, k_t = my_k;
-        const int nxt = r0 + 32 + lane;
-        if (nxt < n_runs)
+        const int r = r0 + lane;
+        PedRunInfo me;
+        me.bin = -1;
+        me.bs = me.be = me.ne = 0;
+        me.sums[0] = me.sums[1] = me.sums[2] = me.sums[3] = 0.;
+        if (r < n_runs)
         {
-            my_w = wins[nxt];
-            my_f = sums[2 * nxt];
-            my_k = sums[2 * nxt + 1];
+            const int4 w = wins[r];
+            const double2 f = sums[2 * r], k = sums[2 * r + 1];
+            me.bin = w.x; me.bs = w.y; me.be = w.z; me.ne = w.w;
+            me.sums[0] = f.x; me.sums[1] = f.y; me.sums[2] = k.x; me.sums[3] = k.y;
         }
-        const int cnt = min(32, n_runs - r0);
-        for (int m = 0; m < cnt; ++m)
+        const int first_bin = __shfl_sync(0xffffffffu, me.bin, 0);
+        int prev_top = __shfl_up_sync(0xffffffffu, me.bin, 1);
+        if (lane == 0) prev_top = top;
+        const bool regular = use_scan && r < n_runs && ped_run_regular(me, first_bin, prev_top);
+        const unsigned mask = __ballot_sync(0xffffffffu, regular);
+        const int len = (mask == 0xffffffffu) ? 32 : __ffs(~mask) - 1;
+        if (len >= 2)
         {
-            const int bin = __shfl_sync(0xffffffffu, w_t.x, m);
-            if (bin < 0)
-            {
-                continue;   // the reference does not process these lines on this grid
-            }
-            const int bs = __shfl_sync(0xffffffffu, w_t.y, m);
-            const int be = __shfl_sync(0xffffffffu, w_t.z, m);
-            const int ne = __shfl_sync(0xffffffffu, w_t.w, m);
-            double s4[4];
-            s4[0] = __shfl_sync(0xffffffffu, f_t.x, m);
-            s4[1] = __shfl_sync(0xffffffffu, f_t.y, m);
-            s4[2] = __shfl_sync(0xffffffffu, k_t.x, m);
-            s4[3] = __shfl_sync(0xffffffffu, k_t.y, m);
-            double ps = 0., pe = 0.;
-            for (int k = lane; k < ns; k += 32) ps += bins[bs + k];
-            const bool e_side = be <= top;    // else every bin of the range is still zero
-            if (e_side)
-            {
-                for (int k = lane; k < ne; k += 32) pe += bins[be + k];
-            }
+            const bool in = lane < len;
+            const double alpha = in ? me.sums[1] + me.sums[3] : 0.;
+            const double h = in ? (me.sums[0] + me.sums[2]) - ped_prior_window(bins, me.bs, first_bin)
+                                : 1.0e300;
+            double prefix = alpha;          // S_i = alpha_0 + ... + alpha_i
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1)
+            for (int o = 1; o < 32; o <<= 1)
             {
-                ps += __shfl_xor_sync(0xffffffffu, ps, o);
-                if (e_side) pe += __shfl_xor_sync(0xffffffffu, pe, o);
+                const double t = __shfl_up_sync(0xffffffffu, prefix, o);
+                if (lane >= o) prefix += t;
             }
-            const double pedestal = ped_chain_run(s4, ps, pe);
-            if (lane == 0) bins[bin] += pedestal;
-            top = max(top, bin);
+            double low = h - prefix;        // min over k <= i of (h_k - S_k)
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1)
+            {
+                const double t = __shfl_up_sync(0xffffffffu, low, o);
+                if (lane >= o) low = fmin(low, t);
+            }
+            const double q = prefix + fmin(low, 0.);
+            double q_prev = __shfl_up_sync(0xffffffffu, q, 1);
+            if (lane == 0) q_prev = 0.;
+            if (in) bins[me.bin] += fmin(alpha, h - q_prev);
+            top = __shfl_sync(0xffffffffu, me.bin, len - 1);
+            r0 += len;
             __syncwarp();
+            continue;
         }
+        // the sequential step for run r0 (lane 0 holds it)
+        r0 += 1;
+        const int bin = first_bin;
+        if (bin < 0)
+        {
+            continue;   // the reference does not process these lines on this grid
+        }
+        const int bs = __shfl_sync(0xffffffffu, me.bs, 0);
+        const int be = __shfl_sync(0xffffffffu, me.be, 0);
+        const int ne = __shfl_sync(0xffffffffu, me.ne, 0);
+        double s4[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) s4[q] = __shfl_sync(0xffffffffu, me.sums[q], 0);
+        double ps = 0., pe = 0.;
+        for (int k = lane; k < ns; k += 32) ps += bins[bs + k];
+        const bool e_side = be <= top;    // else every bin of the range is still zero
+        if (e_side)
+        {
+            for (int k = lane; k < ne; k += 32) pe += bins[be + k];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+        {
+            ps += __shfl_xor_sync(0xffffffffu, ps, o);
+            if (e_side) pe += __shfl_xor_sync(0xffffffffu, pe, o);
+        }
+        const double pedestal = ped_chain_run(s4, ps, pe);
+        if (lane == 0) bins[bin] += pedestal;
+        top = max(top, bin);
+        __syncwarp();
     }
     if (bins_in_smem)
     {

@@ -1663,6 +1663,47 @@ LBL_HD double ped_chain_run(const double (&sums)[4], double sum_ps, double sum_p
     return d_end > 0. ? sums[1] + ke0 : sums[0] + ks0;
 }
 
+// ---------------------------------------------------------------------------------------
+// The chain over runs as a (min,+) scan.  Call a stretch of consecutive runs REGULAR when their
+// pedestal bins are strictly increasing and above every bin touched so far, none is skipped,
+// every run's k[e] range is still empty (no earlier line reaches its k[e]), and the first
+// run's bin lies inside every run's k[s] range.  (In a nu-sorted database all runs are like
+// that except where pressure shifts put neighbouring lines' cells out of order, and the last
+// 2*cut+2 cells, whose k[e] is the clamped end of the grid.)  For such a stretch, with
+//     alpha_i = sum f[e] + B_i                       (k[e] before the run is B_i: no pedestal reaches it)
+//     h_i     = sum f[s] + A_i - W_i ,   W_i = the pedestals already binned inside the run's k[s] range
+//     q_i     = sum of the pedestals of runs 0..i of the stretch,
+// ped_chain_run reads  P_i = min(alpha_i, h_i - q_(i-1)),  i.e.  q_i = min(q_(i-1) + alpha_i, h_i):
+// a Lindley-type recursion whose solution is a prefix minimum,
+//     q_i = S_i + min(0, min_(k<=i) (h_k - S_k)) ,   S_i = alpha_0 + ... + alpha_i ,
+// two warp scans for up to 32 runs instead of 32 dependent steps.  All sums stay local to the
+// stretch and the 2*cut+2 bins before it (no spectrum-wide prefix sums, so a distant strong band
+// cannot cancel against local values).  Irregular runs take the sequential step (ped_chain_run
+// with explicit sums over the bins).
+// ---------------------------------------------------------------------------------------
+struct PedRunInfo
+{
+    int bin;       // own pedestal bin (cb + cut + 1), -1: the reference skips these lines
+    int bs;        // first bin of the k[s] range [bs, bs + 2*cut + 2)
+    int be, ne;    // k[e] range [be, be + ne)
+    double sums[4];
+};
+
+// Is run `cur` the continuation of a regular stretch that started at bin `first_bin`, after a
+// run (or, for the first run, after everything so far) whose highest bin is `prev_top`?
+LBL_HD bool ped_run_regular(const PedRunInfo& cur, int first_bin, int prev_top)
+{
+    return cur.bin >= 0 && cur.bin > prev_top && cur.be > prev_top && cur.bs <= first_bin;
+}
+
+// W_i: pedestals binned in [bs, first_bin) (sequential sum: few terms, deterministic).
+LBL_HD double ped_prior_window(const double* bins, int bs, int first_bin)
+{
+    double w = 0.;
+    for (int b = bs; b < first_bin; ++b) w += bins[b];
+    return w;
+}
+
 // K4a: pedestal seen by the points of one cell: corr[0] for r > 0, corr[1] for r == 0.
 LBL_HD void pedestal_cell(const double* bins, int cell, int cut_off, double* corr2)
 {

@@ -91,9 +91,10 @@ class Mixture(object):
             layer_groups: the layers are taken in this many consecutive groups, all gases of a
                           group before the next group, so that a finished group's rows are on
                           their way to the host while the next group computes (only the last
-                          group's copy is exposed).  None = automatic: groups of at least 12
-                          layers, at most 5.  Worth it when the copy is slow next to the kernels
-                          (several GPUs sharing the host's PCIe and memory bandwidth).
+                          group's copy is exposed).  None = one group.  Worth it when the copy
+                          is slow next to the kernels (several GPUs sharing the host's PCIe and
+                          memory bandwidth); every extra group costs kernel tails and one more
+                          pedestal recurrence per gas.
         """
         v0, vn, n_per_v = bounds if bounds is not None else grid_to_ints(grid)
         t = np.ascontiguousarray(temperature, dtype=np.float64).ravel()
@@ -112,13 +113,19 @@ class Mixture(object):
             out = np.empty((n_layers, n))
         if out.shape != (n_layers, n) or out.dtype != np.float64 or not out.flags["C_CONTIGUOUS"]:
             raise ValueError("out must be a C-contiguous float64 array of shape (n_layers, n)")
+        if continuum is not None:
+            # every continuum of every gas, summed in one pass over the accumulator
+            from .continuum import continua_of
+            names = [name for formula in volume_mixing_ratio for name in continua_of(formula)]
+            if names:
+                continuum.spectra(names, t, p, volume_mixing_ratio, bounds=(v0, vn, n_per_v), mix=self._mix)
         # Every gas is submitted without waiting for the one before: their scaling kernels and
         # pedestal chains overlap, the summation kernels run gas after gas, and each gas is
         # added into the accumulator on the device as soon as it is done.  The gas with the most
         # lines goes last in every layer group; what it completes is copied to the host while
         # the next layers compute.
         if layer_groups is None:
-            layer_groups = max(1, min(5, n_layers // 12))
+            layer_groups = 1
         layer_groups = max(1, min(int(layer_groups), n_layers))
         edges = [n_layers * g // layer_groups for g in range(layer_groups + 1)]
         order = sorted(self.gases.items(), key=lambda item: item[1]._handle(self.device).stats()["n_lines"])

@@ -6,6 +6,7 @@
 // recurrence) against the oracle without a GPU.  The product never loads this file; the
 // MUFU reciprocal seed is emulated (see rcp_seed in lbl_core.cuh).
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -199,17 +200,68 @@ static void run_chain_sorted(const PedRunArgs& ra, int layer, const LayerIn* lay
         if (j == 0 || ra.rec.chk[off + j].cb != ra.rec.chk[off + j - 1].cb) starts.push_back(j);
     }
     starts.push_back(ra.n_rows);
-    for (size_t r = 0; r + 1 < starts.size(); ++r)
+    // the runs' gathered sums and windows (ped_nodes_kernel)
+    const int n_runs = (int)starts.size() - 1;
+    std::vector<PedRunInfo> runs((size_t)std::max(n_runs, 0));
+    for (int r = 0; r < n_runs; ++r)
     {
-        double sums[4];
-        ped_run_sums(ra, layer, starts[r], starts[r + 1], 0, 1, sums);
+        ped_run_sums(ra, layer, starts[r], starts[r + 1], 0, 1, runs[r].sums);
         const int cb = ra.rec.chk[off + starts[r]].cb;
         const PedPoints pp = ped_points(cb, g);
-        if (pp.skip) continue;
+        runs[r].bin = pp.skip ? -1 : cb + g.cut_off + 1;
+        runs[r].bs = pp.bs;
+        runs[r].be = pp.be;
+        runs[r].ne = pp.ne;
+    }
+    // the chain (ped_chain_runs_kernel): regular stretches of up to 32 runs by the (min,+) scan,
+    // everything else by the sequential step
+    const bool scan = getenv("EMU_PED_SEQUENTIAL") == nullptr;
+    const int ns = 2 * g.cut_off + 2;
+    int top = -1;
+    int r0 = 0;
+    while (r0 < n_runs)
+    {
+        int len = 0;
+        if (scan)
+        {
+            int prev_top = top;
+            while (len < 32 && r0 + len < n_runs && ped_run_regular(runs[r0 + len], runs[r0].bin, prev_top))
+            {
+                prev_top = runs[r0 + len].bin;
+                ++len;
+            }
+        }
+        if (len >= 2)
+        {
+            double prefix = 0., running_min = 0., q_prev = 0.;
+            std::vector<double> ped(len);
+            for (int i = 0; i < len; ++i)
+            {
+                const PedRunInfo& ri = runs[r0 + i];
+                const double alpha = ri.sums[1] + ri.sums[3];
+                const double h = (ri.sums[0] + ri.sums[2]) - ped_prior_window(bins, ri.bs, runs[r0].bin);
+                prefix += alpha;                                   // S_i
+                running_min = std::min(running_min, h - prefix);   // min(0, min_k (h_k - S_k))
+                const double q = prefix + running_min;
+                ped[i] = std::min(alpha, h - q_prev);
+                q_prev = q;
+            }
+            for (int i = 0; i < len; ++i) bins[runs[r0 + i].bin] += ped[i];
+            top = runs[r0 + len - 1].bin;
+            r0 += len;
+            continue;
+        }
+        const PedRunInfo& ri = runs[r0];
+        ++r0;
+        if (ri.bin < 0) continue;
         double ps = 0., pe = 0.;
-        for (int k = 0; k < pp.ns; ++k) ps += bins[pp.bs + k];
-        for (int k = 0; k < pp.ne; ++k) pe += bins[pp.be + k];
-        bins[cb + g.cut_off + 1] += ped_chain_run(sums, ps, pe);
+        for (int k = 0; k < ns; ++k) ps += bins[ri.bs + k];
+        if (ri.be <= top)
+        {
+            for (int k = 0; k < ri.ne; ++k) pe += bins[ri.be + k];
+        }
+        bins[ri.bin] += ped_chain_run(ri.sums, ps, pe);
+        top = std::max(top, ri.bin);
     }
 }
 

@@ -194,9 +194,11 @@ def test_config4_million_lines_bands(db_dir):
 
 
 def test_config2_pedestal_formulations_agree(config2, monkeypatch):
-    """The run-based pedestal recurrence (nu-sorted databases, the default) against the slot-ring
-    kernels it replaces there (PYLBL_B200_PEDRUNS=0; still used for unsorted databases), on the
-    longest line list of the benchmark's workload; both were checked against the oracle above."""
+    """The run-based pedestal recurrence (nu-sorted databases, the default: regular stretches of
+    runs by the (min,+) scan) against the same with every run taken by the sequential step
+    (PYLBL_B200_PEDSCAN=0) and against the slot-ring kernels it replaces there
+    (PYLBL_B200_PEDRUNS=0; still used for unsorted databases), on the longest line list of the
+    benchmark's workload; the default was checked against the oracle above."""
     path, _ = config2
     col = synth.standard_column(60)
     bounds = synth.config_grid(2)
@@ -204,8 +206,11 @@ def test_config2_pedestal_formulations_agree(config2, monkeypatch):
     t, p, x = col.t[layers], col.p[layers], col.vmr["CO2"][layers]
     gas = Gas(path, "CO2")
     runs = gas.absorption_coefficients(t, p, x, bounds=bounds, remove_pedestal=True)
+    monkeypatch.setenv("PYLBL_B200_PEDSCAN", "0")          # every run by the sequential step
+    stepwise = gas.absorption_coefficients(t, p, x, bounds=bounds, remove_pedestal=True)
     monkeypatch.setenv("PYLBL_B200_PEDRUNS", "0")
     slots = gas.absorption_coefficients(t, p, x, bounds=bounds, remove_pedestal=True)
     for row in range(3):
         assert scaled_error(runs[row], slots[row], bounds[2]) <= 1e-12
+        assert scaled_error(runs[row], stepwise[row], bounds[2]) <= 1e-13
     gas.close()

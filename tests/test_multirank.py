@@ -26,8 +26,16 @@ WORKER = textwrap.dedent("""
     ranks.barrier()
     total_t = ranks.sum(float(col.t.sum()))
     slowest = ranks.max(10.0 + rank)
+    # the shards of the other two modes: columns round-robin (configs[4]), one band of the grid
+    # per rank (configs[3]); every rank contributes its share to the same reductions
+    mine = bench.rank_columns(11, world, rank)
+    n_cols = ranks.sum(float(len(mine)))
+    col_ids = ranks.sum(float(sum(mine)))
+    lo, hi = bench.rank_band([0, 1700, 3491], rank)
+    cells = ranks.sum(float(hi - lo))
     if rank == 0:
-        print(json.dumps(dict(world=world, total_t=total_t, slowest=slowest)))
+        print(json.dumps(dict(world=world, total_t=total_t, slowest=slowest, n_cols=n_cols,
+                              col_ids=col_ids, cells=cells)))
     dist.destroy_process_group()
 """)
 
@@ -56,6 +64,7 @@ def test_two_ranks_agree_on_totals(tmp_path):
     assert line["world"] == 2
     assert abs(line["total_t"] - want) < 1e-9
     assert line["slowest"] == 11.0
+    assert line["n_cols"] == 11 and line["col_ids"] == sum(range(11)) and line["cells"] == 3491
     # columns differ between ranks (weak scaling: each rank has its own work)
     assert not np.array_equal(bench.rank_column(0).t, bench.rank_column(1).t)
 
