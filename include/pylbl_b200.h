@@ -57,6 +57,8 @@ typedef struct lbl_stats
     float fixup_ms;         /* K2b (near-zone and node terms) */
     float pedestal_ms;      /* K3 + K4 */
     float total_ms;         /* first enqueue -> last copy complete */
+    float copy_tail_ms;     /* last kernel of the call done -> last copy to the host complete: the
+                               part of the device->host copy that nothing of this call hides */
 } lbl_stats;
 
 /* ---- (1) the reference's own entry point ---------------------------------------------

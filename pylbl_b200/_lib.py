@@ -34,7 +34,7 @@ class Stats(Structure):
         ("total_launches", c_int), ("fp32_used", c_int),
         ("scale_ms", c_float), ("sum_ms", c_float), ("fixup_ms", c_float),
         ("pedestal_ms", c_float),
-        ("total_ms", c_float),
+        ("total_ms", c_float), ("copy_tail_ms", c_float),
     ]
 
     def as_dict(self):

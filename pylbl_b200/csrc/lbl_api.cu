@@ -178,6 +178,7 @@ struct lbl_gas
     cudaEvent_t ev_out_ready[2] = {nullptr, nullptr}, ev_out_free[2] = {nullptr, nullptr};
     bool out_busy[2] = {false, false};
     bool pending = false;
+    bool copies_in_call = false;
     bool farfield_last = false;
     lbl_stats stats{};
     // what is resident after the last call (for windows/scaled/device_result)
@@ -803,7 +804,7 @@ static int open_handle(std::unique_ptr<lbl_gas>& g, int device, lbl_gas** out)
     g->s_main = g->streams->main;
     LBL_CUDA(cudaEventCreate(&g->ev_call_begin));
     LBL_CUDA(cudaEventCreate(&g->ev_call_end));
-    LBL_CUDA(cudaEventCreateWithFlags(&g->ev_compute_end, cudaEventDisableTiming));
+    LBL_CUDA(cudaEventCreate(&g->ev_compute_end));
     for (int i = 0; i < 2; ++i)
     {
         LBL_CUDA(cudaEventCreateWithFlags(&g->ev_out_ready[i], cudaEventDisableTiming));
@@ -1590,6 +1591,7 @@ static int submit_call(lbl_gas* g, const CallSpec& call)
     {
         LBL_CUDA(cudaEventRecord(mix->ev_added, sl));
     }
+    g->copies_in_call = k_host || (mix && call.mix_host);
     if (k_host || (mix && call.mix_host))
     {
         // The call ends when the last copy has landed: the end mark goes on the copy stream,
@@ -1642,6 +1644,11 @@ int lbl_gas_wait(lbl_gas* g)
     }
     LBL_CUDA(cudaEventElapsedTime(&ms, g->ev_call_begin, g->ev_call_end));
     st.total_ms = ms;
+    if (g->copies_in_call)
+    {
+        LBL_CUDA(cudaEventElapsedTime(&ms, g->ev_compute_end, g->ev_call_end));
+        st.copy_tail_ms = ms;
+    }
     if (getenv("PYLBL_B200_TIMELINE"))
     {
         // debugging aid: when this call's kernels and copies ended, relative to lbl_timer_start

@@ -10,6 +10,7 @@ per-gas spectra on the GPU, applies the number densities there and returns one a
 from __future__ import annotations
 
 import ctypes
+import time
 from ctypes import c_void_p
 
 import numpy as np
@@ -36,6 +37,8 @@ class Mixture(object):
         self._shape = None
 
         self._owns_gases = True
+        self._auto_groups = 1
+        self.last_layer_groups = 1
 
     @classmethod
     def from_gases(cls, gases, device=None):
@@ -47,6 +50,8 @@ class Mixture(object):
         self._mix = None
         self._shape = None
         self._owns_gases = False
+        self._auto_groups = 1
+        self.last_layer_groups = 1
         return self
 
     def close(self):
@@ -91,10 +96,12 @@ class Mixture(object):
             layer_groups: the layers are taken in this many consecutive groups, all gases of a
                           group before the next group, so that a finished group's rows are on
                           their way to the host while the next group computes (only the last
-                          group's copy is exposed).  None = one group.  Worth it when the copy
-                          is slow next to the kernels (several GPUs sharing the host's PCIe and
-                          memory bandwidth); every extra group costs kernel tails and one more
-                          pedestal recurrence per gas.
+                          group's copy is exposed).  Worth it when the copy is slow next to the
+                          kernels (several GPUs sharing the host's PCIe and memory bandwidth);
+                          every extra group costs about a millisecond of kernel tails and
+                          small launches.  None = automatic: one group, and one more (up to 4)
+                          whenever the previous call of this object ended with more than 12 %
+                          of its time spent on a copy that nothing hid (`copy_tail_ms`).
         """
         v0, vn, n_per_v = bounds if bounds is not None else grid_to_ints(grid)
         t = np.ascontiguousarray(temperature, dtype=np.float64).ravel()
@@ -124,9 +131,11 @@ class Mixture(object):
         # added into the accumulator on the device as soon as it is done.  The gas with the most
         # lines goes last in every layer group; what it completes is copied to the host while
         # the next layers compute.
-        if layer_groups is None:
-            layer_groups = 1
+        adaptive = layer_groups is None
+        if adaptive:
+            layer_groups = self._auto_groups if n_layers >= 8 * self._auto_groups else 1
         layer_groups = max(1, min(int(layer_groups), n_layers))
+        t_begin = time.perf_counter()
         edges = [n_layers * g // layer_groups for g in range(layer_groups + 1)]
         order = sorted(self.gases.items(), key=lambda item: item[1]._handle(self.device).stats()["n_lines"])
         states = {formula: np.ascontiguousarray(volume_mixing_ratio[formula], dtype=np.float64).ravel()
@@ -161,4 +170,10 @@ class Mixture(object):
             gas.last_stats = [totals[formula]]
         if not handles:
             lib.lbl_mix_download(self._mix, out.ctypes.data_as(c_void_p))
+        elif adaptive:
+            wall_ms = (time.perf_counter() - t_begin) * 1e3
+            tail_ms = handles[-1][2].stats()["copy_tail_ms"]
+            if tail_ms > 0.12 * wall_ms and self._auto_groups < 4:
+                self._auto_groups += 1
+        self.last_layer_groups = layer_groups
         return out
