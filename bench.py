@@ -509,6 +509,7 @@ def run_ours(args, rank, local_rank, world, dist):
 
     e2e_total = time_e2e(step_e2e_total)
     e2e_total["layer_groups"] = mixture.last_layer_groups
+    e2e_total["last_call_uncovered_copy_ms"] = mixture.last_copy_tail_ms
     e2e_total["output"] = ("total: sum over gases of n_gas*k_gas formed on the device, one "
                            "(60, 500000) f64 array per column back to pinned host memory "
                            "(pyLBL output_format='total'); public API Mixture.total_absorption")

@@ -1580,30 +1580,30 @@ static int submit_call(lbl_gas* g, const CallSpec& call)
         g->last_chunk_layers = nl;
         g->last_slot = slot;
     }
-    LBL_CUDA(cudaMemcpyAsync(g->evals_host, g->evals_dev.p, sizeof(unsigned long long) * n_layers,
-                             cudaMemcpyDeviceToHost, sl));
-    if (farfield)
-    {
-        LBL_CUDA(cudaMemcpyAsync(g->executed_host, g->executed_dev.p, sizeof(unsigned long long),
-                                 cudaMemcpyDeviceToHost, sl));
-    }
     if (mix)
     {
         LBL_CUDA(cudaEventRecord(mix->ev_added, sl));
     }
+    // The small statistics copies go where they cannot hold anything up: all device-to-host
+    // copies share one DMA queue, and on the late stream they would sit behind this call's bulk
+    // copies -- and with them every later gas's correction kernels.
     g->copies_in_call = k_host || (mix && call.mix_host);
-    if (k_host || (mix && call.mix_host))
+    LBL_CUDA(cudaEventRecord(g->ev_compute_end, sl));      // the last kernel of the call
+    cudaStream_t s_end = g->copies_in_call ? g->s_copy : sl;
+    if (g->copies_in_call)
     {
         // The call ends when the last copy has landed: the end mark goes on the copy stream,
         // after the kernels' end mark.
-        LBL_CUDA(cudaEventRecord(g->ev_compute_end, sl));
         LBL_CUDA(cudaStreamWaitEvent(g->s_copy, g->ev_compute_end, 0));
-        LBL_CUDA(cudaEventRecord(g->ev_call_end, g->s_copy));
     }
-    else
+    LBL_CUDA(cudaMemcpyAsync(g->evals_host, g->evals_dev.p, sizeof(unsigned long long) * n_layers,
+                             cudaMemcpyDeviceToHost, s_end));
+    if (farfield)
     {
-        LBL_CUDA(cudaEventRecord(g->ev_call_end, sl));
+        LBL_CUDA(cudaMemcpyAsync(g->executed_host, g->executed_dev.p, sizeof(unsigned long long),
+                                 cudaMemcpyDeviceToHost, s_end));
     }
+    LBL_CUDA(cudaEventRecord(g->ev_call_end, s_end));
     g->pending = true;
     if (mix) g->last_chunk_layers = 0;   // the spectra went into the accumulator, uncorrected here
     return 0;

@@ -10,6 +10,7 @@ per-gas spectra on the GPU, applies the number densities there and returns one a
 from __future__ import annotations
 
 import ctypes
+import os
 import time
 from ctypes import c_void_p
 
@@ -39,6 +40,7 @@ class Mixture(object):
         self._owns_gases = True
         self._auto_groups = 1
         self.last_layer_groups = 1
+        self.last_copy_tail_ms = self.last_wall_ms = 0.
 
     @classmethod
     def from_gases(cls, gases, device=None):
@@ -52,6 +54,7 @@ class Mixture(object):
         self._owns_gases = False
         self._auto_groups = 1
         self.last_layer_groups = 1
+        self.last_copy_tail_ms = self.last_wall_ms = 0.
         return self
 
     def close(self):
@@ -68,6 +71,9 @@ class Mixture(object):
             self.close()
         except Exception:
             pass
+
+    # automatic layer groups: one more whenever the uncovered copy exceeds this share of a call
+    TAIL_FRACTION = float(os.environ.get("PYLBL_B200_MIX_TAIL_FRACTION", "0.12"))
 
     @staticmethod
     def _add_stats(totals, formula, stats):
@@ -173,7 +179,8 @@ class Mixture(object):
         elif adaptive:
             wall_ms = (time.perf_counter() - t_begin) * 1e3
             tail_ms = handles[-1][2].stats()["copy_tail_ms"]
-            if tail_ms > 0.12 * wall_ms and self._auto_groups < 4:
+            self.last_copy_tail_ms, self.last_wall_ms = tail_ms, wall_ms
+            if tail_ms > self.TAIL_FRACTION * wall_ms and self._auto_groups < 4:
                 self._auto_groups += 1
         self.last_layer_groups = layer_groups
         return out
