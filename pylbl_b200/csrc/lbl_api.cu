@@ -1385,9 +1385,9 @@ static int submit_call(lbl_gas* g, const CallSpec& call)
                                                                    g->ped_tiles.as<int>(), ra.run_row, ra.n_runs);
                     // about one run per occupied cell: enough warps to take them in a few rounds
                     // (with few layers -- the scalar plugin call -- more warps per layer)
+                    // (a warp takes 32 runs; eight warps per block)
                     const int runs_guess = std::min(ped_rows, grid.ncell + 2 * cut_off + 8);
-                    const int per_layer = std::max(64, 1184 / nl);
-                    dim3 gn(std::max(1, std::min(per_layer, (runs_guess + 7) / 8)), nl);
+                    dim3 gn(std::max(1, (runs_guess + 255) / 256), nl);
                     ped_nodes_kernel<<<gn, 256, 0, ss>>>(ra);
                 }
                 else
