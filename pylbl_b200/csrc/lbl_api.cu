@@ -1385,9 +1385,9 @@ static int submit_call(lbl_gas* g, const CallSpec& call)
                                                                    g->ped_tiles.as<int>(), ra.run_row, ra.n_runs);
                     // about one run per occupied cell: enough warps to take them in a few rounds
                     // (with few layers -- the scalar plugin call -- more warps per layer)
-                    // (a warp takes 32 runs; eight warps per block)
                     const int runs_guess = std::min(ped_rows, grid.ncell + 2 * cut_off + 8);
-                    dim3 gn(std::max(1, (runs_guess + 255) / 256), nl);
+                    const int per_layer = std::max(64, 1184 / nl);
+                    dim3 gn(std::max(1, std::min(per_layer, (runs_guess + 7) / 8)), nl);
                     ped_nodes_kernel<<<gn, 256, 0, ss>>>(ra);
                 }
                 else
@@ -1740,21 +1740,27 @@ int lbl_gas_band_edges(lbl_gas* g, int v0, int vn, int n_per_v, int cut_off, int
     if (!g || !edges) return fail("Error: null argument.");
     const int ncell = vn - v0;
     if (ncell <= 0 || n_bands < 1 || n_per_v < 1 || cut_off < 0) return fail("Error: invalid grid or band count.");
-    // Cost model of one cell (all layers alike): the lines of its window (far field: a few node
-    // evaluations each), the lines next to it (evaluated at every one of its n_per_v points),
-    // and a fixed part (searches, transforms, interpolation).
+    // Cost model of one cell (all layers alike), in units of one far-line node evaluation,
+    // calibrated on BASELINE configs[3] (tools/band_cost.py, profiles/): a fixed part (range
+    // boundaries, transforms, interpolation), the lines of its window (a few node evaluations
+    // each), the lines next to it (evaluated at every one of its n_per_v points), and their near
+    // zones, whose width grows with the wavenumber (Doppler width: 2*kappa*nu*n_per_v points).
     const int na = active_prefix(g->mol, v0, vn, cut_off);
     std::vector<double> nu(g->mol.nu.begin(), g->mol.nu.begin() + na);
     if (!g->mol.sorted) std::sort(nu.begin(), nu.end());
     auto count = [&](double lo, double hi) {
         return (double)(std::lower_bound(nu.begin(), nu.end(), hi) - std::lower_bound(nu.begin(), nu.end(), lo));
     };
+    const double mass = g->mol.min_mass > 0. ? g->mol.min_mass : 30.;
+    const double kappa = 148.3 * std::sqrt(kR2 * 250. / mass) / kVlight;
     std::vector<double> cum((size_t)ncell + 1, 0.);
     for (int c = 0; c < ncell; ++c)
     {
         const double w = (double)v0 + c;
+        const double beside = count(w - 0.5, w + 1.5);
+        const double zone_points = 2. * kappa * std::fabs(w + 0.5) * n_per_v;
         const double cost = 400. + 0.3 * n_per_v + count(w - cut_off, w + cut_off + 1.) +
-                            0.125 * n_per_v * count(w - 0.5, w + 1.5);
+                            0.125 * n_per_v * beside + 0.33 * zone_points * beside;
         cum[c + 1] = cum[c] + cost;
     }
     edges[0] = 0;

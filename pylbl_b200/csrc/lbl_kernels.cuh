@@ -1523,118 +1523,43 @@ ped_run_scatter_kernel(const LineChk* __restrict__ chk, int stride, int n_rows,
     }
 }
 
-// K3n.  The four gathered sums of every run (the quantities ped_run_sums defines).  A warp takes
-// 32 consecutive runs of one layer, one per lane, and walks the rows any of them needs ONCE:
-// every row is a uniform (broadcast) load, each lane decides by itself whether the row belongs
-// to its run, or is an earlier row whose window covers its k[s] / k[e], and evaluates it at its
-// own one or two points -- the direct-sum kernel's structure with 32 runs for points.  (One warp
-// per run with the lanes over the rows, the first form of this kernel, read every row through
-// L2 once per run that needs it: 2*cut+2 = 52 times; on a million-line list that alone was
-// 150 GB per call and bound the kernel at L2 bandwidth.)
-// grid = (blocks, layers), the warps of a layer striding over its tiles of 32 runs.
+// K3n.  The four gathered sums of every run (ped_run_sums): a warp per run, lanes over the rows.
+// grid = (blocks, layers), the warps of a layer striding over its runs.
 __global__ void __launch_bounds__(256)
 ped_nodes_kernel(const PedRunArgs a)
 {
-    const GridSpec& g = a.grid;
     const int layer = blockIdx.y;
     const int lane = threadIdx.x & 31;
     const int warps = (gridDim.x * blockDim.x) >> 5;
     const int n_runs = a.n_runs[layer];
     const int* rows = a.run_row + (size_t)layer * (a.n_rows + 1);
-    const size_t off = (size_t)layer * a.lines.n;
-    const LineChk* chk = a.rec.chk + off;
-    const FarAB* ab = a.rec.ab + off;
-    const double* cc = a.rec.cc + off;
-    const double slack = a.layers[layer].slack;
-    const int ns = 2 * g.cut_off + 2;
-    for (int tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; tile * 32 < n_runs; tile += warps)
+    for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_runs; r += warps)
     {
-        const int r = tile * 32 + lane;
-        const bool have = r < n_runs;
-        int row_lo = 0, row_hi = 0, cb = 0;
-        PedPoints pp;
-        pp.skip = true;
-        pp.i_s = pp.i_e = pp.bs = pp.be = pp.ns = pp.ne = 0;
-        if (have)
-        {
-            row_lo = rows[r];
-            row_hi = rows[r + 1];
-            cb = __ldg(reinterpret_cast<const int4*>(chk + row_lo)).x;
-            pp = ped_points(cb, g);
-        }
-        const bool live = have && !pp.skip;
-        const double v_s = grid_point(g.v0, g.dv, pp.i_s);
-        const double v_e = grid_point(g.v0, g.dv, pp.i_e);
-        // rows this lane can need: from the first row that can cover one of its points to the
-        // end of its own run; the warp walks the union
-        int j_first = 0x7fffffff, j_last = 0;
-        if (live)
-        {
-            const int b_min = min(pp.bs, pp.be);
-            j_first = min(row_lo, first_line_at(a.lines, (double)g.v0 + (double)(b_min - g.cut_off - 1) - slack));
-            j_last = row_hi;
-        }
+        const int row_lo = rows[r], row_hi = rows[r + 1];
+        double sums[4];
+        ped_run_sums(a, layer, row_lo, row_hi, lane, 32, sums);
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1)
+        for (int q = 0; q < 4; ++q)
         {
-            j_first = min(j_first, __shfl_xor_sync(0xffffffffu, j_first, o));
-            j_last = max(j_last, __shfl_xor_sync(0xffffffffu, j_last, o));
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sums[q] += __shfl_xor_sync(0xffffffffu, sums[q], o);
         }
-        double own_s = 0., own_e = 0., prev_s = 0., prev_e = 0.;
-        for (int j = j_first; j < j_last; ++j)
-        {
-            const int4 ck = __ldg(reinterpret_cast<const int4*>(chk + j));
-            const double2 l = __ldg(reinterpret_cast<const double2*>(ab + j));
-            const double c = __ldg(cc + j);
-            const int bin = ck.x + g.cut_off + 1;
-            const bool own = live && j >= row_lo && j < row_hi;
-            const bool before = live && j < row_lo;
-            const bool at_s = own || (before && (unsigned)(bin - pp.bs) < (unsigned)ns);
-            const bool at_e = own || (before && (unsigned)(bin - pp.be) < (unsigned)pp.ne);
-            // inside the line's near zone the full profile replaces the Lorentz form (rare: the
-            // line must lie within a fraction of a cm-1 of the point)
-            const bool near_s = at_s && pp.i_s >= ck.y && pp.i_s <= ck.z;
-            const bool near_e = at_e && pp.i_e >= ck.y && pp.i_e <= ck.z;
-            double t_s = far_term(v_s, l.x, l.y, (at_s && !near_s) ? c : kBig, 0.);
-            double t_e = 0.;
-            if (__any_sync(0xffffffffu, at_e))
-            {
-                t_e = far_term(v_e, l.x, l.y, (at_e && !near_e) ? c : kBig, 0.);
-            }
-            if (__any_sync(0xffffffffu, near_s || near_e))
-            {
-                if (near_s || near_e)
-                {
-                    const LineGen gen = a.rec.gen[off + j];
-                    if (near_s) t_s = voigt_general(v_s, gen.nu, gen.repwid, gen.y, gen.cof, gen.xlim0, gen.xlim1);
-                    if (near_e) t_e = voigt_general(v_e, gen.nu, gen.repwid, gen.y, gen.cof, gen.xlim0, gen.xlim1);
-                }
-            }
-            if (own)
-            {
-                own_s += t_s;
-                own_e += t_e;
-            }
-            else
-            {
-                prev_s += at_s ? t_s : 0.;
-                prev_e += at_e ? t_e : 0.;
-            }
-        }
-        if (have)
+        if (lane == 0)
         {
             // with the sums, what the chain needs of the run's window (ped_points): its own bin
             // and the first bin of the two ranges that cover k[s] and k[e], packed into one int4
             const size_t o = (size_t)layer * a.n_rows + r;
+            const int cb = a.rec.chk[(size_t)layer * a.lines.n + row_lo].cb;
+            const PedPoints pp = ped_points(cb, a.grid);
             int4 w;
-            w.x = pp.skip ? -1 : cb + g.cut_off + 1;      // own bin (-1: not processed)
+            w.x = pp.skip ? -1 : cb + a.grid.cut_off + 1;      // own bin (-1: not processed)
             w.y = pp.bs;
             w.z = pp.be;
             w.w = pp.ne;
             reinterpret_cast<int4*>(a.run_cb)[o] = w;
             double2* dst = reinterpret_cast<double2*>(a.run_sums + 4 * o);
-            dst[0] = make_double2(own_s, own_e);
-            dst[1] = make_double2(prev_s, prev_e);
+            dst[0] = make_double2(sums[0], sums[1]);
+            dst[1] = make_double2(sums[2], sums[3]);
         }
     }
 }
