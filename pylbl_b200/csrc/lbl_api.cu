@@ -1387,7 +1387,7 @@ static int submit_call(lbl_gas* g, const CallSpec& call)
                     // (with few layers -- the scalar plugin call -- more warps per layer)
                     const int runs_guess = std::min(ped_rows, grid.ncell + 2 * cut_off + 8);
                     const int per_layer = std::max(64, 1184 / nl);
-                    dim3 gn(std::max(1, std::min(per_layer, (runs_guess + 7) / 8)), nl);
+                    dim3 gn(std::max(1, std::min(per_layer, (runs_guess / kNodeRuns + 7) / 8)), nl);
                     ped_nodes_kernel<<<gn, 256, 0, ss>>>(ra);
                 }
                 else

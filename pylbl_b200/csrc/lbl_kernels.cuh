@@ -1523,44 +1523,149 @@ ped_run_scatter_kernel(const LineChk* __restrict__ chk, int stride, int n_rows,
     }
 }
 
-// K3n.  The four gathered sums of every run (ped_run_sums): a warp per run, lanes over the rows.
-// grid = (blocks, layers), the warps of a layer striding over its runs.
+// K3n.  The four gathered sums of every run (the quantities ped_run_sums defines).  The large one
+// is the sum, at the run's k[s] point, of the earlier rows whose windows cover it: the lines of
+// the 2*cut+1 cells below the run.  Consecutive runs need nearly the same rows, so a warp takes
+// kNodeRuns consecutive runs: every lane loads a row ONCE and evaluates it at the k[s] points of
+// all of them (the run descriptors are uniform reads from shared memory), then the lanes'
+// partial sums are reduced per run.  (A warp per run, the first form of this kernel, read every
+// row through L2 once per run that needs it, 2*cut+1 = 51 times: 150 GB per call on a
+// million-line list, L2-bound.)  Row j goes to lane j mod 32 whatever the tile holds, so a run's
+// sums do not depend on which other runs the call covers (spectral bands stop at different rows).
+// The small sums -- the run's own lines at its two points, and earlier rows at k[e], which only
+// out-of-order cells produce -- stay per run with the lanes over the rows.
+// grid = (blocks, layers), the warps of a layer striding over its tiles of kNodeRuns runs.
+constexpr int kNodeRuns = 8;
+
+struct NodeRun
+{
+    int row_lo;       // rows before this one are "earlier" (0: run absent or skipped)
+    int first_bin;    // bins [first_bin, first_bin + 2*cut+2) cover k[s]
+    int i_s;
+    int pad;
+    double v_s;
+};
+
 __global__ void __launch_bounds__(256)
 ped_nodes_kernel(const PedRunArgs a)
 {
+    __shared__ NodeRun s_runs[8][kNodeRuns];
+    const GridSpec& g = a.grid;
     const int layer = blockIdx.y;
     const int lane = threadIdx.x & 31;
+    NodeRun* tile_runs = s_runs[threadIdx.x >> 5];
     const int warps = (gridDim.x * blockDim.x) >> 5;
     const int n_runs = a.n_runs[layer];
     const int* rows = a.run_row + (size_t)layer * (a.n_rows + 1);
-    for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n_runs; r += warps)
+    const size_t off = (size_t)layer * a.lines.n;
+    const unsigned ns = 2 * g.cut_off + 2;
+    for (int tile = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; tile * kNodeRuns < n_runs; tile += warps)
     {
-        const int row_lo = rows[r], row_hi = rows[r + 1];
-        double sums[4];
-        ped_run_sums(a, layer, row_lo, row_hi, lane, 32, sums);
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
+        // lanes 0..kNodeRuns-1 describe the runs of the tile
+        const int r = tile * kNodeRuns + lane;
+        const bool have = lane < kNodeRuns && r < n_runs;
+        int row_lo = 0, row_hi = 0, cb = 0;
+        PedPoints pp;
+        pp.skip = true;
+        pp.i_s = pp.i_e = pp.bs = pp.be = pp.ns = pp.ne = 0;
+        if (have)
         {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) sums[q] += __shfl_xor_sync(0xffffffffu, sums[q], o);
+            row_lo = rows[r];
+            row_hi = rows[r + 1];
+            cb = LBL_LDG(reinterpret_cast<const int4*>(a.rec.chk + off + row_lo)).x;
+            pp = ped_points(cb, g);
         }
-        if (lane == 0)
+        const bool live = have && !pp.skip;
+        int j_first = live ? ped_first_covering_row(a, layer, pp.bs) : 0x7fffffff;
+        int j_end = live ? row_lo : 0;
+        if (lane < kNodeRuns)
+        {
+            NodeRun nr;
+            nr.row_lo = live ? row_lo : 0;
+            nr.first_bin = pp.bs;
+            nr.i_s = pp.i_s;
+            nr.pad = 0;
+            nr.v_s = grid_point(g.v0, g.dv, pp.i_s);
+            tile_runs[lane] = nr;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+        {
+            j_first = min(j_first, __shfl_xor_sync(0xffffffffu, j_first, o));
+            j_end = max(j_end, __shfl_xor_sync(0xffffffffu, j_end, o));
+        }
+        __syncwarp();
+        double before_s[kNodeRuns];
+#pragma unroll
+        for (int q = 0; q < kNodeRuns; ++q) before_s[q] = 0.;
+        for (int base = j_first & ~31; base < j_end; base += 32)
+        {
+            const int j = base + lane;
+            const bool in = j < j_end;
+            int4 ck = make_int4(-0x40000000, 0, -1, 0);
+            double2 l = make_double2(0., 0.);
+            double c = 1.;
+            if (in)
+            {
+                ck = LBL_LDG(reinterpret_cast<const int4*>(a.rec.chk + off + j));
+                l = LBL_LDG(reinterpret_cast<const double2*>(a.rec.ab + off + j));
+                c = LBL_LDG(a.rec.cc + off + j);
+            }
+            const int bin = ck.x + g.cut_off + 1;
+#pragma unroll
+            for (int q = 0; q < kNodeRuns; ++q)
+            {
+                const NodeRun nr = tile_runs[q];
+                const bool cover = j < nr.row_lo && (unsigned)(bin - nr.first_bin) < ns;
+                double t = far_term(nr.v_s, l.x, l.y, c, 0.);
+                if (cover && nr.i_s >= ck.y && nr.i_s <= ck.z)
+                {
+                    // inside the line's near zone the summation kernels hold the full profile
+                    const LineGen gen = a.rec.gen[off + j];
+                    t = voigt_general(nr.v_s, gen.nu, gen.repwid, gen.y, gen.cof, gen.xlim0, gen.xlim1);
+                }
+                before_s[q] += cover ? t : 0.;
+            }
+        }
+        double mine[4] = {0., 0., 0., 0.};
+#pragma unroll
+        for (int q = 0; q < kNodeRuns; ++q)
+        {
+            const int q_lo = __shfl_sync(0xffffffffu, row_lo, q);
+            const int q_hi = __shfl_sync(0xffffffffu, row_hi, q);
+            const int q_cb = __shfl_sync(0xffffffffu, cb, q);
+            const bool q_live = __shfl_sync(0xffffffffu, (int)live, q) != 0;
+            double sums[4] = {0., 0., before_s[q], 0.};
+            if (q_live)
+            {
+                const PedPoints qp = ped_points(q_cb, g);
+                ped_sum_own(a, off, q_lo, q_hi, qp, lane, 32, sums[0], sums[1]);
+                sums[3] = ped_sum_before(a, layer, off, q_lo, qp.be, qp.ne, qp.i_e, lane, 32);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+            {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) sums[k] += __shfl_xor_sync(0xffffffffu, sums[k], o);
+                if (lane == q) mine[k] = sums[k];
+            }
+        }
+        if (have)
         {
             // with the sums, what the chain needs of the run's window (ped_points): its own bin
             // and the first bin of the two ranges that cover k[s] and k[e], packed into one int4
             const size_t o = (size_t)layer * a.n_rows + r;
-            const int cb = a.rec.chk[(size_t)layer * a.lines.n + row_lo].cb;
-            const PedPoints pp = ped_points(cb, a.grid);
             int4 w;
-            w.x = pp.skip ? -1 : cb + a.grid.cut_off + 1;      // own bin (-1: not processed)
+            w.x = pp.skip ? -1 : cb + g.cut_off + 1;      // own bin (-1: not processed)
             w.y = pp.bs;
             w.z = pp.be;
             w.w = pp.ne;
             reinterpret_cast<int4*>(a.run_cb)[o] = w;
             double2* dst = reinterpret_cast<double2*>(a.run_sums + 4 * o);
-            dst[0] = make_double2(sums[0], sums[1]);
-            dst[1] = make_double2(sums[2], sums[3]);
+            dst[0] = make_double2(mine[0], mine[1]);
+            dst[1] = make_double2(mine[2], mine[3]);
         }
+        __syncwarp();
     }
 }
 

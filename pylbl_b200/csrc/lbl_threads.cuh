@@ -1604,48 +1604,65 @@ LBL_HD double ped_line_at(const PedRunArgs& a, size_t o, const int4& ck, double 
     return far_term(v, l.x, l.y, LBL_LDG(a.rec.cc + o), 0.);
 }
 
-// This lane's share (rows lane, lane + nlanes, ...) of the four sums of the run [row_lo, row_hi).
-LBL_HD void ped_run_sums(const PedRunArgs& a, int layer, int row_lo, int row_hi, int lane, int nlanes,
-                         double (&out)[4])
+// This lane's share (rows row_lo + lane, + nlanes, ...) of the sums of a run's own lines at its
+// two points.
+LBL_HD void ped_sum_own(const PedRunArgs& a, size_t off, int row_lo, int row_hi, const PedPoints& pp,
+                        int lane, int nlanes, double& at_s, double& at_e)
 {
     const GridSpec& g = a.grid;
-    const size_t off = (size_t)layer * a.lines.n;
-    out[0] = out[1] = out[2] = out[3] = 0.;
-    const int cb = LBL_LDG(reinterpret_cast<const int4*>(a.rec.chk + off + row_lo)).x;
-    const PedPoints pp = ped_points(cb, g);
-    if (pp.skip)
-    {
-        return;
-    }
     const double v_s = grid_point(g.v0, g.dv, pp.i_s);
     const double v_e = grid_point(g.v0, g.dv, pp.i_e);
     for (int j = row_lo + lane; j < row_hi; j += nlanes)
     {
         const int4 ck = LBL_LDG(reinterpret_cast<const int4*>(a.rec.chk + off + j));
-        out[0] += ped_line_at(a, off + j, ck, v_s, pp.i_s);
-        out[1] += ped_line_at(a, off + j, ck, v_e, pp.i_e);
+        at_s += ped_line_at(a, off + j, ck, v_s, pp.i_s);
+        at_e += ped_line_at(a, off + j, ck, v_e, pp.i_e);
     }
-    // Earlier rows that can cover a point: cell >= first covering cell, i.e. shifted centre
-    // >= v0 + that cell, i.e. unshifted centre within `slack` of it.
-    const double slack = a.layers[layer].slack;
-    const int j_s = first_line_at(a.lines, (double)g.v0 + (double)(pp.bs - g.cut_off - 1) - slack);
-    for (int j = j_s + lane; j < row_lo; j += nlanes)
+}
+
+// First earlier row that can cover a point whose covering bins start at `first_bin`: cell >=
+// first covering cell, i.e. shifted centre >= v0 + that cell, i.e. unshifted centre within
+// `slack` of it.
+LBL_HD int ped_first_covering_row(const PedRunArgs& a, int layer, int first_bin)
+{
+    const GridSpec& g = a.grid;
+    return first_line_at(a.lines, (double)g.v0 + (double)(first_bin - g.cut_off - 1) - a.layers[layer].slack);
+}
+
+// This lane's share of the sum, at grid point i, of the rows before row_lo whose pedestal bin
+// lies in [first_bin, first_bin + n_bins).
+LBL_HD double ped_sum_before(const PedRunArgs& a, int layer, size_t off, int row_lo, int first_bin, int n_bins,
+                             int i, int lane, int nlanes)
+{
+    const GridSpec& g = a.grid;
+    const double v = grid_point(g.v0, g.dv, i);
+    double sum = 0.;
+    for (int j = ped_first_covering_row(a, layer, first_bin) + lane; j < row_lo; j += nlanes)
     {
         const int4 ck = LBL_LDG(reinterpret_cast<const int4*>(a.rec.chk + off + j));
-        if ((unsigned)(ck.x + g.cut_off + 1 - pp.bs) < (unsigned)pp.ns)
+        if ((unsigned)(ck.x + g.cut_off + 1 - first_bin) < (unsigned)n_bins)
         {
-            out[2] += ped_line_at(a, off + j, ck, v_s, pp.i_s);
+            sum += ped_line_at(a, off + j, ck, v, i);
         }
     }
-    const int j_e = first_line_at(a.lines, (double)g.v0 + (double)(pp.be - g.cut_off - 1) - slack);
-    for (int j = j_e + lane; j < row_lo; j += nlanes)
+    return sum;
+}
+
+// This lane's share of the four sums of the run [row_lo, row_hi).
+LBL_HD void ped_run_sums(const PedRunArgs& a, int layer, int row_lo, int row_hi, int lane, int nlanes,
+                         double (&out)[4])
+{
+    const size_t off = (size_t)layer * a.lines.n;
+    out[0] = out[1] = out[2] = out[3] = 0.;
+    const int cb = LBL_LDG(reinterpret_cast<const int4*>(a.rec.chk + off + row_lo)).x;
+    const PedPoints pp = ped_points(cb, a.grid);
+    if (pp.skip)
     {
-        const int4 ck = LBL_LDG(reinterpret_cast<const int4*>(a.rec.chk + off + j));
-        if ((unsigned)(ck.x + g.cut_off + 1 - pp.be) < (unsigned)pp.ne)
-        {
-            out[3] += ped_line_at(a, off + j, ck, v_e, pp.i_e);
-        }
+        return;
     }
+    ped_sum_own(a, off, row_lo, row_hi, pp, lane, nlanes, out[0], out[1]);
+    out[2] = ped_sum_before(a, layer, off, row_lo, pp.bs, pp.ns, pp.i_s, lane, nlanes);
+    out[3] = ped_sum_before(a, layer, off, row_lo, pp.be, pp.ne, pp.i_e, lane, nlanes);
 }
 
 // The sequential step: the run's pedestal sum from its four gathered sums and the pedestals
