@@ -1492,7 +1492,8 @@ static int submit_call(lbl_gas* g, const CallSpec& call)
                     kernel<<<gridc, kSumBlock, 0, sm>>>(ca);
                     return cudaSuccess;
                 };
-                if (cells_per_warp == 2) LBL_CUDA(launch(sum_cell_kernel<2, 0>));
+                if (cells_per_warp == 2 && far_mode == 0) LBL_CUDA(launch(sum_cell_kernel<2, 0>));
+                else if (cells_per_warp == 2) LBL_CUDA(launch(sum_cell_kernel<2, 1>));
                 else if (far_mode == 2) LBL_CUDA(launch(sum_cell_kernel<1, 2>));
                 else if (far_mode == 0) LBL_CUDA(launch(sum_cell_kernel<1, 0>));
                 else LBL_CUDA(launch(sum_cell_kernel<1, 1>));

@@ -118,8 +118,18 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
         : "memory");
 }
 
-constexpr int kStageLines = 256;   // lines per staged chunk (4 KB of (a,b) + 2 KB of c)
-constexpr int kStages = 3;
+// Staging ring of the far-field kernel: lines per chunk (8 KB of (a,b) + 4 KB of c) and chunks in
+// flight.  Measured on config 2 (K2c per step): 128x6 16.3 ms, 256x3 15.2, 384x2 14.7, 512x2 14.6,
+// 640x2 14.9, 512x3 15.5 (shared memory then caps the resident blocks) -- fewer, larger chunks
+// mean fewer block-wide barriers and fewer passes over the range table.
+#ifndef LBL_STAGE_LINES
+#define LBL_STAGE_LINES 512
+#endif
+#ifndef LBL_STAGES
+#define LBL_STAGES 2
+#endif
+constexpr int kStageLines = LBL_STAGE_LINES;
+constexpr int kStages = LBL_STAGES;
 
 // Mid lines [jb, je) of one staged chunk, operands in shared memory (index j - base).
 template <int G>
@@ -270,7 +280,7 @@ sum_cell_kernel(const CellArgs a)
     // ---- phase 1: far fields at the nodes ------------------------------------------------
     // The four warps of a block own neighbouring cell groups, so their far-line ranges
     // [j1, j4) u [j5, j8) overlap almost entirely.  The block walks the union in chunks that
-    // one thread stages into shared memory with TMA bulk copies (3-deep ring, mbarrier per
+    // one thread stages into shared memory with TMA bulk copies (ring of kStages, mbarrier per
     // stage); each warp takes from a chunk what lies inside its own ranges.
     if (lane == 0)
     {
@@ -375,7 +385,7 @@ sum_cell_kernel(const CellArgs a)
                     }
                 }
             }
-            else if (G == 1 && M == 1)
+            else if (M == 1)
             {
 #pragma unroll 1
                 for (int k = 0; k < 6; ++k)
@@ -388,11 +398,13 @@ sum_cell_kernel(const CellArgs a)
                         // (the stride is a literal in each call: three copies of the loop, not six)
                         const int kind = (k < 3) ? k : 5 - k;     // 0: 8 nodes, 1: 16 nodes, 2: 32 nodes
                         if (kind == 0)
-                            f8 += node16_plain_staged(s_ab[stage], s_cc[stage], first, b, e, m8.first, 4, v8);
+                            f8 += node16_plain_staged(s_ab[stage], s_cc[stage], first, b, e, m8.first, 4 / G, v8);
                         else if (kind == 1)
-                            f16 += node16_plain_staged(s_ab[stage], s_cc[stage], first, b, e, m16.first, 2, v16);
-                        else
+                            f16 += node16_plain_staged(s_ab[stage], s_cc[stage], first, b, e, m16.first, 2 / G, v16);
+                        else if (G == 1)
                             f[0] += node16_plain_staged(s_ab[stage], s_cc[stage], first, b, e, 0, 1, v[0]);
+                        else
+                            node_plain_staged<G>(s_ab[stage], s_cc[stage], first, b, e, v, f);
                     }
                 }
             }

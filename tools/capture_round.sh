@@ -1,0 +1,48 @@
+#!/bin/bash
+# Evidence of one round, taken in ONE gpurun call on one B200 (see profiles/README.md).
+#   gpurun --timeout 2400 -- 'bash tools/capture_round.sh r2'
+# Every ncu pass runs after the same command has exited 0 without ncu.  Output: gpurun_out/<tag>_*.
+tag=${1:-r2}
+out=gpurun_out
+mkdir -p $out
+export PYTHONUNBUFFERED=1
+
+python -m pytest tests -m gpu -q > $out/${tag}_pytest_gpu.txt 2>&1; echo "pytest rc=$?"
+tail -2 $out/${tag}_pytest_gpu.txt
+
+python bench.py > $out/${tag}_bench.json 2> $out/${tag}_bench.err; echo "bench rc=$?"
+python bench.py --impl reference --steps 3 --warmup 1 > $out/${tag}_bench_reference.json 2> $out/${tag}_bench_reference.err
+echo "reference rc=$?"
+
+python tools/step_breakdown.py > $out/${tag}_step_breakdown.txt 2>&1
+python tools/step_breakdown.py --config5 > $out/${tag}_step_breakdown_config5.txt 2>&1
+python tools/scalar_latency.py > $out/${tag}_scalar_latency.txt 2>&1
+python tools/continuum_bench.py 256 > $out/${tag}_continuum.jsonl 2>&1
+python tools/band_cost.py 8 > $out/${tag}_band_cost.jsonl 2>&1
+./tools/microbench > $out/${tag}_microbench.jsonl 2>&1
+python bench.py --config 4 --steps 5 --warmup 3 > $out/${tag}_config4_n1.json 2> $out/${tag}_config4_n1.err
+python bench.py --config 5 --steps 2 --warmup 1 > $out/${tag}_config5_n1.json 2> $out/${tag}_config5_n1.err
+tail -1 $out/${tag}_step_breakdown.txt
+
+# launch list of one bench step (serialised, cold cache: shares, not absolutes)
+step="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-check"
+$step > /dev/null 2>&1 && \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $out/${tag}_launches.csv \
+    $step > $out/${tag}_launches_run.log 2>&1
+echo "launch list rc=$?"
+
+# --set full of the summation kernel (five launches of a step), then of the near-zone and
+# pedestal kernels on the largest gas
+ncu --set full --clock-control none --import-source on -k regex:sum_cell -s 10 -c 5 -f \
+    -o $out/${tag}_sum_cell $step > $out/${tag}_ncu_sum_cell.log 2>&1
+echo "ncu sum_cell rc=$?"
+python tools/one_gas.py CO2 2 > /dev/null 2>&1 && \
+ncu --set full --clock-control none --import-source on \
+    -k regex:"near_block|ped_nodes|ped_chain_runs|ped_run_|scale_kernel|apply_kernel|cell_keys" -s 8 -c 8 -f \
+    -o $out/${tag}_near_ped python tools/one_gas.py CO2 2 > $out/${tag}_ncu_near_ped.log 2>&1
+echo "ncu near/ped rc=$?"
+python tools/one_gas.py CO2 2 --config5 > /dev/null 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:"sum_kernel|fixup_kernel" -s 2 -c 2 -f \
+    -o $out/${tag}_sum_direct python tools/one_gas.py CO2 2 --config5 > $out/${tag}_ncu_sum_direct.log 2>&1
+echo "ncu direct rc=$?"
+ls -la $out | tail -30
