@@ -1038,7 +1038,16 @@ static int submit_call(lbl_gas* g, const CallSpec& call)
         cells_per_warp = 1;
         if (const char* env = getenv("PYLBL_B200_CELLS")) cells_per_warp = atoi(env) == 2 ? 2 : 1;
     }
-    const int cell_groups = farfield ? (grid.cell_hi - grid.cell_lo + cells_per_warp - 1) / cells_per_warp : 0;
+    // K2c's blocks sit at absolute cell positions (cell_block_base): the groups run from the block
+    // that holds the band's first cell to the end of the block that holds its last
+    int cell_groups = 0, cell_first = 0;
+    if (farfield)
+    {
+        const int block_cells = (kCellBlock / 32) * cells_per_warp;
+        cell_first = cell_block_base(grid, block_cells);
+        const int cell_end = std::min(grid.ncell, (grid.cell_hi + block_cells - 1) / block_cells * block_cells);
+        cell_groups = (cell_end - cell_first + cells_per_warp - 1) / cells_per_warp;
+    }
     bool hoisted_keys = farfield;
     if (const char* env = getenv("PYLBL_B200_KEYS")) hoisted_keys = farfield && atoi(env) != 0;
     const int P = farfield ? kCellP : pick_points_per_thread(n_per_v);
@@ -1343,7 +1352,7 @@ static int submit_call(lbl_gas* g, const CallSpec& call)
             if (hoisted_keys)
             {
                 dim3 gridk((cell_groups * kKeyStride + 255) / 256, nl);
-                cell_keys_kernel<<<gridk, 256, 0, sc>>>(lines, grid, layers_c, cells_per_warp, cell_groups,
+                cell_keys_kernel<<<gridk, 256, 0, sc>>>(lines, grid, layers_c, cells_per_warp, cell_first, cell_groups,
                                                         g->cell_keys.as<int>());
                 st.total_launches++;
             }
@@ -1480,7 +1489,7 @@ static int submit_call(lbl_gas* g, const CallSpec& call)
                 ca.sum = sa;
                 ca.key_layer0 = q0;
                 const int groups = cell_groups;
-                dim3 gridc((groups + kSumBlock / 32 - 1) / (kSumBlock / 32), q1 - q0);
+                dim3 gridc((groups + kCellBlock / 32 - 1) / (kCellBlock / 32), q1 - q0);
                 // 23 KB of static shared memory per block: ask for the large carve-out so that
                 // shared memory does not cap the resident blocks below the register limit.
                 int far_mode = 1;
@@ -1489,7 +1498,7 @@ static int submit_call(lbl_gas* g, const CallSpec& call)
                     cudaError_t ce = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                                                           cudaSharedmemCarveoutMaxShared);
                     if (ce != cudaSuccess) return ce;
-                    kernel<<<gridc, kSumBlock, 0, sm>>>(ca);
+                    kernel<<<gridc, kCellBlock, 0, sm>>>(ca);
                     return cudaSuccess;
                 };
                 if (cells_per_warp == 2 && far_mode == 0) LBL_CUDA(launch(sum_cell_kernel<2, 0>));

@@ -128,6 +128,11 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 #ifndef LBL_STAGES
 #define LBL_STAGES 2
 #endif
+// Warps (cells, or cell pairs) per block of the far-field kernel: they share one staging ring.
+#ifndef LBL_CELL_WARPS
+#define LBL_CELL_WARPS 4
+#endif
+constexpr int kCellBlock = 32 * LBL_CELL_WARPS;
 constexpr int kStageLines = LBL_STAGE_LINES;
 constexpr int kStages = LBL_STAGES;
 
@@ -217,7 +222,7 @@ __device__ __forceinline__ double node16_plain_staged(const double2* __restrict_
 // of dependent ones.  grid = (ceil(groups*16/256), layers of the chunk).
 __global__ void __launch_bounds__(256)
 cell_keys_kernel(LinesView lines, GridSpec g, const LayerIn* __restrict__ layers, int cells_per_group,
-                 int groups, int* __restrict__ keys)
+                 int first_cell, int groups, int* __restrict__ keys)
 {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int group = idx / kKeyStride;
@@ -227,7 +232,7 @@ cell_keys_kernel(LinesView lines, GridSpec g, const LayerIn* __restrict__ layers
         return;
     }
     const int layer = blockIdx.y;
-    const int cell0 = g.cell_lo + group * cells_per_group;
+    const int cell0 = first_cell + group * cells_per_group;
     keys[((size_t)layer * groups + group) * kKeyStride + which] =
         first_line_at(lines, cell_search_key(g, layers[layer], cell0, cells_per_group, which));
 }
@@ -235,10 +240,13 @@ cell_keys_kernel(LinesView lines, GridSpec g, const LayerIn* __restrict__ layers
 // M: how the far-range loops are instantiated (2: one generic copy, 1: one copy per node count
 // with literal strides, 0: one per range).
 template <int G, int M>
-__global__ void __launch_bounds__(kSumBlock, 8)
+#ifndef LBL_CELL_RESIDENT
+#define LBL_CELL_RESIDENT (1024 / kCellBlock)
+#endif
+__global__ void __launch_bounds__(kCellBlock, LBL_CELL_RESIDENT)
 sum_cell_kernel(const CellArgs a)
 {
-    constexpr int kWarps = kSumBlock / 32;
+    constexpr int kWarps = kCellBlock / 32;
     __shared__ double fields[kWarps][G][kNodes];
     __shared__ double fields16[kWarps][G][kNodes16];
     __shared__ double fields8[kWarps][G][kNodes8];
@@ -251,11 +259,19 @@ sum_cell_kernel(const CellArgs a)
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int layer = blockIdx.y + a.sum.layer0;
-    const int cell0 = g.cell_lo + (blockIdx.x * kWarps + warp) * G;
-    const bool active = cell0 < g.cell_hi;    // idle warps of the last block still join the barriers
+    // A block takes kWarps * G consecutive cells at an ABSOLUTE position of the grid: a spectral
+    // band that starts inside such a group finds the same blocks as the whole grid does.  Cells
+    // of the group outside the band still give their line ranges to the block's staging range
+    // -- the chunks are then cut where the whole-grid call cuts them and every sum is formed in
+    // the same order, to the same bits -- but compute nothing.
+    const int cell0 = cell_block_base(g, kWarps * G) + (blockIdx.x * kWarps + warp) * G;
+    const bool exists = cell0 < g.ncell;      // idle warps of the last block still join the barriers
+    const int q_lo = max(0, g.cell_lo - cell0);
+    const int q_hi = min(G, g.cell_hi - cell0);
+    const bool active = exists && q_lo < q_hi;
     // the ten range boundaries, one per lane, shared by shuffle
     int mine = 0;
-    if (active && lane < kCellKeys)
+    if (exists && lane < kCellKeys)
     {
         if (a.keys)
         {
@@ -274,8 +290,6 @@ sum_cell_kernel(const CellArgs a)
         found[which] = __shfl_sync(0xffffffffu, mine, which);
     }
     const CellSegments seg = cell_segments_from(found);
-    int cells = active ? g.cell_hi - cell0 : 0;
-    if (cells > G) cells = G;
 
     // ---- phase 1: far fields at the nodes ------------------------------------------------
     // The four warps of a block own neighbouring cell groups, so their far-line ranges
@@ -284,8 +298,8 @@ sum_cell_kernel(const CellArgs a)
     // stage); each warp takes from a chunk what lies inside its own ranges.
     if (lane == 0)
     {
-        s_range[warp][0] = active ? seg.j[1] : 0x7fffffff;
-        s_range[warp][1] = active ? seg.j[8] : 0;
+        s_range[warp][0] = exists ? seg.j[1] : 0x7fffffff;
+        s_range[warp][1] = exists ? seg.j[8] : 0;
     }
     if (threadIdx.x == 0)
     {
@@ -300,12 +314,12 @@ sum_cell_kernel(const CellArgs a)
         hi_all = max(hi_all, s_range[w][1]);
     }
     const size_t off = (size_t)layer * a.sum.lines.n;
-    // 16-byte alignment of the c[] source (8-byte elements): the chunk must start at an even
-    // ABSOLUTE element index; at worst this stages one element of the previous layer.
-    lo_all -= (int)((off + (size_t)lo_all) & 1);
     const FarAB* ab = a.sum.rec.ab + off;
     const double* cc = a.sum.rec.cc + off;
     const LineChk* chk = a.sum.rec.chk + off;
+    // 16-byte alignment of the c[] source (8-byte elements): the chunk must start at an even
+    // ABSOLUTE element index; at worst this stages one element of the previous layer.
+    lo_all -= (int)((off + (size_t)lo_all) & 1);
     const int n_chunks = (hi_all > lo_all) ? (hi_all - lo_all + kStageLines - 1) / kStageLines : 0;
     auto issue = [&](int t) {
         const int stage = t % kStages;
@@ -450,8 +464,10 @@ sum_cell_kernel(const CellArgs a)
     if ((lane & 8) == 0 && (G >= 2 || lane < 8)) field8[m8.cell_off][m8.node] = f8;
 
     // ---- phase 2: direct lines, Lorentz form ------------------------------------------------
+    // (Running this phase first, while the first bulk copies are in flight, was measured 2 %
+    // slower: the warps of a block then reach the chunk loop out of step.)
     const int chunks = (g.n_per_v + 32 * kCellP - 1) / (32 * kCellP);
-    for (int q = 0; q < cells; ++q)
+    for (int q = q_lo; q < q_hi; ++q)
     {
         for (int chunk = 0; chunk < chunks; ++chunk)
         {
@@ -477,7 +493,7 @@ sum_cell_kernel(const CellArgs a)
         for (int q = 0; q < G; ++q) field[q][lane] = c[q];
         __syncwarp();
     }
-    for (int q = 0; q < cells; ++q)
+    for (int q = q_lo; q < q_hi; ++q)
     {
         cell_field_lane(a, layer, cell0 + q, lane, 32, field[q]);
     }
@@ -490,7 +506,7 @@ sum_cell_kernel(const CellArgs a)
         const unsigned long long far8 = (unsigned long long)((seg.j[2] - seg.j[1]) + (seg.j[8] - seg.j[7]));
         const unsigned long long direct = (unsigned long long)(seg.j[5] - seg.j[4]);
         atomicAdd(a.executed, mid * (kNodes * G) + vfar * (kNodes16 * G) + far8 * (kNodes8 * G) +
-                              direct * (unsigned long long)(cells * chunks * 32 * kCellP));
+                              direct * (unsigned long long)((q_hi - q_lo) * chunks * 32 * kCellP));
     }
 }
 
@@ -941,7 +957,10 @@ __device__ __forceinline__ void near_core_range(const NearLine& nl, const GridSp
     c_hi = (int)fmax(fmin(hi, (double)nl.nhi), (double)c_lo - 1.);
 }
 
-__global__ void __launch_bounds__(128, 8)
+#ifndef LBL_NEAR_RESIDENT
+#define LBL_NEAR_RESIDENT 8
+#endif
+__global__ void __launch_bounds__(128, LBL_NEAR_RESIDENT)
 near_block_kernel(const SumArgs a)
 {
     __shared__ double acc[4][kNbSpan];

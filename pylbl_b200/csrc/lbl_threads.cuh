@@ -99,6 +99,9 @@ struct GridSpec
     int cell_lo, cell_hi;
 };
 
+// First cell of the far-field kernel's block that holds the band's first cell (blocks of
+// `block_cells` consecutive cells at absolute positions of the grid).
+LBL_HD int cell_block_base(const GridSpec& g, int block_cells) { return g.cell_lo - g.cell_lo % block_cells; }
 LBL_HD int band_first_point(const GridSpec& g) { return g.cell_lo * g.n_per_v; }
 LBL_HD int band_end_point(const GridSpec& g) { return g.cell_hi * g.n_per_v; }   // exclusive
 

@@ -516,6 +516,29 @@ def test_bands_concatenate_to_the_wide_call_bit_for_bit(small_db, atmosphere, bo
     gas.close()
 
 
+def test_bands_of_a_dense_list_bit_for_bit(tmp_path, atmosphere, monkeypatch):
+    """The far-field kernel on a list dense enough (50 lines per cm-1: 2500 lines in a window)
+    that every cell's line ranges span several staged chunks: where the ranges are cut must not
+    depend on how a band groups the cells into blocks (chunks are cut at absolute line
+    indices), or the sums would round differently."""
+    monkeypatch.setenv("PYLBL_B200_FARFIELD", "2")
+    path = str(tmp_path / "config3_third.db")
+    synth.write_database(path, synth.config_line_lists(3, scale=1. / 3.))
+    bounds = (500, 851, 200)
+    gas = Gas(path, "CO2")
+    t, p, x = atmosphere.t, atmosphere.p, atmosphere.vmr["CO2"]
+    for ped in (False, True):
+        wide = gas.absorption_coefficients(t, p, x, bounds=bounds, remove_pedestal=ped)
+        assert gas.last_stats[0]["cells_per_warp"] == 1
+        joined = np.full_like(wide, np.nan)
+        edges = [0, 3, 118, 233, 350, 351]
+        for lo, hi in zip(edges[:-1], edges[1:]):
+            gas.absorption_band(t, p, x, bounds, (lo, hi), remove_pedestal=ped,
+                                out=joined[:, lo * 200:hi * 200])
+        assert np.array_equal(joined, wide)
+    gas.close()
+
+
 def test_band_of_an_unsorted_database(tmp_path, atmosphere):
     """Rows out of nu order: the recurrence must still walk every active row for a band."""
     lines = synth.make_line_list("CO2", 600, 560.0, 760.0, seed=3)

@@ -45,4 +45,10 @@ python tools/one_gas.py CO2 2 --config5 > /dev/null 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:"sum_kernel|fixup_kernel" -s 2 -c 2 -f \
     -o $out/${tag}_sum_direct python tools/one_gas.py CO2 2 --config5 > $out/${tag}_ncu_sum_direct.log 2>&1
 echo "ncu direct rc=$?"
+# memory checker on a small case through every kernel (the pool may refuse the tool: logged)
+python tools/memcheck_case.py > /dev/null 2>&1 && \
+timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python tools/memcheck_case.py \
+    > $out/${tag}_memcheck.log 2>&1
+echo "memcheck rc=$?"
+tail -3 $out/${tag}_memcheck.log
 ls -la $out | tail -30
