@@ -1750,11 +1750,14 @@ int lbl_gas_band_edges(lbl_gas* g, int v0, int vn, int n_per_v, int cut_off, int
     if (!g || !edges) return fail("Error: null argument.");
     const int ncell = vn - v0;
     if (ncell <= 0 || n_bands < 1 || n_per_v < 1 || cut_off < 0) return fail("Error: invalid grid or band count.");
-    // Cost model of one cell (all layers alike), in units of one far-line node evaluation,
-    // calibrated on BASELINE configs[3] (tools/band_cost.py, profiles/): a fixed part (range
-    // boundaries, transforms, interpolation), the lines of its window (a few node evaluations
-    // each), the lines next to it (evaluated at every one of its n_per_v points), and their near
-    // zones, whose width grows with the wavenumber (Doppler width: 2*kappa*nu*n_per_v points).
+    // Cost model, in units of one far-line node evaluation, fitted to the kernel times of equal
+    // and of unequal bands of BASELINE configs[3] (tools/band_cost.py; all 16 within 0.3 ms of
+    // 10-34 ms).  A cell costs a fixed part (range boundaries, transforms, interpolation), the
+    // lines of its window (a few node evaluations each), the lines next to it (evaluated at
+    // every one of its n_per_v points) and their near zones, whose width grows with the
+    // wavenumber (Doppler width: 2*kappa*nu*n_per_v points).  A BAND costs its cells plus the
+    // pedestal recurrence over every active row up to its last window (the prefix of the whole
+    // grid) -- about 55 evaluations per row, run beside the band's own kernels.
     const int na = active_prefix(g->mol, v0, vn, cut_off);
     std::vector<double> nu(g->mol.nu.begin(), g->mol.nu.begin() + na);
     if (!g->mol.sorted) std::sort(nu.begin(), nu.end());
@@ -1763,24 +1766,62 @@ int lbl_gas_band_edges(lbl_gas* g, int v0, int vn, int n_per_v, int cut_off, int
     };
     const double mass = g->mol.min_mass > 0. ? g->mol.min_mass : 30.;
     const double kappa = 148.3 * std::sqrt(kR2 * 250. / mass) / kVlight;
-    std::vector<double> cum((size_t)ncell + 1, 0.);
+    std::vector<double> cum((size_t)ncell + 1, 0.), prefix((size_t)ncell + 1, 0.);
     for (int c = 0; c < ncell; ++c)
     {
         const double w = (double)v0 + c;
         const double beside = count(w - 0.5, w + 1.5);
         const double zone_points = 2. * kappa * std::fabs(w + 0.5) * n_per_v;
         const double cost = 400. + 0.3 * n_per_v + count(w - cut_off, w + cut_off + 1.) +
-                            0.125 * n_per_v * beside + 0.33 * zone_points * beside;
+                            0.125 * n_per_v * beside + 0.41 * zone_points * beside;
         cum[c + 1] = cum[c] + cost;
+        prefix[c + 1] = 55. * count(-1e300, w + 1. + cut_off + 1.);   // rows a band ending here walks
+    }
+    // Smallest T such that n_bands bands of cost <= T cover the grid (bands taken greedily as
+    // wide as T allows: the cost of a band grows with its end), by bisection.
+    auto bands_for = [&](double T, int* out) {
+        int lo = 0, used = 0;
+        while (lo < ncell && used < n_bands)
+        {
+            int l = lo, h = ncell;
+            while (l < h)
+            {
+                const int m = (l + h + 1) / 2;
+                if (cum[m] - cum[lo] + prefix[m] <= T) l = m;
+                else h = m - 1;
+            }
+            if (l == lo) return false;   // not even one cell fits
+            lo = l;
+            if (out) out[++used] = lo;
+            else ++used;
+        }
+        return lo == ncell;
+    };
+    double t_lo = 0., t_hi = cum[ncell] + prefix[ncell];
+    for (int it = 0; it < 60; ++it)
+    {
+        const double mid = 0.5 * (t_lo + t_hi);
+        if (bands_for(mid, nullptr)) t_hi = mid;
+        else t_lo = mid;
     }
     edges[0] = 0;
-    for (int b = 1; b < n_bands; ++b)
+    for (int b = 1; b <= n_bands; ++b) edges[b] = ncell;
+    bands_for(t_hi, edges);
+    // fewer bands than asked for (a grid of few cells, or one cell that outweighs the rest):
+    // split the widest until every band that can be non-empty is
+    std::vector<int> e(edges, edges + n_bands + 1);
+    e.erase(std::unique(e.begin(), e.end()), e.end());
+    while ((int)e.size() < n_bands + 1 && (int)e.size() - 1 < ncell)
     {
-        const double target = cum[ncell] * b / n_bands;
-        int e = (int)(std::lower_bound(cum.begin(), cum.end(), target) - cum.begin());
-        e = std::max(e, edges[b - 1]);
-        edges[b] = std::min(e, ncell);
+        size_t widest = 0;
+        for (size_t k = 0; k + 1 < e.size(); ++k)
+        {
+            if (e[k + 1] - e[k] > e[widest + 1] - e[widest]) widest = k;
+        }
+        if (e[widest + 1] - e[widest] < 2) break;
+        e.insert(e.begin() + widest + 1, (e[widest] + e[widest + 1]) / 2);
     }
+    for (int b = 0; b <= n_bands; ++b) edges[b] = b < (int)e.size() ? e[b] : ncell;
     edges[n_bands] = ncell;
     return 0;
 }

@@ -7,6 +7,15 @@
 
 #include <math.h>
 #include <stdint.h>
+// Opt-in index checks at the places where a kernel indexes shared memory, the record arrays or
+// the spectrum from computed ranges (build with -DLBL_DEBUG_BOUNDS; compute-sanitizer is not
+// available on every pool).  A failing check stops the kernel with a device-side assert.
+#ifdef LBL_DEBUG_BOUNDS
+#include <assert.h>
+#define LBL_CHECK(cond) assert(cond)
+#else
+#define LBL_CHECK(cond) ((void)0)
+#endif
 
 #if defined(__CUDACC__)
 #define LBL_HD __host__ __device__ __forceinline__

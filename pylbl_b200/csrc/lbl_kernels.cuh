@@ -150,6 +150,7 @@ __device__ __forceinline__ void node_plain_staged(const double2* __restrict__ s_
         for (int c = 0; c < G; ++c) acc[u][c] = 0.;
     int j = jb - base;
     const int stop = je - base;
+    LBL_CHECK(j >= 0 && stop <= kStageLines);
     for (; j + 2 * U - 1 < stop; j += 2 * U)
     {
 #pragma unroll
@@ -184,6 +185,7 @@ __device__ __forceinline__ double node16_plain_staged(const double2* __restrict_
     const double vv[1] = {v};
     const int b = jb - base;
     const int pairs = (je - jb) >> 1;
+    LBL_CHECK(b >= 0 && je - base <= kStageLines);
     int p = first;
     for (; p + 3 * stride < pairs; p += 4 * stride)
     {
@@ -906,6 +908,7 @@ __device__ __forceinline__ void near_block_drain(const GridSpec& g, const NearLi
             const unsigned peers = __match_any_sync(todo, k);
             if (lane == __ffs(peers) - 1)
             {
+                LBL_CHECK(k >= 0 && k < kNbSpan);
                 mine[k] += val;
                 pending = false;
             }
@@ -927,6 +930,7 @@ __device__ __forceinline__ void near_block_push(const GridSpec& g, const NearLin
     }
     if (push)
     {
+        LBL_CHECK(qn + __popc(m & below) < kNbQueue);
         q[qn + __popc(m & below)] = entry;
     }
     qn += __popc(m);
@@ -1016,6 +1020,7 @@ near_block_kernel(const SumArgs a)
             nl.nlo = max(ck.y, p0);   // the zone, clipped to the span
             nl.nhi = min(ck.z, p1);
             near_core_range(nl, g, nl.c_lo, nl.c_hi);
+            LBL_CHECK(__popc(listed & below) + (warp == 1 ? batch_count[0] : 0) < kNbBatch);
             slots[__popc(listed & below) + (warp == 1 ? batch_count[0] : 0)] = nl;
         }
         __syncthreads();
@@ -1065,6 +1070,7 @@ near_block_kernel(const SumArgs a)
                 {
                     add = nl.cof * voigt_outer(abx, xq, nl.y, xlim0);
                 }
+                LBL_CHECK(!inside || (i >= p0 && i <= p1));
                 if (inside) mine[i - p0] += add;
             }
         }
@@ -1112,6 +1118,7 @@ near_block_kernel(const SumArgs a)
             {
                 part += __shfl_xor_sync(0xffffffffu, part, o);
             }
+            LBL_CHECK(i_node >= p0 && i_node <= p1);
             if (lane == 0) mine[i_node - p0] += part;
         }
     }
@@ -1626,6 +1633,7 @@ ped_nodes_kernel(const PedRunArgs a)
             j_end = max(j_end, __shfl_xor_sync(0xffffffffu, j_end, o));
         }
         __syncwarp();
+        LBL_CHECK(j_end <= a.lines.n && (j_first >= 0 || j_end == 0));
         double before_s[kNodeRuns];
 #pragma unroll
         for (int q = 0; q < kNodeRuns; ++q) before_s[q] = 0.;
@@ -1768,6 +1776,7 @@ ped_chain_runs_kernel(const PedRunArgs a, int bins_in_smem, int use_scan)
             const double q = prefix + fmin(low, 0.);
             double q_prev = __shfl_up_sync(0xffffffffu, q, 1);
             if (lane == 0) q_prev = 0.;
+            LBL_CHECK(!in || (me.bin >= 0 && me.bin < nb));
             if (in) bins[me.bin] += fmin(alpha, h - q_prev);
             top = __shfl_sync(0xffffffffu, me.bin, len - 1);
             r0 += len;
@@ -1788,10 +1797,12 @@ ped_chain_runs_kernel(const PedRunArgs a, int bins_in_smem, int use_scan)
 #pragma unroll
         for (int q = 0; q < 4; ++q) s4[q] = __shfl_sync(0xffffffffu, me.sums[q], 0);
         double ps = 0., pe = 0.;
+        LBL_CHECK(bs >= 0 && bs + ns <= nb);
         for (int k = lane; k < ns; k += 32) ps += bins[bs + k];
         const bool e_side = be <= top;    // else every bin of the range is still zero
         if (e_side)
         {
+            LBL_CHECK(be >= 0 && be + ne <= nb);
             for (int k = lane; k < ne; k += 32) pe += bins[be + k];
         }
 #pragma unroll
@@ -1801,6 +1812,7 @@ ped_chain_runs_kernel(const PedRunArgs a, int bins_in_smem, int use_scan)
             if (e_side) pe += __shfl_xor_sync(0xffffffffu, pe, o);
         }
         const double pedestal = ped_chain_run(s4, ps, pe);
+        LBL_CHECK(bin >= 0 && bin < nb);
         if (lane == 0) bins[bin] += pedestal;
         top = max(top, bin);
         __syncwarp();

@@ -881,6 +881,8 @@ LBL_HD void cell_direct_lane(const CellArgs& a, int layer, int cell, int chunk, 
         acc[p] = 0.;
     }
     const size_t off = (size_t)layer * a.sum.lines.n;
+    LBL_CHECK(!valid || (i_first >= 0 && i_first + count <= g.n));
+    LBL_CHECK(seg.j[4] >= 0 && seg.j[4] <= seg.j[5] && seg.j[5] <= a.sum.lines.n);
     if (g.cut_off >= 4)
     {
         // Direct lines lie within kFarMin of the (at most 2-cell) group: their window cell is
@@ -1615,6 +1617,7 @@ LBL_HD void ped_sum_own(const PedRunArgs& a, size_t off, int row_lo, int row_hi,
     const GridSpec& g = a.grid;
     const double v_s = grid_point(g.v0, g.dv, pp.i_s);
     const double v_e = grid_point(g.v0, g.dv, pp.i_e);
+    LBL_CHECK(row_lo >= 0 && row_hi <= a.lines.n && pp.i_s >= 0 && pp.i_e < g.n);
     for (int j = row_lo + lane; j < row_hi; j += nlanes)
     {
         const int4 ck = LBL_LDG(reinterpret_cast<const int4*>(a.rec.chk + off + j));
@@ -1640,6 +1643,7 @@ LBL_HD double ped_sum_before(const PedRunArgs& a, int layer, size_t off, int row
     const GridSpec& g = a.grid;
     const double v = grid_point(g.v0, g.dv, i);
     double sum = 0.;
+    LBL_CHECK(ped_first_covering_row(a, layer, first_bin) >= 0 && row_lo <= a.lines.n);
     for (int j = ped_first_covering_row(a, layer, first_bin) + lane; j < row_lo; j += nlanes)
     {
         const int4 ck = LBL_LDG(reinterpret_cast<const int4*>(a.rec.chk + off + j));

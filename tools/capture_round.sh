@@ -45,10 +45,14 @@ python tools/one_gas.py CO2 2 --config5 > /dev/null 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:"sum_kernel|fixup_kernel" -s 2 -c 2 -f \
     -o $out/${tag}_sum_direct python tools/one_gas.py CO2 2 --config5 > $out/${tag}_ncu_sum_direct.log 2>&1
 echo "ncu direct rc=$?"
-# memory checker on a small case through every kernel (the pool may refuse the tool: logged)
-python tools/memcheck_case.py > /dev/null 2>&1 && \
-timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python tools/memcheck_case.py \
-    > $out/${tag}_memcheck.log 2>&1
-echo "memcheck rc=$?"
-tail -3 $out/${tag}_memcheck.log
+# index checks of our own (compute-sanitizer is closed on this pool): the GPU suite and a small
+# case through every kernel on a build with device-side asserts at the indexing sites
+# (python tools/build_variant.py bounds -DLBL_DEBUG_BOUNDS, before the call)
+if [ -f variants/bounds.so ]; then
+  cp pylbl_b200/libpylbl_b200.so /tmp/default.so
+  cp variants/bounds.so pylbl_b200/libpylbl_b200.so
+  python -m pytest tests -m gpu -q > $out/${tag}_bounds_check_pytest.txt 2>&1; echo "bounds pytest rc=$?"
+  python tools/memcheck_case.py >> $out/${tag}_bounds_check_pytest.txt 2>&1; echo "bounds case rc=$?"
+  cp /tmp/default.so pylbl_b200/libpylbl_b200.so
+fi
 ls -la $out | tail -30
