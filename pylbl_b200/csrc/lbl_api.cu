@@ -1595,17 +1595,14 @@ static int submit_call(lbl_gas* g, const CallSpec& call)
         LBL_CUDA(cudaEventRecord(mix->ev_added, sl));
     }
     // The small statistics copies go where they cannot hold anything up: all device-to-host
-    // copies share one DMA queue, and on the late stream they would sit behind this call's bulk
-    // copies -- and with them every later gas's correction kernels.
+    // copies share one DMA queue, and on the late stream they would sit behind the bulk copies
+    // in flight -- this call's, or those of another gas of the column (the previous layer group
+    // of a gas sum) -- and with them every later gas's correction kernels.  They ride the copy
+    // stream, after the kernels' end mark; the call ends when the last copy has landed.
     g->copies_in_call = k_host || (mix && call.mix_host);
     LBL_CUDA(cudaEventRecord(g->ev_compute_end, sl));      // the last kernel of the call
-    cudaStream_t s_end = g->copies_in_call ? g->s_copy : sl;
-    if (g->copies_in_call)
-    {
-        // The call ends when the last copy has landed: the end mark goes on the copy stream,
-        // after the kernels' end mark.
-        LBL_CUDA(cudaStreamWaitEvent(g->s_copy, g->ev_compute_end, 0));
-    }
+    cudaStream_t s_end = g->s_copy;
+    LBL_CUDA(cudaStreamWaitEvent(g->s_copy, g->ev_compute_end, 0));
     LBL_CUDA(cudaMemcpyAsync(g->evals_host, g->evals_dev.p, sizeof(unsigned long long) * n_layers,
                              cudaMemcpyDeviceToHost, s_end));
     if (farfield)

@@ -510,6 +510,14 @@ LBL_HD double voigt_general(double v, double nu, double repwid, double y, double
     return cof * voigt_core(xi, y, xlim0);
 }
 
+// The same as a real call: for kernels that need it at a rare point only (the pedestal sums:
+// a node inside a line's near zone) and would otherwise carry its registers through their loops.
+static LBL_HD_NOINLINE double voigt_general_call(double v, double nu, double repwid, double y, double cof,
+                                                 double xlim0, double xlim1)
+{
+    return voigt_general(v, nu, repwid, y, cof, xlim0, xlim1);
+}
+
 // ---- per-(layer, line) scaling: spectra.c:17-45 plus the derived records -----------------
 struct LineIn
 {

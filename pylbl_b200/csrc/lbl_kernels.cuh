@@ -1573,7 +1573,16 @@ ped_run_scatter_kernel(const LineChk* __restrict__ chk, int stride, int n_rows,
 // The small sums -- the run's own lines at its two points, and earlier rows at k[e], which only
 // out-of-order cells produce -- stay per run with the lanes over the rows.
 // grid = (blocks, layers), the warps of a layer striding over its tiles of kNodeRuns runs.
-constexpr int kNodeRuns = 8;
+#ifndef LBL_NODE_RUNS
+#define LBL_NODE_RUNS 8
+#endif
+// (Resident blocks of 256 threads per SM: 2 / 3 / 4 = 128 / 80 / 64 registers.  The kernel waits on
+// loads more than on anything else: 3 and 4 both take 0.8 ms off the benchmark step, 3 spills less;
+// 16 runs per warp was slower at either.)
+#ifndef LBL_NODES_RESIDENT
+#define LBL_NODES_RESIDENT 3
+#endif
+constexpr int kNodeRuns = LBL_NODE_RUNS;
 
 struct NodeRun
 {
@@ -1584,7 +1593,7 @@ struct NodeRun
     double v_s;
 };
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, LBL_NODES_RESIDENT)
 ped_nodes_kernel(const PedRunArgs a)
 {
     __shared__ NodeRun s_runs[8][kNodeRuns];
@@ -1661,7 +1670,7 @@ ped_nodes_kernel(const PedRunArgs a)
                 {
                     // inside the line's near zone the summation kernels hold the full profile
                     const LineGen gen = a.rec.gen[off + j];
-                    t = voigt_general(nr.v_s, gen.nu, gen.repwid, gen.y, gen.cof, gen.xlim0, gen.xlim1);
+                    t = voigt_general_call(nr.v_s, gen.nu, gen.repwid, gen.y, gen.cof, gen.xlim0, gen.xlim1);
                 }
                 before_s[q] += cover ? t : 0.;
             }

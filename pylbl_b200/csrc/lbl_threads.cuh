@@ -1603,7 +1603,7 @@ LBL_HD double ped_line_at(const PedRunArgs& a, size_t o, const int4& ck, double 
     if (i >= ck.y && i <= ck.z)
     {
         const LineGen gen = a.rec.gen[o];
-        return voigt_general(v, gen.nu, gen.repwid, gen.y, gen.cof, gen.xlim0, gen.xlim1);
+        return voigt_general_call(v, gen.nu, gen.repwid, gen.y, gen.cof, gen.xlim0, gen.xlim1);
     }
     const double2 l = LBL_LDG(reinterpret_cast<const double2*>(a.rec.ab + o));
     return far_term(v, l.x, l.y, LBL_LDG(a.rec.cc + o), 0.);
