@@ -1675,43 +1675,74 @@ ped_nodes_kernel(const PedRunArgs a)
                 before_s[q] += cover ? t : 0.;
             }
         }
-        double mine[4] = {0., 0., 0., 0.};
-#pragma unroll
-        for (int q = 0; q < kNodeRuns; ++q)
+        // The eight partial sums of every lane -> one total per run, landing in the four lanes
+        // lane >> 2 == run: each exchange halves the values a lane still carries (7 exchanges
+        // instead of 8 x 5), the last two add up the four lanes of a group.
+        static_assert(kNodeRuns == 8, "the reduction below pairs 8 runs with 8 groups of 4 lanes");
         {
-            const int q_lo = __shfl_sync(0xffffffffu, row_lo, q);
-            const int q_hi = __shfl_sync(0xffffffffu, row_hi, q);
-            const int q_cb = __shfl_sync(0xffffffffu, cb, q);
-            const bool q_live = __shfl_sync(0xffffffffu, (int)live, q) != 0;
-            double sums[4] = {0., 0., before_s[q], 0.};
-            if (q_live)
+            const bool up16 = (lane & 16) != 0, up8 = (lane & 8) != 0, up4 = (lane & 4) != 0;
+            double four[4], two[2];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
             {
-                const PedPoints qp = ped_points(q_cb, g);
-                ped_sum_own(a, off, q_lo, q_hi, qp, lane, 32, sums[0], sums[1]);
-                sums[3] = ped_sum_before(a, layer, off, q_lo, qp.be, qp.ne, qp.i_e, lane, 32);
+                const double keep = up16 ? before_s[i + 4] : before_s[i];
+                const double give = up16 ? before_s[i] : before_s[i + 4];
+                four[i] = keep + __shfl_xor_sync(0xffffffffu, give, 16);
             }
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
+            for (int i = 0; i < 2; ++i)
             {
+                const double keep = up8 ? four[i + 2] : four[i];
+                const double give = up8 ? four[i] : four[i + 2];
+                two[i] = keep + __shfl_xor_sync(0xffffffffu, give, 8);
+            }
+            const double keep = up4 ? two[1] : two[0];
+            const double give = up4 ? two[0] : two[1];
+            double one = keep + __shfl_xor_sync(0xffffffffu, give, 4);
+            one += __shfl_xor_sync(0xffffffffu, one, 2);
+            one += __shfl_xor_sync(0xffffffffu, one, 1);
+            before_s[0] = one;      // run (lane >> 2): bit 4 chose runs 4-7, bit 3 the upper pair, bit 2 the odd one
+        }
+        // The small sums, the eight runs side by side: group q = lanes 4q .. 4q+3 takes run q (its
+        // own rows at its two points; earlier rows at k[e]), so the eight chains of dependent
+        // loads -- two range searches and a row loop each -- overlap instead of following one
+        // another.
+        const int q = lane >> 2, sub = lane & 3;
+        const int q_lo = __shfl_sync(0xffffffffu, row_lo, q);
+        const int q_hi = __shfl_sync(0xffffffffu, row_hi, q);
+        const int q_cb = __shfl_sync(0xffffffffu, cb, q);
+        const bool q_have = __shfl_sync(0xffffffffu, (int)have, q) != 0;
+        const bool q_live = __shfl_sync(0xffffffffu, (int)live, q) != 0;
+        PedPoints qp = ped_points(q_cb, g);
+        double sums[4] = {0., 0., before_s[0], 0.};
+        if (q_live)
+        {
+            ped_sum_own(a, off, q_lo, q_hi, qp, sub, 4, sums[0], sums[1]);
+            sums[3] = ped_sum_before(a, layer, off, q_lo, qp.be, qp.ne, qp.i_e, sub, 4);
+        }
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) sums[k] += __shfl_xor_sync(0xffffffffu, sums[k], o);
-                if (lane == q) mine[k] = sums[k];
+        for (int k = 0; k < 4; ++k)
+        {
+            if (k != 2)
+            {
+                sums[k] += __shfl_xor_sync(0xffffffffu, sums[k], 2);
+                sums[k] += __shfl_xor_sync(0xffffffffu, sums[k], 1);
             }
         }
-        if (have)
+        if (q_have && sub == 0)
         {
             // with the sums, what the chain needs of the run's window (ped_points): its own bin
             // and the first bin of the two ranges that cover k[s] and k[e], packed into one int4
-            const size_t o = (size_t)layer * a.n_rows + r;
+            const size_t o = (size_t)layer * a.n_rows + tile * kNodeRuns + q;
             int4 w;
-            w.x = pp.skip ? -1 : cb + g.cut_off + 1;      // own bin (-1: not processed)
-            w.y = pp.bs;
-            w.z = pp.be;
-            w.w = pp.ne;
+            w.x = qp.skip ? -1 : q_cb + g.cut_off + 1;      // own bin (-1: not processed)
+            w.y = qp.bs;
+            w.z = qp.be;
+            w.w = qp.ne;
             reinterpret_cast<int4*>(a.run_cb)[o] = w;
             double2* dst = reinterpret_cast<double2*>(a.run_sums + 4 * o);
-            dst[0] = make_double2(mine[0], mine[1]);
-            dst[1] = make_double2(mine[2], mine[3]);
+            dst[0] = make_double2(sums[0], sums[1]);
+            dst[1] = make_double2(sums[2], sums[3]);
         }
         __syncwarp();
     }
