@@ -1635,11 +1635,22 @@ ped_nodes_kernel(const PedRunArgs a)
             nr.v_s = grid_point(g.v0, g.dv, pp.i_s);
             tile_runs[lane] = nr;
         }
+        // what all runs of the tile have in common (the fast path below): rows before the first
+        // run, in the bins every run's k[s] range holds, with no k[s] point in their near zone
+        int row_lo_min = live ? row_lo : 0x7fffffff;
+        int bs_max = live ? pp.bs : -0x40000000, bs_min = live ? pp.bs : 0x40000000;
+        int is_min = live ? pp.i_s : 0x7fffffff, is_max = live ? pp.i_s : -1;
+        const bool all_live = __ballot_sync(0xffffffffu, live) == (1u << kNodeRuns) - 1u;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1)
         {
             j_first = min(j_first, __shfl_xor_sync(0xffffffffu, j_first, o));
             j_end = max(j_end, __shfl_xor_sync(0xffffffffu, j_end, o));
+            row_lo_min = min(row_lo_min, __shfl_xor_sync(0xffffffffu, row_lo_min, o));
+            bs_max = max(bs_max, __shfl_xor_sync(0xffffffffu, bs_max, o));
+            bs_min = min(bs_min, __shfl_xor_sync(0xffffffffu, bs_min, o));
+            is_min = min(is_min, __shfl_xor_sync(0xffffffffu, is_min, o));
+            is_max = max(is_max, __shfl_xor_sync(0xffffffffu, is_max, o));
         }
         __syncwarp();
         LBL_CHECK(j_end <= a.lines.n && (j_first >= 0 || j_end == 0));
@@ -1660,19 +1671,35 @@ ped_nodes_kernel(const PedRunArgs a)
                 c = LBL_LDG(a.rec.cc + off + j);
             }
             const int bin = ck.x + g.cut_off + 1;
+            // Three quarters of the chunks lie where every row counts for every run of the tile and
+            // no run's point is near a row's centre: no test per (row, run) then, the term goes
+            // straight into the sum.  (Both paths add a term by the same fused operation, so a
+            // run's sum does not depend on which path its tile's chunks took.)
+            const bool plain = in && j < row_lo_min && bin >= bs_max && (unsigned)(bin - bs_min) < ns &&
+                               !(ck.y <= is_max && ck.z >= is_min);
+            if (all_live && __all_sync(0xffffffffu, plain))
+            {
+#pragma unroll
+                for (int q = 0; q < kNodeRuns; ++q)
+                {
+                    before_s[q] = far_term(tile_runs[q].v_s, l.x, l.y, c, before_s[q]);
+                }
+                continue;
+            }
 #pragma unroll
             for (int q = 0; q < kNodeRuns; ++q)
             {
                 const NodeRun nr = tile_runs[q];
                 const bool cover = j < nr.row_lo && (unsigned)(bin - nr.first_bin) < ns;
-                double t = far_term(nr.v_s, l.x, l.y, c, 0.);
+                double t = far_term(nr.v_s, l.x, l.y, c, before_s[q]);
                 if (cover && nr.i_s >= ck.y && nr.i_s <= ck.z)
                 {
                     // inside the line's near zone the summation kernels hold the full profile
                     const LineGen gen = a.rec.gen[off + j];
-                    t = voigt_general_call(nr.v_s, gen.nu, gen.repwid, gen.y, gen.cof, gen.xlim0, gen.xlim1);
+                    t = before_s[q] +
+                        voigt_general_call(nr.v_s, gen.nu, gen.repwid, gen.y, gen.cof, gen.xlim0, gen.xlim1);
                 }
-                before_s[q] += cover ? t : 0.;
+                before_s[q] = cover ? t : before_s[q];
             }
         }
         // The eight partial sums of every lane -> one total per run, landing in the four lanes
