@@ -137,6 +137,30 @@ def test_grid_shapes(small_db, atmosphere, bounds, remove_pedestal):
         assert scaled_error(k[layer], k_ref, n_per_v) <= FP64_TOL
 
 
+@pytest.mark.parametrize("n_per_v", [64, 65, 96, 127, 129, 250, 333])
+def test_far_field_kernel_on_odd_grids(small_db, atmosphere, n_per_v, monkeypatch):
+    """The far-field kernel where the points of a cell do not fill its lanes evenly (the direct
+    part takes 128 points per pass, the interpolation 32 per step): points per cm-1 at and
+    around the kernel's lower limit and the pass sizes, forced whatever the line density."""
+    monkeypatch.setenv("PYLBL_B200_FARFIELD", "2")
+    bounds = (1, 251, n_per_v)
+    gas = Gas(small_db, "H2O")
+    ref = OracleGas(small_db, "H2O")
+    for remove_pedestal in (False, True):
+        k = gas.absorption_coefficients(atmosphere.t, atmosphere.p, atmosphere.vmr["H2O"],
+                                        bounds=bounds, remove_pedestal=remove_pedestal)
+        assert gas.last_stats[0]["cells_per_warp"] == 1
+        for layer in range(atmosphere.t.size):
+            k_ref = ref.absorption(atmosphere.t[layer], atmosphere.p[layer],
+                                   atmosphere.vmr["H2O"][layer], *bounds, remove_pedestal)
+            assert np.any(k_ref)
+            if remove_pedestal:
+                assert scaled_error(k[layer], k_ref, n_per_v) <= FP64_TOL
+            else:
+                assert relative_error(k[layer], k_ref) <= FP64_TOL
+    gas.close()
+
+
 @pytest.mark.parametrize("cut_off", [0, 1, 5, 40, 70])
 def test_cut_off(small_db, atmosphere, cut_off):
     gas = Gas(small_db, "H2O")
