@@ -1571,8 +1571,10 @@ ped_run_scatter_kernel(const LineChk* __restrict__ chk, int stride, int n_rows,
 // million-line list, L2-bound.)  Row j goes to lane j mod 32 whatever the tile holds, so a run's
 // sums do not depend on which other runs the call covers (spectral bands stop at different rows).
 // The small sums -- the run's own lines at its two points, and earlier rows at k[e], which only
-// out-of-order cells produce -- stay per run with the lanes over the rows.
+// out-of-order cells produce -- are taken by the eight runs side by side, four lanes each.
 // grid = (blocks, layers), the warps of a layer striding over its tiles of kNodeRuns runs.
+// (The lane layout of the second half fixes kNodeRuns at 8; 16 runs per warp was measured slower
+// with the first half alone.)
 #ifndef LBL_NODE_RUNS
 #define LBL_NODE_RUNS 8
 #endif
