@@ -78,3 +78,39 @@ def test_band_edges_partition_the_grid(small_db):
     for n_bands in (1, 2, 3, 8):
         edges = gas.band_edges((1, 2001, 100), n_bands)
         assert edges[0] == 0 and edges[-1] == 2000 and np.all(np.diff(edges) >= 0)
+
+
+def test_to_dataset_layout_with_a_stand_in_for_xarray(monkeypatch):
+    """`to_dataset` against the reference's `_create_output_dataset` (pyLBL/spectroscopy.py:208-236):
+    which variables exist, their dimensions and units, for the three output formats.  xarray is
+    not in this image; a stand-in that records what it is given is enough to check the layout
+    (tests/test_pylbl_integration.py runs the real one where it is installed)."""
+    import sys
+    import types
+
+    class DataArray(object):
+        def __init__(self, data, dims=None, attrs=None):
+            self.data, self.dims, self.attrs = np.asarray(data), tuple(dims), dict(attrs or {})
+
+    class Dataset(object):
+        def __init__(self, data_vars=None):
+            self.data_vars = dict(data_vars)
+
+    monkeypatch.setitem(sys.modules, "xarray", types.SimpleNamespace(DataArray=DataArray, Dataset=Dataset))
+    grid = np.arange(1., 11., 0.01)
+    s = Spectroscopy(atmosphere((2, 3)), grid, "no-such.db")
+    n = grid.size
+    everything = {"H2O_absorption": np.zeros((2, 3, len(MECHANISMS), n)), "mechanism": list(MECHANISMS)}
+    ds = s.to_dataset(everything, dims=["y", "x"]).data_vars
+    assert set(ds) == {"wavenumber", "mechanism", "H2O_absorption"}
+    assert ds["wavenumber"].dims == ("wavenumber",) and ds["wavenumber"].attrs == {"units": "cm-1"}
+    assert np.array_equal(ds["wavenumber"].data, grid)
+    assert ds["mechanism"].dims == ("mechanism",) and list(ds["mechanism"].data) == list(MECHANISMS)
+    assert ds["H2O_absorption"].dims == ("y", "x", "mechanism", "wavenumber")
+    assert ds["H2O_absorption"].attrs == {"units": "m-1"}
+    per_gas = s.to_dataset({"H2O_absorption": np.zeros((2, 3, n))}, dims=["y", "x"]).data_vars
+    assert set(per_gas) == {"wavenumber", "H2O_absorption"}
+    assert per_gas["H2O_absorption"].dims == ("y", "x", "wavenumber")       # the mechanism axis summed away
+    total = s.to_dataset({"absorption": np.zeros((2, 3, n))}).data_vars
+    assert total["absorption"].dims == ("dim_0", "dim_1", "wavenumber")
+    assert total["absorption"].attrs == {"units": "m-1"}
