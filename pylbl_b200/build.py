@@ -17,7 +17,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libpylbl_b200.so"
 SOURCES = ["lbl_api.cu", "lbl_db.cpp", "lbl_pack.cpp"]
-HEADERS = ["lbl_core.cuh", "lbl_threads.cuh", "lbl_kernels.cuh", "lbl_continuum.cuh", "lbl_db.h", "lbl_cheb.h",
+HEADERS = ["lbl_core.cuh", "lbl_threads.cuh", "lbl_kernels.cuh", "lbl_continuum.cuh", "lbl_db.h", "lbl_cheb.h", "lbl_bands.h",
            "../../include/pylbl_b200.h"]
 
 NVCC_FLAGS = [

@@ -20,6 +20,7 @@
 
 #include "../../include/pylbl_b200.h"
 #include "lbl_cheb.h"
+#include "lbl_bands.h"
 #include "lbl_db.h"
 #include "lbl_kernels.cuh"
 
@@ -1774,52 +1775,7 @@ int lbl_gas_band_edges(lbl_gas* g, int v0, int vn, int n_per_v, int cut_off, int
         cum[c + 1] = cum[c] + cost;
         prefix[c + 1] = 55. * count(-1e300, w + 1. + cut_off + 1.);   // rows a band ending here walks
     }
-    // Smallest T such that n_bands bands of cost <= T cover the grid (bands taken greedily as
-    // wide as T allows: the cost of a band grows with its end), by bisection.
-    auto bands_for = [&](double T, int* out) {
-        int lo = 0, used = 0;
-        while (lo < ncell && used < n_bands)
-        {
-            int l = lo, h = ncell;
-            while (l < h)
-            {
-                const int m = (l + h + 1) / 2;
-                if (cum[m] - cum[lo] + prefix[m] <= T) l = m;
-                else h = m - 1;
-            }
-            if (l == lo) return false;   // not even one cell fits
-            lo = l;
-            if (out) out[++used] = lo;
-            else ++used;
-        }
-        return lo == ncell;
-    };
-    double t_lo = 0., t_hi = cum[ncell] + prefix[ncell];
-    for (int it = 0; it < 60; ++it)
-    {
-        const double mid = 0.5 * (t_lo + t_hi);
-        if (bands_for(mid, nullptr)) t_hi = mid;
-        else t_lo = mid;
-    }
-    edges[0] = 0;
-    for (int b = 1; b <= n_bands; ++b) edges[b] = ncell;
-    bands_for(t_hi, edges);
-    // fewer bands than asked for (a grid of few cells, or one cell that outweighs the rest):
-    // split the widest until every band that can be non-empty is
-    std::vector<int> e(edges, edges + n_bands + 1);
-    e.erase(std::unique(e.begin(), e.end()), e.end());
-    while ((int)e.size() < n_bands + 1 && (int)e.size() - 1 < ncell)
-    {
-        size_t widest = 0;
-        for (size_t k = 0; k + 1 < e.size(); ++k)
-        {
-            if (e[k + 1] - e[k] > e[widest + 1] - e[widest]) widest = k;
-        }
-        if (e[widest + 1] - e[widest] < 2) break;
-        e.insert(e.begin() + widest + 1, (e[widest] + e[widest + 1]) / 2);
-    }
-    for (int b = 0; b <= n_bands; ++b) edges[b] = b < (int)e.size() ? e[b] : ncell;
-    edges[n_bands] = ncell;
+    partition_bands(cum, prefix, n_bands, edges);
     return 0;
 }
 

@@ -13,6 +13,7 @@
 
 #include "../../pylbl_b200/csrc/lbl_cheb.h"
 #include "../../pylbl_b200/csrc/lbl_threads.cuh"
+#include "../../pylbl_b200/csrc/lbl_bands.h"
 
 using namespace lbl;
 
@@ -481,5 +482,16 @@ extern "C" int emu_absorption(int n_layers, const double* pressure, const double
             }
         }
     }
+    return 0;
+}
+
+// The band partition of lbl_gas_band_edges (pylbl_b200/csrc/lbl_bands.h) on given costs:
+// cell_cost[ncell], prefix_cost[ncell + 1] (what a band ending at that cell pays on top).
+extern "C" int emu_partition_bands(const double* cell_cost, const double* prefix_cost, int ncell,
+                                   int n_bands, int* edges)
+{
+    std::vector<double> cum((size_t)ncell + 1, 0.), prefix(prefix_cost, prefix_cost + ncell + 1);
+    for (int c = 0; c < ncell; ++c) cum[c + 1] = cum[c] + cell_cost[c];
+    lbl::partition_bands(cum, prefix, n_bands, edges);
     return 0;
 }

@@ -26,7 +26,8 @@ EMU_DIR = Path(__file__).resolve().parent / "emu"
 def emu():
     so, src = EMU_DIR / "libemu.so", EMU_DIR / "emu.cpp"
     core = EMU_DIR.parent.parent / "pylbl_b200" / "csrc"
-    newest = max(p.stat().st_mtime for p in (src, core / "lbl_core.cuh", core / "lbl_threads.cuh"))
+    newest = max(p.stat().st_mtime for p in (src, core / "lbl_core.cuh", core / "lbl_threads.cuh",
+                                             core / "lbl_bands.h"))
     if not so.exists() or so.stat().st_mtime < newest:
         subprocess.run(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off",
                         "-o", str(so), str(src)], check=True)
@@ -36,6 +37,8 @@ def emu():
     lib.emu_absorption.argtypes = [c_int, f64, f64, f64, c_int, c_int, c_int, f64, c_int] + \
         [f64] * 7 + [i32, f64, c_int, c_int, f64, f64, c_int, c_int, c_int, c_int, POINTER(c_longlong)]
     lib.emu_absorption.restype = c_int
+    lib.emu_partition_bands.argtypes = [f64, f64, c_int, c_int, i32]
+    lib.emu_partition_bands.restype = c_int
     return lib
 
 
@@ -207,3 +210,56 @@ def test_run_based_pedestal_against_the_slot_ring(emu, tmp_path, monkeypatch, bo
             continue
         assert scaled_error(runs[layer], k_ref, bounds[2], max(cut, 1)) <= FP64_TOL
         assert scaled_error(runs[layer], slots[layer], bounds[2], max(cut, 1)) <= 1e-12
+
+
+def partition(emu, cell_cost, prefix_cost, n_bands):
+    cell_cost = np.ascontiguousarray(cell_cost, dtype=np.float64)
+    prefix_cost = np.ascontiguousarray(prefix_cost, dtype=np.float64)
+    edges = np.zeros(n_bands + 1, dtype=np.int32)
+    assert emu.emu_partition_bands(cell_cost, prefix_cost, cell_cost.size, n_bands, edges) == 0
+    return edges
+
+
+def band_costs(cell_cost, prefix_cost, edges):
+    cum = np.concatenate([[0.], np.cumsum(cell_cost)])
+    return np.array([cum[hi] - cum[lo] + prefix_cost[hi] for lo, hi in zip(edges[:-1], edges[1:]) if hi > lo])
+
+
+def test_band_partition_minimises_the_largest_band(emu):
+    """The arithmetic behind `lbl_gas_band_edges` (pylbl_b200/csrc/lbl_bands.h; SURVEY.md 8(e):
+    contiguous bands balanced by cost): the edges cover the grid once, no band is empty while
+    there are cells, and the largest band cost -- cells plus what the pedestal recurrence over
+    the rows before the band's end costs -- is the smallest any contiguous partition reaches
+    (checked by exhaustive search on small grids)."""
+    import itertools
+    rng = np.random.default_rng(11)
+    for ncell, n_bands in ((7, 3), (9, 4), (12, 3), (10, 5)):
+        for trial in range(6):
+            cell = rng.uniform(0.1, 3.0, ncell) * (1. + 20. * (rng.random(ncell) < 0.15))
+            prefix = np.concatenate([[0.], np.cumsum(rng.uniform(0., 0.6, ncell))]) * (trial % 2)
+            edges = partition(emu, cell, prefix, n_bands)
+            assert edges[0] == 0 and edges[-1] == ncell and np.all(np.diff(edges) >= 1)
+            best = min(band_costs(cell, prefix, (0,) + cut + (ncell,)).max()
+                       for cut in itertools.combinations(range(1, ncell), n_bands - 1))
+            assert band_costs(cell, prefix, edges).max() <= best * (1. + 1e-12)
+
+
+def test_band_partition_edge_cases(emu):
+    # more bands than cells: one cell each, the rest empty at the end
+    edges = partition(emu, [1., 1., 1.], [0., 0., 0., 0.], 5)
+    assert list(edges) == [0, 1, 2, 3, 3, 3]
+    # one band
+    assert list(partition(emu, np.ones(10), np.zeros(11), 1)) == [0, 10]
+    # one cell that outweighs the rest: it gets a band of its own, the others still non-empty
+    cell = np.ones(8)
+    cell[3] = 1000.
+    edges = partition(emu, cell, np.zeros(9), 4)
+    assert edges[0] == 0 and edges[-1] == 8 and np.all(np.diff(edges) >= 1)
+    assert any(lo == 3 and hi == 4 for lo, hi in zip(edges[:-1], edges[1:]))
+    # no cost at all (a grid beyond the line list): still a valid cover
+    edges = partition(emu, np.zeros(6), np.zeros(7), 3)
+    assert edges[0] == 0 and edges[-1] == 6 and np.all(np.diff(edges) >= 0)
+    # uniform cells, a prefix cost that grows along the grid: later bands are narrower
+    edges = partition(emu, np.ones(400), 0.5 * np.arange(401), 4)
+    widths = np.diff(edges)
+    assert np.all(widths[:-1] >= widths[1:]) and widths[0] > widths[-1]
