@@ -114,3 +114,63 @@ def test_to_dataset_layout_with_a_stand_in_for_xarray(monkeypatch):
     total = s.to_dataset({"absorption": np.zeros((2, 3, n))}).data_vars
     assert total["absorption"].dims == ("dim_0", "dim_1", "wavenumber")
     assert total["absorption"].attrs == {"units": "m-1"}
+
+
+class FillingRecorder(object):
+    """Stands in for the library: records the calls; a submitted gas 'returns' a spectrum equal
+    to its own volume mixing ratio in every point of every layer (so that what the adapter does
+    with it afterwards can be checked); opening 'XeF6' fails the way a missing molecule does."""
+
+    def __init__(self):
+        self.calls = []
+
+    def lbl_last_error(self):
+        return b"Error: molecule XeF6 not found in database."
+
+    def __getattr__(self, name):
+        def call(*args):
+            self.calls.append((name, args))
+            if name == "lbl_gas_open" and args[1] == b"XeF6":
+                raise ValueError("Error inside c functions.")
+            if name == "lbl_gas_submit":
+                ptr, n_layers, p, t, x, v0, vn, npv, cut, ped, prec, dst = args
+                import ctypes
+                n = (vn - v0) * npv
+                k = np.ctypeslib.as_array(ctypes.cast(dst, ctypes.POINTER(ctypes.c_double)), shape=(n_layers, n))
+                k[:] = np.asarray(x)[:, None]
+            return 0
+        return call
+
+
+def test_per_gas_formats_against_the_reference_loop(monkeypatch):
+    """`compute_absorption("gas" | "all")` with the library replaced: beta = n * k[:grid.size] per
+    gas (pyLBL/spectroscopy.py:181-191), the mechanism axis of "all" with only "lines" filled
+    (:131,225-234), zeros for a molecule the database does not hold (:53-57), every gas submitted
+    before any is waited for, and remove_pedestal following the continuum backend (:163-164)."""
+    from pylbl_b200 import gas_optics, spectroscopy
+    rec = FillingRecorder()
+    for module in (gas_optics, spectroscopy):
+        monkeypatch.setattr(module._lib, "library", lambda: rec)
+    monkeypatch.setattr(Spectroscopy, "PINNED_LIMIT", 0)            # ordinary staging arrays
+    shape = (2, 3)
+    a = atmosphere(shape)
+    a["gases"]["CO2"] = np.full(shape, 4e-4)
+    a["gases"]["XeF6"] = np.full(shape, 1e-12)
+    grid = np.arange(1., 11., 0.01)[:-7]                            # the grid may stop short of vn
+    s = Spectroscopy(a, grid, "spectral.db", continua_backend=None)
+    per_gas = s.compute_absorption("gas")
+    assert set(per_gas) == {"wavenumber", "H2O_absorption", "CO2_absorption", "XeF6_absorption"}
+    n = number_density(a["temperature"], a["pressure"], a["gases"]["H2O"])
+    assert per_gas["H2O_absorption"].shape == shape + (grid.size,)
+    assert np.allclose(per_gas["H2O_absorption"], (n * 1e-3)[..., None])      # n * k, k == vmr here
+    assert not per_gas["XeF6_absorption"].any()
+    names = [c[0] for c in rec.calls if c[0] in ("lbl_gas_submit", "lbl_gas_wait")]
+    assert names == ["lbl_gas_submit"] * 2 + ["lbl_gas_wait"] * 2             # all in flight, then collected
+    assert all(c[1][9] == 0 for c in rec.calls if c[0] == "lbl_gas_submit")   # no continuum: no pedestal removal
+    everything = s.compute_absorption("all", remove_pedestal=True)
+    assert everything["mechanism"] == list(MECHANISMS)
+    h2o = everything["H2O_absorption"]
+    assert h2o.shape == shape + (len(MECHANISMS), grid.size)
+    assert np.array_equal(h2o[..., 0, :], per_gas["H2O_absorption"]) and not h2o[..., 1:, :].any()
+    assert [c[1][9] for c in rec.calls if c[0] == "lbl_gas_submit"][-2:] == [1, 1]
+    s.close()
