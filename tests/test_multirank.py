@@ -85,3 +85,44 @@ def test_layer_shards_cover_all_layers():
             sizes = np.diff(edges)
             assert edges[0] == 0 and edges[-1] == n_layers and np.all(sizes >= 1)
             assert sizes.max() - sizes.min() <= 1
+
+
+def test_no_collective_is_conditional_on_the_rank():
+    """Every rank must reach every collective: a reduction or barrier inside `if rank == 0:` (or
+    any branch on the rank) leaves the other ranks waiting until the watchdog fires -- a bench at
+    N > 1 that hangs for minutes instead of failing.  Static check of bench.py: no call of the
+    rank-wide helpers (Ranks.barrier / max / sum and the names bound to them, torch.distributed
+    collectives) inside a branch whose condition reads the rank."""
+    import ast
+    source = (Path(__file__).resolve().parent.parent / "bench.py").read_text()
+    tree = ast.parse(source)
+    collective = {"barrier", "max_over_ranks", "sum_over_ranks", "all_reduce", "all_gather", "broadcast",
+                  "reduce", "gather", "scatter", "all_to_all"}
+    rank_wide_methods = {"barrier", "max", "sum", "_reduce"}
+
+    def reads_rank(node):
+        return any(isinstance(n, ast.Name) and n.id in ("rank", "local_rank") for n in ast.walk(node)) or \
+            any(isinstance(n, ast.Attribute) and n.attr in ("rank", "local_rank") for n in ast.walk(node))
+
+    def is_collective(call):
+        f = call.func
+        if isinstance(f, ast.Name):
+            return f.id in collective
+        if isinstance(f, ast.Attribute):
+            owner = f.value.id if isinstance(f.value, ast.Name) else getattr(f.value, "attr", "")
+            if owner == "ranks" and f.attr in rank_wide_methods:
+                return True
+            return owner in ("dist", "distributed") and f.attr in collective
+        return False
+
+    offenders = []
+    for node in ast.walk(tree):
+        if isinstance(node, (ast.If, ast.IfExp, ast.While)) and reads_rank(node.test):
+            for branch in (node.body, node.orelse):
+                for stmt in (branch if isinstance(branch, list) else [branch]):
+                    for inner in ast.walk(stmt):
+                        if isinstance(inner, ast.Call) and is_collective(inner):
+                            offenders.append(inner.lineno)
+    assert offenders == [], f"collectives under a condition on the rank at bench.py lines {offenders}"
+    # and the check does see the helpers where they are legitimately used
+    assert sum(1 for n in ast.walk(tree) if isinstance(n, ast.Call) and is_collective(n)) >= 10
