@@ -134,8 +134,11 @@ LBL_API int lbl_gas_submit_band(lbl_gas* gas, int n_layers, const double* pressu
 /* k_pitch: doubles between the starts of consecutive host rows (0 = dense, m); with
  * k_pitch = (vn-v0)*n_per_v and k_host pointing at column band_lo*n_per_v of a whole-grid array,
  * the bands of several devices land side by side in one array.
- * lbl_gas_band_edges proposes n_bands contiguous bands of about equal work for this molecule:
- * edges[0..n_bands] are cell indices, band b = [edges[b], edges[b+1]).  Needs no GPU work. */
+ * lbl_gas_band_edges proposes n_bands contiguous bands for this molecule such that the costliest
+ * band is as cheap as possible (a band costs its cells -- window lines, direct lines and near
+ * zones, which widen with the wavenumber -- plus the pedestal recurrence over the rows before
+ * its end; the model assumes the pedestal is removed): edges[0..n_bands] are cell indices,
+ * band b = [edges[b], edges[b+1]), non-empty while there are cells.  Needs no GPU work. */
 LBL_API int lbl_gas_band_edges(lbl_gas* gas, int v0, int vn, int n_per_v, int cut_off, int n_bands,
                    int* edges);
 
